@@ -125,6 +125,9 @@ enum {
 
 /* rollupConfig.Do rollup.go:688; out has P = 1+(end-start)/step entries. returns samplesScanned */
 uint64_t vmo_rollup_do(const vmo_rollup_cfg* cfg, double* out, const double* values, const int64_t* timestamps, size_t n);
+double vmo_rollup_func_call(int func_id, double prev_value, int64_t prev_ts, const double* values, const int64_t* ts,
+                            size_t n, double real_prev, double real_next, int64_t curr_ts, size_t idx, int64_t window,
+                            const double* args, const double* args2);
 int64_t vmo_rollup_points(int64_t start, int64_t end, int64_t step);
 void vmo_remove_counter_resets(double* values, const int64_t* timestamps, size_t n, int64_t max_staleness);
 void vmo_delta_values(double* values, size_t n);

@@ -1,0 +1,42 @@
+import json
+import os
+import struct
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+STALE_NAN = struct.unpack("<d", struct.pack("<Q", 0x7FF0000000000002))[0]
+
+
+def gofloat(s):
+    """decode the float encoding used by tests/golden/go_kats.json"""
+    if s == "nan":
+        return float("nan")
+    if s == "inf":
+        return float("inf")
+    if s == "-inf":
+        return float("-inf")
+    if s == "stale":
+        return STALE_NAN
+    return float.fromhex(s)
+
+
+@pytest.fixture(scope="session")
+def kats():
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "go_kats.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle_lib
+    oracle_lib.lib()
+    return oracle_lib

@@ -80,6 +80,8 @@ def lib():
         "vmo_block_header_unmarshal": (None, [C.POINTER(BlockHeader), u8p]),
         "vmo_block_unmarshal": (C.c_int64, [i64p, f64p, i64p, C.POINTER(BlockHeader), u8p, u8p, C.c_int64, C.c_int64]),
         "vmo_rollup_do": (C.c_uint64, [C.POINTER(RollupCfg), f64p, f64p, i64p, sz]),
+        "vmo_rollup_func_call": (C.c_double, [C.c_int, C.c_double, C.c_int64, f64p, i64p, sz, C.c_double, C.c_double,
+                                              C.c_int64, sz, C.c_int64, f64p, f64p]),
         "vmo_rollup_points": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
         "vmo_remove_counter_resets": (None, [f64p, i64p, sz, C.c_int64]),
         "vmo_delta_values": (None, [f64p, sz]),
