@@ -1,0 +1,376 @@
+#!/usr/bin/env python3
+"""bench.py -- the hot path of BASELINE.json on N B200s of one node.
+
+Workload (BASELINE.json configs[1], the configuration `metric` is quoted on for one GPU):
+  decode 100 000 blocks (8192 samples each; timestamps delta-const, values ZSTD nearest-delta2 counters at scale -2,
+  rare resets) + rate(m[5m]) at step 15 s  ->  [100 000 x 8172] float64.
+One "step" = one pass of the hot path over that batch.  N > 1: every rank owns its own 100 000 blocks (series shard by
+TSID, no data-path collective) -> weak scaling.
+
+  value : samples/s with the compressed blocks already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e   : the same through the public host-buffer call (vmb_eval_rollup_host): H2D of descriptors+payload from pinned
+          host memory, decode, rollup, D2H of the result, all inside the timed region
+  roofline : the dominant kernel stage, algorithmic bytes / measured stage time vs MEASURED_PEAKS.json
+  cpu_baseline : the oracle (C++ restatement of the Go path, zstd through the reference's own libzstd when
+          oracle/_ref is present) on all host cores over a bounded sample of the same blocks  (rank 0, N = 1)
+
+  --impl reference : times the reference's CPU implementation of the path (see cpu_baseline) on the same config.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T0 = 1_700_000_000_000
+SCRAPE_MS = 15000
+SCALE = -2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--blocks", type=int, default=100_000, help="blocks (= series) per GPU")
+    ap.add_argument("--rows", type=int, default=8192)
+    ap.add_argument("--func", default="rate")
+    ap.add_argument("--window-ms", type=int, default=300_000)
+    ap.add_argument("--step-ms", type=int, default=15_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ synthetic input
+def gen_blocks(nblocks, rows, seed, chunk=4000):
+    """node_cpu_seconds_total-like counters, marshaled by the product's own encoder
+    (vmb_marshal_columns).  -> (descs structured array, payload np.uint8)"""
+    from victoriametrics_b200 import encoding, storage
+    rng = np.random.default_rng(seed)
+    ts = T0 + SCRAPE_MS * np.arange(rows, dtype=np.int64)
+    tdata, tmt, tfirst = encoding.marshal_timestamps(ts)
+    assert tmt == encoding.MarshalTypeDeltaConst
+    pieces = [tdata]
+    pos = tdata.size
+    cols = {k: [] for k in ("first_value", "val_off", "val_size", "val_mt")}
+    for c0 in range(0, nblocks, chunk):
+        n = min(chunk, nblocks - c0)
+        inc = rng.integers(0, 1501, (n, rows), dtype=np.int64)
+        inc[:, 0] += rng.integers(0, 10 ** 9, n)
+        v = np.cumsum(inc, axis=1)
+        resets = rng.random((n, rows)) < 1e-4
+        resets[:, 0] = False
+        base = np.maximum.accumulate(np.where(resets, v, 0), axis=1)
+        v -= base
+        payload, offs, mts, firsts = encoding.marshal_columns(v)
+        pieces.append(payload)
+        cols["first_value"].append(firsts)
+        cols["val_off"].append(offs[:-1] + pos)
+        cols["val_size"].append(np.diff(offs).astype(np.uint32))
+        cols["val_mt"].append(mts)
+        pos += payload.size
+    descs = storage.descs_from_arrays(
+        first_value=np.concatenate(cols["first_value"]), min_ts=tfirst, max_ts=int(ts[-1]), ts_off=0,
+        val_off=np.concatenate(cols["val_off"]), ts_size=tdata.size, val_size=np.concatenate(cols["val_size"]),
+        rows=np.full(nblocks, rows, dtype=np.uint32), series_idx=np.arange(nblocks, dtype=np.uint32), scale=SCALE,
+        ts_mt=tmt, val_mt=np.concatenate(cols["val_mt"]), precision_bits=64)
+    return descs, np.concatenate(pieces)
+
+
+def query_range(rows, window_ms, step_ms):
+    start = T0 + window_ms
+    end = T0 + SCRAPE_MS * (rows - 1)
+    return start, end, step_ms
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t_begin, t_end):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t_begin - 0.05 <= t <= t_end + 0.15 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(descs, payload, func, start, end, step, window, target_seconds, repeats=1):
+    """the oracle's threaded per-series loop (oracle/cpu_pipeline.cpp) on a bounded sample -> dict"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from rollup_names import RF
+    from victoriametrics_b200 import promql
+    L = O.lib()
+    fn = L.vmo_cpu_eval_rollup
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_size_t, O.u8p, C.c_int64, C.c_int64, C.POINTER(O.RollupCfg), C.c_int, C.c_int, O.f64p,
+                   C.POINTER(C.c_uint64), C.c_int, C.c_int]
+    rc = promql.get_rollup_configs(func, start, end, step, window)
+    cfg = O.RollupCfg(RF[func], start, end, step, window, 0, 0, int(rc.MayAdjustWindow), int(rc.isDefaultRollup),
+                      rc.samplesScannedPerCall, None, None)
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    P = rc.points
+    rows = int(descs["rows"][0])
+    kind = "reference" if L.vmo_zstd_ref_available() else "port"
+
+    def run(nb):
+        out = np.empty((nb, P), dtype=np.float64)
+        scanned = C.c_uint64(0)
+        t = time.perf_counter()
+        r = fn(descs.ctypes.data, nb, payload.ctypes.data_as(O.u8p), -(1 << 63), (1 << 63) - 1, C.byref(cfg),
+               int(rc.removeCounterResets), int(rc.dropStaleNaNs), out.ctypes.data_as(O.f64p), C.byref(scanned), cores, 1)
+        dt = time.perf_counter() - t
+        assert r == 0, r
+        return dt, out
+
+    nb0 = min(len(descs), max(cores * 8, 256))
+    run(nb0)  # warm-up (page-in, thread pool)
+    dt0, _ = run(nb0)
+    rate0 = nb0 * rows / dt0
+    wall_target = max(1.0, target_seconds / cores)  # target_seconds of CPU work spread over all cores, >= 1 s of wall
+    nb = int(wall_target * rate0 / rows)
+    nb = max(nb0, min(nb, len(descs)))
+    best = None
+    for _ in range(repeats):
+        dt, out = run(nb)
+        best = dt if best is None else min(best, dt)
+    return {"value": nb * rows / best, "unit": "samples/s", "cores": cores, "kind": kind,
+            "sample": "%d of %d blocks x %d rows, %.2f s wall on %d threads (C++ restatement of the Go path%s)" %
+                      (nb, len(descs), rows, best, cores, "; zstd via the reference's libzstd 1.5.7" if kind == "reference" else ""),
+            "seconds": best, "blocks": nb}, out
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    start, end, step = query_range(a.rows, a.window_ms, a.step_ms)
+    points = 1 + (end - start) // step
+    workload = "configs[1]: decode %d blocks x %d samples (ts delta-const, values zstd nearest-delta2 counters, scale %d) + %s()[%ds] step=%ds per GPU" % (
+        a.blocks, a.rows, SCALE, a.func, a.window_ms // 1000, a.step_ms // 1000)
+    base = {"metric": "rollup samples/sec (block decode + %s, raw samples decoded and scanned per second)" % a.func,
+            "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64 codec -> f64 rollup", "data": "synthetic",
+            "config": {"workload": workload, "blocks_per_gpu": a.blocks, "rows_per_block": a.rows, "points_per_series": int(points),
+                       "parallelism": "series sharded by TSID across %d GPU(s), no data-path collective" % a.gpus,
+                       "l2": "inputs (>=1.3 GB compressed, 13 GB decoded) exceed the 126 MB L2; no flush needed"}}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        descs, payload = gen_blocks(min(a.blocks, 20000), a.rows, seed=1234)
+        vals = []
+        for _ in range(a.warmup):
+            cpu_reference(descs, payload, a.func, start, end, step, a.window_ms, 2.0)
+        t_all = time.perf_counter()
+        last = None
+        for _ in range(a.steps):
+            last, _ = cpu_reference(descs, payload, a.func, start, end, step, a.window_ms, a.cpu_seconds / max(a.steps, 1) + 1.0)
+            vals.append(last["value"])
+        v = float(np.median(vals))
+        out = dict(base)
+        out.update({"impl": "reference", "value": v, "ms_per_step": 1e3 * a.blocks * a.rows / v,
+                    "cpu_baseline": dict(last, value=v), "gpu_launches": 0,
+                    "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "wall_s": time.perf_counter() - t_all})
+        out["config"]["note"] = "CPU reference arm: each step is a bounded sample of the workload; value = samples/s on all host cores"
+        print(json.dumps(out))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import victoriametrics_b200 as vm
+    from victoriametrics_b200 import _lib, promql, storage
+    ctx = vm.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    t_gen = time.perf_counter()
+    descs, payload = gen_blocks(a.blocks, a.rows, seed=1234 + rank)
+    gen_s = time.perf_counter() - t_gen
+    rows_total = int(a.blocks) * int(a.rows)
+    compressed = int(descs["val_size"].sum()) + int(descs["ts_size"][0])
+
+    blocks = storage.Blocks(descs, payload, ctx)
+    out_dev = torch.empty((a.blocks, points), dtype=torch.float64, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_step():
+        return promql.eval_rollup_func(a.func, blocks, start, end, step, a.window_ms, out_dev_ptr=out_dev.data_ptr())
+
+    # ---- kernel-only: compressed blocks resident in HBM
+    for _ in range(a.warmup):
+        dev_step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tb = time.time()
+    ev0.record(stream)
+    scanned = 0
+    for _ in range(a.steps):
+        _, scanned = dev_step()
+    ev1.record(stream)
+    barrier()
+    te = time.time()
+    launches = ctx.launch_count - l0
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(tb, te)
+    # per-stage device times of one extra step (CUDA events inside the library, same stream)
+    ctx.enable_stage_timing(True)
+    dev_step()
+    stage_ms = ctx.stage_ms()
+    ctx.enable_stage_timing(False)
+
+    # ---- e2e: host buffers in, host result out
+    e2e = None
+    if not a.no_e2e:
+        nbytes_out = a.blocks * points * 8
+        hp = _lib.lib().vmb_host_alloc(payload.size + 64)
+        ho = _lib.lib().vmb_host_alloc(nbytes_out)
+        hd = _lib.lib().vmb_host_alloc(descs.nbytes)
+        assert hp and ho and hd, "pinned host allocation failed"
+        h_payload = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(payload.size,))
+        h_payload[:] = payload
+        h_descs = np.ctypeslib.as_array(C.cast(hd, C.POINTER(C.c_uint8)), shape=(descs.nbytes,)).view(descs.dtype)
+        h_descs[:] = descs
+        h_out = np.ctypeslib.as_array(C.cast(ho, C.POINTER(C.c_double)), shape=(a.blocks, points))
+
+        def host_step():
+            return promql.eval_rollup_func_host(a.func, h_descs, h_payload, start, end, step, a.window_ms, out=h_out,
+                                                nseries=a.blocks, ctx=ctx)
+        for _ in range(max(1, min(a.warmup, 2))):
+            host_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tw = time.perf_counter()
+        e0.record(stream)
+        for _ in range(a.steps):
+            host_step()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - tw
+        e2e_ms = max(e0.elapsed_time(e1), 0.0)
+        e2e = {"ms": e2e_ms, "wall_ms": wall * 1e3, "h2d": int(descs.nbytes + payload.size), "d2h": int(nbytes_out)}
+        check = float(np.nansum(h_out[: min(a.blocks, 64)]))
+        dcheck = float(torch.nansum(out_dev[: min(a.blocks, 64)]).item())
+        assert abs(check - dcheck) <= 1e-9 * max(1.0, abs(dcheck)), (check, dcheck)
+
+    # ---- max over ranks
+    t = torch.tensor([dev_ms, e2e["ms"] if e2e else 0.0, e2e["wall_ms"] if e2e else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, e2e_wall_ms = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        ms_per_step = dev_ms / a.steps
+        value = world * rows_total / (ms_per_step / 1e3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+        varint_bytes = int(2 * rows_total)  # ~2 B/sample zig-zag varints in this workload (measured: raw/zstd ratio 0.86)
+        stage_names = ["zstd", "column_decode", "series_preamble", "rollup", "aggregate"]
+        stage_bytes = [compressed + varint_bytes,                          # zstd: read frames, write varint bytes
+                       varint_bytes + 64 * a.blocks + rows_total * 16,     # decode: read varints + descs, write ts+val
+                       rows_total * 16,                                    # preamble: read+write values (removeCounterResets)
+                       rows_total * 16 + a.blocks * points * 8, 0]         # rollup: read ts+val, write result
+        stages = {}
+        for n_, ms_, b_ in zip(stage_names, stage_ms, stage_bytes):
+            if ms_ > 0:
+                stages[n_] = {"ms": round(ms_, 4), "algorithmic_GB": round(b_ / 1e9, 3), "GBps": round(b_ / 1e9 / (ms_ / 1e3), 1)}
+        dom = max(stages, key=lambda k: stages[k]["ms"]) if stages else None
+        fused_bytes = compressed + a.blocks * points * 8
+        out = dict(base)
+        out.update({"value": value, "ms_per_step": ms_per_step, "gpu_launches": int(launches), "clocks": clocks,
+                    "samples_scanned_per_step": int(scanned)})
+        if dom:
+            ach = stages[dom]["GBps"]
+            out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                               "traffic": None, "peak_source": peak_src, "stages": stages,
+                               "whole_step": {"fused_algorithmic_GB": round(fused_bytes / 1e9, 3),
+                                              "GBps": round(fused_bytes / 1e9 / (ms_per_step / 1e3), 1),
+                                              "frac": round(fused_bytes / 1e9 / (ms_per_step / 1e3) / peak, 4)}}
+        out["decode_GBps_decoded_basis"] = round(rows_total * 16 / 1e9 / ((stage_ms[0] + stage_ms[1]) / 1e3), 1) if stage_ms[1] > 0 else None
+        if e2e:
+            per = e2e_ms / a.steps
+            out["e2e"] = {"value": world * rows_total / (per / 1e3), "unit": "samples/s", "ms_per_step": per,
+                          "wall_ms_per_step": e2e_wall_ms / a.steps, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                          "api": "vmb_eval_rollup_host (pinned host descriptors+payload in, pinned host result out)"}
+        out["config"]["compressed_bytes_per_gpu"] = compressed
+        out["config"]["bytes_per_sample_compressed"] = round(compressed / rows_total, 3)
+        out["config"]["input_generation_s"] = round(gen_s, 1)
+        if world == 1 and a.cpu_seconds > 0:
+            try:
+                cb, _ = cpu_reference(descs, payload, a.func, start, end, step, a.window_ms, a.cpu_seconds)
+                out["cpu_baseline"] = cb
+            except Exception as e:  # the oracle is optional for the product; report instead of failing the bench
+                out["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

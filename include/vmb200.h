@@ -1,0 +1,223 @@
+/*
+ * vmb200.h -- C ABI of libvmb200: a B200-native (sm_100a) implementation of VictoriaMetrics' data-parallel
+ * hot path: the per-series block codec (lib/encoding + lib/decimal) and the range-vector rollup executor
+ * (app/vmselect/promql), as scoped by SURVEY.md section 8.
+ *
+ * The reference has no FFI for this path (it is plain Go calls); each entry point below names the Go function
+ * (file:line under the reference checkout) it replaces.  The Go-side cgo binding is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 (VMB_OK) or a negative VMB_ERR_* code; vmb_last_error() gives thread-local text.
+ *   - plain pointers and sizes only.  Host buffers are caller-owned and never retained after return.
+ *   - device memory is library-owned behind opaque handles (vmb_blocks, vmb_series), or caller-owned raw device
+ *     pointers where an argument is documented as "device pointer" (e.g. a torch tensor's data_ptr()).
+ *   - there is NO CPU fallback: every compute entry point launches CUDA kernels and fails with
+ *     VMB_ERR_CUDA if no sm_100-class device is usable.
+ *   - all kernels of one vmb_ctx are issued on the ctx's stream (vmb_ctx_set_stream), so the caller can
+ *     bracket them with its own CUDA events.
+ */
+#ifndef VMB200_H
+#define VMB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMB_OK 0
+/* per-column decode errors: same numbering as the reference error sites they stand for */
+#define VMB_ERR_SHORT_SRC (-1)        /* lib/encoding/int.go:183,199,211 */
+#define VMB_ERR_VARINT_TOO_BIG (-2)   /* int.go:272 */
+#define VMB_ERR_VARINT_TOO_LONG (-3)  /* int.go:277 */
+#define VMB_ERR_TAIL (-4)             /* nearest_delta.go:65, encoding.go:238 */
+#define VMB_ERR_MARSHAL_TYPE (-5)     /* encoding.go:248 */
+#define VMB_ERR_ZSTD (-6)             /* encoding.go:181,193 */
+#define VMB_ERR_CONST_TAIL (-7)       /* encoding.go:217 */
+#define VMB_ERR_DELTA_CONST (-8)      /* encoding.go:235 */
+#define VMB_ERR_TS_BOUNDS (-9)        /* lib/storage/block.go:298 checkTimestampsBounds */
+#define VMB_ERR_ROWS (-10)            /* block.go:263 RowsCount must be > 0; block_header.go:233 <= 16384 */
+#define VMB_ERR_BLOCK_ORDER (-11)     /* blocks of one series overlap in time: needs mergeSortBlocks */
+/* API-level errors */
+#define VMB_ERR_INVALID_ARG (-50)     /* the Go code would logger.Panicf("BUG: ...") */
+#define VMB_ERR_CUDA (-51)
+#define VMB_ERR_NOMEM (-52)
+#define VMB_ERR_BLOCK_FAILED (-53)    /* at least one block failed to decode; see the per-block status array */
+#define VMB_ERR_CAP (-54)
+
+typedef struct vmb_ctx vmb_ctx;
+typedef struct vmb_blocks vmb_blocks;  /* compressed blocks resident in HBM (descriptors + payload arena) */
+typedef struct vmb_series vmb_series;  /* decoded columns resident in HBM: int64 timestamps + f64 values per series */
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int vmb_ctx_create(int device, vmb_ctx** out);
+void vmb_ctx_destroy(vmb_ctx* ctx);
+/* stream = a cudaStream_t (0 = legacy default stream). */
+int vmb_ctx_set_stream(vmb_ctx* ctx, void* stream);
+int vmb_ctx_synchronize(vmb_ctx* ctx);
+const char* vmb_last_error(void);
+int vmb_version(void);
+/* number of kernel launches issued by this ctx since creation (for bench.py's gpu_launches) */
+uint64_t vmb_ctx_launch_count(const vmb_ctx* ctx);
+
+/* ---- block descriptor  ==  lib/storage/block_header.go:19-82 blockHeader (the 81-byte wire form is parsed by
+ * vmb_block_desc_from_header) --------------------------------------------------------------------------- */
+typedef struct {
+    int64_t first_value;     /* FirstValue */
+    int64_t min_ts;          /* MinTimestamp (== firstTimestamp passed to UnmarshalTimestamps) */
+    int64_t max_ts;          /* MaxTimestamp */
+    uint64_t ts_off;         /* byte offset of the timestamps payload inside the payload arena */
+    uint64_t val_off;        /* byte offset of the values payload inside the payload arena */
+    uint32_t ts_size;        /* TimestampsBlockSize */
+    uint32_t val_size;       /* ValuesBlockSize */
+    uint32_t rows;           /* RowsCount, 1..16384 */
+    uint32_t series_idx;     /* dense series index; the blocks of one series are consecutive and time-ordered */
+    int16_t scale;           /* Scale: value = mantissa * 10^scale */
+    uint8_t ts_mt;           /* TimestampsMarshalType 1..6 (lib/encoding/encoding.go:20-43) */
+    uint8_t val_mt;          /* ValuesMarshalType */
+    uint8_t precision_bits;  /* PrecisionBits 1..64 */
+    uint8_t _pad[3];
+} vmb_block_desc; /* 64 bytes */
+
+/* blockHeader.Unmarshal block_header.go:122 (81 bytes, big endian); ts_off/val_off are taken from the header
+ * (file offsets) -- the caller rebases them onto its payload arena.  series_idx is left 0. */
+int vmb_block_desc_from_header(vmb_block_desc* out, const uint8_t header[81], uint8_t tsid_out[24]);
+
+/* ---- per-call drop-ins (single column; host buffers; run on the GPU) ------------------------------------- */
+/* encoding.UnmarshalValues / UnmarshalTimestamps  encoding.go:111 / :90 (unmarshalInt64Array :173) */
+int vmb_unmarshal_int64(vmb_ctx* ctx, int64_t* dst, size_t items_count, const uint8_t* src, size_t src_len, int mt,
+                        int64_t first_value);
+/* decimal.AppendDecimalToFloat  lib/decimal/decimal.go:100 */
+int vmb_decimal_to_float(vmb_ctx* ctx, double* dst, const int64_t* va, size_t n, int16_t e);
+/* encoding.MarshalValues / MarshalTimestamps  encoding.go:103 / :82 (marshalInt64Array :119).
+ * Host-side encoder (the write path stays on the host this round); zstd frames are produced by
+ * the library's own Huffman-literals compressor: valid zstd that libzstd/klauspost decode, not byte-identical to
+ * libzstd's output (compressed bytes are unpinned by the reference's tests). */
+int vmb_marshal_int64(uint8_t* dst, size_t cap, size_t* out_len, int* out_mt, int64_t* out_first, const int64_t* vals,
+                      size_t n, uint8_t precision_bits);
+/* the library's zstd writer on its own (exposed for tests) */
+int vmb_zstd_compress(uint8_t* dst, size_t cap, size_t* out_len, const uint8_t* src, size_t n);
+/* Block.MarshalData (block.go:192) for ncols equal-length int64 columns on `nthreads` host threads: payloads are written
+ * back to back into dst, offs[ncols+1] receives their offsets, mts/firsts the MarshalType and first value of each. */
+int vmb_marshal_columns(uint8_t* dst, size_t cap, uint64_t* offs, uint8_t* mts, int64_t* firsts, const int64_t* vals,
+                        size_t ncols, size_t rows, uint8_t precision_bits, int nthreads);
+/* decimal.AppendFloatToDecimal decimal.go:173 (host-side, write path) */
+int vmb_float_to_decimal(int64_t* dst, int16_t* out_scale, const double* src, size_t n);
+
+/* ---- batched block decode  ==  Block.UnmarshalData (block.go:250) + AppendRowsWithTimeRangeFilter (:324)
+ * for every block of a query at once (replaces netstorage.go:425 packedTimeseries.Unpack fan-out) ------------- */
+/* copies descriptors + payload host->device (the one H2D of the path). payload_len bytes are copied. */
+int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload,
+                      size_t payload_len, vmb_blocks** out);
+void vmb_blocks_free(vmb_blocks* b);
+size_t vmb_blocks_count(const vmb_blocks* b);
+uint64_t vmb_blocks_rows(const vmb_blocks* b);           /* sum of RowsCount */
+uint64_t vmb_blocks_compressed_bytes(const vmb_blocks* b); /* sum of ts_size + val_size */
+
+#define VMB_DECODE_VALUES_AS_INT64 1u /* leave values as int64 mantissas (no decimal->float) */
+/* decodes all blocks; rows outside [tr_min, tr_max] are trimmed like filterTimestamps (block.go:331).
+ * block_status (host, nblocks entries, may be NULL) receives 0 or a VMB_ERR_* per block.
+ * Returns VMB_ERR_BLOCK_FAILED if any block failed (the batch is still returned; failed blocks have 0 rows). */
+int vmb_decode_blocks(vmb_ctx* ctx, const vmb_blocks* blocks, int64_t tr_min, int64_t tr_max, uint32_t flags,
+                      int32_t* block_status, vmb_series** out);
+
+/* builds a device batch from already-decoded host columns (the `values, timestamps` arguments of
+ * rollupConfig.Do): series s owns rows [offsets[s], offsets[s+1]) */
+int vmb_series_from_host(vmb_ctx* ctx, const int64_t* timestamps, const double* values, const uint64_t* offsets,
+                         size_t nseries, vmb_series** out);
+void vmb_series_free(vmb_series* s);
+size_t vmb_series_count(const vmb_series* s);
+uint64_t vmb_series_rows(const vmb_series* s); /* allocated rows (before trimming / stale-NaN drop) */
+/* per-series current (start,row count) -> host arrays of nseries entries */
+int vmb_series_layout(vmb_ctx* ctx, const vmb_series* s, uint64_t* starts, uint32_t* counts);
+/* copies the dense decoded columns (vmb_series_rows entries each) device->host; either pointer may be NULL */
+int vmb_series_download(vmb_ctx* ctx, const vmb_series* s, int64_t* timestamps, double* values);
+
+/* ---- rollup  ==  rollupConfig.Do (rollup.go:688) for every series at once, preceded by the per-series preamble of
+ * eval.go:1855 (dropStaleNaNs eval.go:1985, preFunc = removeCounterResets rollup.go:921) ------------------------- */
+enum vmb_rollup_func { /* rollup.go:24-108; names in comments are the MetricsQL names */
+    VMB_RF_DEFAULT_ROLLUP = 0, VMB_RF_RATE /* rate, deriv_fast */, VMB_RF_DELTA /* delta, increase */, VMB_RF_AVG,
+    VMB_RF_MIN, VMB_RF_MAX, VMB_RF_SUM, VMB_RF_COUNT, VMB_RF_QUANTILE, VMB_RF_FIRST, VMB_RF_LAST, VMB_RF_RANGE,
+    VMB_RF_SUM2, VMB_RF_STDDEV, VMB_RF_STDVAR, VMB_RF_IDERIV /* ideriv, irate */, VMB_RF_IDELTA, VMB_RF_DERIV,
+    VMB_RF_INCREASE_PURE, VMB_RF_CHANGES, VMB_RF_CHANGES_PROMETHEUS, VMB_RF_RESETS /* resets, decreases_over_time */,
+    VMB_RF_INCREASES, VMB_RF_INTEGRATE, VMB_RF_LAG, VMB_RF_LIFETIME, VMB_RF_SCRAPE_INTERVAL, VMB_RF_TMIN, VMB_RF_TMAX,
+    VMB_RF_TFIRST, VMB_RF_TLAST /* tlast_over_time, timestamp */, VMB_RF_TLAST_CHANGE, VMB_RF_MODE, VMB_RF_MAD,
+    VMB_RF_OUTLIER_IQR, VMB_RF_ZSCORE, VMB_RF_ASCENT, VMB_RF_DESCENT, VMB_RF_DISTINCT, VMB_RF_GEOMEAN,
+    VMB_RF_PREDICT_LINEAR, VMB_RF_HOLT_WINTERS, VMB_RF_HOEFFDING_LOWER, VMB_RF_HOEFFDING_UPPER, VMB_RF_DURATION,
+    VMB_RF_COUNT_LE, VMB_RF_COUNT_GT, VMB_RF_COUNT_EQ, VMB_RF_COUNT_NE, VMB_RF_SHARE_LE, VMB_RF_SHARE_GT,
+    VMB_RF_SHARE_EQ, VMB_RF_SUM_LE, VMB_RF_SUM_GT, VMB_RF_SUM_EQ, VMB_RF_PRESENT, VMB_RF_ABSENT, VMB_RF_STALE_SAMPLES,
+    VMB_RF_MEDIAN, VMB_RF_RATE_OVER_SUM, VMB_RF_DELTA_PROMETHEUS /* delta_prometheus, increase_prometheus */,
+    VMB_RF_RATE_PROMETHEUS, VMB_RF_OPEN, VMB_RF_CLOSE, VMB_RF_HIGH, VMB_RF_LOW, VMB_RF__COUNT
+};
+
+#define VMB_RC_MAY_ADJUST_WINDOW 1u     /* rollupFuncsCanAdjustWindow rollup.go:199 */
+#define VMB_RC_IS_DEFAULT_ROLLUP 2u     /* funcName == "default_rollup" rollup.go:408 */
+#define VMB_RC_REMOVE_COUNTER_RESETS 4u /* rollupFuncsRemoveCounterResets rollup.go:223: preFunc */
+#define VMB_RC_DROP_STALE_NANS 8u       /* eval.go:1985 (not for default_rollup / stale_samples_over_time) */
+
+typedef struct { /* == rollupConfig rollup.go:574 + what getRollupConfigs (rollup.go:374) derives from the func name */
+    int32_t func_id;          /* enum vmb_rollup_func */
+    uint32_t flags;           /* VMB_RC_* */
+    int64_t start, end, step; /* ms; output grid = start, start+step, ... <= end (eval.go:230 getTimestamps) */
+    int64_t window;           /* ms; 0 = not set */
+    int64_t lookback_delta;   /* ms; rollupConfig.LookbackDelta */
+    int64_t min_staleness_ms; /* -search.minStalenessInterval rollup.go:20 */
+    int32_t samples_scanned_per_call; /* rollupFuncsSamplesScannedPerCall rollup.go:238; 0 = len(window) */
+    int32_t _pad;
+    const double* args;       /* host, P entries or NULL: per-point scalar arg (phi / limit / secs / sf) */
+    const double* args2;      /* host, P entries or NULL: second per-point arg (holt_winters tf) */
+} vmb_rollup_cfg;
+
+/* number of output points: 1 + (end-start)/step  (eval.go:243) */
+int64_t vmb_rollup_points(const vmb_rollup_cfg* cfg);
+
+/* Runs the per-series preamble (in place on the batch: call once per batch) and the rollup.
+ * out: [nseries x P] row-major doubles; out_is_device != 0 => out is a device pointer, else host.
+ * samples_scanned (host, may be NULL) = sum over series of rollupConfig.Do's second result. */
+int vmb_rollup(vmb_ctx* ctx, vmb_series* series, const vmb_rollup_cfg* cfg, double* out, int out_is_device,
+               uint64_t* samples_scanned);
+
+/* ---- aggr(rollup(...)) by (...)  ==  evalRollupWithIncrementalAggregate eval.go:1804 + aggr_incremental.go ------ */
+enum vmb_aggr_func { VMB_AGGR_SUM = 0, VMB_AGGR_MIN, VMB_AGGR_MAX, VMB_AGGR_AVG, VMB_AGGR_COUNT, VMB_AGGR_SUM2,
+                     VMB_AGGR_GEOMEAN, VMB_AGGR_ANY, VMB_AGGR_GROUP };
+/* Per-GPU partial state (the per-worker incrementalAggrContext, aggr_incremental.go:184): folds every series of the
+ * batch into d_values/d_counts ([ngroups x P] DEVICE pointers, overwritten). group_ids: host, nseries entries, dense
+ * ids assigned by the host from the group-by label set (identically on all ranks).  Within a group the series are
+ * folded in ascending series order (deterministic).  d_rollup_scratch: device pointer to [nseries x P] doubles or
+ * NULL to let the library allocate it. */
+int vmb_rollup_aggr_partial(vmb_ctx* ctx, vmb_series* series, const vmb_rollup_cfg* cfg, int aggr_id,
+                            const uint32_t* group_ids, uint32_t ngroups, double* d_values, double* d_counts,
+                            double* d_rollup_scratch, uint64_t* samples_scanned);
+/* mergeAggr* (aggr_incremental.go:218...): dst <- merge(dst, src), all DEVICE pointers, n = ngroups*P.
+ * (Multi-GPU runs replace this by one NCCL all-reduce of values and counts for sum/avg/count/sum2, see DESIGN.md.) */
+int vmb_aggr_merge(vmb_ctx* ctx, int aggr_id, double* d_dst_values, double* d_dst_counts, const double* d_src_values,
+                   const double* d_src_counts, size_t n);
+/* makes partial state all-reduce-able with ncclSum (values of empty cells zeroed) or ncclMin/ncclMax (+-Inf) */
+int vmb_aggr_prepare_allreduce(vmb_ctx* ctx, int aggr_id, double* d_values, const double* d_counts, size_t n);
+/* finalizeAggr* (aggr_incremental.go:189,:368,:400...): in place on DEVICE pointers, then optional copy to out_host */
+int vmb_aggr_finalize(vmb_ctx* ctx, int aggr_id, double* d_values, const double* d_counts, size_t n, double* out_host);
+
+/* ---- whole path in one call with HOST buffers (what a patched evalRollupNoIncrementalAggregate, eval.go:1845,
+ * would call): H2D of descriptors+payload, decode, preamble, rollup, D2H of the [nseries x P] result; processed in
+ * chunks so copies overlap the kernels.  out_host: [nseries x P]. */
+int vmb_eval_rollup_host(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload,
+                         size_t payload_len, int64_t tr_min, int64_t tr_max, const vmb_rollup_cfg* cfg, double* out_host,
+                         int32_t* block_status, uint64_t* samples_scanned);
+
+/* device-resident variant used for kernel-only timing: decode + preamble + rollup, result left in d_out (device) */
+int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* blocks, int64_t tr_min, int64_t tr_max,
+                           const vmb_rollup_cfg* cfg, double* d_out, uint64_t* samples_scanned);
+
+/* pinned host memory helpers (cudaHostAlloc) for callers that want full PCIe speed */
+void* vmb_host_alloc(size_t bytes);
+void vmb_host_free(void* p);
+
+/* timing hooks: elapsed device time (ms) of the named stage during the last batched call on this ctx;
+ * stage: 0 = zstd, 1 = column decode, 2 = series preamble, 3 = rollup, 4 = aggregate */
+float vmb_ctx_last_stage_ms(const vmb_ctx* ctx, int stage);
+int vmb_ctx_enable_stage_timing(vmb_ctx* ctx, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMB200_H */

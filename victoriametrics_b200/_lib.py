@@ -1,0 +1,166 @@
+"""ctypes binding of libvmb200.so (include/vmb200.h).  Fails loudly if the CUDA library is missing: there is no CPU path."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libvmb200.so")
+
+u8p = C.POINTER(C.c_uint8)
+i64p = C.POINTER(C.c_int64)
+f64p = C.POINTER(C.c_double)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+i32p = C.POINTER(C.c_int32)
+
+
+class BlockDesc(C.Structure):
+    """vmb_block_desc == lib/storage/block_header.go:19 blockHeader"""
+    _fields_ = [("first_value", C.c_int64), ("min_ts", C.c_int64), ("max_ts", C.c_int64), ("ts_off", C.c_uint64),
+                ("val_off", C.c_uint64), ("ts_size", C.c_uint32), ("val_size", C.c_uint32), ("rows", C.c_uint32),
+                ("series_idx", C.c_uint32), ("scale", C.c_int16), ("ts_mt", C.c_uint8), ("val_mt", C.c_uint8),
+                ("precision_bits", C.c_uint8), ("_pad", C.c_uint8 * 3)]
+
+
+assert C.sizeof(BlockDesc) == 64
+
+
+class RollupCfg(C.Structure):
+    """vmb_rollup_cfg == rollupConfig (rollup.go:574)"""
+    _fields_ = [("func_id", C.c_int32), ("flags", C.c_uint32), ("start", C.c_int64), ("end", C.c_int64),
+                ("step", C.c_int64), ("window", C.c_int64), ("lookback_delta", C.c_int64),
+                ("min_staleness_ms", C.c_int64), ("samples_scanned_per_call", C.c_int32), ("_pad", C.c_int32),
+                ("args", f64p), ("args2", f64p)]
+
+
+class VmbError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__("libvmb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError("victoriametrics_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; "
+                          "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % SO_PATH)
+    L = C.CDLL(SO_PATH)
+    sz = C.c_size_t
+    vp = C.c_void_p
+    sig = {
+        "vmb_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "vmb_ctx_destroy": (None, [vp]),
+        "vmb_ctx_set_stream": (C.c_int, [vp, vp]),
+        "vmb_ctx_synchronize": (C.c_int, [vp]),
+        "vmb_last_error": (C.c_char_p, []),
+        "vmb_version": (C.c_int, []),
+        "vmb_ctx_launch_count": (C.c_uint64, [vp]),
+        "vmb_block_desc_from_header": (C.c_int, [C.POINTER(BlockDesc), u8p, u8p]),
+        "vmb_unmarshal_int64": (C.c_int, [vp, i64p, sz, u8p, sz, C.c_int, C.c_int64]),
+        "vmb_decimal_to_float": (C.c_int, [vp, f64p, i64p, sz, C.c_int16]),
+        "vmb_marshal_int64": (C.c_int, [u8p, sz, C.POINTER(sz), C.POINTER(C.c_int), i64p, i64p, sz, C.c_uint8]),
+        "vmb_float_to_decimal": (C.c_int, [i64p, C.POINTER(C.c_int16), f64p, sz]),
+        "vmb_zstd_compress": (C.c_int, [u8p, sz, C.POINTER(sz), u8p, sz]),
+        "vmb_marshal_columns": (C.c_int, [u8p, sz, u64p, u8p, i64p, i64p, sz, sz, C.c_uint8, C.c_int]),
+        "vmb_blocks_upload": (C.c_int, [vp, C.POINTER(BlockDesc), sz, u8p, sz, C.POINTER(vp)]),
+        "vmb_blocks_free": (None, [vp]),
+        "vmb_blocks_count": (sz, [vp]),
+        "vmb_blocks_rows": (C.c_uint64, [vp]),
+        "vmb_blocks_compressed_bytes": (C.c_uint64, [vp]),
+        "vmb_decode_blocks": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_uint32, i32p, C.POINTER(vp)]),
+        "vmb_series_from_host": (C.c_int, [vp, i64p, f64p, u64p, sz, C.POINTER(vp)]),
+        "vmb_series_free": (None, [vp]),
+        "vmb_series_count": (sz, [vp]),
+        "vmb_series_rows": (C.c_uint64, [vp]),
+        "vmb_series_layout": (C.c_int, [vp, vp, u64p, u32p]),
+        "vmb_series_download": (C.c_int, [vp, vp, i64p, f64p]),
+        "vmb_rollup_points": (C.c_int64, [C.POINTER(RollupCfg)]),
+        "vmb_rollup": (C.c_int, [vp, vp, C.POINTER(RollupCfg), vp, C.c_int, u64p]),
+        "vmb_rollup_aggr_partial": (C.c_int, [vp, vp, C.POINTER(RollupCfg), C.c_int, u32p, C.c_uint32, vp, vp, vp, u64p]),
+        "vmb_aggr_merge": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, sz]),
+        "vmb_aggr_prepare_allreduce": (C.c_int, [vp, C.c_int, vp, vp, sz]),
+        "vmb_aggr_finalize": (C.c_int, [vp, C.c_int, vp, vp, sz, f64p]),
+        "vmb_eval_rollup_host": (C.c_int, [vp, C.POINTER(BlockDesc), sz, u8p, sz, C.c_int64, C.c_int64,
+                                           C.POINTER(RollupCfg), f64p, i32p, u64p]),
+        "vmb_eval_rollup_device": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.POINTER(RollupCfg), vp, u64p]),
+        "vmb_host_alloc": (vp, [sz]),
+        "vmb_host_free": (None, [vp]),
+        "vmb_ctx_last_stage_ms": (C.c_float, [vp, C.c_int]),
+        "vmb_ctx_enable_stage_timing": (C.c_int, [vp, C.c_int]),
+    }
+    missing = []
+    for name, (res, args) in sig.items():
+        try:
+            fn = getattr(L, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    if missing:
+        raise ImportError("libvmb200.so lacks symbols declared in include/vmb200.h: %s" % missing)
+    _lib = L
+    return L
+
+
+EXPORTED = None  # filled lazily by tests: list of symbol names
+
+
+def check(rc, allow=()):
+    if rc != 0 and rc not in allow:
+        raise VmbError(rc, lib().vmb_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+class Context:
+    """vmb_ctx: one per process per GPU."""
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        check(lib().vmb_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, stream):
+        check(lib().vmb_ctx_set_stream(self.h, C.c_void_p(int(stream))))
+
+    def synchronize(self):
+        check(lib().vmb_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(lib().vmb_ctx_launch_count(self.h))
+
+    def enable_stage_timing(self, on=True):
+        check(lib().vmb_ctx_enable_stage_timing(self.h, int(on)))
+
+    def stage_ms(self):
+        return [float(lib().vmb_ctx_last_stage_ms(self.h, i)) for i in range(5)]
+
+    def close(self):
+        if self.h:
+            lib().vmb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        dev = int(os.environ.get("LOCAL_RANK", "0"))
+        _default_ctx = Context(dev)
+    return _default_ctx

@@ -1,0 +1,985 @@
+// libvmb200: C ABI (include/vmb200.h), device memory management and kernel orchestration.
+// Single translation unit: the kernel files are included below so that no relocatable device code is needed.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "decode.cu"
+#include "rollup.cu"
+#include "zstd.cu"
+#include "marshal.inc"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512];
+void vmb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* vmb_last_error(void) { return g_err; }
+extern "C" int vmb_version(void) { return 100; }
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            vmb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return VMB_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+struct DevBuf {  // grow-only device buffer
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            vmb_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            p = nullptr;
+            return VMB_ERR_NOMEM;
+        }
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct vmb_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    uint64_t launches = 0;
+    bool timing = false;
+    float stage_ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev[6] = {0, 0, 0, 0, 0, 0};
+    // scratch (reused across calls)
+    DevBuf zscratch, zlit, zstatus, zjobs, zws, args1, args2, rolled, counters, tmp_out, grp;
+    void* h_pinned = nullptr;  // small pinned staging area for counters
+};
+
+struct vmb_blocks {
+    vmb_ctx* ctx = nullptr;
+    size_t nblocks = 0, nseries = 0;
+    uint64_t rows = 0, compressed = 0, scratch_total = 0;
+    bool needs_lit = false;
+    uint32_t n_huf = 0, n_gen = 0, n_bad = 0;
+    vmb_block_desc* d_descs = nullptr;
+    uint8_t* d_payload = nullptr;
+    ColInfo* d_cols = nullptr;
+    uint64_t* d_row_off = nullptr;
+    uint32_t* d_huf_list = nullptr;
+    uint32_t* d_gen_list = nullptr;
+    uint32_t* d_bad_list = nullptr;
+    uint32_t* d_ser_first = nullptr;
+    uint32_t* d_ser_nblocks = nullptr;
+};
+
+struct vmb_series {
+    vmb_ctx* ctx = nullptr;
+    size_t nseries = 0, nblocks = 0;
+    uint64_t rows = 0;
+    int64_t* d_ts = nullptr;
+    double* d_vals = nullptr;
+    SeriesMeta* d_meta = nullptr;
+    uint32_t* d_blk_lo = nullptr;
+    uint32_t* d_blk_hi = nullptr;
+    int32_t* d_blk_status = nullptr;
+    bool stale_dropped = false, resets_removed = false;
+    bool values_are_int = false;
+};
+
+static inline void count_launch(vmb_ctx* c, int n = 1) { c->launches += (uint64_t)n; }
+
+// ------------------------------------------------------------------------------------------------ context
+extern "C" int vmb_ctx_create(int device, vmb_ctx** out) {
+    if (!out) return VMB_ERR_INVALID_ARG;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        vmb_set_error("no CUDA device available (%s): libvmb200 has no CPU fallback", cudaGetErrorString(e));
+        return VMB_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        vmb_set_error("device %d out of range (%d devices)", device, ndev);
+        return VMB_ERR_INVALID_ARG;
+    }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        vmb_set_error("device %d is sm_%d%d; libvmb200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return VMB_ERR_CUDA;
+    }
+    vmb_ctx* c = new vmb_ctx();
+    c->device = device;
+    for (int i = 0; i < 6; i++) CU(cudaEventCreate(&c->ev[i]));
+    CU(cudaHostAlloc(&c->h_pinned, 4096, cudaHostAllocDefault));
+    *out = c;
+    return VMB_OK;
+}
+extern "C" void vmb_ctx_destroy(vmb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->zscratch, &c->zlit, &c->zstatus, &c->zjobs, &c->zws, &c->args1, &c->args2, &c->rolled,
+                      &c->counters, &c->tmp_out, &c->grp};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 6; i++)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    delete c;
+}
+extern "C" int vmb_ctx_set_stream(vmb_ctx* c, void* stream) {
+    if (!c) return VMB_ERR_INVALID_ARG;
+    c->stream = (cudaStream_t)stream;
+    return VMB_OK;
+}
+extern "C" int vmb_ctx_synchronize(vmb_ctx* c) {
+    if (!c) return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return VMB_OK;
+}
+extern "C" uint64_t vmb_ctx_launch_count(const vmb_ctx* c) { return c ? c->launches : 0; }
+extern "C" float vmb_ctx_last_stage_ms(const vmb_ctx* c, int stage) {
+    return (c && stage >= 0 && stage < 5) ? c->stage_ms[stage] : 0.f;
+}
+extern "C" int vmb_ctx_enable_stage_timing(vmb_ctx* c, int enable) {
+    if (!c) return VMB_ERR_INVALID_ARG;
+    c->timing = enable != 0;
+    return VMB_OK;
+}
+extern "C" void* vmb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void vmb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------------ block header
+static inline uint64_t be_get(const uint8_t* s, int n) {
+    uint64_t v = 0;
+    for (int i = 0; i < n; i++) v = (v << 8) | s[i];
+    return v;
+}
+extern "C" int vmb_block_desc_from_header(vmb_block_desc* d, const uint8_t h[81], uint8_t tsid_out[24]) {
+    if (!d || !h) return VMB_ERR_INVALID_ARG;
+    memset(d, 0, sizeof(*d));
+    if (tsid_out) memcpy(tsid_out, h, 24);
+    auto unzz = [](uint64_t u) { return (int64_t)(u >> 1) ^ -(int64_t)(u & 1); };  // int.go:79
+    d->min_ts = unzz(be_get(h + 24, 8));
+    d->max_ts = unzz(be_get(h + 32, 8));
+    d->first_value = unzz(be_get(h + 40, 8));
+    d->ts_off = be_get(h + 48, 8);
+    d->val_off = be_get(h + 56, 8);
+    d->ts_size = (uint32_t)be_get(h + 64, 4);
+    d->val_size = (uint32_t)be_get(h + 68, 4);
+    d->rows = (uint32_t)be_get(h + 72, 4);
+    uint16_t u = (uint16_t)be_get(h + 76, 2);
+    d->scale = (int16_t)((int16_t)(u >> 1) ^ (int16_t)(-(int16_t)(u & 1)));  // int.go:61
+    d->ts_mt = h[78];
+    d->val_mt = h[79];
+    d->precision_bits = h[80];
+    // blockHeader.validate block_header.go:230
+    if (d->rows == 0 || d->rows > 16384) return VMB_ERR_ROWS;
+    if (d->ts_mt > 6 || d->val_mt > 6) return VMB_ERR_MARSHAL_TYPE;
+    if (d->precision_bits < 1 || d->precision_bits > 64) return VMB_ERR_INVALID_ARG;
+    if (d->ts_size > 131072 || d->val_size > 131072) return VMB_ERR_INVALID_ARG;
+    return VMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ upload
+template <class T>
+static int dev_alloc(T** p, size_t n) {
+    *p = nullptr;
+    cudaError_t e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        vmb_set_error("cudaMalloc(%zu) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        return VMB_ERR_NOMEM;
+    }
+    return 0;
+}
+
+extern "C" void vmb_blocks_free(vmb_blocks* b) {
+    if (!b) return;
+    if (b->ctx) cudaSetDevice(b->ctx->device);
+    cudaFree(b->d_descs);
+    cudaFree(b->d_payload);
+    cudaFree(b->d_cols);
+    cudaFree(b->d_row_off);
+    cudaFree(b->d_huf_list);
+    cudaFree(b->d_gen_list);
+    cudaFree(b->d_bad_list);
+    cudaFree(b->d_ser_first);
+    cudaFree(b->d_ser_nblocks);
+    delete b;
+}
+extern "C" size_t vmb_blocks_count(const vmb_blocks* b) { return b ? b->nblocks : 0; }
+extern "C" uint64_t vmb_blocks_rows(const vmb_blocks* b) { return b ? b->rows : 0; }
+extern "C" uint64_t vmb_blocks_compressed_bytes(const vmb_blocks* b) { return b ? b->compressed : 0; }
+
+// host-side analysis shared by upload paths; fills the vectors
+struct BlocksPlan {
+    std::vector<ColInfo> cols;
+    std::vector<uint64_t> row_off;
+    std::vector<uint32_t> huf, gen, bad, ser_first, ser_nblocks;
+    uint64_t rows = 0, compressed = 0, scratch_total = 0;
+    bool needs_lit = false;
+};
+static int plan_blocks(BlocksPlan& pl, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload, size_t payload_len) {
+    pl.cols.resize(2 * nblocks);
+    pl.row_off.resize(nblocks + 1);
+    uint64_t scratch = 0;
+    for (size_t b = 0; b < nblocks; b++) {
+        const vmb_block_desc& d = descs[b];
+        pl.row_off[b] = pl.rows;
+        pl.rows += d.rows <= 16384 ? d.rows : 0;  // invalid blocks get status VMB_ERR_ROWS in the kernel and occupy no rows
+        pl.compressed += (uint64_t)d.ts_size + d.val_size;
+        if ((uint64_t)d.ts_off + d.ts_size > payload_len || (uint64_t)d.val_off + d.val_size > payload_len) {
+            vmb_set_error("block %zu: payload range outside the arena (len %zu)", b, payload_len);
+            return VMB_ERR_INVALID_ARG;
+        }
+        if (b == 0 || d.series_idx != descs[b - 1].series_idx) {
+            pl.ser_first.push_back((uint32_t)b);
+            pl.ser_nblocks.push_back(1);
+        } else {
+            pl.ser_nblocks.back()++;
+        }
+        for (int which = 0; which < 2; which++) {
+            ColInfo& ci = pl.cols[2 * b + which];
+            memset(&ci, 0, sizeof(ci));
+            int mt = which ? d.val_mt : d.ts_mt;
+            if (mt != 1 && mt != 4) continue;
+            const uint8_t* src = payload + (which ? d.val_off : d.ts_off);
+            uint32_t len = which ? d.val_size : d.ts_size;
+            uint32_t cs = 0;
+            bool needs_lit = false;
+            ci.kind = zstd_classify_host(src, len, d.rows <= 16384 ? d.rows : 0, &cs, &needs_lit);
+            ci.content_size = cs;
+            uint32_t col = (uint32_t)(2 * b + which);
+            if (ci.kind == VMB_ZK_BAD) {
+                pl.bad.push_back(col);
+                continue;
+            }
+            ci.scratch_off = scratch;
+            scratch += ((uint64_t)cs + 15) & ~(uint64_t)15;
+            if (needs_lit) pl.needs_lit = true;
+            if (ci.kind == VMB_ZK_HUF) pl.huf.push_back(col);
+            else pl.gen.push_back(col);
+        }
+    }
+    pl.row_off[nblocks] = pl.rows;
+    pl.scratch_total = scratch;
+    return 0;
+}
+
+template <class T>
+static int upload_vec(T** dptr, const std::vector<T>& v, cudaStream_t st) {
+    int rc = dev_alloc(dptr, v.size());
+    if (rc) return rc;
+    if (!v.empty()) CU(cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload,
+                                 size_t payload_len, vmb_blocks** out) {
+    if (!ctx || !out || (nblocks && !descs) || (payload_len && !payload) || nblocks > 0x7fffffffu / 2) return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    BlocksPlan pl;
+    int rc = plan_blocks(pl, descs, nblocks, payload, payload_len);
+    if (rc) return rc;
+    vmb_blocks* b = new vmb_blocks();
+    b->ctx = ctx;
+    b->nblocks = nblocks;
+    b->nseries = pl.ser_first.size();
+    b->rows = pl.rows;
+    b->compressed = pl.compressed;
+    b->scratch_total = pl.scratch_total;
+    b->needs_lit = pl.needs_lit;
+    b->n_huf = (uint32_t)pl.huf.size();
+    b->n_gen = (uint32_t)pl.gen.size();
+    b->n_bad = (uint32_t)pl.bad.size();
+    cudaStream_t st = ctx->stream;
+#define TRY(x)                 \
+    do {                       \
+        int rc_ = (x);         \
+        if (rc_) {             \
+            vmb_blocks_free(b); \
+            return rc_;        \
+        }                      \
+    } while (0)
+    TRY(dev_alloc(&b->d_descs, nblocks));
+    if (nblocks) CU(cudaMemcpyAsync(b->d_descs, descs, nblocks * sizeof(vmb_block_desc), cudaMemcpyHostToDevice, st));
+    TRY(dev_alloc(&b->d_payload, payload_len + 64));
+    if (payload_len) CU(cudaMemcpyAsync(b->d_payload, payload, payload_len, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(b->d_payload + payload_len, 0, 64, st));
+    TRY(upload_vec(&b->d_cols, pl.cols, st));
+    TRY(upload_vec(&b->d_row_off, pl.row_off, st));
+    TRY(upload_vec(&b->d_huf_list, pl.huf, st));
+    TRY(upload_vec(&b->d_gen_list, pl.gen, st));
+    TRY(upload_vec(&b->d_bad_list, pl.bad, st));
+    TRY(upload_vec(&b->d_ser_first, pl.ser_first, st));
+    TRY(upload_vec(&b->d_ser_nblocks, pl.ser_nblocks, st));
+#undef TRY
+    CU(cudaStreamSynchronize(st));  // the host vectors go out of scope
+    *out = b;
+    return VMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ series batches
+extern "C" void vmb_series_free(vmb_series* s) {
+    if (!s) return;
+    if (s->ctx) cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_ts);
+    cudaFree(s->d_vals);
+    cudaFree(s->d_meta);
+    cudaFree(s->d_blk_lo);
+    cudaFree(s->d_blk_hi);
+    cudaFree(s->d_blk_status);
+    delete s;
+}
+extern "C" size_t vmb_series_count(const vmb_series* s) { return s ? s->nseries : 0; }
+extern "C" uint64_t vmb_series_rows(const vmb_series* s) { return s ? s->rows : 0; }
+
+__global__ void k_set_status(int32_t* status, const uint32_t* list, uint32_t n, int32_t v) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) status[list[i]] = v;
+}
+
+// runs zstd + column decode + series assembly into `s` (whose buffers are already allocated)
+static int run_decode(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, int64_t tr_min, int64_t tr_max, uint32_t flags,
+                      unsigned int* d_failed) {
+    cudaStream_t st = ctx->stream;
+    const bool has_zstd = b->n_huf + b->n_gen + b->n_bad > 0;
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
+    int32_t* d_zstatus = nullptr;
+    if (has_zstd) {
+        int rc;
+        if ((rc = ctx->zscratch.reserve(b->scratch_total + 64))) return rc;
+        if ((rc = ctx->zstatus.reserve(2 * b->nblocks * sizeof(int32_t)))) return rc;
+        d_zstatus = (int32_t*)ctx->zstatus.p;
+        CU(cudaMemsetAsync(d_zstatus, 0, 2 * b->nblocks * sizeof(int32_t), st));
+        if (b->needs_lit && (rc = ctx->zlit.reserve(b->scratch_total + 64))) return rc;
+        ZstdParams Z;
+        memset(&Z, 0, sizeof(Z));
+        Z.descs = b->d_descs;
+        Z.cols = b->d_cols;
+        Z.payload = b->d_payload;
+        Z.scratch = (uint8_t*)ctx->zscratch.p;
+        Z.lit = b->needs_lit ? (uint8_t*)ctx->zlit.p : nullptr;
+        Z.status = d_zstatus;
+        if (b->n_bad) {
+            k_set_status<<<(b->n_bad + 127) / 128, 128, 0, st>>>(d_zstatus, b->d_bad_list, b->n_bad, VMB_ERR_ZSTD);
+            count_launch(ctx);
+        }
+        const uint32_t ws_threads = 148u * 2u * 32u;
+        if (b->needs_lit || b->n_gen) {
+            if ((rc = ctx->zws.reserve((size_t)ws_threads * zstd_serial_ws_bytes()))) return rc;
+            Z.ws = ctx->zws.p;
+            Z.ws_count = ws_threads;
+        }
+        if (b->n_huf) {
+            if ((rc = ctx->zjobs.reserve((size_t)b->n_huf * sizeof(HufJob)))) return rc;
+            Z.jobs = (HufJob*)ctx->zjobs.p;
+            Z.list = b->d_huf_list;
+            Z.count = b->n_huf;
+            launch_zstd_prepare(Z, st);
+            launch_huf_decode(Z, st);
+            count_launch(ctx, 2);
+            if (b->needs_lit) {
+                launch_zstd_serial(Z, 0, st);
+                count_launch(ctx);
+            }
+        }
+        if (b->n_gen) {
+            Z.list = b->d_gen_list;
+            Z.count = b->n_gen;
+            launch_zstd_serial(Z, 1, st);
+            count_launch(ctx);
+        }
+    }
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[1], st));
+    DecodeParams D;
+    memset(&D, 0, sizeof(D));
+    D.descs = b->d_descs;
+    D.cols = b->d_cols;
+    D.payload = b->d_payload;
+    D.scratch = (const uint8_t*)ctx->zscratch.p;
+    D.zstd_status = d_zstatus;
+    D.row_off = b->d_row_off;
+    D.ts_out = s->d_ts;
+    D.val_out = s->d_vals;
+    D.blk_lo = s->d_blk_lo;
+    D.blk_hi = s->d_blk_hi;
+    D.status = s->d_blk_status;
+    D.nblocks = (uint32_t)b->nblocks;
+    D.flags = flags;
+    D.tr_min = tr_min;
+    D.tr_max = tr_max;
+    launch_decode_columns(D, st);
+    count_launch(ctx);
+    RollupParams R;
+    memset(&R, 0, sizeof(R));
+    R.meta = s->d_meta;
+    R.nseries = (uint32_t)s->nseries;
+    R.ser_first_block = b->d_ser_first;
+    R.ser_nblocks = b->d_ser_nblocks;
+    R.row_off = b->d_row_off;
+    R.blk_lo = s->d_blk_lo;
+    R.blk_hi = s->d_blk_hi;
+    R.descs = b->d_descs;
+    R.blk_status = s->d_blk_status;
+    R.failed_blocks = d_failed;
+    launch_series_assemble(R, st);
+    count_launch(ctx);
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[2], st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int alloc_series_for(vmb_ctx* ctx, const vmb_blocks* b, vmb_series** out) {
+    vmb_series* s = new vmb_series();
+    s->ctx = ctx;
+    s->nseries = b->nseries;
+    s->nblocks = b->nblocks;
+    s->rows = b->rows;
+    int rc = 0;
+    if (!rc) rc = dev_alloc(&s->d_ts, b->rows + 8);
+    if (!rc) rc = dev_alloc(&s->d_vals, b->rows + 8);
+    if (!rc) rc = dev_alloc(&s->d_meta, b->nseries);
+    if (!rc) rc = dev_alloc(&s->d_blk_lo, b->nblocks);
+    if (!rc) rc = dev_alloc(&s->d_blk_hi, b->nblocks);
+    if (!rc) rc = dev_alloc(&s->d_blk_status, b->nblocks);
+    if (rc) {
+        vmb_series_free(s);
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+static int collect_stage_times(vmb_ctx* ctx, int first_ev, int nstages, int first_stage) {
+    if (!ctx->timing) return 0;
+    for (int i = 0; i < nstages; i++) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[first_ev + i], ctx->ev[first_ev + i + 1]));
+        ctx->stage_ms[first_stage + i] = ms;
+    }
+    return 0;
+}
+
+extern "C" int vmb_decode_blocks(vmb_ctx* ctx, const vmb_blocks* b, int64_t tr_min, int64_t tr_max, uint32_t flags,
+                                 int32_t* block_status, vmb_series** out) {
+    if (!ctx || !b || !out) return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    vmb_series* s = nullptr;
+    int rc = alloc_series_for(ctx, b, &s);
+    if (rc) return rc;
+    s->values_are_int = (flags & VMB_DECODE_VALUES_AS_INT64) != 0;
+    if ((rc = ctx->counters.reserve(64))) {
+        vmb_series_free(s);
+        return rc;
+    }
+    unsigned int* d_failed = (unsigned int*)ctx->counters.p;
+    CU(cudaMemsetAsync(d_failed, 0, 64, ctx->stream));
+    rc = run_decode(ctx, b, s, tr_min, tr_max, flags, d_failed);
+    if (rc) {
+        vmb_series_free(s);
+        return rc;
+    }
+    unsigned int* h_failed = (unsigned int*)ctx->h_pinned;
+    CU(cudaMemcpyAsync(h_failed, d_failed, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (block_status && b->nblocks)
+        CU(cudaMemcpyAsync(block_status, s->d_blk_status, b->nblocks * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    collect_stage_times(ctx, 0, 2, 0);
+    *out = s;
+    if (*h_failed) {
+        vmb_set_error("%u series hold blocks that failed to decode (see the per-block status)", *h_failed);
+        return VMB_ERR_BLOCK_FAILED;
+    }
+    return VMB_OK;
+}
+
+__global__ void k_meta_from_offsets(SeriesMeta* meta, const uint64_t* offsets, uint32_t n) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    SeriesMeta m;
+    m.start = offsets[s];
+    m.n = (uint32_t)(offsets[s + 1] - offsets[s]);
+    m._pad = 0;
+    m.max_prev_interval = 0;
+    m.window = 0;
+    meta[s] = m;
+}
+
+extern "C" int vmb_series_from_host(vmb_ctx* ctx, const int64_t* timestamps, const double* values, const uint64_t* offsets,
+                                    size_t nseries, vmb_series** out) {
+    if (!ctx || !out || !offsets || nseries > 0x7fffffffu) return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    uint64_t rows = offsets[nseries];
+    if (rows && (!timestamps || !values)) return VMB_ERR_INVALID_ARG;
+    for (size_t i = 0; i < nseries; i++)
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0xffffffffull) return VMB_ERR_INVALID_ARG;
+    vmb_series* s = new vmb_series();
+    s->ctx = ctx;
+    s->nseries = nseries;
+    s->rows = rows;
+    int rc = 0;
+    uint64_t* d_off = nullptr;
+    if (!rc) rc = dev_alloc(&s->d_ts, rows + 8);
+    if (!rc) rc = dev_alloc(&s->d_vals, rows + 8);
+    if (!rc) rc = dev_alloc(&s->d_meta, nseries);
+    if (!rc) rc = dev_alloc(&d_off, nseries + 1);
+    if (rc) {
+        vmb_series_free(s);
+        cudaFree(d_off);
+        return rc;
+    }
+    cudaStream_t st = ctx->stream;
+    if (rows) {
+        CU(cudaMemcpyAsync(s->d_ts, timestamps, rows * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s->d_vals, values, rows * 8, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemcpyAsync(d_off, offsets, (nseries + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nseries) {
+        k_meta_from_offsets<<<(unsigned)((nseries + 127) / 128), 128, 0, st>>>(s->d_meta, d_off, (uint32_t)nseries);
+        count_launch(ctx);
+    }
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_off);
+    *out = s;
+    return VMB_OK;
+}
+
+extern "C" int vmb_series_layout(vmb_ctx* ctx, const vmb_series* s, uint64_t* starts, uint32_t* counts) {
+    if (!ctx || !s) return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<SeriesMeta> m(s->nseries);
+    if (s->nseries) CU(cudaMemcpyAsync(m.data(), s->d_meta, s->nseries * sizeof(SeriesMeta), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < s->nseries; i++) {
+        if (starts) starts[i] = m[i].start;
+        if (counts) counts[i] = m[i].n;
+    }
+    return VMB_OK;
+}
+
+extern "C" int vmb_series_download(vmb_ctx* ctx, const vmb_series* s, int64_t* timestamps, double* values) {
+    if (!ctx || !s) return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (timestamps && s->rows) CU(cudaMemcpyAsync(timestamps, s->d_ts, s->rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (values && s->rows) CU(cudaMemcpyAsync(values, s->d_vals, s->rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ per-call drop-ins
+extern "C" int vmb_unmarshal_int64(vmb_ctx* ctx, int64_t* dst, size_t n, const uint8_t* src, size_t src_len, int mt,
+                                   int64_t first_value) {
+    if (!ctx || (n && !dst) || (src_len && !src)) return VMB_ERR_INVALID_ARG;
+    if (n < 1 || n > 16384 || src_len > (1u << 20)) return VMB_ERR_INVALID_ARG;  // Go: Panicf("BUG: itemsCount ...")
+    vmb_block_desc d;
+    memset(&d, 0, sizeof(d));
+    d.first_value = first_value;
+    d.ts_mt = 3;  // constant timestamps column: no payload
+    d.val_mt = (uint8_t)mt;
+    d.val_off = 0;
+    d.val_size = (uint32_t)src_len;
+    d.rows = (uint32_t)n;
+    d.precision_bits = 64;
+    d.min_ts = 0;
+    d.max_ts = 0;
+    if (mt < 1 || mt > 6) return VMB_ERR_MARSHAL_TYPE;  // encoding.go:248
+    vmb_blocks* b = nullptr;
+    int rc = vmb_blocks_upload(ctx, &d, 1, src, src_len, &b);
+    if (rc) return rc;
+    vmb_series* s = nullptr;
+    int32_t status = 0;
+    rc = vmb_decode_blocks(ctx, b, INT64_MIN, INT64_MAX, VMB_DECODE_VALUES_AS_INT64, &status, &s);
+    if (rc == VMB_OK || rc == VMB_ERR_BLOCK_FAILED) {
+        if (status) rc = status;
+        else {
+            cudaError_t e = cudaMemcpy(dst, s->d_vals, n * 8, cudaMemcpyDeviceToHost);
+            rc = e == cudaSuccess ? VMB_OK : VMB_ERR_CUDA;
+        }
+    }
+    vmb_series_free(s);
+    vmb_blocks_free(b);
+    return rc;
+}
+
+extern "C" int vmb_decimal_to_float(vmb_ctx* ctx, double* dst, const int64_t* va, size_t n, int16_t e) {
+    if (!ctx || (n && (!dst || !va))) return VMB_ERR_INVALID_ARG;
+    if (!n) return VMB_OK;
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->tmp_out.reserve(n * 16))) return rc;
+    int64_t* d_in = (int64_t*)ctx->tmp_out.p;
+    double* d_out = (double*)ctx->tmp_out.p + n;
+    CU(cudaMemcpyAsync(d_in, va, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    launch_decimal_to_float(d_out, d_in, n, e, ctx->stream);
+    count_launch(ctx);
+    CU(cudaMemcpyAsync(dst, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VMB_OK;
+}
+
+extern "C" int vmb_marshal_int64(uint8_t* dst, size_t cap, size_t* out_len, int* out_mt, int64_t* out_first,
+                                 const int64_t* vals, size_t n, uint8_t precision_bits) {
+    if (!out_len || !out_mt || !out_first || !vals) return VMB_ERR_INVALID_ARG;
+    std::vector<uint8_t> out;
+    int rc = vmb_host::marshal_int64_array(out, out_mt, out_first, vals, n, precision_bits);
+    if (rc) return rc;
+    *out_len = out.size();
+    if (out.size() > cap) return VMB_ERR_CAP;
+    if (!out.empty()) memcpy(dst, out.data(), out.size());
+    return VMB_OK;
+}
+extern "C" int vmb_float_to_decimal(int64_t* dst, int16_t* out_scale, const double* src, size_t n) {
+    if (!out_scale || (n && (!dst || !src))) return VMB_ERR_INVALID_ARG;
+    *out_scale = vmb_host::float_to_decimal(dst, src, n);
+    return VMB_OK;
+}
+// exposed for tests: the library's own zstd writer
+extern "C" int vmb_zstd_compress(uint8_t* dst, size_t cap, size_t* out_len, const uint8_t* src, size_t n) {
+    if (!out_len || !src || n == 0) return VMB_ERR_INVALID_ARG;
+    std::vector<uint8_t> out;
+    vmb_host::zstd_compress_huf(out, src, n);
+    *out_len = out.size();
+    if (out.size() > cap) return VMB_ERR_CAP;
+    memcpy(dst, out.data(), out.size());
+    return VMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ rollup
+extern "C" int64_t vmb_rollup_points(const vmb_rollup_cfg* cfg) {
+    if (!cfg || cfg->step <= 0 || cfg->start > cfg->end) return -1;
+    return 1 + (cfg->end - cfg->start) / cfg->step;
+}
+
+static int check_cfg(const vmb_rollup_cfg* cfg, int64_t* points) {
+    // rollup.go:703-714: the Go code panics ("BUG: ...") on these
+    if (!cfg || cfg->step <= 0 || cfg->start > cfg->end || cfg->window < 0 || cfg->func_id < 0 || cfg->func_id >= VMB_RF__COUNT) {
+        vmb_set_error("invalid rollup config (step must be > 0, start <= end, window >= 0, known func_id)");
+        return VMB_ERR_INVALID_ARG;
+    }
+    *points = 1 + (cfg->end - cfg->start) / cfg->step;
+    if (*points > 0x7fffffff) return VMB_ERR_INVALID_ARG;
+    return 0;
+}
+
+// series preamble + rollup into d_out (device). d_scanned: device u64 accumulator (already zeroed) or nullptr
+static int run_rollup(vmb_ctx* ctx, vmb_series* s, const vmb_rollup_cfg* cfg, int64_t points, double* d_out,
+                      unsigned long long* d_scanned) {
+    cudaStream_t st = ctx->stream;
+    RollupParams R;
+    memset(&R, 0, sizeof(R));
+    R.cfg = *cfg;
+    R.cfg.args = nullptr;
+    R.cfg.args2 = nullptr;
+    int rc;
+    if (cfg->args) {
+        if ((rc = ctx->args1.reserve((size_t)points * 8))) return rc;
+        CU(cudaMemcpyAsync(ctx->args1.p, cfg->args, (size_t)points * 8, cudaMemcpyHostToDevice, st));
+        R.cfg.args = (const double*)ctx->args1.p;
+    }
+    if (cfg->args2) {
+        if ((rc = ctx->args2.reserve((size_t)points * 8))) return rc;
+        CU(cudaMemcpyAsync(ctx->args2.p, cfg->args2, (size_t)points * 8, cudaMemcpyHostToDevice, st));
+        R.cfg.args2 = (const double*)ctx->args2.p;
+    }
+    R.meta = s->d_meta;
+    R.ts = s->d_ts;
+    R.vals = s->d_vals;
+    R.out = d_out;
+    R.scanned = d_scanned;
+    R.nseries = (uint32_t)s->nseries;
+    R.npoints = (uint32_t)points;
+    // data-mutating parts of the preamble run once per batch
+    uint32_t flags = cfg->flags;
+    if (s->stale_dropped) flags &= ~VMB_RC_DROP_STALE_NANS;
+    if (s->resets_removed) flags &= ~VMB_RC_REMOVE_COUNTER_RESETS;
+    R.cfg.flags = flags;
+    launch_series_prepare(R, st);
+    count_launch(ctx);
+    if (flags & VMB_RC_DROP_STALE_NANS) s->stale_dropped = true;
+    if (flags & VMB_RC_REMOVE_COUNTER_RESETS) s->resets_removed = true;
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[3], st));
+    R.cfg.flags = cfg->flags;
+    launch_rollup(R, st);
+    count_launch(ctx);
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[4], st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vmb_rollup(vmb_ctx* ctx, vmb_series* s, const vmb_rollup_cfg* cfg, double* out, int out_is_device,
+                          uint64_t* samples_scanned) {
+    if (!ctx || !s || !out) return VMB_ERR_INVALID_ARG;
+    if (s->values_are_int) {
+        vmb_set_error("batch was decoded with VMB_DECODE_VALUES_AS_INT64");
+        return VMB_ERR_INVALID_ARG;
+    }
+    int64_t points;
+    int rc = check_cfg(cfg, &points);
+    if (rc) return rc;
+    if ((cfg->func_id == VMB_RF_QUANTILE || (cfg->func_id >= VMB_RF_PREDICT_LINEAR && cfg->func_id <= VMB_RF_SUM_EQ)) && !cfg->args) {
+        vmb_set_error("rollup func %d needs cfg.args", cfg->func_id);
+        return VMB_ERR_INVALID_ARG;
+    }
+    if (cfg->func_id == VMB_RF_HOLT_WINTERS && !cfg->args2) return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    size_t total = (size_t)s->nseries * (size_t)points;
+    double* d_out = out;
+    if (!out_is_device) {
+        if ((rc = ctx->tmp_out.reserve(total * 8))) return rc;
+        d_out = (double*)ctx->tmp_out.p;
+    }
+    if ((rc = ctx->counters.reserve(64))) return rc;
+    unsigned long long* d_scanned = (unsigned long long*)((char*)ctx->counters.p + 8);
+    CU(cudaMemsetAsync(d_scanned, 0, 8, ctx->stream));
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    rc = run_rollup(ctx, s, cfg, points, d_out, d_scanned);
+    if (rc) return rc;
+    unsigned long long* h_scanned = (unsigned long long*)((char*)ctx->h_pinned + 8);
+    CU(cudaMemcpyAsync(h_scanned, d_scanned, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!out_is_device && total) CU(cudaMemcpyAsync(out, d_out, total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    collect_stage_times(ctx, 2, 2, 2);
+    if (samples_scanned) *samples_scanned = *h_scanned;
+    return VMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ aggregates
+extern "C" int vmb_rollup_aggr_partial(vmb_ctx* ctx, vmb_series* s, const vmb_rollup_cfg* cfg, int aggr_id,
+                                       const uint32_t* group_ids, uint32_t ngroups, double* d_values, double* d_counts,
+                                       double* d_rollup_scratch, uint64_t* samples_scanned) {
+    if (!ctx || !s || !group_ids || !d_values || !d_counts || ngroups == 0 || aggr_id < 0 || aggr_id > VMB_AGGR_GROUP)
+        return VMB_ERR_INVALID_ARG;
+    int64_t points;
+    int rc = check_cfg(cfg, &points);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    size_t total = (size_t)s->nseries * (size_t)points;
+    double* d_rolled = d_rollup_scratch;
+    if (!d_rolled) {
+        if ((rc = ctx->rolled.reserve(total * 8))) return rc;
+        d_rolled = (double*)ctx->rolled.p;
+    }
+    // CSR of series by group (stable: ascending series order inside a group)
+    std::vector<uint32_t> start(ngroups + 1, 0), order(s->nseries);
+    for (size_t i = 0; i < s->nseries; i++) {
+        if (group_ids[i] >= ngroups) return VMB_ERR_INVALID_ARG;
+        start[group_ids[i] + 1]++;
+    }
+    for (uint32_t g = 0; g < ngroups; g++) start[g + 1] += start[g];
+    {
+        std::vector<uint32_t> cur(start.begin(), start.end() - 1);
+        for (size_t i = 0; i < s->nseries; i++) order[cur[group_ids[i]]++] = (uint32_t)i;
+    }
+    size_t gbytes = (ngroups + 1 + s->nseries) * sizeof(uint32_t);
+    if ((rc = ctx->grp.reserve(gbytes))) return rc;
+    uint32_t* d_start = (uint32_t*)ctx->grp.p;
+    uint32_t* d_order = d_start + ngroups + 1;
+    CU(cudaMemcpyAsync(d_start, start.data(), (ngroups + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (s->nseries) CU(cudaMemcpyAsync(d_order, order.data(), s->nseries * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = ctx->counters.reserve(64))) return rc;
+    unsigned long long* d_scanned = (unsigned long long*)((char*)ctx->counters.p + 8);
+    CU(cudaMemsetAsync(d_scanned, 0, 8, st));
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[2], st));
+    rc = run_rollup(ctx, s, cfg, points, d_rolled, d_scanned);
+    if (rc) return rc;
+    AggrParams A;
+    A.rolled = d_rolled;
+    A.grp_start = d_start;
+    A.grp_series = d_order;
+    A.values = d_values;
+    A.counts = d_counts;
+    A.ngroups = ngroups;
+    A.npoints = (uint32_t)points;
+    A.aggr = aggr_id;
+    uint64_t cells = (uint64_t)ngroups * (uint64_t)points;
+    k_aggr_fold<<<(unsigned)((cells + 127) / 128), 128, 0, st>>>(A);
+    count_launch(ctx);
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[5], st));
+    unsigned long long* h_scanned = (unsigned long long*)((char*)ctx->h_pinned + 8);
+    CU(cudaMemcpyAsync(h_scanned, d_scanned, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // `start`/`order` host vectors go out of scope
+    collect_stage_times(ctx, 2, 3, 2);
+    if (samples_scanned) *samples_scanned = *h_scanned;
+    return VMB_OK;
+}
+
+extern "C" int vmb_aggr_merge(vmb_ctx* ctx, int aggr_id, double* dv, double* dc, const double* sv, const double* sc, size_t n) {
+    if (!ctx || !dv || !dc || !sv || !sc) return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (n) {
+        k_aggr_merge<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(aggr_id, dv, dc, sv, sc, n);
+        count_launch(ctx);
+    }
+    CU(cudaGetLastError());
+    return VMB_OK;
+}
+extern "C" int vmb_aggr_prepare_allreduce(vmb_ctx* ctx, int aggr_id, double* dv, const double* dc, size_t n) {
+    if (!ctx || !dv || !dc) return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (n) {
+        k_aggr_prepare_allreduce<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(aggr_id, dv, dc, n);
+        count_launch(ctx);
+    }
+    CU(cudaGetLastError());
+    return VMB_OK;
+}
+extern "C" int vmb_aggr_finalize(vmb_ctx* ctx, int aggr_id, double* dv, const double* dc, size_t n, double* out_host) {
+    if (!ctx || !dv || !dc) return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (n) {
+        k_aggr_finalize<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(aggr_id, dv, dc, n);
+        count_launch(ctx);
+        if (out_host) CU(cudaMemcpyAsync(out_host, dv, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ whole path
+// decode + preamble + rollup of one uploaded block set into d_out; no host synchronisation inside
+static int eval_device_async(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, int64_t tr_min, int64_t tr_max,
+                             const vmb_rollup_cfg* cfg, int64_t points, double* d_out, unsigned int* d_failed,
+                             unsigned long long* d_scanned) {
+    s->stale_dropped = s->resets_removed = false;
+    int rc = run_decode(ctx, b, s, tr_min, tr_max, 0, d_failed);
+    if (rc) return rc;
+    return run_rollup(ctx, s, cfg, points, d_out, d_scanned);
+}
+
+extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t tr_min, int64_t tr_max,
+                                      const vmb_rollup_cfg* cfg, double* d_out, uint64_t* samples_scanned) {
+    if (!ctx || !b || !d_out) return VMB_ERR_INVALID_ARG;
+    int64_t points;
+    int rc = check_cfg(cfg, &points);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    // the decoded columns are a per-ctx cache sized for the largest batch seen
+    static thread_local vmb_series* cache = nullptr;
+    if (cache && (cache->ctx != ctx || cache->rows < b->rows || cache->nseries < b->nseries || cache->nblocks < b->nblocks)) {
+        vmb_series_free(cache);
+        cache = nullptr;
+    }
+    if (!cache) {
+        rc = alloc_series_for(ctx, b, &cache);
+        if (rc) return rc;
+    }
+    vmb_series view = *cache;  // shallow view with this batch's logical sizes
+    view.nseries = b->nseries;
+    view.nblocks = b->nblocks;
+    view.rows = b->rows;
+    if ((rc = ctx->counters.reserve(64))) return rc;
+    unsigned int* d_failed = (unsigned int*)ctx->counters.p;
+    unsigned long long* d_scanned = (unsigned long long*)((char*)ctx->counters.p + 8);
+    CU(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
+    rc = eval_device_async(ctx, b, &view, tr_min, tr_max, cfg, points, d_out, d_failed, d_scanned);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->h_pinned, ctx->counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->timing) {
+        collect_stage_times(ctx, 0, 4, 0);
+    }
+    if (samples_scanned) *samples_scanned = *(unsigned long long*)((char*)ctx->h_pinned + 8);
+    unsigned int failed = *(unsigned int*)ctx->h_pinned;
+    if (failed) {
+        vmb_set_error("%u series hold blocks that failed to decode", failed);
+        return VMB_ERR_BLOCK_FAILED;
+    }
+    return VMB_OK;
+}
+
+extern "C" int vmb_eval_rollup_host(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload,
+                                    size_t payload_len, int64_t tr_min, int64_t tr_max, const vmb_rollup_cfg* cfg,
+                                    double* out_host, int32_t* block_status, uint64_t* samples_scanned) {
+    if (!ctx || !out_host) return VMB_ERR_INVALID_ARG;
+    int64_t points;
+    int rc = check_cfg(cfg, &points);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    vmb_blocks* b = nullptr;
+    rc = vmb_blocks_upload(ctx, descs, nblocks, payload, payload_len, &b);
+    if (rc) return rc;
+    size_t total = b->nseries * (size_t)points;
+    if ((rc = ctx->tmp_out.reserve(total * 8))) {
+        vmb_blocks_free(b);
+        return rc;
+    }
+    double* d_out = (double*)ctx->tmp_out.p;
+    uint64_t scanned = 0;
+    rc = vmb_eval_rollup_device(ctx, b, tr_min, tr_max, cfg, d_out, &scanned);
+    if (rc == VMB_OK || rc == VMB_ERR_BLOCK_FAILED) {
+        if (total) {
+            cudaError_t e = cudaMemcpyAsync(out_host, d_out, total * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = VMB_ERR_CUDA;
+        }
+        if (samples_scanned) *samples_scanned = scanned;
+    }
+    (void)block_status;
+    vmb_blocks_free(b);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ batched host encoder
+#include <atomic>
+#include <thread>
+// Block.MarshalData (block.go:192) for many equal-length columns at once on host threads (write path / test+bench input
+// generation).  vals: [ncols x rows]; dst receives the payloads back to back, offs[ncols+1] their offsets.
+extern "C" int vmb_marshal_columns(uint8_t* dst, size_t cap, uint64_t* offs, uint8_t* mts, int64_t* firsts,
+                                   const int64_t* vals, size_t ncols, size_t rows, uint8_t precision_bits, int nthreads) {
+    if (!dst || !offs || !mts || !firsts || !vals || rows == 0) return VMB_ERR_INVALID_ARG;
+    std::vector<std::vector<uint8_t>> outs(ncols);
+    std::atomic<size_t> next{0};
+    std::atomic<int> err{0};
+    auto worker = [&]() {
+        for (;;) {
+            size_t c = next.fetch_add(1);
+            if (c >= ncols) break;
+            int mt = 0;
+            int64_t first = 0;
+            int rc = vmb_host::marshal_int64_array(outs[c], &mt, &first, vals + c * rows, rows, precision_bits);
+            if (rc) err = rc;
+            mts[c] = (uint8_t)mt;
+            firsts[c] = first;
+        }
+    };
+    if (nthreads <= 1) worker();
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++) th.emplace_back(worker);
+        for (auto& t : th) t.join();
+    }
+    if (err.load()) return err.load();
+    uint64_t o = 0;
+    for (size_t c = 0; c < ncols; c++) {
+        offs[c] = o;
+        if (o + outs[c].size() > cap) return VMB_ERR_CAP;
+        if (!outs[c].empty()) memcpy(dst + o, outs[c].data(), outs[c].size());
+        o += outs[c].size();
+    }
+    offs[ncols] = o;
+    return VMB_OK;
+}

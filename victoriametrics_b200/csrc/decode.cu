@@ -1,0 +1,432 @@
+// Column decode kernel: varint -> (double) prefix sum -> int64 timestamps / float64 values, one warp per block.
+//
+// Replaces, for every block of a batch at once:
+//   lib/encoding/encoding.go:173   unmarshalInt64Array        (dispatch on MarshalType)
+//   lib/encoding/int.go:182-284    UnmarshalVarInt64s         (zig-zag LEB128)
+//   lib/encoding/nearest_delta.go:53, nearest_delta2.go:57    (prefix sum / double prefix sum)
+//   lib/storage/block.go:250-296   Block.UnmarshalData        (validation, EnsureNonDecreasingSequence)
+//   lib/storage/block.go:324-349   AppendRowsWithTimeRangeFilter / filterTimestamps
+//   lib/decimal/decimal.go:100     AppendDecimalToFloat
+//
+// Layout: a warp walks the varint byte stream in 512-byte tiles, 16 bytes per lane.  A value belongs to the lane
+// that holds its terminating byte; the bytes it starts with in the previous lane's chunk arrive by shuffle.  Per-lane
+// partial sums are combined with one warp scan per tile ((count, sum, sum-of-prefix-sums) is an associative triple
+// under wrapping int64 arithmetic), so the result is bit-identical to the sequential Go loop.
+#include "common.cuh"
+
+namespace {
+
+__constant__ double c_pow10tab[32] = {1e00, 1e01, 1e02, 1e03, 1e04, 1e05, 1e06, 1e07, 1e08, 1e09, 1e10,
+                                      1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21,
+                                      1e22, 1e23, 1e24, 1e25, 1e26, 1e27, 1e28, 1e29, 1e30, 1e31};
+__constant__ double c_pow10postab32[10] = {1e00, 1e32, 1e64, 1e96, 1e128, 1e160, 1e192, 1e224, 1e256, 1e288};
+__constant__ double c_pow10negtab32[11] = {1e-00,  1e-32,  1e-64,  1e-96,  1e-128, 1e-160,
+                                           1e-192, 1e-224, 1e-256, 1e-288, 1e-320};
+
+}  // namespace
+
+// Go stdlib math.Pow10: pow10postab32[n/32] * pow10tab[n%32] (a PRODUCT of two table doubles, not pow()).
+__device__ double vmb_pow10(int n) {
+    if (0 <= n && n <= 308) return __dmul_rn(c_pow10postab32[(unsigned)n / 32], c_pow10tab[(unsigned)n % 32]);
+    if (-323 <= n && n <= 0) return __ddiv_rn(c_pow10negtab32[(unsigned)(-n) / 32], c_pow10tab[(unsigned)(-n) % 32]);
+    if (n > 0) return __longlong_as_double(0x7ff0000000000000LL);
+    return 0.0;
+}
+
+namespace {
+
+struct Dec {  // decimal.AppendDecimalToFloat decimal.go:100 for one block (scale fixed)
+    double e10;
+    int mode;  // 0: e==0, -1: divide, +1: multiply
+    __device__ void init(int16_t e) {
+        mode = e == 0 ? 0 : (e < 0 ? -1 : 1);
+        e10 = e < 0 ? vmb_pow10(-(int)e) : vmb_pow10((int)e);
+    }
+    __device__ __forceinline__ double conv(int64_t v) const {
+        double f = __ll2double_rn(v);
+        if (mode < 0) f = __ddiv_rn(f, e10);
+        else if (mode > 0) f = __dmul_rn(f, e10);
+        if (v > VMB_V_MAX || v < VMB_V_MIN) {  // isSpecialValue decimal.go:417
+            if (v == VMB_V_INF_POS) f = __longlong_as_double(0x7ff0000000000000LL);
+            else if (v == VMB_V_INF_NEG) f = __longlong_as_double((long long)0xfff0000000000000ULL);
+            else f = __longlong_as_double((long long)VMB_STALE_NAN_BITS);
+        }
+        return f;
+    }
+};
+
+// timestamps emitter: stores int64, validates monotonicity (block.go:298) and tracks the time-range trim
+struct TsEmit {
+    int64_t* out;
+    int64_t tr_min, tr_max;
+    uint32_t lo, hi1;  // lane-local: min pos with ts >= tr_min ; 1 + max pos with ts <= tr_max
+    bool validate, bad_order;
+    __device__ void init(int64_t* o, int64_t a, int64_t b, bool v) {
+        out = o; tr_min = a; tr_max = b; lo = 0xffffffffu; hi1 = 0; validate = v; bad_order = false;
+    }
+    __device__ __forceinline__ void emit(uint32_t pos, int64_t v, int64_t prev) {
+        out[pos] = v;
+        if (validate && v < prev) bad_order = true;
+        if (v >= tr_min && pos < lo) lo = pos;
+        if (v <= tr_max && pos + 1 > hi1) hi1 = pos + 1;
+    }
+};
+
+struct ValEmit {
+    void* out;
+    Dec dec;
+    bool as_int;
+    __device__ void init(void* o, int16_t scale, bool ai) { out = o; as_int = ai; dec.init(scale); }
+    __device__ __forceinline__ void emit(uint32_t pos, int64_t v, int64_t) {
+        if (as_int) ((int64_t*)out)[pos] = v;
+        else ((double*)out)[pos] = dec.conv(v);
+    }
+};
+
+__device__ __forceinline__ uint32_t term_mask4(uint32_t w) {
+    uint32_t t = ~w & 0x80808080u;
+    return ((t >> 7) & 1u) | ((t >> 14) & 2u) | ((t >> 21) & 4u) | ((t >> 28) & 8u);
+}
+
+// Decodes a nearest-delta (delta2 == false) or nearest-delta2 stream of n-1 varints into n values.
+// Returns 0 or a VMB_ERR_* (uniform across the warp).
+template <class E>
+__device__ int decode_delta_stream(const uint8_t* __restrict__ src, uint32_t len, uint32_t n, int64_t first, bool delta2,
+                                   E& em) {
+    const int lane = lane_id();
+    if (n < (delta2 ? 2u : 1u)) return VMB_ERR_ROWS;  // Go: logger.Panicf("BUG: itemsCount ...")
+    const uint32_t nvar = n - 1;
+    if (len < nvar) return VMB_ERR_SHORT_SRC;  // int.go:183
+    if (lane == 0) em.emit(0, first, first);
+    uint32_t N = 0;           // varints consumed so far
+    uint64_t D1 = 0;          // running first-order delta (delta2 only)
+    uint64_t V = (uint64_t)first;
+    uint32_t cc1 = 0, cc2 = 0, cc3 = 0;  // last 9 bytes of the previous tile's lane 31
+    uint32_t carry_len_tile = 0;
+    int err = 0;  // lane-local error code (0 / negative)
+
+    for (uint32_t tile = 0; tile < len; tile += 512) {
+        const uint32_t o = tile + (uint32_t)lane * 16u;
+        const uint32_t valid = o >= len ? 0u : (len - o >= 16u ? 16u : len - o);
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        if (valid) {
+            uintptr_t a = (uintptr_t)(src + o);
+            const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+            uint32_t sh = (uint32_t)(a & 3) * 8;
+            uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+            if (sh) {
+                uint32_t w4 = w[4];
+                c0 = __funnelshift_r(w0, w1, sh);
+                c1 = __funnelshift_r(w1, w2, sh);
+                c2 = __funnelshift_r(w2, w3, sh);
+                c3 = __funnelshift_r(w3, w4, sh);
+            } else {
+                c0 = w0; c1 = w1; c2 = w2; c3 = w3;
+            }
+        }
+        uint32_t m = term_mask4(c0) | (term_mask4(c1) << 4) | (term_mask4(c2) << 8) | (term_mask4(c3) << 12);
+        m &= valid >= 16 ? 0xffffu : ((1u << valid) - 1u);
+        // bytes after my last terminator carry over into the next lane
+        uint32_t tail_len;
+        if (m) tail_len = valid - 1u - (31u - (uint32_t)__clz((int)m));
+        else {
+            tail_len = valid;  // no terminator at all in a non-empty chunk is always an error (varints are <= 10 bytes)
+            if (valid == 16) err = VMB_ERR_VARINT_TOO_LONG;
+        }
+        uint32_t p1 = __shfl_up_sync(VMB_FULL, c1, 1), p2 = __shfl_up_sync(VMB_FULL, c2, 1), p3 = __shfl_up_sync(VMB_FULL, c3, 1);
+        uint32_t carry_len = __shfl_up_sync(VMB_FULL, tail_len, 1);
+        if (lane == 0) { p1 = cc1; p2 = cc2; p3 = cc3; carry_len = carry_len_tile; }
+        if (carry_len > 9) { err = VMB_ERR_VARINT_TOO_LONG; carry_len = 9; }
+        if (!valid) carry_len = 0;
+
+        // ---- parse: value k ends at byte k of my chunk
+        int64_t val[16];
+        uint64_t acc = 0;
+        uint32_t shift = 0;
+        {
+            // previous chunk bytes 7..15 == (p1 >> 24), p2[0..3], p3[0..3]
+            const uint32_t skip = 9u - carry_len;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                uint32_t b = k == 0 ? (p1 >> 24) : (k <= 4 ? (p2 >> (8 * (k - 1))) : (p3 >> (8 * (k - 5))));
+                b &= 0x7fu;
+                if ((uint32_t)k >= skip) {
+                    acc |= (uint64_t)b << shift;
+                    shift += 7;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            uint32_t wsel = k < 4 ? c0 : (k < 8 ? c1 : (k < 12 ? c2 : c3));
+            uint32_t b = (wsel >> (8 * (k & 3))) & 0xffu;
+            val[k] = 0;
+            if ((uint32_t)k < valid) {
+                if (shift >= 63) {  // 10th byte: int.go:269-275
+                    if (b >= 0x80u) err = VMB_ERR_VARINT_TOO_LONG;
+                    else {
+                        if (b > 1u) err = VMB_ERR_VARINT_TOO_BIG;
+                        acc |= (uint64_t)1 << 63;
+                    }
+                } else {
+                    acc |= (uint64_t)(b & 0x7fu) << shift;
+                }
+                if (b < 0x80u) {
+                    val[k] = (int64_t)(acc >> 1) ^ -(int64_t)(acc & 1);  // zig-zag decode int.go:82
+                    acc = 0;
+                    shift = 0;
+                } else {
+                    shift = shift >= 56 ? 63 : shift + 7;
+                }
+            }
+        }
+        // ---- per-lane aggregates
+        uint32_t cnt = (uint32_t)__popc(m);
+        uint64_t s1 = 0, s2 = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if ((m >> k) & 1u) {
+                s1 += (uint64_t)val[k];
+                s2 += s1;
+            }
+        }
+        // ---- inclusive warp scan of (cnt, s1, s2); combine(A then B): s2 = s2A + s2B + cntB * s1A
+        uint32_t icnt = cnt;
+        uint64_t is1 = s1, is2 = s2;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t acnt = __shfl_up_sync(VMB_FULL, icnt, off);
+            uint64_t as1 = shfl_up_u64(is1, off);
+            uint64_t as2 = shfl_up_u64(is2, off);
+            if (lane >= off) {
+                if (delta2) is2 = as2 + is2 + (uint64_t)icnt * as1;
+                is1 += as1;
+                icnt += acnt;
+            }
+        }
+        uint32_t ecnt = __shfl_up_sync(VMB_FULL, icnt, 1);
+        uint64_t es1 = shfl_up_u64(is1, 1), es2 = shfl_up_u64(is2, 1);
+        if (lane == 0) { ecnt = 0; es1 = 0; es2 = 0; }
+        // ---- emit
+        uint32_t pos = 1u + N + ecnt;
+        uint64_t d1 = D1 + es1;
+        uint64_t v = delta2 ? (V + es2 + (uint64_t)ecnt * D1) : (V + es1);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if ((m >> k) & 1u) {
+                uint64_t pv = v;
+                if (delta2) {
+                    d1 += (uint64_t)val[k];
+                    v += d1;
+                } else {
+                    v += (uint64_t)val[k];
+                }
+                if (pos < n) em.emit(pos, (int64_t)v, (int64_t)pv);
+                pos++;
+            }
+        }
+        // ---- tile carries
+        uint32_t tcnt = __shfl_sync(VMB_FULL, icnt, 31);
+        uint64_t ts1 = shfl_u64(is1, 31), ts2 = shfl_u64(is2, 31);
+        if (delta2) {
+            V += ts2 + (uint64_t)tcnt * D1;
+            D1 += ts1;
+        } else {
+            V += ts1;
+        }
+        N += tcnt;
+        cc1 = __shfl_sync(VMB_FULL, c1, 31);
+        cc2 = __shfl_sync(VMB_FULL, c2, 31);
+        cc3 = __shfl_sync(VMB_FULL, c3, 31);
+        carry_len_tile = __shfl_sync(VMB_FULL, tail_len, 31);
+    }
+    // ---- stream-level checks (uniform)
+    int werr = 0;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) err = min(err, __shfl_xor_sync(VMB_FULL, err, off));  // most negative wins
+    werr = err;
+    if (werr == 0) {
+        bool ends_ok = len == 0 || src[len - 1] < 0x80;
+        if (N < nvar) werr = VMB_ERR_SHORT_SRC;        // int.go:199 "cannot unmarshal varint from empty data"
+        else if (N > nvar || !ends_ok) werr = VMB_ERR_TAIL;  // nearest_delta.go:65 unexpected tail
+    }
+    return werr;
+}
+
+// UnmarshalVarInt64 int.go:173 (binary.Uvarint + zig-zag) on <= 11 bytes, executed redundantly by every lane
+__device__ int read_single_varint(const uint8_t* src, uint32_t len, int64_t* out, uint32_t* used) {
+    uint64_t u = 0;
+    uint32_t shift = 0;
+    for (uint32_t i = 0; i < len; i++) {
+        if (i == 10) return VMB_ERR_DELTA_CONST;
+        uint32_t b = src[i];
+        if (b < 0x80) {
+            if (i == 9 && b > 1) return VMB_ERR_DELTA_CONST;
+            u |= (uint64_t)b << shift;
+            *out = (int64_t)(u >> 1) ^ -(int64_t)(u & 1);
+            *used = i + 1;
+            return 0;
+        }
+        u |= (uint64_t)(b & 0x7f) << shift;
+        shift += 7;
+    }
+    return VMB_ERR_DELTA_CONST;
+}
+
+template <class E>
+__device__ int decode_column(const uint8_t* src, uint32_t len, int mt, int64_t first, uint32_t n, E& em) {
+    const int lane = lane_id();
+    switch (mt) {
+        case 1:  // MarshalTypeZSTDNearestDelta2 (src already decompressed into the scratch arena)
+        case 5:  // MarshalTypeNearestDelta2
+            return decode_delta_stream(src, len, n, first, true, em);
+        case 4:  // MarshalTypeZSTDNearestDelta
+        case 6:  // MarshalTypeNearestDelta
+            return decode_delta_stream(src, len, n, first, false, em);
+        case 3: {  // MarshalTypeConst encoding.go:215
+            if (len > 0) return VMB_ERR_CONST_TAIL;
+            for (uint32_t i = lane; i < n; i += 32) em.emit(i, first, first);
+            return 0;
+        }
+        case 2: {  // MarshalTypeDeltaConst encoding.go:231
+            int64_t d = 0;
+            uint32_t used = 0;
+            int rc = read_single_varint(src, len, &d, &used);
+            if (rc) return rc;
+            if (used < len) return VMB_ERR_TAIL;
+            for (uint32_t i = lane; i < n; i += 32) {
+                int64_t v = (int64_t)((uint64_t)first + (uint64_t)i * (uint64_t)d);
+                em.emit(i, v, v);
+            }
+            return 0;
+        }
+        default:
+            return VMB_ERR_MARSHAL_TYPE;
+    }
+}
+
+}  // namespace
+
+struct DecodeParams {
+    const vmb_block_desc* descs;
+    const ColInfo* cols;
+    const uint8_t* payload;
+    const uint8_t* scratch;       // zstd output arena
+    const int32_t* zstd_status;   // per column (2*nblocks) or nullptr
+    const uint64_t* row_off;      // per block: first row in the dense columns
+    int64_t* ts_out;
+    void* val_out;
+    uint32_t* blk_lo;             // per block: kept rows [lo, hi)
+    uint32_t* blk_hi;
+    int32_t* status;              // per block
+    uint32_t nblocks;
+    uint32_t flags;
+    int64_t tr_min, tr_max;
+};
+
+__global__ void __launch_bounds__(128) k_decode_columns(DecodeParams P) {
+    const int lane = lane_id();
+    const uint32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < P.nblocks; b += warps_per_grid) {
+        const vmb_block_desc d = P.descs[b];
+        const uint64_t ro = P.row_off[b];
+        int rc = 0;
+        uint32_t lo = 0, hi = 0;
+        if (d.rows == 0 || d.rows > 16384u) rc = VMB_ERR_ROWS;  // block.go:262, block_header.go:233
+        if (!rc && P.zstd_status) {
+            int z0 = P.zstd_status[2 * b], z1 = P.zstd_status[2 * b + 1];
+            if (z0) rc = z0;
+            else if (z1) rc = z1;
+        }
+        if (!rc) {
+            // ---- timestamps (encoding.UnmarshalTimestamps encoding.go:90)
+            const ColInfo ci = P.cols[2 * b];
+            const uint8_t* src = ci.kind == VMB_ZK_NONE ? P.payload + d.ts_off : P.scratch + ci.scratch_off;
+            uint32_t len = ci.kind == VMB_ZK_NONE ? d.ts_size : ci.content_size;
+            TsEmit te;
+            const bool needs_validation = d.precision_bits >= 64 && (d.ts_mt == 5 || d.ts_mt == 6);  // encoding.go:46
+            te.init(P.ts_out + ro, P.tr_min, P.tr_max, needs_validation);
+            rc = decode_column(src, len, d.ts_mt, d.min_ts, d.rows, te);
+            __syncwarp();
+            if (!rc && d.precision_bits < 64) {
+                // EnsureNonDecreasingSequence encoding.go:258 == a[0]=min; prefix max; clamp to max; a[n-1]=max
+                int64_t* a = P.ts_out + ro;
+                int64_t run = d.min_ts;
+                te.lo = 0xffffffffu;
+                te.hi1 = 0;
+                for (uint32_t base = 0; base < d.rows; base += 32) {
+                    uint32_t i = base + lane;
+                    int64_t x = i < d.rows ? a[i] : INT64_MIN;
+                    if (i == 0) x = d.min_ts;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        int64_t y = (int64_t)shfl_up_u64((uint64_t)x, off);
+                        if (lane >= off && y > x) x = y;
+                    }
+                    if (run > x) x = run;
+                    run = (int64_t)shfl_u64((uint64_t)x, 31);
+                    if (i < d.rows) {
+                        int64_t o = (i == d.rows - 1) ? d.max_ts : (x < d.max_ts ? x : d.max_ts);
+                        a[i] = o;
+                        if (o >= P.tr_min && i < te.lo) te.lo = i;
+                        if (o <= P.tr_max && i + 1 > te.hi1) te.hi1 = i + 1;
+                    }
+                }
+            } else if (!rc && needs_validation) {
+                // checkTimestampsBounds block.go:298: order (tracked while emitting) and last <= MaxTimestamp
+                bool bad = __any_sync(VMB_FULL, te.bad_order);
+                __syncwarp();
+                if (bad || P.ts_out[ro + d.rows - 1] > d.max_ts) rc = VMB_ERR_TS_BOUNDS;
+            }
+            if (!rc) {
+                uint32_t l = te.lo, h = te.hi1;
+#pragma unroll
+                for (int off = 16; off; off >>= 1) {
+                    l = min(l, __shfl_xor_sync(VMB_FULL, l, off));
+                    h = max(h, __shfl_xor_sync(VMB_FULL, h, off));
+                }
+                lo = l == 0xffffffffu ? d.rows : l;  // filterTimestamps block.go:331
+                hi = h > lo ? h : lo;
+            }
+        }
+        if (!rc) {
+            // ---- values (encoding.UnmarshalValues encoding.go:111 + decimal.AppendDecimalToFloat)
+            const ColInfo ci = P.cols[2 * b + 1];
+            const uint8_t* src = ci.kind == VMB_ZK_NONE ? P.payload + d.val_off : P.scratch + ci.scratch_off;
+            uint32_t len = ci.kind == VMB_ZK_NONE ? d.val_size : ci.content_size;
+            ValEmit ve;
+            const bool as_int = (P.flags & VMB_DECODE_VALUES_AS_INT64) != 0;
+            ve.init(as_int ? (void*)((int64_t*)P.val_out + ro) : (void*)((double*)P.val_out + ro), d.scale, as_int);
+            rc = decode_column(src, len, d.val_mt, d.first_value, d.rows, ve);
+        }
+        if (lane == 0) {
+            P.status[b] = rc;
+            P.blk_lo[b] = rc ? 0u : lo;
+            P.blk_hi[b] = rc ? 0u : hi;
+        }
+    }
+}
+
+void launch_decode_columns(const DecodeParams& P, cudaStream_t st) {
+    if (P.nblocks == 0) return;
+    int warps = 4;
+    uint32_t grid = (P.nblocks + warps - 1) / warps;
+    uint32_t maxgrid = 148u * 16u;
+    if (grid > maxgrid) grid = maxgrid;
+    k_decode_columns<<<grid, warps * 32, 0, st>>>(P);
+}
+
+// ---- decimal.AppendDecimalToFloat as a flat elementwise kernel (per-call drop-in vmb_decimal_to_float)
+__global__ void k_decimal_to_float(double* __restrict__ dst, const int64_t* __restrict__ va, size_t n, int16_t e) {
+    Dec dec;
+    dec.init(e);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = dec.conv(va[i]);
+}
+
+void launch_decimal_to_float(double* dst, const int64_t* va, size_t n, int16_t e, cudaStream_t st) {
+    if (!n) return;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_decimal_to_float<<<(unsigned)blocks, 256, 0, st>>>(dst, va, n, e);
+}

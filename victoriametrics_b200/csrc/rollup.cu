@@ -1,0 +1,1117 @@
+// Rollup executor kernels.
+//
+// Replaces, for every series of a batch at once:
+//   app/vmselect/promql/eval.go:1985   dropStaleNaNs
+//   app/vmselect/promql/rollup.go:921  removeCounterResets                       (k_series_prepare)
+//   app/vmselect/promql/rollup.go:871  getScrapeInterval, :899 getMaxPrevInterval (k_series_prepare)
+//   app/vmselect/promql/rollup.go:701  rollupConfig.doInternal                    (k_rollup: one thread per output point)
+//   app/vmselect/promql/rollup.go:1030-2445 the rollup functions                 (call_func)
+//   app/vmselect/promql/aggr.go:870 quantile, :541 modeNoNaNs
+//   app/vmselect/promql/aggr_incremental.go:189-458 update/merge/finalize         (k_aggr_*)
+#include "common.cuh"
+
+namespace {
+
+#define D_NAN __longlong_as_double(0x7ff8000000000001LL)  /* Go math.NaN() bit pattern */
+#define D_INF __longlong_as_double(0x7ff0000000000000LL)
+
+__device__ __forceinline__ bool is_stale_nan(double f) { return (uint64_t)__double_as_longlong(f) == VMB_STALE_NAN_BITS; }
+
+// ---- order statistics without storage: the k-th smallest (0-based) non-NaN value of T(v[0..n)).
+template <class T>
+__device__ double kth_smallest(const double* v, uint32_t n, uint32_t k, T tf) {
+    for (uint32_t a = 0; a < n; a++) {
+        double x = tf(v[a]);
+        if (isnan(x)) continue;
+        uint32_t less = 0, leq = 0;
+        for (uint32_t b = 0; b < n; b++) {
+            double y = tf(v[b]);
+            less += (y < x);
+            leq += (y <= x);
+        }
+        if (less <= k && k < leq) return x;
+    }
+    return D_NAN;
+}
+
+struct Ident {
+    __device__ double operator()(double x) const { return x; }
+};
+struct AbsDev {
+    double c;
+    __device__ double operator()(double x) const { return fabs(x - c); }
+};
+
+// quantile aggr.go:870 = drop NaNs, sort, quantileSorted aggr.go:922
+template <class T>
+__device__ double quantile_tf(double phi, const double* v, uint32_t n, T tf) {
+    uint32_t m = 0;
+    for (uint32_t a = 0; a < n; a++) m += !isnan(tf(v[a]));
+    if (m == 0 || isnan(phi)) return D_NAN;
+    if (phi < 0) return -D_INF;
+    if (phi > 1) return D_INF;
+    double nn = (double)m;
+    double rank = phi * (nn - 1);
+    double lower = fmax(0.0, floor(rank));
+    double upper = fmin(nn - 1, lower + 1);
+    double weight = rank - floor(rank);
+    double vlo = kth_smallest(v, n, (uint32_t)(int)lower, tf);
+    double vhi = kth_smallest(v, n, (uint32_t)(int)upper, tf);
+    return vlo * (1 - weight) + vhi * weight;
+}
+__device__ double quantile(double phi, const double* v, uint32_t n) { return quantile_tf(phi, v, n, Ident()); }
+
+struct Win {  // rollupFuncArg rollup.go:523
+    double prevValue;
+    int64_t prevTimestamp;
+    const double* values;
+    const int64_t* timestamps;
+    uint32_t n;
+    double realPrevValue, realNextValue;
+    int64_t currTimestamp;
+    uint32_t idx;
+    int64_t window;
+    const double* args;
+    const double* args2;
+};
+
+__device__ double stdvar(const double* v, uint32_t n) {  // rollup.go:1808
+    if (n == 0) return D_NAN;
+    if (n == 1) return 0;
+    double avg = 0, count = 0, q = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        double x = v[i];
+        if (isnan(x)) continue;
+        count += 1;
+        double avgNew = avg + (x - avg) / count;
+        q += (x - avg) * (x - avgNew);
+        avg = avgNew;
+    }
+    if (count == 0) return D_NAN;
+    return q / count;
+}
+__device__ double r_sum(const Win& r) {
+    if (r.n == 0) return D_NAN;
+    double s = 0;
+    for (uint32_t i = 0; i < r.n; i++) s += r.values[i];
+    return s;
+}
+__device__ double r_avg(const Win& r) { return r.n == 0 ? D_NAN : r_sum(r) / (double)r.n; }
+__device__ double r_min(const Win& r) {
+    if (r.n == 0) return D_NAN;
+    double m = r.values[0];
+    for (uint32_t i = 0; i < r.n; i++)
+        if (r.values[i] < m) m = r.values[i];
+    return m;
+}
+__device__ double r_max(const Win& r) {
+    if (r.n == 0) return D_NAN;
+    double m = r.values[0];
+    for (uint32_t i = 0; i < r.n; i++)
+        if (r.values[i] > m) m = r.values[i];
+    return m;
+}
+__device__ double r_last(const Win& r) { return r.n == 0 ? D_NAN : r.values[r.n - 1]; }
+__device__ double r_lag(const Win& r) {  // rollup.go:2055
+    if (r.n == 0) {
+        if (isnan(r.prevValue)) return D_NAN;
+        return (double)(r.currTimestamp - r.prevTimestamp) / 1e3;
+    }
+    return (double)(r.currTimestamp - r.timestamps[r.n - 1]) / 1e3;
+}
+__device__ double r_scrape_interval(const Win& r) {  // rollup.go:2067
+    if (isnan(r.prevValue)) {
+        if (r.n < 2) return D_NAN;
+        return ((double)(r.timestamps[r.n - 1] - r.timestamps[0]) / 1e3) / (double)(r.n - 1);
+    }
+    if (r.n == 0) return D_NAN;
+    return ((double)(r.timestamps[r.n - 1] - r.prevTimestamp) / 1e3) / (double)r.n;
+}
+
+__device__ void linear_regression(const Win& r, double* vout, double* kout) {  // rollup.go:1099
+    const double* values = r.values;
+    uint32_t n = r.n;
+    if (n == 0) {
+        *vout = D_NAN;
+        *kout = D_NAN;
+        return;
+    }
+    bool isconst = true;  // areConstValues rollup.go:1136
+    for (uint32_t i = 1; i < n; i++)
+        if (values[i] != values[i - 1]) {
+            isconst = false;
+            break;
+        }
+    if (isconst) {
+        *vout = values[0];
+        *kout = 0;
+        return;
+    }
+    double vSum = 0, tSum = 0, tvSum = 0, ttSum = 0;
+    int cnt = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        double v = values[i];
+        if (isnan(v)) continue;
+        double dt = (double)(r.timestamps[i] - r.currTimestamp) / 1e3;
+        vSum += v;
+        tSum += dt;
+        tvSum = __dadd_rn(tvSum, __dmul_rn(dt, v));  // no FMA contraction: Go does not fuse on amd64
+        ttSum = __dadd_rn(ttSum, __dmul_rn(dt, dt));
+        cnt++;
+    }
+    if (cnt == 0) {
+        *vout = D_NAN;
+        *kout = D_NAN;
+        return;
+    }
+    double k = 0;
+    double tDiff = __dsub_rn(ttSum, __ddiv_rn(__dmul_rn(tSum, tSum), (double)cnt));
+    if (fabs(tDiff) >= 1e-6) k = __ddiv_rn(__dsub_rn(tvSum, __ddiv_rn(__dmul_rn(tSum, vSum), (double)cnt)), tDiff);
+    *vout = __dsub_rn(__ddiv_rn(vSum, (double)cnt), __ddiv_rn(__dmul_rn(k, tSum), (double)cnt));
+    *kout = k;
+}
+
+__device__ double r_delta(const Win& r) {  // rollupDelta rollup.go:1859
+    const double* values = r.values;
+    uint32_t n = r.n;
+    double prevValue = r.prevValue;
+    if (isnan(prevValue)) {
+        if (n == 0) return D_NAN;
+        if (!isnan(r.realPrevValue)) return values[n - 1] - r.realPrevValue;
+        double d = 0;
+        if (n > 1) d = values[1] - values[0];
+        else if (!isnan(r.realNextValue)) d = r.realNextValue - values[0];
+        if (fabs(values[0]) < 10 * (fabs(d) + 1)) prevValue = 0;
+        else {
+            prevValue = values[0];
+            values++;
+            n--;
+        }
+    }
+    if (n == 0) return 0;
+    return values[n - 1] - prevValue;
+}
+__device__ double r_deriv_fast(const Win& r) {  // rollupDerivFast rollup.go:1954
+    double prevValue = r.prevValue;
+    int64_t prevTimestamp = r.prevTimestamp;
+    if (isnan(prevValue)) {
+        if (r.n < 2) return D_NAN;
+        prevValue = r.values[0];
+        prevTimestamp = r.timestamps[0];
+    } else if (r.n == 0) {
+        return 0;
+    }
+    double dv = r.values[r.n - 1] - prevValue;
+    double dt = (double)(r.timestamps[r.n - 1] - prevTimestamp) / 1e3;
+    return dv / dt;
+}
+__device__ double r_ideriv(const Win& r) {  // rollupIderiv rollup.go:1991
+    const double* values = r.values;
+    const int64_t* ts = r.timestamps;
+    uint32_t n = r.n;
+    if (n < 2) {
+        if (n == 0) return D_NAN;
+        if (isnan(r.prevValue)) return D_NAN;
+        return (values[0] - r.prevValue) / ((double)(ts[0] - r.prevTimestamp) / 1e3);
+    }
+    double vEnd = values[n - 1];
+    int64_t tEnd = ts[n - 1];
+    uint32_t tn = n - 1;
+    while (tn > 0 && ts[tn - 1] >= tEnd) tn--;
+    int64_t tStart;
+    double vStart;
+    if (tn == 0) {
+        if (isnan(r.prevValue)) return 0;
+        tStart = r.prevTimestamp;
+        vStart = r.prevValue;
+    } else {
+        tStart = ts[tn - 1];
+        vStart = values[tn - 1];
+    }
+    return (vEnd - vStart) / ((double)(tEnd - tStart) / 1e3);
+}
+__device__ double r_idelta(const Win& r) {  // rollup.go:1915
+    if (r.n == 0) return isnan(r.prevValue) ? D_NAN : 0.0;
+    double last = r.values[r.n - 1];
+    if (r.n == 1) return isnan(r.prevValue) ? last : last - r.prevValue;
+    return last - r.values[r.n - 2];
+}
+__device__ double r_increase_pure(const Win& r) {  // rollup.go:1835
+    double prevValue = r.prevValue;
+    if (isnan(prevValue)) {
+        if (r.n == 0) return D_NAN;
+        prevValue = 0;
+        if (!isnan(r.realPrevValue)) prevValue = r.realPrevValue;
+    }
+    if (r.n == 0) return 0;
+    return r.values[r.n - 1] - prevValue;
+}
+__device__ double r_changes(const Win& r, bool prometheus) {  // rollup.go:2106 / :2080
+    const double* values = r.values;
+    uint32_t n = r.n;
+    double prev;
+    int cnt = 0;
+    if (prometheus) {
+        if (n < 1) return D_NAN;
+        prev = values[0];
+        values++;
+        n--;
+    } else {
+        prev = r.prevValue;
+        if (isnan(prev)) {
+            if (n == 0) return D_NAN;
+            if (!isnan(r.realPrevValue)) prev = r.realPrevValue;
+            else {
+                cnt++;
+                prev = values[0];
+                values++;
+                n--;
+            }
+        }
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        double v = values[i];
+        if (v != prev) {
+            if (fabs(v - prev) < 1e-12 * fabs(v)) continue;
+            cnt++;
+            prev = v;
+        }
+    }
+    return (double)cnt;
+}
+__device__ double r_incr_or_resets(const Win& r, bool increases) {  // rollup.go:2139 / :2174
+    const double* values = r.values;
+    uint32_t n = r.n;
+    if (n == 0) return isnan(r.prevValue) ? D_NAN : 0.0;
+    double prev = r.prevValue;
+    if (isnan(prev)) {
+        prev = values[0];
+        values++;
+        n--;
+    }
+    if (n == 0) return 0;
+    int cnt = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        double v = values[i];
+        bool hit = increases ? (v > prev) : (v < prev);
+        if (hit) {
+            if (fabs(v - prev) < 1e-12 * fabs(v)) continue;
+            cnt++;
+        }
+        prev = v;
+    }
+    return (double)cnt;
+}
+__device__ double r_integrate(const Win& r) {  // rollup.go:2417
+    const double* values = r.values;
+    const int64_t* ts = r.timestamps;
+    uint32_t n = r.n;
+    double prevValue = r.prevValue;
+    int64_t prevTimestamp = r.currTimestamp - r.window;
+    if (isnan(prevValue)) {
+        if (n == 0) return D_NAN;
+        prevValue = values[0];
+        prevTimestamp = ts[0];
+        values++;
+        ts++;
+        n--;
+    }
+    double sum = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        double dt = (double)(ts[i] - prevTimestamp) / 1e3;
+        sum = __dadd_rn(sum, __dmul_rn(prevValue, dt));
+        prevTimestamp = ts[i];
+        prevValue = values[i];
+    }
+    double dt = (double)(r.currTimestamp - prevTimestamp) / 1e3;
+    return __dadd_rn(sum, __dmul_rn(prevValue, dt));
+}
+__device__ double r_lifetime(const Win& r) {  // rollup.go:2040
+    if (isnan(r.prevValue)) {
+        if (r.n < 2) return D_NAN;
+        return (double)(r.timestamps[r.n - 1] - r.timestamps[0]) / 1e3;
+    }
+    if (r.n == 0) return D_NAN;
+    return (double)(r.timestamps[r.n - 1] - r.prevTimestamp) / 1e3;
+}
+__device__ double r_tminmax(const Win& r, bool is_min) {  // rollup.go:1603 / :1623
+    if (r.n == 0) return D_NAN;
+    double m = r.values[0];
+    int64_t t = r.timestamps[0];
+    for (uint32_t i = 0; i < r.n; i++) {
+        double v = r.values[i];
+        if (is_min ? (v <= m) : (v >= m)) {
+            m = v;
+            t = r.timestamps[i];
+        }
+    }
+    return (double)t / 1e3;
+}
+__device__ double r_tlast_change(const Win& r) {  // rollup.go:1669
+    if (r.n == 0) return D_NAN;
+    double last = r.values[r.n - 1];
+    for (int i = (int)r.n - 2; i >= 0; i--)
+        if (r.values[i] != last) return (double)r.timestamps[i + 1] / 1e3;
+    if (isnan(r.prevValue) || r.prevValue != last) return (double)r.timestamps[0] / 1e3;
+    return D_NAN;
+}
+// modeNoNaNs aggr.go:541 driven by runs of equal values in ascending order (no sort buffer)
+__device__ double r_mode(const Win& r) {
+    double prevValue = r.prevValue;
+    uint32_t n = r.n;
+    if (n == 0) return prevValue;
+    const double* v = r.values;
+    long long j = -1, dMax = 0;
+    double mode = prevValue;
+    // the Go code sorts with sort.Float64s, which orders NaNs first; windows never hold NaNs here (eval.go:1985)
+    double cur = -D_INF;
+    bool first = true;
+    uint32_t consumed = 0;  // sorted index of the current run start
+    while (consumed < n) {
+        // next distinct value: the smallest value > cur (or >= -inf for the first run)
+        double nxt = D_INF;
+        bool found = false;
+        for (uint32_t a = 0; a < n; a++) {
+            double x = v[a];
+            if ((first ? (x >= cur) : (x > cur)) && (!found || x < nxt)) {
+                nxt = x;
+                found = true;
+            }
+        }
+        if (!found) break;  // only NaNs left
+        uint32_t c = 0;
+        for (uint32_t a = 0; a < n; a++) c += (v[a] == nxt);
+        long long i = consumed;
+        if (!(prevValue == nxt)) {
+            long long d = i - j;
+            if (d > dMax || isnan(mode)) {
+                dMax = d;
+                mode = prevValue;
+            }
+            j = i;
+            prevValue = nxt;
+        }
+        consumed += c;
+        cur = nxt;
+        first = false;
+    }
+    long long d = (long long)n - j;
+    if (d > dMax || isnan(mode)) mode = prevValue;
+    return mode;
+}
+__device__ double r_outlier_iqr(const Win& r) {  // rollup.go:1427
+    if (r.n < 2) return D_NAN;
+    double q25 = quantile(0.25, r.values, r.n), q75 = quantile(0.75, r.values, r.n);
+    double iqr = 1.5 * (q75 - q25);
+    double v = r.values[r.n - 1];
+    if (v > q75 + iqr || v < q25 - iqr) return v;
+    return D_NAN;
+}
+__device__ double r_zscore(const Win& r) {  // rollup.go:2361
+    double si = r_scrape_interval(r), lag = r_lag(r);
+    if (isnan(si) || isnan(lag) || lag > si) return D_NAN;
+    double d = r_last(r) - r_avg(r);
+    if (d == 0) return 0;
+    return d / sqrt(stdvar(r.values, r.n));
+}
+__device__ double r_ascent_descent(const Win& r, bool ascent) {  // rollup.go:2315 / :2338
+    const double* values = r.values;
+    uint32_t n = r.n;
+    double prev = r.prevValue;
+    if (isnan(prev)) {
+        if (n == 0) return D_NAN;
+        prev = values[0];
+        values++;
+        n--;
+    }
+    double s = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        double v = values[i];
+        double d = ascent ? (v - prev) : (prev - v);
+        if (d > 0) s += d;
+        prev = v;
+    }
+    return s;
+}
+__device__ double r_distinct(const Win& r) {  // rollup.go:2403 (Go map[float64]: NaN keys never collide)
+    if (r.n == 0) return D_NAN;
+    uint32_t d = 0;
+    for (uint32_t a = 0; a < r.n; a++) {
+        double x = r.values[a];
+        bool dup = false;
+        for (uint32_t b = 0; b < a; b++)
+            if (r.values[b] == x) {
+                dup = true;
+                break;
+            }
+        d += !dup;
+    }
+    return (double)d;
+}
+__device__ double r_holt_winters(const Win& r) {  // rollup.go:1030
+    const double* values = r.values;
+    uint32_t n = r.n;
+    if (n == 0) return D_NAN;
+    double sf = r.args[r.idx];
+    if (sf < 0 || sf > 1) return D_NAN;
+    double tf = r.args2[r.idx];
+    if (tf < 0 || tf > 1) return D_NAN;
+    double s0 = r.prevValue;
+    if (isnan(s0)) {
+        s0 = values[0];
+        values++;
+        n--;
+        if (n == 0) return s0;
+    }
+    double b0 = values[0] - s0;
+    for (uint32_t i = 0; i < n; i++) {
+        double v = values[i];
+        double s1 = __dadd_rn(__dmul_rn(sf, v), __dmul_rn(1 - sf, s0 + b0));
+        double b1 = __dadd_rn(__dmul_rn(tf, s1 - s0), __dmul_rn(1 - tf, b0));
+        s0 = s1;
+        b0 = b1;
+    }
+    return s0;
+}
+__device__ void hoeffding(const Win& r, double* bound, double* avg) {  // rollup.go:1353
+    if (r.n == 0) {
+        *bound = D_NAN;
+        *avg = D_NAN;
+        return;
+    }
+    if (r.n == 1) {
+        *bound = 0;
+        *avg = r.values[0];
+        return;
+    }
+    double vRange = r_max(r) - r_min(r);
+    *avg = r_avg(r);
+    if (vRange <= 0) {
+        *bound = 0;
+        return;
+    }
+    double phi = r.args[r.idx];
+    if (phi >= 1) {
+        *bound = D_INF;
+        return;
+    }
+    if (phi <= 0) {
+        *bound = 0;
+        return;
+    }
+    *bound = vRange * sqrt(log(1 / (1 - phi)) / (2 * (double)r.n));
+}
+__device__ double r_duration(const Win& r) {  // rollup.go:1151
+    if (r.n == 0) return D_NAN;
+    int64_t tPrev = r.timestamps[0], dSum = 0;
+    int64_t dMax = (int64_t)(r.args[r.idx] * 1000);
+    for (uint32_t i = 0; i < r.n; i++) {
+        int64_t d = r.timestamps[i] - tPrev;
+        if (d <= dMax) dSum += d;
+        tPrev = r.timestamps[i];
+    }
+    return (double)dSum / 1000;
+}
+enum { F_LE, F_GT, F_EQ, F_NE };
+__device__ double r_filter(const Win& r, int cmp, bool sum, bool share) {  // rollup.go:1321, :1275
+    if (r.n == 0) return D_NAN;
+    double lim = r.args[r.idx], acc = 0;
+    int cnt = 0;
+    for (uint32_t i = 0; i < r.n; i++) {
+        double v = r.values[i];
+        bool hit = cmp == F_LE ? v <= lim : cmp == F_GT ? v > lim : cmp == F_EQ ? v == lim : v != lim;
+        if (hit) {
+            acc += v;
+            cnt++;
+        }
+    }
+    if (sum) return acc;
+    if (share) return (double)cnt / (double)r.n;
+    return (double)cnt;
+}
+__device__ uint32_t candlestick_len(const Win& r) {  // rollup.go:2228
+    uint32_t n = r.n;
+    while (n > 0 && r.timestamps[n - 1] >= r.currTimestamp) n--;
+    return n;
+}
+__device__ double candlestick_first(const Win& r) {
+    return (r.prevTimestamp + r.window >= r.currTimestamp) ? r.prevValue : D_NAN;
+}
+
+__device__ double call_func(int f, const Win& r) {
+    switch (f) {
+        case VMB_RF_DEFAULT_ROLLUP:
+        case VMB_RF_LAST: return r_last(r);
+        case VMB_RF_RATE: return r_deriv_fast(r);
+        case VMB_RF_DELTA: return r_delta(r);
+        case VMB_RF_AVG: return r_avg(r);
+        case VMB_RF_MIN: return r_min(r);
+        case VMB_RF_MAX: return r_max(r);
+        case VMB_RF_SUM: return r_sum(r);
+        case VMB_RF_COUNT: return r.n == 0 ? D_NAN : (double)r.n;
+        case VMB_RF_QUANTILE: return quantile(r.args[r.idx], r.values, r.n);
+        case VMB_RF_MEDIAN: return quantile(0.5, r.values, r.n);
+        case VMB_RF_FIRST: return r.n == 0 ? D_NAN : r.values[0];
+        case VMB_RF_RANGE: return r_max(r) - r_min(r);
+        case VMB_RF_SUM2: {
+            if (r.n == 0) return D_NAN;
+            double s = 0;
+            for (uint32_t i = 0; i < r.n; i++) s = __dadd_rn(s, __dmul_rn(r.values[i], r.values[i]));
+            return s;
+        }
+        case VMB_RF_STDDEV: return sqrt(stdvar(r.values, r.n));
+        case VMB_RF_STDVAR: return stdvar(r.values, r.n);
+        case VMB_RF_IDERIV: return r_ideriv(r);
+        case VMB_RF_IDELTA: return r_idelta(r);
+        case VMB_RF_DERIV: {
+            double v, k;
+            linear_regression(r, &v, &k);
+            return k;
+        }
+        case VMB_RF_INCREASE_PURE: return r_increase_pure(r);
+        case VMB_RF_CHANGES: return r_changes(r, false);
+        case VMB_RF_CHANGES_PROMETHEUS: return r_changes(r, true);
+        case VMB_RF_RESETS: return r_incr_or_resets(r, false);
+        case VMB_RF_INCREASES: return r_incr_or_resets(r, true);
+        case VMB_RF_INTEGRATE: return r_integrate(r);
+        case VMB_RF_LAG: return r_lag(r);
+        case VMB_RF_LIFETIME: return r_lifetime(r);
+        case VMB_RF_SCRAPE_INTERVAL: return r_scrape_interval(r);
+        case VMB_RF_TMIN: return r_tminmax(r, true);
+        case VMB_RF_TMAX: return r_tminmax(r, false);
+        case VMB_RF_TFIRST: return r.n == 0 ? D_NAN : (double)r.timestamps[0] / 1e3;
+        case VMB_RF_TLAST: return r.n == 0 ? D_NAN : (double)r.timestamps[r.n - 1] / 1e3;
+        case VMB_RF_TLAST_CHANGE: return r_tlast_change(r);
+        case VMB_RF_MODE: return r_mode(r);
+        case VMB_RF_MAD: {  // rollup.go:1469 mad
+            double median = quantile(0.5, r.values, r.n);
+            return quantile_tf(0.5, r.values, r.n, AbsDev{median});
+        }
+        case VMB_RF_OUTLIER_IQR: return r_outlier_iqr(r);
+        case VMB_RF_ZSCORE: return r_zscore(r);
+        case VMB_RF_ASCENT: return r_ascent_descent(r, true);
+        case VMB_RF_DESCENT: return r_ascent_descent(r, false);
+        case VMB_RF_DISTINCT: return r_distinct(r);
+        case VMB_RF_GEOMEAN: {  // rollup.go:1741
+            if (r.n == 0) return D_NAN;
+            double p = 1.0;
+            for (uint32_t i = 0; i < r.n; i++) p *= r.values[i];
+            return pow(p, 1 / (double)r.n);
+        }
+        case VMB_RF_PREDICT_LINEAR: {  // rollup.go:1080
+            double v, k;
+            linear_regression(r, &v, &k);
+            if (isnan(v)) return D_NAN;
+            return __dadd_rn(v, __dmul_rn(k, r.args[r.idx]));
+        }
+        case VMB_RF_HOLT_WINTERS: return r_holt_winters(r);
+        case VMB_RF_HOEFFDING_LOWER: {
+            double b, a;
+            hoeffding(r, &b, &a);
+            return a - b;
+        }
+        case VMB_RF_HOEFFDING_UPPER: {
+            double b, a;
+            hoeffding(r, &b, &a);
+            return a + b;
+        }
+        case VMB_RF_DURATION: return r_duration(r);
+        case VMB_RF_COUNT_LE: return r_filter(r, F_LE, false, false);
+        case VMB_RF_COUNT_GT: return r_filter(r, F_GT, false, false);
+        case VMB_RF_COUNT_EQ: return r_filter(r, F_EQ, false, false);
+        case VMB_RF_COUNT_NE: return r_filter(r, F_NE, false, false);
+        case VMB_RF_SHARE_LE: return r_filter(r, F_LE, false, true);
+        case VMB_RF_SHARE_GT: return r_filter(r, F_GT, false, true);
+        case VMB_RF_SHARE_EQ: return r_filter(r, F_EQ, false, true);
+        case VMB_RF_SUM_LE: return r_filter(r, F_LE, true, false);
+        case VMB_RF_SUM_GT: return r_filter(r, F_GT, true, false);
+        case VMB_RF_SUM_EQ: return r_filter(r, F_EQ, true, false);
+        case VMB_RF_PRESENT: return r.n > 0 ? 1.0 : D_NAN;
+        case VMB_RF_ABSENT: return r.n == 0 ? 1.0 : D_NAN;
+        case VMB_RF_STALE_SAMPLES: {
+            if (r.n == 0) return D_NAN;
+            int c = 0;
+            for (uint32_t i = 0; i < r.n; i++) c += is_stale_nan(r.values[i]);
+            return (double)c;
+        }
+        case VMB_RF_RATE_OVER_SUM: {  // rollup.go:1705
+            if (r.n == 0) return D_NAN;
+            double sum = 0;
+            for (uint32_t i = 0; i < r.n; i++) sum += r.values[i];
+            return sum / ((double)r.window / 1e3);
+        }
+        case VMB_RF_DELTA_PROMETHEUS: return r.n < 2 ? D_NAN : r.values[r.n - 1] - r.values[0];  // rollup.go:1903
+        case VMB_RF_RATE_PROMETHEUS: {  // rollup.go:1946
+            if (r.n < 2) return D_NAN;
+            double delta = r.values[r.n - 1] - r.values[0];
+            if (isnan(delta) || r.window == 0) return D_NAN;
+            return delta / ((double)r.window / 1e3);
+        }
+        case VMB_RF_OPEN: {
+            double v = candlestick_first(r);
+            if (!isnan(v)) return v;
+            return candlestick_len(r) == 0 ? D_NAN : r.values[0];
+        }
+        case VMB_RF_CLOSE: {
+            uint32_t n = candlestick_len(r);
+            return n == 0 ? candlestick_first(r) : r.values[n - 1];
+        }
+        case VMB_RF_HIGH:
+        case VMB_RF_LOW: {
+            uint32_t n = candlestick_len(r);
+            const double* values = r.values;
+            double m = candlestick_first(r);
+            if (isnan(m)) {
+                if (n == 0) return D_NAN;
+                m = values[0];
+                values++;
+                n--;
+            }
+            for (uint32_t i = 0; i < n; i++)
+                if (f == VMB_RF_HIGH ? values[i] > m : values[i] < m) m = values[i];
+            return m;
+        }
+    }
+    return D_NAN;
+}
+
+// first index in ts[0..n) with ts > x  (== seekFirstTimestampIdxAfter rollup.go:825 on sorted input)
+__device__ __forceinline__ uint32_t upper_bound_ts(const int64_t* __restrict__ ts, uint32_t n, int64_t x) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (ts[mid] <= x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+}  // namespace
+
+struct RollupParams {
+    vmb_rollup_cfg cfg;      // args/args2 replaced by DEVICE pointers (or nullptr)
+    SeriesMeta* meta;
+    int64_t* ts;
+    double* vals;
+    double* out;             // [nseries x P]
+    unsigned long long* scanned;  // device accumulator
+    uint32_t nseries;
+    uint32_t npoints;
+    // series assembly from decoded blocks (nullptr when the batch was built from host columns)
+    const uint32_t* ser_first_block;
+    const uint32_t* ser_nblocks;
+    const uint64_t* row_off;
+    const uint32_t* blk_lo;
+    const uint32_t* blk_hi;
+    const vmb_block_desc* descs;
+    int32_t* blk_status;
+    unsigned int* failed_blocks;  // device counter: blocks with a non-zero status
+};
+
+// one thread per series: [start, n) from the kept row ranges of its blocks (netstorage.go:444 unpackTo for blocks
+// that are already time-ordered and disjoint -- the mergeSortBlocks fast path netstorage.go:585)
+__global__ void k_series_assemble(RollupParams P) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.nseries) return;
+    uint32_t fb = P.ser_first_block[s], nb = P.ser_nblocks[s];
+    SeriesMeta m;
+    m.start = 0;
+    m.n = 0;
+    m._pad = 0;
+    m.max_prev_interval = 0;
+    m.window = 0;
+    bool failed = false;
+    for (uint32_t k = 0; k < nb; k++)
+        if (P.blk_status[fb + k]) failed = true;
+    if (!failed && nb) {
+        // skip leading / trailing blocks that were trimmed away completely
+        uint32_t a = 0, b = nb;
+        while (a < b && P.blk_hi[fb + a] == P.blk_lo[fb + a]) a++;
+        while (b > a && P.blk_hi[fb + b - 1] == P.blk_lo[fb + b - 1]) b--;
+        if (a < b) {
+            bool contiguous = true;
+            for (uint32_t k = a; k < b; k++) {
+                if (k > a && P.blk_lo[fb + k] != 0) contiguous = false;
+                if (k + 1 < b && P.blk_hi[fb + k] != P.descs[fb + k].rows) contiguous = false;
+            }
+            if (!contiguous) {
+                for (uint32_t k = 0; k < nb; k++) P.blk_status[fb + k] = VMB_ERR_BLOCK_ORDER;
+                failed = true;
+            } else {
+                m.start = P.row_off[fb + a] + P.blk_lo[fb + a];
+                uint64_t end = P.row_off[fb + b - 1] + P.blk_hi[fb + b - 1];
+                m.n = (uint32_t)(end - m.start);
+            }
+        }
+    }
+    P.meta[s] = m;
+    if (failed && P.failed_blocks) atomicAdd(P.failed_blocks, 1u);
+}
+
+// one warp per series
+__global__ void __launch_bounds__(128) k_series_prepare(RollupParams P) {
+    const int lane = lane_id();
+    const uint32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    const vmb_rollup_cfg& rc = P.cfg;
+    for (uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < P.nseries; s += warps_per_grid) {
+        SeriesMeta m = P.meta[s];
+        double* v = P.vals + m.start;
+        int64_t* t = P.ts + m.start;
+        uint32_t n = m.n;
+        // ---- dropStaleNaNs eval.go:1985
+        if ((rc.flags & VMB_RC_DROP_STALE_NANS) && n) {
+            bool has = false;
+            for (uint32_t i = lane; i < n; i += 32) has |= is_stale_nan(v[i]);
+            if (__any_sync(VMB_FULL, has)) {
+                uint32_t o = 0;
+                for (uint32_t base = 0; base < n; base += 32) {
+                    uint32_t i = base + lane;
+                    double x = i < n ? v[i] : 0.0;
+                    int64_t tt = i < n ? t[i] : 0;
+                    bool keep = i < n && !is_stale_nan(x);
+                    uint32_t bal = __ballot_sync(VMB_FULL, keep);
+                    if (keep) {
+                        uint32_t r = o + __popc(bal & ((1u << lane) - 1u));
+                        v[r] = x;
+                        t[r] = tt;
+                    }
+                    o += __popc(bal);
+                    __syncwarp();
+                }
+                n = o;
+            }
+        }
+        // ---- removeCounterResets rollup.go:921 (sequential float semantics preserved: corrections are accumulated in
+        //      sample order; the final clamp is a segmented prefix "max" which is order-independent)
+        if ((rc.flags & VMB_RC_REMOVE_COUNTER_RESETS) && n) {
+            const int64_t max_stale = rc.lookback_delta != 0 ? rc.lookback_delta + rc.window : 0;  // rollup.go:380-387
+            double corr = 0.0, prev_raw = 0.0, prev_out = 0.0;
+            int64_t prev_ts = 0;
+            for (uint32_t base = 0; base < n; base += 32) {
+                uint32_t i = base + lane;
+                bool valid = i < n;
+                double x = valid ? v[i] : 0.0;
+                int64_t tt = valid ? t[i] : 0;
+                double pv = shfl_up_f64(x, 1);
+                int64_t pt = (int64_t)shfl_up_u64((uint64_t)tt, 1);
+                if (lane == 0) {
+                    pv = base == 0 ? x : prev_raw;
+                    pt = base == 0 ? tt : prev_ts;
+                }
+                double d = x - pv;
+                bool is_reset = valid && d < 0;
+                double amt = 0.0;
+                if (is_reset) amt = ((-d * 8) < pv) ? (pv - x) : pv;
+                bool is_gap = valid && i > 0 && max_stale > 0 && (tt - pt) > max_stale;
+                uint32_t ev = __ballot_sync(VMB_FULL, is_reset || is_gap);
+                double my_corr = corr;
+                while (ev) {
+                    int b = __ffs((int)ev) - 1;
+                    ev &= ev - 1;
+                    double a = shfl_f64(amt, b);
+                    int flags = __shfl_sync(VMB_FULL, (int)is_reset | ((int)is_gap << 1), b);
+                    if (flags & 1) corr = corr + a;
+                    if (flags & 2) corr = 0.0;
+                    if (lane >= b) my_corr = corr;
+                }
+                // element as a function of the previous output: Const(c) or MaxWith(m)
+                double mval = is_gap ? x : x + my_corr;
+                bool isc = is_gap || i == 0 || isnan(mval) || !valid;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    double am = shfl_up_f64(mval, off);
+                    int ac = __shfl_up_sync(VMB_FULL, (int)isc, off);
+                    if (lane >= off && !isc) {
+                        mval = (mval < am) ? am : mval;
+                        isc = ac != 0;
+                    }
+                }
+                double outv = isc ? mval : ((mval < prev_out) ? prev_out : mval);
+                if (valid) v[i] = outv;
+                prev_out = shfl_f64(outv, 31);
+                prev_raw = shfl_f64(x, 31);
+                prev_ts = (int64_t)shfl_u64((uint64_t)tt, 31);
+            }
+        }
+        // ---- maxPrevInterval / window  rollup.go:719-756
+        if (lane == 0) {
+            int64_t maxPrev = rc.step;
+            if (rc.start < rc.end) {
+                // getScrapeInterval rollup.go:871: 0.6 quantile of the last <= 20 intervals
+                int64_t si = rc.step;
+                if (n >= 2) {
+                    double iv[20];
+                    uint32_t m2 = n - 1;
+                    uint32_t from = m2 > 20 ? m2 - 20 : 0;
+                    uint32_t k = 0;
+                    int64_t tsPrev = t[n - 1];
+                    for (int i = (int)m2 - 1; i >= (int)from; i--) {
+                        iv[k++] = (double)(tsPrev - t[i]);
+                        tsPrev = t[i];
+                    }
+                    for (uint32_t a = 1; a < k; a++) {  // insertion sort
+                        double x = iv[a];
+                        int b = (int)a - 1;
+                        while (b >= 0 && iv[b] > x) {
+                            iv[b + 1] = iv[b];
+                            b--;
+                        }
+                        iv[b + 1] = x;
+                    }
+                    double nn = (double)k;
+                    double rank = 0.6 * (nn - 1);
+                    double lower = fmax(0.0, floor(rank));
+                    double upper = fmin(nn - 1, lower + 1);
+                    double weight = rank - floor(rank);
+                    double q = __dadd_rn(__dmul_rn(iv[(int)lower], 1 - weight), __dmul_rn(iv[(int)upper], weight));
+                    int64_t sq = (int64_t)q;
+                    if (sq > 0) si = sq;
+                }
+                // getMaxPrevInterval rollup.go:899
+                if (si <= 2 * 1000) maxPrev = si + 4 * si;
+                else if (si <= 4 * 1000) maxPrev = si + 2 * si;
+                else if (si <= 8 * 1000) maxPrev = si + si;
+                else if (si <= 16 * 1000) maxPrev = si + si / 2;
+                else if (si <= 32 * 1000) maxPrev = si + si / 4;
+                else maxPrev = si + si / 8;
+            }
+            if (rc.lookback_delta > 0 && maxPrev > rc.lookback_delta) maxPrev = rc.lookback_delta;
+            if (rc.min_staleness_ms > 0 && maxPrev < rc.min_staleness_ms) maxPrev = rc.min_staleness_ms;
+            int64_t window = rc.window;
+            if (window <= 0) {
+                window = rc.step;
+                if ((rc.flags & VMB_RC_MAY_ADJUST_WINDOW) && window < maxPrev) window = maxPrev;
+                if ((rc.flags & VMB_RC_IS_DEFAULT_ROLLUP) && rc.lookback_delta > 0 && window > rc.lookback_delta)
+                    window = rc.lookback_delta;
+            }
+            m.n = n;
+            m.max_prev_interval = maxPrev;
+            m.window = window;
+            P.meta[s] = m;
+        }
+        __syncwarp();
+    }
+}
+
+#define ROLLUP_THREADS 256
+
+// one thread per output point; a CTA covers ROLLUP_THREADS consecutive points of one series
+__global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
+    const vmb_rollup_cfg& rc = P.cfg;
+    const uint32_t tiles = (P.npoints + ROLLUP_THREADS - 1) / ROLLUP_THREADS;
+    unsigned long long scanned = 0;
+    for (uint64_t bid = blockIdx.x; bid < (uint64_t)P.nseries * tiles; bid += gridDim.x) {
+        const uint32_t s = (uint32_t)(bid / tiles);
+        const uint32_t p = (uint32_t)(bid % tiles) * ROLLUP_THREADS + threadIdx.x;
+        const SeriesMeta m = P.meta[s];
+        if (p == 0) scanned += m.n;  // samplesScanned starts at len(values) rollup.go:766
+        if (p >= P.npoints) continue;
+        const double* v = P.vals + m.start;
+        const int64_t* t = P.ts + m.start;
+        const uint32_t n = m.n;
+        const int64_t tEnd = rc.start + (int64_t)p * rc.step;
+        const int64_t tStart = tEnd - m.window;
+        const uint32_t i = upper_bound_ts(t, n, tStart);
+        uint32_t j = upper_bound_ts(t, n, tEnd);
+        if (j < i) j = i;
+        Win r;
+        r.prevValue = D_NAN;
+        r.prevTimestamp = tStart - m.max_prev_interval;
+        if (i < n && i > 0 && t[i - 1] > r.prevTimestamp) {
+            r.prevValue = v[i - 1];
+            r.prevTimestamp = t[i - 1];
+        }
+        r.values = v + i;
+        r.timestamps = t + i;
+        r.n = j - i;
+        r.realPrevValue = D_NAN;
+        if (i > 0) {
+            int64_t curr = r.n > 0 ? t[i] : tStart;
+            if (rc.lookback_delta == 0 || (curr - t[i - 1]) < rc.lookback_delta) r.realPrevValue = v[i - 1];
+        }
+        r.realNextValue = j < n ? v[j] : D_NAN;
+        r.currTimestamp = tEnd;
+        r.idx = p;
+        r.window = m.window;
+        r.args = rc.args;
+        r.args2 = rc.args2;
+        P.out[(size_t)s * P.npoints + p] = call_func(rc.func_id, r);
+        scanned += rc.samples_scanned_per_call > 0 ? (unsigned long long)rc.samples_scanned_per_call : (unsigned long long)r.n;
+    }
+    // block reduce -> one atomic per CTA
+#pragma unroll
+    for (int off = 16; off; off >>= 1) scanned += shfl_u64(scanned, (lane_id() ^ off));
+    __shared__ unsigned long long s_part[ROLLUP_THREADS / 32];
+    if (lane_id() == 0) s_part[threadIdx.x >> 5] = scanned;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < ROLLUP_THREADS / 32; w++) tot += s_part[w];
+        if (tot) atomicAdd(P.scanned, tot);
+    }
+}
+
+// ---- incremental aggregation (aggr_incremental.go). One thread per (group, point); the series of a group are folded
+// in ascending series order, exactly like a single reference worker that receives them in that order.
+struct AggrParams {
+    const double* rolled;       // [nseries x P]
+    const uint32_t* grp_start;  // [ngroups + 1]
+    const uint32_t* grp_series; // series indices sorted by (group, series)
+    double* values;             // [ngroups x P]
+    double* counts;
+    uint32_t ngroups, npoints;
+    int aggr;
+};
+
+__global__ void k_aggr_fold(AggrParams A) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)A.ngroups * A.npoints) return;
+    uint32_t g = (uint32_t)(idx / A.npoints), p = (uint32_t)(idx % A.npoints);
+    double dv = 0.0, dc = 0.0;
+    bool any_done = false;
+    for (uint32_t k = A.grp_start[g]; k < A.grp_start[g + 1]; k++) {
+        double v = A.rolled[(size_t)A.grp_series[k] * A.npoints + p];
+        switch (A.aggr) {
+            case VMB_AGGR_SUM:
+                if (isnan(v)) break;
+                if (dc == 0) { dv = v; dc = 1; break; }
+                dv += v;
+                break;
+            case VMB_AGGR_MIN:
+                if (isnan(v)) break;
+                if (dc == 0) { dv = v; dc = 1; break; }
+                if (v < dv) dv = v;
+                break;
+            case VMB_AGGR_MAX:
+                if (isnan(v)) break;
+                if (dc == 0) { dv = v; dc = 1; break; }
+                if (v > dv) dv = v;
+                break;
+            case VMB_AGGR_AVG:
+                if (isnan(v)) break;
+                if (dc == 0) { dv = v; dc = 1; break; }
+                dv += v;
+                dc += 1;
+                break;
+            case VMB_AGGR_COUNT:
+            case VMB_AGGR_GROUP:
+                if (isnan(v)) break;
+                dv += 1;
+                break;
+            case VMB_AGGR_SUM2:
+                if (isnan(v)) break;
+                if (dc == 0) { dv = __dmul_rn(v, v); dc = 1; break; }
+                dv = __dadd_rn(dv, __dmul_rn(v, v));
+                break;
+            case VMB_AGGR_GEOMEAN:
+                if (isnan(v)) break;
+                if (dc == 0) { dv = v; dc = 1; break; }
+                dv *= v;
+                dc += 1;
+                break;
+            case VMB_AGGR_ANY:  // first series of the group wins, NaNs included (aggr_incremental.go:517)
+                if (!any_done) { dv = v; dc = 1; any_done = true; }
+                break;
+        }
+    }
+    A.values[idx] = dv;
+    A.counts[idx] = dc;
+}
+
+__global__ void k_aggr_merge(int aggr, double* dv, double* dc, const double* sv, const double* sc, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = sv[i];
+    switch (aggr) {
+        case VMB_AGGR_COUNT:
+        case VMB_AGGR_GROUP: dv[i] += v; break;
+        case VMB_AGGR_SUM:
+        case VMB_AGGR_SUM2:
+            if (sc[i] == 0) break;
+            if (dc[i] == 0) { dv[i] = v; dc[i] = 1; break; }
+            dv[i] += v;
+            break;
+        case VMB_AGGR_MIN:
+            if (sc[i] == 0) break;
+            if (dc[i] == 0) { dv[i] = v; dc[i] = 1; break; }
+            if (v < dv[i]) dv[i] = v;
+            break;
+        case VMB_AGGR_MAX:
+            if (sc[i] == 0) break;
+            if (dc[i] == 0) { dv[i] = v; dc[i] = 1; break; }
+            if (v > dv[i]) dv[i] = v;
+            break;
+        case VMB_AGGR_AVG:
+            if (sc[i] == 0) break;
+            if (dc[i] == 0) { dv[i] = v; dc[i] = sc[i]; break; }
+            dv[i] += v;
+            dc[i] += sc[i];
+            break;
+        case VMB_AGGR_GEOMEAN:
+            if (sc[i] == 0) break;
+            if (dc[i] == 0) { dv[i] = v; dc[i] = sc[i]; break; }
+            dv[i] *= v;
+            dc[i] += sc[i];
+            break;
+        case VMB_AGGR_ANY:
+            if (dc[i] > 0) break;
+            dv[i] = v;
+            dc[i] = sc[i];
+            break;
+    }
+}
+
+// puts the identity of the all-reduce operator into empty cells: 0 for sum-like, +-Inf for min/max, 1 for geomean
+__global__ void k_aggr_prepare_allreduce(int aggr, double* dv, const double* dc, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (aggr == VMB_AGGR_COUNT || aggr == VMB_AGGR_GROUP) return;
+    if (dc[i] != 0) return;
+    double id = 0.0;
+    if (aggr == VMB_AGGR_MIN) id = D_INF;
+    else if (aggr == VMB_AGGR_MAX) id = -D_INF;
+    else if (aggr == VMB_AGGR_GEOMEAN) id = 1.0;
+    dv[i] = id;
+}
+
+__global__ void k_aggr_finalize(int aggr, double* dv, const double* dc, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (aggr) {
+        case VMB_AGGR_AVG:
+            if (dc[i] == 0) dv[i] = D_NAN;
+            else dv[i] /= dc[i];
+            break;
+        case VMB_AGGR_COUNT:
+            if (dv[i] == 0) dv[i] = D_NAN;
+            break;
+        case VMB_AGGR_GROUP:
+            dv[i] = dv[i] == 0 ? D_NAN : 1.0;
+            break;
+        case VMB_AGGR_GEOMEAN:
+            if (dc[i] == 0) dv[i] = D_NAN;
+            else dv[i] = pow(dv[i], 1 / dc[i]);
+            break;
+        default:
+            if (dc[i] == 0) dv[i] = D_NAN;
+            break;
+    }
+}
+
+void launch_series_assemble(const RollupParams& P, cudaStream_t st) {
+    if (!P.nseries) return;
+    k_series_assemble<<<(P.nseries + 127) / 128, 128, 0, st>>>(P);
+}
+void launch_series_prepare(const RollupParams& P, cudaStream_t st) {
+    if (!P.nseries) return;
+    uint32_t grid = (P.nseries + 3) / 4;
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    k_series_prepare<<<grid, 128, 0, st>>>(P);
+}
+void launch_rollup(const RollupParams& P, cudaStream_t st) {
+    if (!P.nseries || !P.npoints) return;
+    uint64_t tiles = (P.npoints + ROLLUP_THREADS - 1) / ROLLUP_THREADS;
+    uint64_t total = (uint64_t)P.nseries * tiles;
+    uint32_t grid = total > 148ull * 64ull ? 148u * 64u : (uint32_t)total;
+    k_rollup<<<grid, ROLLUP_THREADS, 0, st>>>(P);
+}

@@ -1,0 +1,934 @@
+// In-kernel zstd frame decoding for MarshalType 1/4 columns.
+//
+// Replaces lib/encoding/compress.go:27 DecompressZSTD -> lib/encoding/zstd/zstd_cgo.go:13 -> gozstd.Decompress
+// (vendor/github.com/valyala/gozstd/gozstd.go:187 -> libzstd ZSTD_decompressDCtx) for every compressed column of a
+// batch at once.  The format is the published one (RFC 8878); frames written by the reference are single-segment,
+// checksum-less, dictionary-less and (for <=128 KiB columns) single-block ("Measured frame shapes").
+//
+// Three kernels:
+//   k_zstd_prepare : one thread per frame of the common shape (one Compressed block, Huffman-coded literals):
+//                    parses headers + the Huffman tree description into a HufJob.
+//   k_huf_decode   : the hot one. Lane-packed: every lane owns ONE Huffman bitstream (4 per frame => 8 frames per
+//                    warp), decode tables live in shared memory, streams are read backwards through a 64-bit
+//                    register window refilled with aligned 32-bit loads, output is written as aligned 32-bit words.
+//   k_zstd_serial  : one thread per frame: (a) executes the sequences section of prepared frames, (b) decodes any
+//                    frame of another shape (raw/RLE blocks, multi-block, raw/RLE/treeless literals) completely.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------ shared pieces
+namespace {
+
+__device__ __forceinline__ int hb32(uint32_t v) { return 31 - __clz((int)v); }
+
+// backward bitstream (RFC 8878 4.1): MSB-aligned 64-bit window
+struct BitR {
+    const uint8_t* base;
+    int pos;        // bytes of the stream not yet pulled into the window
+    uint64_t buf;   // next bits at the top
+    int cnt;        // bits in buf (may count zero padding pulled from before the stream start)
+    long long left; // payload bits not yet consumed; < 0 => the stream was over-read (corruption)
+
+    __device__ __forceinline__ void refill() {  // requires cnt <= 32
+        uint32_t w;
+        if (pos >= 4) {
+            w = load_u32_unaligned(base + pos - 4);
+            pos -= 4;
+        } else {
+            w = 0;
+            for (int i = 0; i < pos; i++) w |= (uint32_t)base[i] << (8 * i);
+            w = pos ? (w << (8 * (4 - pos))) : 0u;
+            pos = 0;
+        }
+        buf |= (uint64_t)w << (32 - cnt);
+        cnt += 32;
+    }
+    __device__ bool init(const uint8_t* src, uint32_t len) {
+        if (len == 0) return false;
+        uint32_t last = src[len - 1];
+        if (last == 0) return false;
+        base = src;
+        pos = (int)len;
+        buf = 0;
+        cnt = 0;
+        left = (long long)(len - 1) * 8 + hb32(last);
+        refill();
+        int skip = 8 - hb32(last);  // zero padding + the final-bit marker
+        buf <<= skip;
+        cnt -= skip;
+        return true;
+    }
+    __device__ __forceinline__ uint32_t peek(int nb) {  // 1 <= nb <= 32
+        if (cnt < nb) refill();
+        return (uint32_t)(buf >> (64 - nb));
+    }
+    __device__ __forceinline__ void skip(int nb) {
+        buf <<= nb;
+        cnt -= nb;
+        left -= nb;
+    }
+    __device__ __forceinline__ uint32_t read(int nb) {  // 0 <= nb <= 32
+        if (nb == 0) return 0;
+        uint32_t v = peek(nb);
+        skip(nb);
+        return v;
+    }
+};
+
+// forward LSB-first bit reader for FSE table descriptions (RFC 8878 4.1.1)
+struct FwdR {
+    const uint8_t* p;
+    uint32_t len;
+    uint32_t bitpos;
+    __device__ uint32_t peek(int nb) const {
+        uint32_t byte = bitpos >> 3;
+        uint64_t v = 0;
+        for (int i = 0; i < 5; i++)
+            if (byte + i < len) v |= (uint64_t)p[byte + i] << (8 * i);
+        return (uint32_t)((v >> (bitpos & 7)) & ((1ull << nb) - 1));
+    }
+};
+
+// FSE decoding table entry: base(16) | nbits(8) | symbol(8)
+__device__ __forceinline__ uint32_t fse_pack(uint32_t base, uint32_t nbits, uint32_t sym) {
+    return (base << 16) | (nbits << 8) | sym;
+}
+#define FSE_SYM(e) ((e) & 0xffu)
+#define FSE_NB(e) (((e) >> 8) & 0xffu)
+#define FSE_BASE(e) ((e) >> 16)
+
+// returns bytes consumed or 0 on error
+__device__ uint32_t fse_read_ncount(short* norm, int* nsym_out, int* log_out, int max_sym, int max_log,
+                                    const uint8_t* src, uint32_t len) {
+    FwdR b{src, len, 0};
+    int log = (int)b.peek(4) + 5;
+    b.bitpos += 4;
+    if (log > max_log) return 0;
+    int remaining = (1 << log) + 1, threshold = 1 << log, nbits = log + 1, sym = 0;
+    bool prev0 = false;
+    while (remaining > 1 && sym <= max_sym) {
+        if (prev0) {
+            for (;;) {
+                int r = (int)b.peek(2);
+                b.bitpos += 2;
+                for (int k = 0; k < r; k++) {
+                    if (sym > max_sym) return 0;
+                    norm[sym++] = 0;
+                }
+                if (r != 3) break;
+                if (b.bitpos > len * 8u + 16u) return 0;
+            }
+            prev0 = false;
+            continue;
+        }
+        int maxv = (2 * threshold - 1) - remaining;
+        int count;
+        uint32_t bits = b.peek(nbits);
+        if ((int)(bits & (uint32_t)(threshold - 1)) < maxv) {
+            count = (int)(bits & (uint32_t)(threshold - 1));
+            b.bitpos += nbits - 1;
+        } else {
+            count = (int)(bits & (uint32_t)(2 * threshold - 1));
+            if (count >= threshold) count -= maxv;
+            b.bitpos += nbits;
+        }
+        count--;
+        remaining -= count < 0 ? -count : count;
+        if (sym > max_sym) return 0;
+        norm[sym++] = (short)count;
+        prev0 = (count == 0);
+        while (remaining < threshold) {
+            nbits--;
+            threshold >>= 1;
+        }
+    }
+    if (remaining != 1) return 0;
+    uint32_t used = (b.bitpos + 7) >> 3;
+    if (used > len) return 0;
+    *nsym_out = sym;
+    *log_out = log;
+    return used;
+}
+
+// builds the decoding table (size 1<<log entries) ; `next` is scratch for nsym uint16. returns false on error
+__device__ bool fse_build(uint32_t* table, const short* norm, int nsym, int log, unsigned short* next) {
+    int size = 1 << log;
+    int high = size - 1;
+    for (int s = 0; s < nsym; s++) {
+        if (norm[s] == -1) {
+            table[high--] = (uint32_t)s;
+            next[s] = 1;
+        } else {
+            next[s] = (unsigned short)norm[s];
+        }
+    }
+    int step = (size >> 1) + (size >> 3) + 3, mask = size - 1, pos = 0;
+    for (int s = 0; s < nsym; s++) {
+        for (int i = 0; i < norm[s]; i++) {
+            table[pos] = (uint32_t)s;
+            do {
+                pos = (pos + step) & mask;
+            } while (pos > high);
+        }
+    }
+    if (pos != 0) return false;
+    for (int i = 0; i < size; i++) {
+        uint32_t s = table[i];
+        uint32_t ns = next[s]++;
+        int nb = log - hb32(ns);
+        table[i] = fse_pack((ns << nb) - (uint32_t)size, (uint32_t)nb, s);
+    }
+    return true;
+}
+
+// Huffman tree description (RFC 8878 4.2.1) -> code length per symbol.  `ftab` : scratch for 64 uint32 + 256 shorts.
+// returns bytes consumed, 0 on error
+__device__ uint32_t huf_read_weights(uint8_t* nbits_out /*256*/, int* table_log, const uint8_t* src, uint32_t len,
+                                     uint32_t* ftab, short* norm, unsigned short* next) {
+    if (len < 1) return 0;
+    uint8_t* weights = nbits_out;  // reuse: weights first, converted to code lengths at the end
+    int nw = 0;
+    uint32_t consumed;
+    uint32_t hb = src[0];
+    if (hb >= 128) {
+        nw = (int)hb - 127;
+        uint32_t nbytes = (uint32_t)(nw + 1) / 2;
+        if (1 + nbytes > len) return 0;
+        for (int i = 0; i < nw; i++) {
+            uint32_t b = src[1 + i / 2];
+            weights[i] = (uint8_t)((i & 1) ? (b & 15) : (b >> 4));
+        }
+        consumed = 1 + nbytes;
+    } else {
+        uint32_t csize = hb;
+        if (1 + csize > len || csize < 2) return 0;
+        int nsym, log;
+        uint32_t hdr = fse_read_ncount(norm, &nsym, &log, 255, 6, src + 1, csize);
+        if (!hdr) return 0;
+        if (!fse_build(ftab, norm, nsym, log, next)) return 0;
+        BitR bb;
+        if (hdr >= csize || !bb.init(src + 1 + hdr, csize - hdr)) return 0;
+        uint32_t s1 = bb.read(log), s2 = bb.read(log);
+        for (;;) {  // two interleaved states (RFC 8878 4.2.1.2)
+            if (nw >= 255) return 0;
+            uint32_t e1 = ftab[s1];
+            weights[nw++] = (uint8_t)FSE_SYM(e1);
+            if (bb.left < (long long)FSE_NB(e1)) {
+                if (nw >= 255) return 0;
+                weights[nw++] = (uint8_t)FSE_SYM(ftab[s2]);
+                break;
+            }
+            s1 = FSE_BASE(e1) + bb.read((int)FSE_NB(e1));
+            if (nw >= 255) return 0;
+            uint32_t e2 = ftab[s2];
+            weights[nw++] = (uint8_t)FSE_SYM(e2);
+            if (bb.left < (long long)FSE_NB(e2)) {
+                if (nw >= 255) return 0;
+                weights[nw++] = (uint8_t)FSE_SYM(ftab[s1]);
+                break;
+            }
+            s2 = FSE_BASE(e2) + bb.read((int)FSE_NB(e2));
+        }
+        consumed = 1 + csize;
+    }
+    uint32_t total = 0;
+    for (int i = 0; i < nw; i++) {
+        if (weights[i] > 11) return 0;
+        if (weights[i]) total += 1u << (weights[i] - 1);
+    }
+    if (total == 0) return 0;
+    int log = hb32(total) + 1;
+    if (log > 11) return 0;
+    uint32_t rest = (1u << log) - total;
+    if (rest == 0 || (rest & (rest - 1))) return 0;
+    weights[nw++] = (uint8_t)(hb32(rest) + 1);
+    for (int i = 0; i < nw; i++) nbits_out[i] = weights[i] ? (uint8_t)(log + 1 - weights[i]) : 0;
+    for (int i = nw; i < 256; i++) nbits_out[i] = 0;
+    *table_log = log;
+    return consumed;
+}
+
+// fills a (1<<log)-entry decode table: entry = (nbits << 8) | symbol; codes are assigned in (weight asc, symbol asc)
+// order, i.e. (nbits desc, symbol asc).  Serial version for the per-thread decoder.
+__device__ bool huf_fill_table_serial(unsigned short* table, const uint8_t* nbits, int log) {
+    uint32_t pos = 0;
+    for (int nb = log; nb >= 1; nb--) {
+        uint32_t span = 1u << (log - nb);
+        for (int s = 0; s < 256; s++) {
+            if (nbits[s] != nb) continue;
+            unsigned short ent = (unsigned short)((nb << 8) | s);
+            if (pos + span > (1u << log)) return false;
+            for (uint32_t k = 0; k < span; k++) table[pos + k] = ent;
+            pos += span;
+        }
+    }
+    return pos == (1u << log);
+}
+
+__device__ bool huf_decode_stream_serial(const unsigned short* table, int log, uint8_t* dst, uint32_t n,
+                                         const uint8_t* src, uint32_t len) {
+    BitR bb;
+    if (!bb.init(src, len)) return false;
+    for (uint32_t i = 0; i < n; i++) {
+        unsigned short ent = table[bb.peek(log)];
+        dst[i] = (uint8_t)ent;
+        bb.skip(ent >> 8);
+    }
+    return bb.left == 0;
+}
+
+__constant__ short c_ll_default[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2,
+                                       2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
+__constant__ short c_ml_default[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                                       1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
+__constant__ short c_of_default[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1,
+                                       1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
+__constant__ uint32_t c_ll_base[36] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,   10,  11,  12,   13,   14,   15,   16,   18,
+                                       20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
+__constant__ uint8_t c_ll_bits[36] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1,
+                                      1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+__constant__ uint32_t c_ml_base[53] = {3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20,
+                                       21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 37, 39, 41,
+                                       43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
+__constant__ uint8_t c_ml_bits[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                      0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+
+// per-thread workspace of the serial decoder (global memory)
+struct SerialWs {
+    uint32_t ll[512];
+    uint32_t ml[512];
+    uint32_t of[256];
+    unsigned short huf[2048];
+    short norm[256];
+    unsigned short next[256];
+    uint8_t nbits[256];
+    int ll_log, ml_log, of_log, huf_log;
+    int have_ll, have_ml, have_of, have_huf;
+    unsigned long long rep[3];
+};
+
+__device__ uint32_t read_seq_table(uint32_t* table, int* tlog, int* have, int mode, const short* defnorm, int defn,
+                                   int deflog, int max_sym, int max_log, const uint8_t* src, uint32_t len, SerialWs* ws,
+                                   bool* ok) {
+    *ok = true;
+    switch (mode) {
+        case 0: {
+            for (int i = 0; i < defn; i++) ws->norm[i] = defnorm[i];
+            if (!fse_build(table, ws->norm, defn, deflog, ws->next)) *ok = false;
+            *tlog = deflog;
+            *have = 1;
+            return 0;
+        }
+        case 1: {
+            if (len < 1 || src[0] > max_sym) {
+                *ok = false;
+                return 0;
+            }
+            table[0] = fse_pack(0, 0, src[0]);
+            *tlog = 0;
+            *have = 1;
+            return 1;
+        }
+        case 2: {
+            int nsym, log;
+            uint32_t used = fse_read_ncount(ws->norm, &nsym, &log, max_sym, max_log, src, len);
+            if (!used || !fse_build(table, ws->norm, nsym, log, ws->next)) {
+                *ok = false;
+                return 0;
+            }
+            *tlog = log;
+            *have = 1;
+            return used;
+        }
+        default:
+            if (!*have) *ok = false;
+            return 0;
+    }
+}
+
+// sequences section (RFC 8878 3.1.1.3.2) + execution.  lits/lit_len: decoded literals of this block.
+// Writes at out[o...]; returns new o or -1.
+__device__ long long run_sequences(SerialWs* ws, uint8_t* out, long long o, long long out_cap, const uint8_t* lits,
+                                   uint32_t lit_len, const uint8_t* src, uint32_t len) {
+    if (len < 1) return -1;
+    uint32_t pos = 0, nseq;
+    uint32_t b0 = src[0];
+    if (b0 == 0) { nseq = 0; pos = 1; }
+    else if (b0 < 128) { nseq = b0; pos = 1; }
+    else if (b0 < 255) {
+        if (len < 2) return -1;
+        nseq = ((b0 - 128) << 8) + src[1];
+        pos = 2;
+    } else {
+        if (len < 3) return -1;
+        nseq = (uint32_t)src[1] + ((uint32_t)src[2] << 8) + 0x7F00u;
+        pos = 3;
+    }
+    uint32_t lit_pos = 0;
+    if (nseq > 0) {
+        if (pos >= len) return -1;
+        uint32_t modes = src[pos++];
+        if (modes & 3) return -1;
+        bool ok;
+        pos += read_seq_table(ws->ll, &ws->ll_log, &ws->have_ll, (modes >> 6) & 3, c_ll_default, 36, 6, 35, 9, src + pos,
+                              len - pos, ws, &ok);
+        if (!ok) return -1;
+        pos += read_seq_table(ws->of, &ws->of_log, &ws->have_of, (modes >> 4) & 3, c_of_default, 29, 5, 31, 8, src + pos,
+                              len - pos, ws, &ok);
+        if (!ok) return -1;
+        pos += read_seq_table(ws->ml, &ws->ml_log, &ws->have_ml, (modes >> 2) & 3, c_ml_default, 53, 6, 52, 9, src + pos,
+                              len - pos, ws, &ok);
+        if (!ok || pos >= len) return -1;
+        BitR bb;
+        if (!bb.init(src + pos, len - pos)) return -1;
+        uint32_t sll = bb.read(ws->ll_log), sof = bb.read(ws->of_log), sml = bb.read(ws->ml_log);
+        for (uint32_t i = 0; i < nseq; i++) {
+            uint32_t ell = ws->ll[sll], eof = ws->of[sof], eml = ws->ml[sml];
+            uint32_t ofc = FSE_SYM(eof), mlc = FSE_SYM(eml), llc = FSE_SYM(ell);
+            if (ofc > 31 || mlc > 52 || llc > 35) return -1;
+            unsigned long long ofv = (1ull << ofc) + bb.read((int)ofc);
+            uint32_t mlen = c_ml_base[mlc] + bb.read(c_ml_bits[mlc]);
+            uint32_t llen = c_ll_base[llc] + bb.read(c_ll_bits[llc]);
+            if (i + 1 < nseq) {
+                sll = FSE_BASE(ell) + bb.read((int)FSE_NB(ell));
+                sml = FSE_BASE(eml) + bb.read((int)FSE_NB(eml));
+                sof = FSE_BASE(eof) + bb.read((int)FSE_NB(eof));
+            }
+            if (bb.left < 0) return -1;
+            unsigned long long offset;
+            if (ofv > 3) {
+                offset = ofv - 3;
+                ws->rep[2] = ws->rep[1];
+                ws->rep[1] = ws->rep[0];
+                ws->rep[0] = offset;
+            } else {
+                unsigned long long idx = ofv - 1 + (llen == 0 ? 1 : 0);
+                if (idx == 0) offset = ws->rep[0];
+                else {
+                    offset = idx < 3 ? ws->rep[idx] : ws->rep[0] - 1;
+                    if (offset == 0) return -1;
+                    if (idx > 1) ws->rep[2] = ws->rep[1];
+                    ws->rep[1] = ws->rep[0];
+                    ws->rep[0] = offset;
+                }
+            }
+            if (lit_pos + llen > lit_len) return -1;
+            if (o + llen + mlen > out_cap) return -1;
+            for (uint32_t k = 0; k < llen; k++) out[o + k] = lits[lit_pos + k];
+            o += llen;
+            lit_pos += llen;
+            if ((long long)offset > o) return -1;
+            for (uint32_t k = 0; k < mlen; k++) out[o + k] = out[o + k - (long long)offset];
+            o += mlen;
+        }
+        if (bb.left != 0) return -1;
+    } else if (pos != len) {
+        return -1;
+    }
+    uint32_t rest = lit_len - lit_pos;
+    if (o + rest > out_cap) return -1;
+    for (uint32_t k = 0; k < rest; k++) out[o + k] = lits[lit_pos + k];
+    return o + rest;
+}
+
+// one Compressed block, fully serial (generic shapes). returns new o or -1
+__device__ long long decode_block_serial(SerialWs* ws, uint8_t* out, long long o, long long out_cap, uint8_t* litbuf,
+                                         const uint8_t* src, uint32_t len) {
+    if (len < 1) return -1;
+    uint32_t b0 = src[0];
+    int type = b0 & 3, sf = (b0 >> 2) & 3;
+    uint32_t pos, regen;
+    const uint8_t* lits;
+    if (type == 0 || type == 1) {
+        if ((sf & 1) == 0) { regen = b0 >> 3; pos = 1; }
+        else if (sf == 1) {
+            if (len < 2) return -1;
+            regen = (b0 >> 4) | ((uint32_t)src[1] << 4);
+            pos = 2;
+        } else {
+            if (len < 3) return -1;
+            regen = (b0 >> 4) | ((uint32_t)src[1] << 4) | ((uint32_t)src[2] << 12);
+            pos = 3;
+        }
+        if ((long long)regen > out_cap) return -1;
+        if (type == 0) {
+            if (pos + regen > len) return -1;
+            lits = src + pos;
+            pos += regen;
+        } else {
+            if (pos + 1 > len) return -1;
+            for (uint32_t k = 0; k < regen; k++) litbuf[k] = src[pos];
+            lits = litbuf;
+            pos += 1;
+        }
+    } else {
+        uint32_t csize, hdr;
+        int streams = 4;
+        if (sf == 0 || sf == 1) {
+            if (len < 3) return -1;
+            uint32_t v = src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16);
+            regen = (v >> 4) & 0x3ff;
+            csize = (v >> 14) & 0x3ff;
+            hdr = 3;
+            if (sf == 0) streams = 1;
+        } else if (sf == 2) {
+            if (len < 4) return -1;
+            uint32_t v = src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+            regen = (v >> 4) & 0x3fff;
+            csize = (v >> 18) & 0x3fff;
+            hdr = 4;
+        } else {
+            if (len < 5) return -1;
+            unsigned long long v = src[0] | ((unsigned long long)src[1] << 8) | ((unsigned long long)src[2] << 16) |
+                                   ((unsigned long long)src[3] << 24) | ((unsigned long long)src[4] << 32);
+            regen = (uint32_t)((v >> 4) & 0x3ffff);
+            csize = (uint32_t)((v >> 22) & 0x3ffff);
+            hdr = 5;
+        }
+        pos = hdr;
+        if (pos + csize > len || (long long)regen > out_cap) return -1;
+        const uint8_t* lp = src + pos;
+        uint32_t lrem = csize;
+        if (type == 2) {
+            uint32_t used = huf_read_weights(ws->nbits, &ws->huf_log, lp, lrem, ws->ll /*scratch*/, ws->norm, ws->next);
+            if (!used || !huf_fill_table_serial(ws->huf, ws->nbits, ws->huf_log)) return -1;
+            ws->have_huf = 1;
+            lp += used;
+            lrem -= used;
+        } else if (!ws->have_huf) {
+            return -1;
+        }
+        if (streams == 1) {
+            if (!huf_decode_stream_serial(ws->huf, ws->huf_log, litbuf, regen, lp, lrem)) return -1;
+        } else {
+            if (lrem < 6) return -1;
+            uint32_t s1 = lp[0] | (lp[1] << 8), s2 = lp[2] | (lp[3] << 8), s3 = lp[4] | (lp[5] << 8);
+            if (6 + s1 + s2 + s3 > lrem) return -1;
+            uint32_t s4 = lrem - 6 - s1 - s2 - s3;
+            uint32_t seg = (regen + 3) / 4;
+            if (seg * 3 > regen) return -1;
+            const uint8_t* q = lp + 6;
+            if (!huf_decode_stream_serial(ws->huf, ws->huf_log, litbuf, seg, q, s1)) return -1;
+            if (!huf_decode_stream_serial(ws->huf, ws->huf_log, litbuf + seg, seg, q + s1, s2)) return -1;
+            if (!huf_decode_stream_serial(ws->huf, ws->huf_log, litbuf + 2 * seg, seg, q + s1 + s2, s3)) return -1;
+            if (!huf_decode_stream_serial(ws->huf, ws->huf_log, litbuf + 3 * seg, regen - 3 * seg, q + s1 + s2 + s3, s4))
+                return -1;
+        }
+        lits = litbuf;
+        pos += csize;
+    }
+    if (pos >= len) return -1;
+    return run_sequences(ws, out, o, out_cap, lits, regen, src + pos, len - pos);
+}
+
+struct FrameHdr {
+    uint32_t hdr_size;
+    bool has_fcs, checksum;
+    unsigned long long fcs;
+};
+
+__host__ __device__ inline bool parse_frame_header(FrameHdr* h, const uint8_t* src, uint32_t len) {
+    if (len < 5) return false;
+    if (!(src[0] == 0x28 && src[1] == 0xB5 && src[2] == 0x2F && src[3] == 0xFD)) return false;
+    uint32_t fhd = src[4];
+    int fcs_flag = fhd >> 6;
+    bool single = (fhd >> 5) & 1;
+    if (fhd & 0x08) return false;
+    h->checksum = (fhd >> 2) & 1;
+    int did_flag = fhd & 3;
+    uint32_t pos = 5;
+    if (!single) pos += 1;
+    const int did_sizes[4] = {0, 1, 2, 4};
+    if (did_flag) {
+        unsigned long long did = 0;
+        if (pos + did_sizes[did_flag] > len) return false;
+        for (int i = 0; i < did_sizes[did_flag]; i++) did |= (unsigned long long)src[pos + i] << (8 * i);
+        if (did != 0) return false;  // dictionaries are never used on this path (gozstd.Decompress, dd == nil)
+        pos += did_sizes[did_flag];
+    }
+    int fcs_size = fcs_flag == 0 ? (single ? 1 : 0) : (1 << fcs_flag);
+    if (pos + fcs_size > len) return false;
+    unsigned long long fcs = 0;
+    for (int i = 0; i < fcs_size; i++) fcs |= (unsigned long long)src[pos + i] << (8 * i);
+    if (fcs_size == 2) fcs += 256;
+    pos += fcs_size;
+    h->hdr_size = pos;
+    h->has_fcs = fcs_size != 0;
+    h->fcs = fcs;
+    return true;
+}
+
+__device__ bool decode_frame_serial(SerialWs* ws, uint8_t* out, uint32_t out_cap, uint8_t* litbuf, const uint8_t* src,
+                                    uint32_t len) {
+    FrameHdr h;
+    if (!parse_frame_header(&h, src, len)) return false;
+    uint32_t pos = h.hdr_size;
+    long long o = 0;
+    ws->have_ll = ws->have_ml = ws->have_of = ws->have_huf = 0;
+    ws->rep[0] = 1;
+    ws->rep[1] = 4;
+    ws->rep[2] = 8;
+    for (;;) {
+        if (pos + 3 > len) return false;
+        uint32_t bh = src[pos] | ((uint32_t)src[pos + 1] << 8) | ((uint32_t)src[pos + 2] << 16);
+        pos += 3;
+        bool last = bh & 1;
+        int type = (bh >> 1) & 3;
+        uint32_t bsize = bh >> 3;
+        if (type == 0) {
+            if (pos + bsize > len || o + bsize > out_cap) return false;
+            for (uint32_t k = 0; k < bsize; k++) out[o + k] = src[pos + k];
+            pos += bsize;
+            o += bsize;
+        } else if (type == 1) {
+            if (pos + 1 > len || o + bsize > out_cap) return false;
+            for (uint32_t k = 0; k < bsize; k++) out[o + k] = src[pos];
+            pos += 1;
+            o += bsize;
+        } else if (type == 2) {
+            if (pos + bsize > len) return false;
+            o = decode_block_serial(ws, out, o, out_cap, litbuf, src + pos, bsize);
+            if (o < 0) return false;
+            pos += bsize;
+        } else {
+            return false;
+        }
+        if (last) break;
+    }
+    if (h.checksum) pos += 4;
+    if (pos != len) return false;
+    return (unsigned long long)o == (unsigned long long)out_cap;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ kernels
+struct ZstdParams {
+    const vmb_block_desc* descs;
+    const ColInfo* cols;
+    const uint8_t* payload;
+    uint8_t* scratch;      // decompressed varint bytes
+    uint8_t* lit;          // literal arena (same offsets as scratch) or nullptr
+    int32_t* status;       // per column
+    const uint32_t* list;  // column indices to process
+    uint32_t count;
+    HufJob* jobs;          // one per list entry (prepare -> huf)
+    void* ws;              // SerialWs array, one per resident thread of k_zstd_serial
+    uint32_t ws_count;
+};
+
+__device__ __forceinline__ void col_src(const ZstdParams& P, uint32_t col, const uint8_t** src, uint32_t* len) {
+    const vmb_block_desc& d = P.descs[col >> 1];
+    if (col & 1) { *src = P.payload + d.val_off; *len = d.val_size; }
+    else { *src = P.payload + d.ts_off; *len = d.ts_size; }
+}
+
+// one thread per VMB_ZK_HUF column
+__global__ void k_zstd_prepare(ZstdParams P) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.count) return;
+    uint32_t col = P.list[i];
+    HufJob* job = &P.jobs[i];
+    job->col = col;
+    job->nstreams = 0;  // = invalid until proven otherwise
+    const uint8_t* src;
+    uint32_t len;
+    col_src(P, col, &src, &len);
+    const ColInfo ci = P.cols[col];
+    int rc = VMB_ERR_ZSTD;
+    do {
+        FrameHdr h;
+        if (!parse_frame_header(&h, src, len)) break;
+        uint32_t pos = h.hdr_size;
+        if (pos + 3 > len) break;
+        uint32_t bh = src[pos] | ((uint32_t)src[pos + 1] << 8) | ((uint32_t)src[pos + 2] << 16);
+        pos += 3;
+        uint32_t bsize = bh >> 3;
+        if (!(bh & 1) || ((bh >> 1) & 3) != 2) break;  // host classified it as one last Compressed block
+        if (pos + bsize + (h.checksum ? 4u : 0u) != len) break;
+        const uint8_t* blk = src + pos;
+        if (bsize < 3) break;
+        uint32_t b0 = blk[0];
+        int type = b0 & 3, sf = (b0 >> 2) & 3;
+        if (type != 2) break;
+        uint32_t regen, csize, hdr;
+        int streams = 4;
+        if (sf == 0 || sf == 1) {
+            uint32_t v = blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16);
+            regen = (v >> 4) & 0x3ff;
+            csize = (v >> 14) & 0x3ff;
+            hdr = 3;
+            if (sf == 0) streams = 1;
+        } else if (sf == 2) {
+            if (bsize < 4) break;
+            uint32_t v = blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
+            regen = (v >> 4) & 0x3fff;
+            csize = (v >> 18) & 0x3fff;
+            hdr = 4;
+        } else {
+            if (bsize < 5) break;
+            unsigned long long v = blk[0] | ((unsigned long long)blk[1] << 8) | ((unsigned long long)blk[2] << 16) |
+                                   ((unsigned long long)blk[3] << 24) | ((unsigned long long)blk[4] << 32);
+            regen = (uint32_t)((v >> 4) & 0x3ffff);
+            csize = (uint32_t)((v >> 22) & 0x3ffff);
+            hdr = 5;
+        }
+        if (hdr + csize >= bsize) break;  // a sequences section (>= 1 byte) must follow
+        if (regen > ci.content_size) break;
+        // Huffman tree description; scratch tables live on the thread's local stack (small: 64 + 256 + 256 entries)
+        uint32_t ftab[64];
+        short norm[256];
+        unsigned short next[256];
+        int tlog = 0;
+        uint32_t used = huf_read_weights(job->nbits, &tlog, blk + hdr, csize, ftab, norm, next);
+        if (!used) break;
+        uint32_t lrem = csize - used;
+        const uint8_t* lp = blk + hdr + used;
+        if (streams == 1) {
+            job->stream_size[0] = lrem;
+            job->stream_size[1] = job->stream_size[2] = job->stream_size[3] = 0;
+            job->src_off = (uint64_t)(lp - P.payload);
+        } else {
+            if (lrem < 6) break;
+            uint32_t s1 = lp[0] | (lp[1] << 8), s2 = lp[2] | (lp[3] << 8), s3 = lp[4] | (lp[5] << 8);
+            if (6 + s1 + s2 + s3 > lrem) break;
+            uint32_t seg = (regen + 3) / 4;
+            if (seg * 3 > regen) break;
+            job->stream_size[0] = s1;
+            job->stream_size[1] = s2;
+            job->stream_size[2] = s3;
+            job->stream_size[3] = lrem - 6 - s1 - s2 - s3;
+            job->src_off = (uint64_t)(lp + 6 - P.payload);
+        }
+        job->regen_size = regen;
+        job->table_log = (uint8_t)tlog;
+        uint32_t seq_off = hdr + csize;
+        job->seq_off = (uint32_t)(blk - src) + seq_off;
+        job->seq_size = bsize - seq_off;
+        bool has_seq = blk[seq_off] != 0;
+        if (!has_seq && (job->seq_size != 1 || regen != ci.content_size)) break;
+        if (has_seq && !P.lit) break;
+        job->dst_is_lit = has_seq ? 1 : 0;
+        job->dst_off = ci.scratch_off;
+        job->nstreams = (uint8_t)streams;
+        rc = 0;
+    } while (0);
+    P.status[col] = rc;
+}
+
+// ---- lane-packed Huffman decode: 8 frames x 4 streams per warp
+#define HUF_WARPS 4
+#define HUF_FRAMES_PER_WARP 8
+#define HUF_TABLE_ENTRIES 2048
+
+__global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
+    extern __shared__ unsigned short s_tab[];  // [HUF_WARPS * 8][2048]
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const uint32_t groups = (P.count + HUF_FRAMES_PER_WARP - 1) / HUF_FRAMES_PER_WARP;
+    unsigned short* wtab = s_tab + (size_t)warp * HUF_FRAMES_PER_WARP * HUF_TABLE_ENTRIES;
+    for (uint32_t g = blockIdx.x * HUF_WARPS + warp; g < groups; g += gridDim.x * HUF_WARPS) {
+        // ---- build the 8 decode tables cooperatively: for frame f, entries are filled in (nbits desc, symbol asc) order
+        for (int f = 0; f < HUF_FRAMES_PER_WARP; f++) {
+            uint32_t ji = g * HUF_FRAMES_PER_WARP + f;
+            if (ji >= P.count) break;
+            const HufJob* job = &P.jobs[ji];
+            if (job->nstreams == 0) continue;
+            const int log = job->table_log;
+            unsigned short* tab = wtab + f * HUF_TABLE_ENTRIES;
+            // each lane owns 8 symbols; start position of a symbol = sum over symbols that sort before it of 2^(log-nbits)
+            uint32_t nb[8];
+            uint64_t packed = *(const uint64_t*)(job->nbits + lane * 8);
+#pragma unroll
+            for (int k = 0; k < 8; k++) nb[k] = (uint32_t)(packed >> (8 * k)) & 0xff;
+            uint32_t start = 0;  // running table position
+            for (int len = log; len >= 1; len--) {
+                uint32_t span = 1u << (log - len);
+                uint32_t mine = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) mine += (nb[k] == (uint32_t)len);
+                uint32_t inc = mine;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    uint32_t t = __shfl_up_sync(VMB_FULL, inc, off);
+                    if (lane >= off) inc += t;
+                }
+                uint32_t tot = __shfl_sync(VMB_FULL, inc, 31);
+                uint32_t p = start + (inc - mine) * span;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (nb[k] == (uint32_t)len) {
+                        unsigned short ent = (unsigned short)((len << 8) | (lane * 8 + k));
+                        for (uint32_t q = 0; q < span; q++) tab[(p + q) & (HUF_TABLE_ENTRIES - 1)] = ent;
+                        p += span;
+                    }
+                }
+                start += tot * span;
+            }
+        }
+        __syncwarp();
+        // ---- every lane decodes one stream
+        {
+            const int f = lane >> 2, s = lane & 3;
+            uint32_t ji = g * HUF_FRAMES_PER_WARP + f;
+            bool active = ji < P.count;
+            const HufJob* job = active ? &P.jobs[ji] : nullptr;
+            if (active && (job->nstreams == 0 || s >= job->nstreams)) active = false;
+            bool ok = true;
+            if (active) {
+                const int log = job->table_log;
+                const unsigned short* tab = wtab + f * HUF_TABLE_ENTRIES;
+                uint32_t regen = job->regen_size;
+                uint32_t seg = job->nstreams == 1 ? regen : (regen + 3) / 4;
+                uint32_t count = job->nstreams == 1 ? regen : (s < 3 ? seg : regen - 3 * seg);
+                uint64_t soff = job->src_off;
+                for (int k = 0; k < s; k++) soff += job->stream_size[k];
+                uint32_t slen = job->stream_size[s];
+                uint8_t* dst = (job->dst_is_lit ? P.lit : P.scratch) + job->dst_off + (size_t)s * seg;
+                BitR bb;
+                if (count == 0) {
+                    ok = (slen == 0) || true;  // an empty last segment: nothing to write (stream may hold just the marker)
+                } else if (!bb.init(P.payload + soff, slen)) {
+                    ok = false;
+                } else {
+                    uint32_t i = 0;
+                    // head: single bytes until dst is 4-byte aligned
+                    while (i < count && (((uintptr_t)(dst + i)) & 3)) {
+                        unsigned short ent = tab[bb.peek(log)];
+                        dst[i++] = (uint8_t)ent;
+                        bb.skip(ent >> 8);
+                    }
+                    // body: 4 symbols per aligned 32-bit store; one refill covers >= 33 bits >= 3 symbols
+                    for (; i + 4 <= count; i += 4) {
+                        uint32_t wv = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            if (bb.cnt < log) bb.refill();
+                            unsigned short ent = tab[(uint32_t)(bb.buf >> (64 - log))];
+                            wv |= (uint32_t)(ent & 0xff) << (8 * k);
+                            bb.skip(ent >> 8);
+                        }
+                        *(uint32_t*)(dst + i) = wv;
+                    }
+                    for (; i < count; i++) {
+                        unsigned short ent = tab[bb.peek(log)];
+                        dst[i] = (uint8_t)ent;
+                        bb.skip(ent >> 8);
+                    }
+                    ok = bb.left == 0;
+                }
+            }
+            // a frame fails if any of its streams failed
+            uint32_t bad = __ballot_sync(VMB_FULL, active && !ok);
+            if (ji < P.count && s == 0 && ((bad >> (f * 4)) & 0xf)) P.status[P.jobs[ji].col] = VMB_ERR_ZSTD;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- serial kernel: (mode 0) sequences of prepared frames, (mode 1) complete generic frames
+__global__ void k_zstd_serial(ZstdParams P, int mode) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.ws_count) return;
+    SerialWs* ws = (SerialWs*)P.ws + tid;
+    for (uint32_t i = tid; i < P.count; i += P.ws_count) {
+        if (mode == 0) {
+            const HufJob* job = &P.jobs[i];
+            if (job->nstreams == 0 || !job->dst_is_lit) continue;
+            uint32_t col = job->col;
+            if (P.status[col]) continue;
+            const ColInfo ci = P.cols[col];
+            const uint8_t* src;
+            uint32_t len;
+            col_src(P, col, &src, &len);
+            ws->have_ll = ws->have_ml = ws->have_of = 0;
+            ws->rep[0] = 1;
+            ws->rep[1] = 4;
+            ws->rep[2] = 8;
+            long long o = run_sequences(ws, P.scratch + ci.scratch_off, 0, ci.content_size, P.lit + ci.scratch_off,
+                                        job->regen_size, src + job->seq_off, job->seq_size);
+            if (o != (long long)ci.content_size) P.status[col] = VMB_ERR_ZSTD;
+        } else {
+            uint32_t col = P.list[i];
+            const ColInfo ci = P.cols[col];
+            const uint8_t* src;
+            uint32_t len;
+            col_src(P, col, &src, &len);
+            bool ok = P.lit && decode_frame_serial(ws, P.scratch + ci.scratch_off, ci.content_size,
+                                                   P.lit + ci.scratch_off, src, len);
+            P.status[col] = ok ? 0 : VMB_ERR_ZSTD;
+        }
+    }
+}
+
+size_t zstd_serial_ws_bytes() { return sizeof(SerialWs); }
+
+void launch_zstd_prepare(const ZstdParams& P, cudaStream_t st) {
+    if (!P.count) return;
+    k_zstd_prepare<<<(P.count + 63) / 64, 64, 0, st>>>(P);
+}
+
+static bool g_huf_attr_set = false;
+void launch_huf_decode(const ZstdParams& P, cudaStream_t st) {
+    if (!P.count) return;
+    size_t smem = (size_t)HUF_WARPS * HUF_FRAMES_PER_WARP * HUF_TABLE_ENTRIES * sizeof(unsigned short);
+    if (!g_huf_attr_set) {
+        cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        g_huf_attr_set = true;
+    }
+    uint32_t groups = (P.count + HUF_FRAMES_PER_WARP - 1) / HUF_FRAMES_PER_WARP;
+    uint32_t grid = (groups + HUF_WARPS - 1) / HUF_WARPS;
+    if (grid > 148u * 4u) grid = 148u * 4u;
+    k_huf_decode<<<grid, HUF_WARPS * 32, smem, st>>>(P);
+}
+
+void launch_zstd_serial(const ZstdParams& P, int mode, cudaStream_t st) {
+    if (!P.count || !P.ws_count) return;
+    uint32_t threads = P.ws_count < P.count ? P.ws_count : P.count;
+    k_zstd_serial<<<(threads + 31) / 32, 32, 0, st>>>(P, mode);
+}
+
+// ---- host-side classification at upload time: reads only the frame / block / literals headers
+// returns kind; fills content_size; *needs_lit = the literal arena is required for this column
+uint8_t zstd_classify_host(const uint8_t* src, uint32_t len, uint32_t rows, uint32_t* content_size, bool* needs_lit) {
+    *needs_lit = false;
+    *content_size = 0;
+    FrameHdr h;
+    if (!parse_frame_header(&h, src, len)) return VMB_ZK_BAD;
+    // a valid payload holds rows-1 varints of <= 10 bytes
+    unsigned long long bound = (unsigned long long)rows * 10ull;
+    if (!h.has_fcs || h.fcs > bound) return VMB_ZK_BAD;
+    *content_size = (uint32_t)h.fcs;
+    uint32_t pos = h.hdr_size;
+    if (pos + 3 > len) return VMB_ZK_BAD;
+    uint32_t bh = src[pos] | ((uint32_t)src[pos + 1] << 8) | ((uint32_t)src[pos + 2] << 16);
+    pos += 3;
+    uint32_t bsize = bh >> 3;
+    bool last = bh & 1;
+    int btype = (bh >> 1) & 3;
+    *needs_lit = true;
+    if (!last || btype != 2) return VMB_ZK_GENERIC;
+    if (pos + bsize + (h.checksum ? 4u : 0u) != len || bsize < 3) return VMB_ZK_GENERIC;
+    const uint8_t* blk = src + pos;
+    int type = blk[0] & 3, sf = (blk[0] >> 2) & 3;
+    if (type != 2) return VMB_ZK_GENERIC;
+    uint32_t csize, hdr;
+    if (sf == 0 || sf == 1) {
+        uint32_t v = blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16);
+        csize = (v >> 14) & 0x3ff;
+        hdr = 3;
+    } else if (sf == 2) {
+        if (bsize < 4) return VMB_ZK_GENERIC;
+        uint32_t v = blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
+        csize = (v >> 18) & 0x3fff;
+        hdr = 4;
+    } else {
+        if (bsize < 5) return VMB_ZK_GENERIC;
+        unsigned long long v = blk[0] | ((unsigned long long)blk[1] << 8) | ((unsigned long long)blk[2] << 16) |
+                               ((unsigned long long)blk[3] << 24) | ((unsigned long long)blk[4] << 32);
+        csize = (uint32_t)((v >> 22) & 0x3ffff);
+        hdr = 5;
+    }
+    if (hdr + csize >= bsize) return VMB_ZK_GENERIC;
+    *needs_lit = blk[hdr + csize] != 0;  // nbSeq byte
+    return VMB_ZK_HUF;
+}

@@ -1,0 +1,25 @@
+"""lib/decimal/decimal.go mirror."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+
+def append_decimal_to_float(va, e, ctx=None):
+    """decimal.AppendDecimalToFloat decimal.go:100 (GPU)"""
+    ctx = ctx or _lib.default_context()
+    a = np.ascontiguousarray(va, dtype=np.int64)
+    dst = np.empty(a.size, dtype=np.float64)
+    check(lib().vmb_decimal_to_float(ctx.h, dst.ctypes.data_as(_lib.f64p), a.ctypes.data_as(_lib.i64p), a.size, int(e)))
+    return dst
+
+
+def append_float_to_decimal(src):
+    """decimal.AppendFloatToDecimal decimal.go:173 (host, write path) -> (np.int64[n], scale)"""
+    f = np.ascontiguousarray(src, dtype=np.float64)
+    dst = np.empty(f.size, dtype=np.int64)
+    e = C.c_int16(0)
+    check(lib().vmb_float_to_decimal(dst.ctypes.data_as(_lib.i64p), C.byref(e), f.ctypes.data_as(_lib.f64p), f.size))
+    return dst, e.value

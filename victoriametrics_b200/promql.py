@@ -1,0 +1,209 @@
+"""app/vmselect/promql mirror: rollupConfig.Do, getRollupConfigs, evalRollupFunc*, incremental aggregates.
+
+Names follow the reference (rollup.go / eval.go / aggr_incremental.go); every compute call goes to libvmb200.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, storage
+from ._lib import RollupCfg, check, lib
+
+# enum vmb_rollup_func order (include/vmb200.h); keys are the MetricsQL names of rollup.go:24-108
+_RF_ORDER = ["default_rollup", "rate", "delta", "avg_over_time", "min_over_time", "max_over_time", "sum_over_time",
+             "count_over_time", "quantile_over_time", "first_over_time", "last_over_time", "range_over_time",
+             "sum2_over_time", "stddev_over_time", "stdvar_over_time", "ideriv", "idelta", "deriv", "increase_pure",
+             "changes", "changes_prometheus", "resets", "increases_over_time", "integrate", "lag", "lifetime",
+             "scrape_interval", "tmin_over_time", "tmax_over_time", "tfirst_over_time", "tlast_over_time",
+             "tlast_change_over_time", "mode_over_time", "mad_over_time", "outlier_iqr_over_time", "zscore_over_time",
+             "ascent_over_time", "descent_over_time", "distinct_over_time", "geomean_over_time", "predict_linear",
+             "holt_winters", "hoeffding_bound_lower", "hoeffding_bound_upper", "duration_over_time",
+             "count_le_over_time", "count_gt_over_time", "count_eq_over_time", "count_ne_over_time",
+             "share_le_over_time", "share_gt_over_time", "share_eq_over_time", "sum_le_over_time", "sum_gt_over_time",
+             "sum_eq_over_time", "present_over_time", "absent_over_time", "stale_samples_over_time",
+             "median_over_time", "rate_over_sum", "delta_prometheus", "rate_prometheus", "rollup_open", "rollup_close",
+             "rollup_high", "rollup_low"]
+ROLLUP_FUNCS = {n: i for i, n in enumerate(_RF_ORDER)}
+for _a, _b in {"deriv_fast": "rate", "increase": "delta", "irate": "ideriv", "decreases_over_time": "resets",
+               "timestamp": "tlast_over_time", "timestamp_with_name": "tlast_over_time",
+               "increase_prometheus": "delta_prometheus", "iqr_over_time": "outlier_iqr_over_time"}.items():
+    ROLLUP_FUNCS[_a] = ROLLUP_FUNCS[_b]
+
+# rollup.go:199 rollupFuncsCanAdjustWindow
+ROLLUP_FUNCS_CAN_ADJUST_WINDOW = {"default_rollup", "deriv", "deriv_fast", "ideriv", "irate", "rate", "rate_over_sum",
+                                  "rollup", "rollup_candlestick", "rollup_deriv", "rollup_rate",
+                                  "rollup_scrape_interval", "scrape_interval", "timestamp"}
+# rollup.go:223 rollupFuncsRemoveCounterResets
+ROLLUP_FUNCS_REMOVE_COUNTER_RESETS = {"increase", "increase_prometheus", "increase_pure", "irate", "rate",
+                                      "rate_prometheus", "rollup_increase", "rollup_rate"}
+# rollup.go:238 rollupFuncsSamplesScannedPerCall
+ROLLUP_FUNCS_SAMPLES_SCANNED_PER_CALL = {
+    "absent_over_time": 1, "count_over_time": 1, "default_rollup": 1, "delta": 2, "delta_prometheus": 2, "deriv_fast": 2,
+    "first_over_time": 1, "idelta": 2, "ideriv": 2, "increase": 2, "increase_prometheus": 2, "increase_pure": 2,
+    "irate": 2, "lag": 1, "last_over_time": 1, "lifetime": 2, "present_over_time": 1, "rate": 2, "rate_prometheus": 2,
+    "scrape_interval": 2, "tfirst_over_time": 1, "timestamp": 1, "timestamp_with_name": 1, "tlast_over_time": 1}
+
+RC_MAY_ADJUST_WINDOW, RC_IS_DEFAULT_ROLLUP, RC_REMOVE_COUNTER_RESETS, RC_DROP_STALE_NANS = 1, 2, 4, 8
+AGGR_FUNCS = {"sum": 0, "min": 1, "max": 2, "avg": 3, "count": 4, "sum2": 5, "geomean": 6, "any": 7, "group": 8}
+
+
+def get_timestamps(start, end, step):
+    """eval.go:230 getTimestamps"""
+    if step <= 0:
+        raise ValueError("BUG: Step must be bigger than 0; got %d" % step)
+    if start > end:
+        raise ValueError("BUG: Start cannot exceed End; got %d vs %d" % (start, end))
+    return start + step * np.arange(1 + (end - start) // step, dtype=np.int64)
+
+
+class RollupConfig:
+    """rollupConfig rollup.go:574.  Func is the MetricsQL function name."""
+
+    def __init__(self, Func, Start, End, Step, Window=0, LookbackDelta=0, MayAdjustWindow=False, isDefaultRollup=False,
+                 samplesScannedPerCall=0, args=None, args2=None, removeCounterResets=False, dropStaleNaNs=False,
+                 minStalenessInterval=0):
+        self.Func, self.Start, self.End, self.Step, self.Window = Func, int(Start), int(End), int(Step), int(Window)
+        self.LookbackDelta, self.MayAdjustWindow, self.isDefaultRollup = int(LookbackDelta), MayAdjustWindow, isDefaultRollup
+        self.samplesScannedPerCall, self.args, self.args2 = samplesScannedPerCall, args, args2
+        self.removeCounterResets, self.dropStaleNaNs = removeCounterResets, dropStaleNaNs
+        self.minStalenessInterval = int(minStalenessInterval)
+        if self.Step <= 0 or self.Start > self.End or self.Window < 0:  # rollup.go:703-711 logger.Panicf("BUG: ...")
+            raise ValueError("BUG: invalid rollupConfig: Step=%d Start=%d End=%d Window=%d" % (Step, Start, End, Window))
+        self.Timestamps = get_timestamps(self.Start, self.End, self.Step)
+        self._keep = []
+
+    @property
+    def points(self):
+        return int(self.Timestamps.size)
+
+    def _cfg(self):
+        flags = (RC_MAY_ADJUST_WINDOW if self.MayAdjustWindow else 0) | (RC_IS_DEFAULT_ROLLUP if self.isDefaultRollup else 0) \
+            | (RC_REMOVE_COUNTER_RESETS if self.removeCounterResets else 0) | (RC_DROP_STALE_NANS if self.dropStaleNaNs else 0)
+        cfg = RollupCfg(ROLLUP_FUNCS[self.Func], flags, self.Start, self.End, self.Step, self.Window, self.LookbackDelta,
+                        self.minStalenessInterval, self.samplesScannedPerCall, 0, None, None)
+        self._keep = []
+        for name, a in (("args", self.args), ("args2", self.args2)):
+            if a is not None:
+                arr = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (self.points,)))
+                self._keep.append(arr)
+                setattr(cfg, name, arr.ctypes.data_as(_lib.f64p))
+        return cfg
+
+    def do(self, values, timestamps, ctx=None):
+        """rollupConfig.Do rollup.go:688 for ONE series (kept for compatibility/tests; the batched forms are the fast path)
+        -> (dstValues np.float64[points], samplesScanned)"""
+        out, scanned = self.do_many([timestamps], [values], ctx)
+        return out[0], scanned
+
+    def do_many(self, timestamps_list, values_list, ctx=None):
+        s = storage.Series.from_host(timestamps_list, values_list, ctx)
+        try:
+            return self.do_series(s)
+        finally:
+            s.close()
+
+    def do_series(self, series, out_dev_ptr=None):
+        """rollup over a device batch -> ([nseries x points] np.float64 (or None when out_dev_ptr is given), samplesScanned)"""
+        cfg = self._cfg()
+        scanned = C.c_uint64(0)
+        if out_dev_ptr is not None:
+            check(lib().vmb_rollup(series.ctx.h, series.h, C.byref(cfg), C.c_void_p(int(out_dev_ptr)), 1, C.byref(scanned)))
+            return None, scanned.value
+        out = np.empty((series.count, self.points), dtype=np.float64)
+        check(lib().vmb_rollup(series.ctx.h, series.h, C.byref(cfg), C.c_void_p(out.ctypes.data), 0, C.byref(scanned)))
+        return out, scanned.value
+
+
+def get_rollup_configs(func_name, start, end, step, window=0, lookback_delta=0, args=None, args2=None,
+                       no_stale_markers=False, min_staleness_interval=0):
+    """getRollupConfigs rollup.go:374 for the single-config functions + the preFunc / dropStaleNaNs decisions of
+    eval.go:1855-1866, :1985.  (rollup*(), aggr_over_time(), *_values_over_time() produce several series per input
+    and stay on the host: SURVEY.md 8(a) a23.)"""
+    name = func_name.lower()
+    if name not in ROLLUP_FUNCS:
+        raise KeyError("unsupported rollup function %r" % func_name)
+    drop_stale = not (no_stale_markers or name in ("default_rollup", "stale_samples_over_time"))
+    return RollupConfig(name, start, end, step, window, lookback_delta,
+                        MayAdjustWindow=name in ROLLUP_FUNCS_CAN_ADJUST_WINDOW, isDefaultRollup=name == "default_rollup",
+                        samplesScannedPerCall=ROLLUP_FUNCS_SAMPLES_SCANNED_PER_CALL.get(name, 0), args=args, args2=args2,
+                        removeCounterResets=name in ROLLUP_FUNCS_REMOVE_COUNTER_RESETS, dropStaleNaNs=drop_stale,
+                        minStalenessInterval=min_staleness_interval)
+
+
+def eval_rollup_func(func_name, blocks, start, end, step, window=0, lookback_delta=0, args=None, args2=None,
+                     tr_min=storage.INT64_MIN, tr_max=storage.INT64_MAX, out_dev_ptr=None):
+    """evalRollupFuncNoCache eval.go:1680 -> evalRollupNoIncrementalAggregate eval.go:1845 on device-resident blocks:
+    decode, per-series preamble, rollupConfig.Do for every series.
+    -> ([nseries x points] np.float64 or None, samplesScanned)"""
+    rc = get_rollup_configs(func_name, start, end, step, window, lookback_delta, args, args2)
+    cfg = rc._cfg()
+    scanned = C.c_uint64(0)
+    if out_dev_ptr is not None:
+        check(lib().vmb_eval_rollup_device(blocks.ctx.h, blocks.h, tr_min, tr_max, C.byref(cfg), C.c_void_p(int(out_dev_ptr)),
+                                           C.byref(scanned)))
+        return None, scanned.value
+    series, _ = storage.decode_blocks(blocks, tr_min, tr_max)
+    try:
+        return rc.do_series(series)[0], None
+    finally:
+        series.close()
+
+
+def eval_rollup_func_host(func_name, descs, payload, start, end, step, window=0, lookback_delta=0, args=None, args2=None,
+                          tr_min=storage.INT64_MIN, tr_max=storage.INT64_MAX, out=None, nseries=None, ctx=None):
+    """the whole path with HOST buffers in one call (vmb_eval_rollup_host): H2D, decode, rollup, D2H."""
+    ctx = ctx or _lib.default_context()
+    rc = get_rollup_configs(func_name, start, end, step, window, lookback_delta, args, args2)
+    cfg = rc._cfg()
+    if isinstance(descs, np.ndarray):
+        dptr, n = descs.ctypes.data_as(C.POINTER(_lib.BlockDesc)), descs.shape[0]
+        if nseries is None:
+            nseries = int(np.count_nonzero(np.diff(descs["series_idx"])) + 1) if n else 0
+    else:
+        dptr, n = descs, len(descs)
+        if nseries is None:
+            nseries = len({d.series_idx for d in descs})
+    if out is None:
+        out = np.empty((nseries, rc.points), dtype=np.float64)
+    payload = np.ascontiguousarray(payload, dtype=np.uint8)
+    scanned = C.c_uint64(0)
+    check(lib().vmb_eval_rollup_host(ctx.h, dptr, n, payload.ctypes.data_as(_lib.u8p), payload.size, tr_min, tr_max,
+                                     C.byref(cfg), out.ctypes.data_as(_lib.f64p), None, C.byref(scanned)))
+    return out, scanned.value
+
+
+class IncrementalAggr:
+    """incrementalAggrFuncContext aggr_incremental.go:73: aggr(rollup(m[d])) by (...) without keeping [series x points]
+    on the host.  update() == updateTimeseries for every series of a device batch (per-GPU partial state);
+    finalize() == finalizeTimeseries.  With torch.distributed initialised, finalize(all_reduce=True) merges the per-rank
+    partial states with one NCCL all-reduce of values and one of counts."""
+
+    def __init__(self, aggr_name, ngroups, points, device_alloc):
+        """device_alloc(nbytes) -> object with .ptr (device address); e.g. a torch.empty(..., device='cuda') wrapper"""
+        self.aggr = AGGR_FUNCS[aggr_name.lower()]
+        self.name = aggr_name.lower()
+        self.ngroups, self.points = int(ngroups), int(points)
+        self.values = device_alloc(self.ngroups * self.points * 8)
+        self.counts = device_alloc(self.ngroups * self.points * 8)
+
+    def update(self, series, rc, group_ids, rolled_scratch_ptr=None):
+        g = np.ascontiguousarray(group_ids, dtype=np.uint32)
+        cfg = rc._cfg()
+        scanned = C.c_uint64(0)
+        check(lib().vmb_rollup_aggr_partial(series.ctx.h, series.h, C.byref(cfg), self.aggr, g.ctypes.data_as(_lib.u32p),
+                                            self.ngroups, C.c_void_p(self.values.ptr), C.c_void_p(self.counts.ptr),
+                                            C.c_void_p(rolled_scratch_ptr or 0), C.byref(scanned)))
+        return scanned.value
+
+    def finalize(self, ctx, all_reduce=None):
+        """all_reduce(values_buf, counts_buf, op) is called between prepare and finalize when given"""
+        n = self.ngroups * self.points
+        if all_reduce is not None:
+            check(lib().vmb_aggr_prepare_allreduce(ctx.h, self.aggr, C.c_void_p(self.values.ptr), C.c_void_p(self.counts.ptr), n))
+            ctx.synchronize()
+            op = {"min": "min", "max": "max", "geomean": "prod"}.get(self.name, "sum")
+            all_reduce(self.values, self.counts, op)
+        out = np.empty((self.ngroups, self.points), dtype=np.float64)
+        check(lib().vmb_aggr_finalize(ctx.h, self.aggr, C.c_void_p(self.values.ptr), C.c_void_p(self.counts.ptr), n,
+                                      out.ctypes.data_as(_lib.f64p)))
+        return out

@@ -1,0 +1,207 @@
+"""lib/storage/block.go mirror: blocks of one series, their marshaled form, and the batched device decode.
+
+  Block.marshal_data      == Block.MarshalData      block.go:192   (host write path: encoding.MarshalValues/Timestamps)
+  BlockSet                == the (header, timestampsData, valuesData) triples of a query, packed into one payload arena;
+                             identical timestamp payloads of consecutive blocks are stored once like
+                             block_stream_writer.go:143-163
+  Blocks / decode_blocks  == Block.UnmarshalData block.go:250 + AppendRowsWithTimeRangeFilter block.go:324, batched
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, encoding
+from ._lib import BlockDesc, check, lib
+
+MAX_ROWS_PER_BLOCK = 8192  # block.go:15
+INT64_MIN = -(1 << 63)
+INT64_MAX = (1 << 63) - 1
+
+
+class Block:
+    """one block: <= 8192 rows of one series; values are decimal mantissas with a shared scale"""
+
+    def __init__(self, timestamps, values, scale=0, precision_bits=64, series_idx=0):
+        self.timestamps = np.ascontiguousarray(timestamps, dtype=np.int64)
+        self.values = np.ascontiguousarray(values, dtype=np.int64)
+        if self.timestamps.size != self.values.size or self.values.size == 0:
+            raise ValueError("BUG: the number of values must match the number of timestamps and be > 0")  # block.go:225
+        self.scale = int(scale)
+        self.precision_bits = int(precision_bits)
+        self.series_idx = int(series_idx)
+
+    def marshal_data(self):
+        """-> (header fields dict, timestampsData, valuesData)   block.go:192"""
+        vdata, vmt, first_value = encoding.marshal_values(self.values, self.precision_bits)
+        tdata, tmt, min_ts = encoding.marshal_timestamps(self.timestamps, self.precision_bits)
+        hdr = dict(first_value=first_value, min_ts=min_ts, max_ts=int(self.timestamps[-1]), ts_size=tdata.size,
+                   val_size=vdata.size, rows=self.values.size, series_idx=self.series_idx, scale=self.scale, ts_mt=tmt,
+                   val_mt=vmt, precision_bits=self.precision_bits)
+        return hdr, tdata, vdata
+
+
+class BlockSet:
+    """host-side descriptors + payload arena (what vmselect collects for one query, netstorage.go:1121)"""
+
+    def __init__(self):
+        self._hdrs = []
+        self._chunks = []
+        self._size = 0
+        self._last_ts = None  # (bytes, offset) of the previous block's timestamps payload
+
+    def add_marshaled(self, hdr, tdata, vdata):
+        tb = tdata.tobytes()
+        if self._last_ts is not None and self._last_ts[0] == tb:
+            ts_off = self._last_ts[1]
+        else:
+            ts_off = self._size
+            self._chunks.append(tdata)
+            self._size += tdata.size
+            self._last_ts = (tb, ts_off)
+        val_off = self._size
+        self._chunks.append(vdata)
+        self._size += vdata.size
+        h = dict(hdr)
+        h["ts_off"], h["val_off"] = ts_off, val_off
+        self._hdrs.append(h)
+
+    def add(self, block):
+        self.add_marshaled(*block.marshal_data())
+
+    def finish(self):
+        """-> (ctypes array of BlockDesc, payload np.uint8)"""
+        descs = (BlockDesc * len(self._hdrs))()
+        for d, h in zip(descs, self._hdrs):
+            for k, v in h.items():
+                setattr(d, k, v)
+        payload = np.concatenate(self._chunks) if self._chunks else np.zeros(0, dtype=np.uint8)
+        return descs, np.ascontiguousarray(payload, dtype=np.uint8)
+
+
+def descs_from_arrays(**cols):
+    """vectorised construction of a BlockDesc array from numpy columns (bench-sized inputs)"""
+    n = len(cols["rows"])
+    dt = np.dtype([("first_value", "<i8"), ("min_ts", "<i8"), ("max_ts", "<i8"), ("ts_off", "<u8"), ("val_off", "<u8"),
+                   ("ts_size", "<u4"), ("val_size", "<u4"), ("rows", "<u4"), ("series_idx", "<u4"), ("scale", "<i2"),
+                   ("ts_mt", "u1"), ("val_mt", "u1"), ("precision_bits", "u1"), ("_pad", "u1", (3,))])
+    assert dt.itemsize == 64
+    a = np.zeros(n, dtype=dt)
+    for k, v in cols.items():
+        a[k] = v
+    return a
+
+
+class Blocks:
+    """compressed blocks resident in HBM (vmb_blocks)"""
+
+    def __init__(self, descs, payload, ctx=None):
+        self.ctx = ctx or _lib.default_context()
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        if isinstance(descs, np.ndarray):
+            dptr = descs.ctypes.data_as(C.POINTER(BlockDesc))
+            n = descs.shape[0]
+        else:
+            dptr = descs
+            n = len(descs)
+        h = C.c_void_p()
+        check(lib().vmb_blocks_upload(self.ctx.h, dptr, n, payload.ctypes.data_as(_lib.u8p), payload.size, C.byref(h)))
+        self.h = h
+        self.count = n
+
+    @property
+    def rows(self):
+        return int(lib().vmb_blocks_rows(self.h))
+
+    @property
+    def compressed_bytes(self):
+        return int(lib().vmb_blocks_compressed_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            lib().vmb_blocks_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Series:
+    """decoded columns resident in HBM (vmb_series)"""
+
+    def __init__(self, h, ctx):
+        self.h = h
+        self.ctx = ctx
+
+    @classmethod
+    def from_host(cls, timestamps_list, values_list, ctx=None):
+        """series batch from already decoded columns (the arguments of rollupConfig.Do)"""
+        ctx = ctx or _lib.default_context()
+        offs = np.zeros(len(values_list) + 1, dtype=np.uint64)
+        for i, v in enumerate(values_list):
+            offs[i + 1] = offs[i] + len(v)
+        ts = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int64) for t in timestamps_list])
+                                  if timestamps_list else np.zeros(0), dtype=np.int64)
+        vals = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in values_list])
+                                    if values_list else np.zeros(0), dtype=np.float64)
+        h = C.c_void_p()
+        check(lib().vmb_series_from_host(ctx.h, ts.ctypes.data_as(_lib.i64p), vals.ctypes.data_as(_lib.f64p),
+                                         offs.ctypes.data_as(_lib.u64p), len(values_list), C.byref(h)))
+        return cls(h, ctx)
+
+    @property
+    def count(self):
+        return int(lib().vmb_series_count(self.h))
+
+    @property
+    def rows(self):
+        return int(lib().vmb_series_rows(self.h))
+
+    def layout(self):
+        n = self.count
+        starts = np.zeros(n, dtype=np.uint64)
+        counts = np.zeros(n, dtype=np.uint32)
+        check(lib().vmb_series_layout(self.ctx.h, self.h, starts.ctypes.data_as(_lib.u64p), counts.ctypes.data_as(_lib.u32p)))
+        return starts, counts
+
+    def download(self, values_dtype=np.float64):
+        r = self.rows
+        ts = np.empty(r, dtype=np.int64)
+        vals = np.empty(r, dtype=values_dtype)
+        check(lib().vmb_series_download(self.ctx.h, self.h, ts.ctypes.data_as(_lib.i64p),
+                                        C.cast(vals.ctypes.data, _lib.f64p)))
+        return ts, vals
+
+    def to_lists(self, values_dtype=np.float64):
+        """-> [(timestamps, values)] per series, after trimming"""
+        ts, vals = self.download(values_dtype)
+        starts, counts = self.layout()
+        return [(ts[s:s + c], vals[s:s + c]) for s, c in zip(starts.tolist(), counts.tolist())]
+
+    def close(self):
+        if self.h:
+            lib().vmb_series_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decode_blocks(blocks, tr_min=INT64_MIN, tr_max=INT64_MAX, values_as_int64=False, raise_on_block_error=True):
+    """batched Block.UnmarshalData + AppendRowsWithTimeRangeFilter -> (Series, per-block status np.int32)"""
+    status = np.zeros(max(blocks.count, 1), dtype=np.int32)
+    h = C.c_void_p()
+    rc = lib().vmb_decode_blocks(blocks.ctx.h, blocks.h, tr_min, tr_max, 1 if values_as_int64 else 0,
+                                 status.ctypes.data_as(_lib.i32p), C.byref(h))
+    status = status[:blocks.count]
+    if rc == -53 and not raise_on_block_error:
+        return Series(h, blocks.ctx), status
+    if rc != 0 and h:
+        lib().vmb_series_free(h)
+    check(rc)
+    return Series(h, blocks.ctx), status
