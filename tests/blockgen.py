@@ -19,8 +19,9 @@ def gen_values(rng, kind, n):
     if kind == "counter_resets":
         inc = rng.integers(0, 1500, n)
         v = np.cumsum(inc)
-        for r in rng.integers(1, max(n, 2), max(n // 500, 1)):
-            v[r:] -= v[r]
+        if n > 1:
+            for r in rng.integers(1, n, max(n // 500, 1)):
+                v[r:] -= v[r]
         return v.astype(np.int64)
     if kind == "counter_big":      # multi-byte varints, incompressible -> plain delta2
         return np.cumsum(rng.integers(0, 1 << 40, n)).astype(np.int64)

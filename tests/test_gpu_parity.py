@@ -265,8 +265,9 @@ def _random_series(rng, n, kind):
     if kind == "counter":
         ts = t0 + 15000 * np.arange(n) + rng.integers(-50, 51, n)
         v = np.cumsum(rng.integers(0, 1500, n)).astype(np.float64) / 100
-        for r in rng.integers(1, max(n, 2), max(n // 300, 1)):
-            v[r:] -= v[r]
+        if n > 1:
+            for r in rng.integers(1, n, max(n // 300, 1)):
+                v[r:] -= v[r]
         return ts.astype(np.int64), v
     if kind == "gauge":
         ts = t0 + np.cumsum(rng.integers(5000, 25000, n))

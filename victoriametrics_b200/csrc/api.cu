@@ -77,7 +77,8 @@ struct vmb_blocks {
     bool needs_lit = false;
     uint32_t n_huf = 0, n_gen = 0, n_bad = 0;
     vmb_block_desc* d_descs = nullptr;
-    uint8_t* d_payload = nullptr;
+    uint8_t* d_payload = nullptr;        // = d_payload_alloc + 64
+    uint8_t* d_payload_alloc = nullptr;
     ColInfo* d_cols = nullptr;
     uint64_t* d_row_off = nullptr;
     uint32_t* d_huf_list = nullptr;
@@ -219,7 +220,7 @@ extern "C" void vmb_blocks_free(vmb_blocks* b) {
     if (!b) return;
     if (b->ctx) cudaSetDevice(b->ctx->device);
     cudaFree(b->d_descs);
-    cudaFree(b->d_payload);
+    cudaFree(b->d_payload_alloc);
     cudaFree(b->d_cols);
     cudaFree(b->d_row_off);
     cudaFree(b->d_huf_list);
@@ -325,7 +326,10 @@ extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size
     } while (0)
     TRY(dev_alloc(&b->d_descs, nblocks));
     if (nblocks) CU(cudaMemcpyAsync(b->d_descs, descs, nblocks * sizeof(vmb_block_desc), cudaMemcpyHostToDevice, st));
-    TRY(dev_alloc(&b->d_payload, payload_len + 64));
+    // 64 bytes of slack on both sides: the bitstream windows of zstd.cu read up to 11 bytes before a stream's first byte
+    TRY(dev_alloc(&b->d_payload_alloc, payload_len + 128));
+    b->d_payload = b->d_payload_alloc + 64;
+    CU(cudaMemsetAsync(b->d_payload_alloc, 0, 64, st));
     if (payload_len) CU(cudaMemcpyAsync(b->d_payload, payload, payload_len, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(b->d_payload + payload_len, 0, 64, st));
     TRY(upload_vec(&b->d_cols, pl.cols, st));

@@ -894,9 +894,45 @@ __global__ void __launch_bounds__(128) k_series_prepare(RollupParams P) {
 }
 
 #define ROLLUP_THREADS 256
+#define ROLLUP_STAGE_ROWS 1280
 
-// one thread per output point; a CTA covers ROLLUP_THREADS consecutive points of one series
+// one thread per output point; a CTA covers ROLLUP_THREADS consecutive points of one series.  The rows those points can
+// touch (a contiguous span: both the samples and the output grid are time-ordered) are staged in shared memory with
+// coalesced loads, so the two window seeks per point and the O(window) functions never go back to HBM/L2.
+// Spans larger than ROLLUP_STAGE_ROWS (huge windows) fall back to reading global memory directly.
+//
+// Window seeks: when the window is a multiple of the step (rate(m[5m]) at step 15 s: 20 steps), the left edge of point p
+// is the right edge of point p - window/step, so the tile computes ONE seek per grid time (ROLLUP_THREADS + window/step of
+// them, s_seek[]) instead of two per point.  A seek is an interpolation guess + a short walk (samples are near-regular
+// inside a tile), falling back to binary search when the walk does not converge.
+//
+// F >= 0 instantiates the kernel for one rollup function (the switch in call_func folds away); F == -1 is generic.
+#define ROLLUP_SEEKS 1024
+
+__device__ __forceinline__ uint32_t seek_after(const int64_t* __restrict__ ts, uint32_t n, int64_t x, double inv_dt) {
+    // first index with ts[idx] > x
+    if (n == 0 || ts[0] > x) return 0;
+    if (ts[n - 1] <= x) return n;
+    uint32_t g = (uint32_t)((double)(x - ts[0]) * inv_dt);
+    if (g >= n) g = n - 1;
+    if (ts[g] <= x) {
+        uint32_t lim = g + 6 < n ? g + 6 : n;
+        do { g++; } while (g < lim && ts[g] <= x);
+        if (g < n && ts[g] <= x) g += upper_bound_ts(ts + g, n - g, x);
+        return g;
+    }
+    uint32_t lim = g > 6 ? g - 6 : 0;
+    while (g > lim && ts[g - 1] > x) g--;
+    if (g > 0 && ts[g - 1] > x) g = upper_bound_ts(ts, g, x);
+    return g;
+}
+
+template <int F>
 __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
+    __shared__ int64_t s_ts[ROLLUP_STAGE_ROWS];
+    __shared__ double s_val[ROLLUP_STAGE_ROWS];
+    __shared__ uint32_t s_seek[ROLLUP_SEEKS];
+    __shared__ uint32_t s_span[2];
     const vmb_rollup_cfg& rc = P.cfg;
     const uint32_t tiles = (P.npoints + ROLLUP_THREADS - 1) / ROLLUP_THREADS;
     unsigned long long scanned = 0;
@@ -905,14 +941,69 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
         const uint32_t p = (uint32_t)(bid % tiles) * ROLLUP_THREADS + threadIdx.x;
         const SeriesMeta m = P.meta[s];
         if (p == 0) scanned += m.n;  // samplesScanned starts at len(values) rollup.go:766
-        if (p >= P.npoints) continue;
+        // ---- stage the rows this tile can touch: [first row after tStart(first point)] - 1 .. [first row after tEnd(last point)]
+        __syncthreads();  // previous tile done with shared memory
+        if (threadIdx.x == 0 || threadIdx.x == 32) {
+            const uint32_t p0 = (uint32_t)(bid % tiles) * ROLLUP_THREADS;
+            const uint32_t p1 = min(p0 + ROLLUP_THREADS, P.npoints) - 1;
+            const int64_t* tg = P.ts + m.start;
+            if (threadIdx.x == 0) {
+                uint32_t lo = upper_bound_ts(tg, m.n, rc.start + (int64_t)p0 * rc.step - m.window);
+                s_span[0] = lo > 0 ? lo - 1 : 0;
+            } else {
+                uint32_t hi = upper_bound_ts(tg, m.n, rc.start + (int64_t)p1 * rc.step);
+                s_span[1] = min(m.n, hi + 1);
+            }
+        }
+        __syncthreads();
+        const uint32_t sbase = s_span[0];
+        const uint32_t scount = s_span[1] > sbase ? s_span[1] - sbase : 0;
+        const bool staged = scount <= ROLLUP_STAGE_ROWS;
+        if (staged) {
+            const int64_t* tg = P.ts + m.start + sbase;
+            const double* vg = P.vals + m.start + sbase;
+            for (uint32_t k = threadIdx.x; k < scount; k += ROLLUP_THREADS) {
+                s_ts[k] = tg[k];
+                s_val[k] = vg[k];
+            }
+        }
+        __syncthreads();
         const double* v = P.vals + m.start;
         const int64_t* t = P.ts + m.start;
         const uint32_t n = m.n;
+        // search domain: the staged rows (shared memory) or the whole series (global memory)
+        const int64_t* st = staged ? s_ts : t;
+        const uint32_t sn = staged ? scount : n;
+        const uint32_t sb = staged ? sbase : 0;
+        double inv_dt = 0.0;
+        if (sn > 1 && st[sn - 1] > st[0]) inv_dt = (double)(sn - 1) / (double)(st[sn - 1] - st[0]);
+        const uint32_t wsteps = (uint32_t)(m.window / rc.step);
+        const bool shared_seeks = (m.window % rc.step) == 0 && wsteps + ROLLUP_THREADS <= ROLLUP_SEEKS;
+        const uint32_t p0 = (uint32_t)(bid % tiles) * ROLLUP_THREADS;
+        if (shared_seeks) {
+            // s_seek[q] = first row after grid time start + (p0 + q - wsteps) * step
+            for (uint32_t q = threadIdx.x; q < ROLLUP_THREADS + wsteps; q += ROLLUP_THREADS) {
+                int64_t x = rc.start + ((int64_t)p0 + (int64_t)q - (int64_t)wsteps) * rc.step;
+                s_seek[q] = sb + seek_after(st, sn, x, inv_dt);
+            }
+            __syncthreads();
+        }
+        if (p >= P.npoints) continue;
         const int64_t tEnd = rc.start + (int64_t)p * rc.step;
         const int64_t tStart = tEnd - m.window;
-        const uint32_t i = upper_bound_ts(t, n, tStart);
-        uint32_t j = upper_bound_ts(t, n, tEnd);
+        uint32_t i, j;
+        if (shared_seeks) {
+            i = s_seek[threadIdx.x];
+            j = s_seek[threadIdx.x + wsteps];
+        } else {
+            i = sb + seek_after(st, sn, tStart, inv_dt);
+            j = sb + seek_after(st, sn, tEnd, inv_dt);
+        }
+        if (staged) {
+            // rebase the pointers so that v[k] / t[k] keep meaning "row k of the series"
+            v = s_val - sbase;
+            t = s_ts - sbase;
+        }
         if (j < i) j = i;
         Win r;
         r.prevValue = D_NAN;
@@ -935,7 +1026,7 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
         r.window = m.window;
         r.args = rc.args;
         r.args2 = rc.args2;
-        P.out[(size_t)s * P.npoints + p] = call_func(rc.func_id, r);
+        P.out[(size_t)s * P.npoints + p] = call_func(F >= 0 ? F : rc.func_id, r);
         scanned += rc.samples_scanned_per_call > 0 ? (unsigned long long)rc.samples_scanned_per_call : (unsigned long long)r.n;
     }
     // block reduce -> one atomic per CTA
@@ -1113,5 +1204,19 @@ void launch_rollup(const RollupParams& P, cudaStream_t st) {
     uint64_t tiles = (P.npoints + ROLLUP_THREADS - 1) / ROLLUP_THREADS;
     uint64_t total = (uint64_t)P.nseries * tiles;
     uint32_t grid = total > 148ull * 64ull ? 148u * 64u : (uint32_t)total;
-    k_rollup<<<grid, ROLLUP_THREADS, 0, st>>>(P);
+    switch (P.cfg.func_id) {  // the functions of BASELINE.json's configs get their own instantiation
+#define ROLLUP_CASE(F) case F: k_rollup<F><<<grid, ROLLUP_THREADS, 0, st>>>(P); break;
+        ROLLUP_CASE(VMB_RF_RATE)
+        ROLLUP_CASE(VMB_RF_DELTA)
+        ROLLUP_CASE(VMB_RF_AVG)
+        ROLLUP_CASE(VMB_RF_MIN)
+        ROLLUP_CASE(VMB_RF_MAX)
+        ROLLUP_CASE(VMB_RF_SUM)
+        ROLLUP_CASE(VMB_RF_COUNT)
+        ROLLUP_CASE(VMB_RF_QUANTILE)
+        ROLLUP_CASE(VMB_RF_DEFAULT_ROLLUP)
+        ROLLUP_CASE(VMB_RF_IDERIV)
+#undef ROLLUP_CASE
+        default: k_rollup<-1><<<grid, ROLLUP_THREADS, 0, st>>>(P); break;
+    }
 }

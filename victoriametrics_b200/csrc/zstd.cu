@@ -784,37 +784,63 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
                 for (int k = 0; k < s; k++) soff += job->stream_size[k];
                 uint32_t slen = job->stream_size[s];
                 uint8_t* dst = (job->dst_is_lit ? P.lit : P.scratch) + job->dst_off + (size_t)s * seg;
-                BitR bb;
+                const uint8_t* base = P.payload + soff;
+                uint32_t last = slen ? base[slen - 1] : 0;
                 if (count == 0) {
-                    ok = (slen == 0) || true;  // an empty last segment: nothing to write (stream may hold just the marker)
-                } else if (!bb.init(P.payload + soff, slen)) {
+                    // an empty last segment: nothing to write (the stream holds just the final-bit marker)
+                } else if (slen == 0 || last == 0) {
                     ok = false;
                 } else {
+                    // Backward bitstream through a 64-bit register window that is re-read from memory (L1) after every 4
+                    // symbols: window = the 8 bytes that end at the byte holding the next unread bit.  Branch-free and
+                    // uniform across lanes (no divergent "refill" path); >= 57 valid bits per reload >= 4 codes of <= 11 bits.
+                    long long bitpos = (long long)(slen - 1) * 8 + hb32(last);  // unread payload bits
+                    bool over = false;
+                    uint64_t buf;
+                    const int sh_idx = 64 - log;
+#define HUF_RELOAD()                                                                   \
+    do {                                                                               \
+        if (bitpos < 0) { over = true; bitpos = 0; }                                   \
+        long long bend_ = (bitpos + 7) >> 3;                                           \
+        uintptr_t a_ = (uintptr_t)(base + bend_ - 8);                                  \
+        const uint32_t* w_ = (const uint32_t*)(a_ & ~(uintptr_t)3);                    \
+        uint32_t sh_ = (uint32_t)(a_ & 3) * 8;                                         \
+        uint32_t w0_ = w_[0], w1_ = w_[1], w2_ = w_[2];                                \
+        uint32_t lo_ = __funnelshift_r(w0_, w1_, sh_), hi_ = __funnelshift_r(w1_, w2_, sh_); \
+        buf = (((uint64_t)hi_ << 32) | lo_) << (uint32_t)(8 * bend_ - bitpos);         \
+    } while (0)
+                    HUF_RELOAD();
                     uint32_t i = 0;
                     // head: single bytes until dst is 4-byte aligned
                     while (i < count && (((uintptr_t)(dst + i)) & 3)) {
-                        unsigned short ent = tab[bb.peek(log)];
+                        unsigned short ent = tab[(uint32_t)(buf >> sh_idx)];
                         dst[i++] = (uint8_t)ent;
-                        bb.skip(ent >> 8);
+                        bitpos -= ent >> 8;
+                        HUF_RELOAD();
                     }
-                    // body: 4 symbols per aligned 32-bit store; one refill covers >= 33 bits >= 3 symbols
+                    // body: 4 symbols per aligned 32-bit store, one window reload per 4 symbols
                     for (; i + 4 <= count; i += 4) {
-                        uint32_t wv = 0;
+                        uint32_t wv = 0, used = 0;
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
-                            if (bb.cnt < log) bb.refill();
-                            unsigned short ent = tab[(uint32_t)(bb.buf >> (64 - log))];
+                            unsigned short ent = tab[(uint32_t)(buf >> sh_idx)];
+                            uint32_t nb = ent >> 8;
                             wv |= (uint32_t)(ent & 0xff) << (8 * k);
-                            bb.skip(ent >> 8);
+                            buf <<= nb;
+                            used += nb;
                         }
                         *(uint32_t*)(dst + i) = wv;
+                        bitpos -= used;
+                        HUF_RELOAD();
                     }
                     for (; i < count; i++) {
-                        unsigned short ent = tab[bb.peek(log)];
+                        unsigned short ent = tab[(uint32_t)(buf >> sh_idx)];
                         dst[i] = (uint8_t)ent;
-                        bb.skip(ent >> 8);
+                        bitpos -= ent >> 8;
+                        HUF_RELOAD();
                     }
-                    ok = bb.left == 0;
+#undef HUF_RELOAD
+                    ok = !over && bitpos == 0;
                 }
             }
             // a frame fails if any of its streams failed
