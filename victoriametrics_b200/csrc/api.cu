@@ -68,6 +68,8 @@ struct vmb_ctx {
     // scratch (reused across calls)
     DevBuf zscratch, zlit, zstatus, zjobs, zws, args1, args2, rolled, counters, tmp_out, grp;
     void* h_pinned = nullptr;  // small pinned staging area for counters
+    void* pipe = nullptr;      // pipeline.inc: streams, events and double-buffered slots of vmb_eval_rollup_host
+    void (*pipe_destroy)(void*) = nullptr;
 };
 
 struct vmb_blocks {
@@ -141,6 +143,7 @@ extern "C" void vmb_ctx_destroy(vmb_ctx* c) {
     for (int i = 0; i < 6; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->pipe && c->pipe_destroy) c->pipe_destroy(c->pipe);
     delete c;
 }
 extern "C" int vmb_ctx_set_stream(vmb_ctx* c, void* stream) {
@@ -915,37 +918,7 @@ extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t
     return VMB_OK;
 }
 
-extern "C" int vmb_eval_rollup_host(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload,
-                                    size_t payload_len, int64_t tr_min, int64_t tr_max, const vmb_rollup_cfg* cfg,
-                                    double* out_host, int32_t* block_status, uint64_t* samples_scanned) {
-    if (!ctx || !out_host) return VMB_ERR_INVALID_ARG;
-    int64_t points;
-    int rc = check_cfg(cfg, &points);
-    if (rc) return rc;
-    CU(cudaSetDevice(ctx->device));
-    vmb_blocks* b = nullptr;
-    rc = vmb_blocks_upload(ctx, descs, nblocks, payload, payload_len, &b);
-    if (rc) return rc;
-    size_t total = b->nseries * (size_t)points;
-    if ((rc = ctx->tmp_out.reserve(total * 8))) {
-        vmb_blocks_free(b);
-        return rc;
-    }
-    double* d_out = (double*)ctx->tmp_out.p;
-    uint64_t scanned = 0;
-    rc = vmb_eval_rollup_device(ctx, b, tr_min, tr_max, cfg, d_out, &scanned);
-    if (rc == VMB_OK || rc == VMB_ERR_BLOCK_FAILED) {
-        if (total) {
-            cudaError_t e = cudaMemcpyAsync(out_host, d_out, total * 8, cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) rc = VMB_ERR_CUDA;
-        }
-        if (samples_scanned) *samples_scanned = scanned;
-    }
-    (void)block_status;
-    vmb_blocks_free(b);
-    return rc;
-}
+#include "pipeline.inc"
 
 // ------------------------------------------------------------------------------------------------ batched host encoder
 #include <atomic>

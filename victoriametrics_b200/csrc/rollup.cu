@@ -894,23 +894,11 @@ __global__ void __launch_bounds__(128) k_series_prepare(RollupParams P) {
 }
 
 #define ROLLUP_THREADS 256
-#define ROLLUP_STAGE_ROWS 1280
+#define ROLLUP_CAP 2048    /* rows of one series resident in shared memory */
+#define ROLLUP_SEEKS 1024  /* grid times whose row index is shared by a tile */
 
-// one thread per output point; a CTA covers ROLLUP_THREADS consecutive points of one series.  The rows those points can
-// touch (a contiguous span: both the samples and the output grid are time-ordered) are staged in shared memory with
-// coalesced loads, so the two window seeks per point and the O(window) functions never go back to HBM/L2.
-// Spans larger than ROLLUP_STAGE_ROWS (huge windows) fall back to reading global memory directly.
-//
-// Window seeks: when the window is a multiple of the step (rate(m[5m]) at step 15 s: 20 steps), the left edge of point p
-// is the right edge of point p - window/step, so the tile computes ONE seek per grid time (ROLLUP_THREADS + window/step of
-// them, s_seek[]) instead of two per point.  A seek is an interpolation guess + a short walk (samples are near-regular
-// inside a tile), falling back to binary search when the walk does not converge.
-//
-// F >= 0 instantiates the kernel for one rollup function (the switch in call_func folds away); F == -1 is generic.
-#define ROLLUP_SEEKS 1024
-
+// first index with ts[idx] > x: interpolation guess + short walk, binary search when the walk does not converge
 __device__ __forceinline__ uint32_t seek_after(const int64_t* __restrict__ ts, uint32_t n, int64_t x, double inv_dt) {
-    // first index with ts[idx] > x
     if (n == 0 || ts[0] > x) return 0;
     if (ts[n - 1] <= x) return n;
     uint32_t g = (uint32_t)((double)(x - ts[0]) * inv_dt);
@@ -927,109 +915,165 @@ __device__ __forceinline__ uint32_t seek_after(const int64_t* __restrict__ ts, u
     return g;
 }
 
+// one output point: rollup.go:769-819.  v/t are indexed by the row number inside the series; rows [i-1, j] must be readable.
+template <int F>
+__device__ __forceinline__ double rollup_point(const vmb_rollup_cfg& rc, const SeriesMeta& m, const double* v, const int64_t* t,
+                                               uint32_t n, uint32_t i, uint32_t j, uint32_t p, unsigned long long& scanned) {
+    const int64_t tEnd = rc.start + (int64_t)p * rc.step;
+    const int64_t tStart = tEnd - m.window;
+    if (j < i) j = i;
+    Win r;
+    r.prevValue = D_NAN;
+    r.prevTimestamp = tStart - m.max_prev_interval;
+    if (i < n && i > 0 && t[i - 1] > r.prevTimestamp) {
+        r.prevValue = v[i - 1];
+        r.prevTimestamp = t[i - 1];
+    }
+    r.values = v + i;
+    r.timestamps = t + i;
+    r.n = j - i;
+    r.realPrevValue = D_NAN;
+    if (i > 0) {
+        int64_t curr = r.n > 0 ? t[i] : tStart;
+        if (rc.lookback_delta == 0 || (curr - t[i - 1]) < rc.lookback_delta) r.realPrevValue = v[i - 1];
+    }
+    r.realNextValue = j < n ? v[j] : D_NAN;
+    r.currTimestamp = tEnd;
+    r.idx = p;
+    r.window = m.window;
+    r.args = rc.args;
+    r.args2 = rc.args2;
+    scanned += rc.samples_scanned_per_call > 0 ? (unsigned long long)rc.samples_scanned_per_call : (unsigned long long)r.n;
+    return call_func(F >= 0 ? F : rc.func_id, r);
+}
+
+// Streaming rollup: one CTA walks one series front to back.  Rows are pulled into shared memory once, in order, with
+// coalesced loads (no per-tile searches in global memory); the CTA computes every output point whose window lies inside the
+// resident rows (one thread per point, tiles of ROLLUP_THREADS points), then slides the resident range forward keeping only
+// the rows the next point still needs.  Both the samples and the output grid are time-ordered, so this visits each row once.
+//
+// Window seeks: when the window is a multiple of the step (rate(m[5m]) at step 15 s: 20 steps), the left edge of point p is
+// the right edge of point p - window/step, so a tile computes ONE seek per grid time (s_seek[]) instead of two per point.
+//
+// A window that does not fit ROLLUP_CAP rows (huge windows / very dense series) is handled for that tile by reading global
+// memory directly.  F >= 0 instantiates the kernel for one rollup function (the switch in call_func folds away).
 template <int F>
 __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
-    __shared__ int64_t s_ts[ROLLUP_STAGE_ROWS];
-    __shared__ double s_val[ROLLUP_STAGE_ROWS];
+    __shared__ int64_t s_ts[ROLLUP_CAP];
+    __shared__ double s_val[ROLLUP_CAP];
     __shared__ uint32_t s_seek[ROLLUP_SEEKS];
-    __shared__ uint32_t s_span[2];
     const vmb_rollup_cfg& rc = P.cfg;
-    const uint32_t tiles = (P.npoints + ROLLUP_THREADS - 1) / ROLLUP_THREADS;
+    const uint32_t tid = threadIdx.x;
     unsigned long long scanned = 0;
-    for (uint64_t bid = blockIdx.x; bid < (uint64_t)P.nseries * tiles; bid += gridDim.x) {
-        const uint32_t s = (uint32_t)(bid / tiles);
-        const uint32_t p = (uint32_t)(bid % tiles) * ROLLUP_THREADS + threadIdx.x;
+    for (uint32_t s = blockIdx.x; s < P.nseries; s += gridDim.x) {
         const SeriesMeta m = P.meta[s];
-        if (p == 0) scanned += m.n;  // samplesScanned starts at len(values) rollup.go:766
-        // ---- stage the rows this tile can touch: [first row after tStart(first point)] - 1 .. [first row after tEnd(last point)]
-        __syncthreads();  // previous tile done with shared memory
-        if (threadIdx.x == 0 || threadIdx.x == 32) {
-            const uint32_t p0 = (uint32_t)(bid % tiles) * ROLLUP_THREADS;
-            const uint32_t p1 = min(p0 + ROLLUP_THREADS, P.npoints) - 1;
-            const int64_t* tg = P.ts + m.start;
-            if (threadIdx.x == 0) {
-                uint32_t lo = upper_bound_ts(tg, m.n, rc.start + (int64_t)p0 * rc.step - m.window);
-                s_span[0] = lo > 0 ? lo - 1 : 0;
-            } else {
-                uint32_t hi = upper_bound_ts(tg, m.n, rc.start + (int64_t)p1 * rc.step);
-                s_span[1] = min(m.n, hi + 1);
-            }
-        }
-        __syncthreads();
-        const uint32_t sbase = s_span[0];
-        const uint32_t scount = s_span[1] > sbase ? s_span[1] - sbase : 0;
-        const bool staged = scount <= ROLLUP_STAGE_ROWS;
-        if (staged) {
-            const int64_t* tg = P.ts + m.start + sbase;
-            const double* vg = P.vals + m.start + sbase;
-            for (uint32_t k = threadIdx.x; k < scount; k += ROLLUP_THREADS) {
-                s_ts[k] = tg[k];
-                s_val[k] = vg[k];
-            }
-        }
-        __syncthreads();
-        const double* v = P.vals + m.start;
-        const int64_t* t = P.ts + m.start;
+        const double* vg = P.vals + m.start;
+        const int64_t* tg = P.ts + m.start;
         const uint32_t n = m.n;
-        // search domain: the staged rows (shared memory) or the whole series (global memory)
-        const int64_t* st = staged ? s_ts : t;
-        const uint32_t sn = staged ? scount : n;
-        const uint32_t sb = staged ? sbase : 0;
-        double inv_dt = 0.0;
-        if (sn > 1 && st[sn - 1] > st[0]) inv_dt = (double)(sn - 1) / (double)(st[sn - 1] - st[0]);
+        double* out = P.out + (size_t)s * P.npoints;
+        if (tid == 0) scanned += n;  // samplesScanned starts at len(values) rollup.go:766
         const uint32_t wsteps = (uint32_t)(m.window / rc.step);
         const bool shared_seeks = (m.window % rc.step) == 0 && wsteps + ROLLUP_THREADS <= ROLLUP_SEEKS;
-        const uint32_t p0 = (uint32_t)(bid % tiles) * ROLLUP_THREADS;
-        if (shared_seeks) {
-            // s_seek[q] = first row after grid time start + (p0 + q - wsteps) * step
-            for (uint32_t q = threadIdx.x; q < ROLLUP_THREADS + wsteps; q += ROLLUP_THREADS) {
-                int64_t x = rc.start + ((int64_t)p0 + (int64_t)q - (int64_t)wsteps) * rc.step;
-                s_seek[q] = sb + seek_after(st, sn, x, inv_dt);
-            }
+        uint32_t base = 0, cnt = 0, p = 0;
+        while (p < P.npoints) {
+            // ---- fill: rows [base + cnt, min(n, base + CAP))
             __syncthreads();
+            const uint32_t want = min(n - base, (uint32_t)ROLLUP_CAP);
+            for (uint32_t k = cnt + tid; k < want; k += ROLLUP_THREADS) {
+                s_ts[k] = tg[base + k];
+                s_val[k] = vg[base + k];
+            }
+            cnt = want;
+            __syncthreads();
+            // ---- points computable from the resident rows: tEnd < last resident timestamp (so that row j is resident),
+            //      or every remaining point once the series end is resident
+            uint32_t p_end;
+            if (base + cnt == n) p_end = P.npoints;
+            else {
+                int64_t tl = s_ts[cnt - 1] - 1 - rc.start;
+                p_end = tl < 0 ? 0u : (uint32_t)min((int64_t)P.npoints, tl / rc.step + 1);
+            }
+            double inv_dt = 0.0;
+            if (cnt > 1 && s_ts[cnt - 1] > s_ts[0]) inv_dt = (double)(cnt - 1) / (double)(s_ts[cnt - 1] - s_ts[0]);
+            if (p_end <= p) {
+                // the window of point p needs more than CAP rows: do one tile from global memory
+                p_end = min(p + ROLLUP_THREADS, P.npoints);
+                uint32_t q = p + tid;
+                if (q < p_end) {
+                    int64_t tEnd = rc.start + (int64_t)q * rc.step;
+                    uint32_t i = upper_bound_ts(tg, n, tEnd - m.window);
+                    uint32_t j = upper_bound_ts(tg, n, tEnd);
+                    out[q] = rollup_point<F>(rc, m, vg, tg, n, i, j, q, scanned);
+                }
+                p = p_end;
+                if (p < P.npoints) {  // restart the resident range at the first row the next point needs
+                    uint32_t lo = upper_bound_ts(tg, n, rc.start + (int64_t)p * rc.step - m.window);
+                    base = lo > 0 ? lo - 1 : 0;
+                    cnt = 0;
+                }
+                continue;
+            }
+            // ---- tiles of ROLLUP_THREADS points
+            const double* v = s_val - base;  // so that v[row] / t[row] index by the row number inside the series
+            const int64_t* t = s_ts - base;
+            for (uint32_t p0 = p; p0 < p_end; p0 += ROLLUP_THREADS) {
+                if (shared_seeks) {
+                    __syncthreads();  // previous tile done with s_seek
+                    for (uint32_t q = tid; q < ROLLUP_THREADS + wsteps; q += ROLLUP_THREADS) {
+                        int64_t x = rc.start + ((int64_t)p0 + (int64_t)q - (int64_t)wsteps) * rc.step;
+                        s_seek[q] = base + seek_after(s_ts, cnt, x, inv_dt);
+                    }
+                    __syncthreads();
+                }
+                const uint32_t q = p0 + tid;
+                if (q < p_end) {
+                    uint32_t i, j;
+                    if (shared_seeks) {
+                        i = s_seek[tid];
+                        j = s_seek[tid + wsteps];
+                    } else {
+                        int64_t tEnd = rc.start + (int64_t)q * rc.step;
+                        i = base + seek_after(s_ts, cnt, tEnd - m.window, inv_dt);
+                        j = base + seek_after(s_ts, cnt, tEnd, inv_dt);
+                    }
+                    // rows before `base` are not resident: the slide rule below keeps row i-1 of the first point resident
+                    out[q] = rollup_point<F>(rc, m, v, t, n, i, j, q, scanned);
+                }
+            }
+            p = p_end;
+            if (p >= P.npoints) break;
+            // ---- slide: keep rows from (first row after tStart(p)) - 1
+            __syncthreads();
+            uint32_t lo = base + seek_after(s_ts, cnt, rc.start + (int64_t)p * rc.step - m.window, inv_dt);
+            uint32_t nb = lo > base ? lo - 1 : base;
+            if (nb > base + cnt - 1) nb = base + cnt - 1;
+            const uint32_t shift = nb - base;
+            if (shift) {
+                const uint32_t keep = cnt - shift;
+                for (uint32_t c = 0; c < keep; c += ROLLUP_THREADS) {
+                    uint32_t k = c + tid;
+                    int64_t a = 0;
+                    double b = 0.0;
+                    if (k < keep) {
+                        a = s_ts[k + shift];
+                        b = s_val[k + shift];
+                    }
+                    __syncthreads();
+                    if (k < keep) {
+                        s_ts[k] = a;
+                        s_val[k] = b;
+                    }
+                }
+                base = nb;
+                cnt = keep;
+            } else if (cnt == ROLLUP_CAP) {
+                // no row can be dropped and the buffer is full: the next point's window does not fit; the global-memory
+                // branch above will take it on the next iteration (p_end <= p)
+            }
         }
-        if (p >= P.npoints) continue;
-        const int64_t tEnd = rc.start + (int64_t)p * rc.step;
-        const int64_t tStart = tEnd - m.window;
-        uint32_t i, j;
-        if (shared_seeks) {
-            i = s_seek[threadIdx.x];
-            j = s_seek[threadIdx.x + wsteps];
-        } else {
-            i = sb + seek_after(st, sn, tStart, inv_dt);
-            j = sb + seek_after(st, sn, tEnd, inv_dt);
-        }
-        if (staged) {
-            // rebase the pointers so that v[k] / t[k] keep meaning "row k of the series"
-            v = s_val - sbase;
-            t = s_ts - sbase;
-        }
-        if (j < i) j = i;
-        Win r;
-        r.prevValue = D_NAN;
-        r.prevTimestamp = tStart - m.max_prev_interval;
-        if (i < n && i > 0 && t[i - 1] > r.prevTimestamp) {
-            r.prevValue = v[i - 1];
-            r.prevTimestamp = t[i - 1];
-        }
-        r.values = v + i;
-        r.timestamps = t + i;
-        r.n = j - i;
-        r.realPrevValue = D_NAN;
-        if (i > 0) {
-            int64_t curr = r.n > 0 ? t[i] : tStart;
-            if (rc.lookback_delta == 0 || (curr - t[i - 1]) < rc.lookback_delta) r.realPrevValue = v[i - 1];
-        }
-        r.realNextValue = j < n ? v[j] : D_NAN;
-        r.currTimestamp = tEnd;
-        r.idx = p;
-        r.window = m.window;
-        r.args = rc.args;
-        r.args2 = rc.args2;
-        P.out[(size_t)s * P.npoints + p] = call_func(F >= 0 ? F : rc.func_id, r);
-        scanned += rc.samples_scanned_per_call > 0 ? (unsigned long long)rc.samples_scanned_per_call : (unsigned long long)r.n;
     }
     // block reduce -> one atomic per CTA
+    __syncthreads();
 #pragma unroll
     for (int off = 16; off; off >>= 1) scanned += shfl_u64(scanned, (lane_id() ^ off));
     __shared__ unsigned long long s_part[ROLLUP_THREADS / 32];
@@ -1201,9 +1245,7 @@ void launch_series_prepare(const RollupParams& P, cudaStream_t st) {
 }
 void launch_rollup(const RollupParams& P, cudaStream_t st) {
     if (!P.nseries || !P.npoints) return;
-    uint64_t tiles = (P.npoints + ROLLUP_THREADS - 1) / ROLLUP_THREADS;
-    uint64_t total = (uint64_t)P.nseries * tiles;
-    uint32_t grid = total > 148ull * 64ull ? 148u * 64u : (uint32_t)total;
+    uint32_t grid = P.nseries > 148u * 16u ? 148u * 16u : P.nseries;  // one CTA per series, grid-stride
     switch (P.cfg.func_id) {  // the functions of BASELINE.json's configs get their own instantiation
 #define ROLLUP_CASE(F) case F: k_rollup<F><<<grid, ROLLUP_THREADS, 0, st>>>(P); break;
         ROLLUP_CASE(VMB_RF_RATE)

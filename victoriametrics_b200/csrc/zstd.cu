@@ -19,6 +19,7 @@
 namespace {
 
 __device__ __forceinline__ int hb32(uint32_t v) { return 31 - __clz((int)v); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // backward bitstream (RFC 8878 4.1): MSB-aligned 64-bit window
 struct BitR {
@@ -791,56 +792,103 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
                 } else if (slen == 0 || last == 0) {
                     ok = false;
                 } else {
-                    // Backward bitstream through a 64-bit register window that is re-read from memory (L1) after every 4
-                    // symbols: window = the 8 bytes that end at the byte holding the next unread bit.  Branch-free and
-                    // uniform across lanes (no divergent "refill" path); >= 57 valid bits per reload >= 4 codes of <= 11 bits.
-                    long long bitpos = (long long)(slen - 1) * 8 + hb32(last);  // unread payload bits
-                    bool over = false;
-                    uint64_t buf;
-                    const int sh_idx = 64 - log;
-#define HUF_RELOAD()                                                                   \
-    do {                                                                               \
-        if (bitpos < 0) { over = true; bitpos = 0; }                                   \
-        long long bend_ = (bitpos + 7) >> 3;                                           \
-        uintptr_t a_ = (uintptr_t)(base + bend_ - 8);                                  \
-        const uint32_t* w_ = (const uint32_t*)(a_ & ~(uintptr_t)3);                    \
-        uint32_t sh_ = (uint32_t)(a_ & 3) * 8;                                         \
-        uint32_t w0_ = w_[0], w1_ = w_[1], w2_ = w_[2];                                \
-        uint32_t lo_ = __funnelshift_r(w0_, w1_, sh_), hi_ = __funnelshift_r(w1_, w2_, sh_); \
-        buf = (((uint64_t)hi_ << 32) | lo_) << (uint32_t)(8 * bend_ - bitpos);         \
-    } while (0)
-                    HUF_RELOAD();
-                    uint32_t i = 0;
-                    // head: single bytes until dst is 4-byte aligned
-                    while (i < count && (((uintptr_t)(dst + i)) & 3)) {
-                        unsigned short ent = tab[(uint32_t)(buf >> sh_idx)];
-                        dst[i++] = (uint8_t)ent;
-                        bitpos -= ent >> 8;
-                        HUF_RELOAD();
+                    // Backward bitstream, lane-private and memory-frugal: the stream is pulled in as aligned 16-byte blocks
+                    // (one LDG.128 per lane per 16 bytes, ~1 every 13 symbols) into a 128-bit register queue; 32-bit words
+                    // are popped from the queue into an MSB-aligned 64-bit bit buffer.  All of it is predicated straight-line
+                    // code: no divergent refill path, and ~10x fewer L1 wavefronts than re-reading a window every 4 symbols.
+                    const uint32_t total_bits = (slen - 1) * 8 + (uint32_t)hb32(last);
+                    uint32_t used_bits = 0;
+                    const uint8_t* endp = base + slen - 1;                                 // byte holding the final-bit marker
+                    const uint4* blk = (const uint4*)((uintptr_t)endp & ~(uintptr_t)15);   // aligned block that holds it
+                    const uint4* blk_min = (const uint4*)(((uintptr_t)base & ~(uintptr_t)15) - 32);  // never read below this
+                    uint64_t qhi, qlo;  // 128-bit queue, next word at the top of qhi
+                    uint32_t qcnt;      // whole 32-bit words left in the queue
+                    uint64_t buf;       // bit buffer, next bit at the top
+                    int cnt;            // valid bits in buf
+                    {
+                        prefetch_l1(blk - 2 > blk_min ? blk - 2 : blk_min);
+                        prefetch_l1(blk - 4 > blk_min ? blk - 4 : blk_min);
+                        uint4 q = *blk;
+                        qlo = ((uint64_t)q.y << 32) | q.x;
+                        qhi = ((uint64_t)q.w << 32) | q.z;
+                        uint32_t nbytes = (uint32_t)((uintptr_t)endp & 15) + 1;  // valid bytes of this block: 1..16
+                        uint32_t drop = (16 - nbytes) * 8;                       // bits above the marker byte (next stream's data)
+                        if (drop >= 64) { qhi = qlo; qlo = 0; drop -= 64; }
+                        if (drop) { qhi = (qhi << drop) | (qlo >> (64 - drop)); qlo <<= drop; }
+                        uint32_t r = nbytes & 3;  // take the odd 1..3 (or 4) top bytes into the bit buffer so that whole words remain
+                        if (r == 0) r = 4;
+                        buf = qhi & ~(~0ull >> (8 * r));
+                        cnt = (int)(8 * r);
+                        if (r == 4) { qhi = (qhi << 32) | (qlo >> 32); qlo <<= 32; }
+                        else { qhi = (qhi << (8 * r)) | (qlo >> (64 - 8 * r)); qlo <<= (8 * r); }
+                        qcnt = (nbytes - r) >> 2;
+                        int skip = 8 - hb32(last);  // zero padding + the final-bit marker
+                        buf <<= skip;
+                        cnt -= skip;
                     }
-                    // body: 4 symbols per aligned 32-bit store, one window reload per 4 symbols
-                    for (; i + 4 <= count; i += 4) {
-                        uint32_t wv = 0, used = 0;
+                    const int sh_idx = 64 - log;
+#define HUF_REFILL()                                                                       \
+    do {                                                                                   \
+        if (cnt <= 32) {                                                                   \
+            if (qcnt == 0) {                                                               \
+                if (blk > blk_min) blk--;                                                  \
+                /* pull the data 64 bytes further down into L1 now (no register written, so the warp does not wait): */ \
+                /* the LDG below then hits L1 instead of exposing an HBM round trip to all 32 lanes */ \
+                prefetch_l1(blk - 4 > blk_min ? blk - 4 : blk_min);                        \
+                uint4 q_ = *blk;                                                           \
+                qlo = ((uint64_t)q_.y << 32) | q_.x;                                       \
+                qhi = ((uint64_t)q_.w << 32) | q_.z;                                       \
+                qcnt = 4;                                                                  \
+            }                                                                              \
+            uint32_t w_ = (uint32_t)(qhi >> 32);                                           \
+            qhi = (qhi << 32) | (qlo >> 32);                                               \
+            qlo <<= 32;                                                                    \
+            qcnt--;                                                                        \
+            buf |= (uint64_t)w_ << (32 - cnt);                                             \
+            cnt += 32;                                                                     \
+        }                                                                                  \
+    } while (0)
+#define HUF_SYM(outv, shift)                                                               \
+    do {                                                                                   \
+        unsigned short ent_ = tab[(uint32_t)(buf >> sh_idx)];                              \
+        uint32_t nb_ = ent_ >> 8;                                                          \
+        outv |= (uint32_t)(ent_ & 0xff) << (shift);                                        \
+        buf <<= nb_;                                                                       \
+        cnt -= (int)nb_;                                                                   \
+        used_bits += nb_;                                                                  \
+    } while (0)
+                    uint32_t i = 0;
+                    // head: single bytes until dst is 16-byte aligned
+                    while (i < count && (((uintptr_t)(dst + i)) & 15)) {
+                        HUF_REFILL();
+                        uint32_t o = 0;
+                        HUF_SYM(o, 0);
+                        dst[i++] = (uint8_t)o;
+                    }
+                    // body: 16 symbols per aligned 128-bit store; one refill check per 2 symbols (<= 22 bits)
+                    for (; i + 16 <= count; i += 16) {
+                        uint32_t o[4];
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            unsigned short ent = tab[(uint32_t)(buf >> sh_idx)];
-                            uint32_t nb = ent >> 8;
-                            wv |= (uint32_t)(ent & 0xff) << (8 * k);
-                            buf <<= nb;
-                            used += nb;
+                        for (int q = 0; q < 4; q++) {
+                            o[q] = 0;
+                            HUF_REFILL();
+                            HUF_SYM(o[q], 0);
+                            HUF_SYM(o[q], 8);
+                            HUF_REFILL();
+                            HUF_SYM(o[q], 16);
+                            HUF_SYM(o[q], 24);
                         }
-                        *(uint32_t*)(dst + i) = wv;
-                        bitpos -= used;
-                        HUF_RELOAD();
+                        *(uint4*)(dst + i) = make_uint4(o[0], o[1], o[2], o[3]);
                     }
                     for (; i < count; i++) {
-                        unsigned short ent = tab[(uint32_t)(buf >> sh_idx)];
-                        dst[i] = (uint8_t)ent;
-                        bitpos -= ent >> 8;
-                        HUF_RELOAD();
+                        HUF_REFILL();
+                        uint32_t o = 0;
+                        HUF_SYM(o, 0);
+                        dst[i] = (uint8_t)o;
                     }
-#undef HUF_RELOAD
-                    ok = !over && bitpos == 0;
+#undef HUF_REFILL
+#undef HUF_SYM
+                    ok = used_bits == total_bits;
                 }
             }
             // a frame fails if any of its streams failed
