@@ -720,6 +720,7 @@ __global__ void k_zstd_prepare(ZstdParams P) {
 #define HUF_WARPS 4
 #define HUF_FRAMES_PER_WARP 8
 #define HUF_TABLE_ENTRIES 2048
+#define HUF_RING 32 /* words of compressed input resident in shared memory per lane (power of two) */
 
 __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
     extern __shared__ unsigned short s_tab[];  // [HUF_WARPS * 8][2048]
@@ -727,6 +728,8 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
     const int warp = threadIdx.x >> 5;
     const uint32_t groups = (P.count + HUF_FRAMES_PER_WARP - 1) / HUF_FRAMES_PER_WARP;
     unsigned short* wtab = s_tab + (size_t)warp * HUF_FRAMES_PER_WARP * HUF_TABLE_ENTRIES;
+    // per-warp input rings behind the tables: HUF_RING words per lane, word-interleaved across lanes
+    uint32_t* wring = (uint32_t*)(s_tab + (size_t)HUF_WARPS * HUF_FRAMES_PER_WARP * HUF_TABLE_ENTRIES) + (size_t)warp * HUF_RING * 32;
     for (uint32_t g = blockIdx.x * HUF_WARPS + warp; g < groups; g += gridDim.x * HUF_WARPS) {
         // ---- build the 8 decode tables cooperatively: for frame f, entries are filled in (nbits desc, symbol asc) order
         for (int f = 0; f < HUF_FRAMES_PER_WARP; f++) {
@@ -792,61 +795,85 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
                 } else if (slen == 0 || last == 0) {
                     ok = false;
                 } else {
-                    // Backward bitstream, lane-private and memory-frugal: the stream is pulled in as aligned 16-byte blocks
-                    // (one LDG.128 per lane per 16 bytes, ~1 every 13 symbols) into a 128-bit register queue; 32-bit words
-                    // are popped from the queue into an MSB-aligned 64-bit bit buffer.  All of it is predicated straight-line
-                    // code: no divergent refill path, and ~10x fewer L1 wavefronts than re-reading a window every 4 symbols.
+                    // Backward bitstream, lane-private, with every memory access at a warp-uniform program point:
+                    //   * the stream is pulled in as aligned 16-byte blocks (LDG.128) that land in registers and are moved
+                    //     into the lane's shared-memory ring TWO phases (16 symbols) later -- the HBM round trip is covered
+                    //     by decoding, and no lane ever makes the other 31 wait on its own load;
+                    //   * 32-bit words are popped from the ring into an MSB-aligned 64-bit bit buffer; the candidate word is
+                    //     re-read (LDS) at every refill check by all lanes, so that read is uniform too.
+                    // The ring is word-interleaved across lanes (word w of lane l at [w*32 + l]): conflict-free.
                     const uint32_t total_bits = (slen - 1) * 8 + (uint32_t)hb32(last);
                     uint32_t used_bits = 0;
                     const uint8_t* endp = base + slen - 1;                                 // byte holding the final-bit marker
                     const uint4* blk = (const uint4*)((uintptr_t)endp & ~(uintptr_t)15);   // aligned block that holds it
                     const uint4* blk_min = (const uint4*)(((uintptr_t)base & ~(uintptr_t)15) - 32);  // never read below this
-                    uint64_t qhi, qlo;  // 128-bit queue, next word at the top of qhi
-                    uint32_t qcnt;      // whole 32-bit words left in the queue
-                    uint64_t buf;       // bit buffer, next bit at the top
-                    int cnt;            // valid bits in buf
+                    uint32_t* ring = wring + lane;  // slot i -> ring[(i & (HUF_RING - 1)) * 32]
+                    uint32_t wr = 0, rd = 0;        // words written / consumed
+                    uint64_t buf;                   // bit buffer, next bit at the top
+                    int cnt;                        // valid bits in buf
                     {
-                        prefetch_l1(blk - 2 > blk_min ? blk - 2 : blk_min);
-                        prefetch_l1(blk - 4 > blk_min ? blk - 4 : blk_min);
                         uint4 q = *blk;
-                        qlo = ((uint64_t)q.y << 32) | q.x;
-                        qhi = ((uint64_t)q.w << 32) | q.z;
+                        uint64_t qlo = ((uint64_t)q.y << 32) | q.x, qhi = ((uint64_t)q.w << 32) | q.z;
                         uint32_t nbytes = (uint32_t)((uintptr_t)endp & 15) + 1;  // valid bytes of this block: 1..16
                         uint32_t drop = (16 - nbytes) * 8;                       // bits above the marker byte (next stream's data)
                         if (drop >= 64) { qhi = qlo; qlo = 0; drop -= 64; }
                         if (drop) { qhi = (qhi << drop) | (qlo >> (64 - drop)); qlo <<= drop; }
-                        uint32_t r = nbytes & 3;  // take the odd 1..3 (or 4) top bytes into the bit buffer so that whole words remain
+                        uint32_t r = nbytes & 3;  // the odd 1..3 (or 4) top bytes go straight into the bit buffer: whole words remain
                         if (r == 0) r = 4;
                         buf = qhi & ~(~0ull >> (8 * r));
                         cnt = (int)(8 * r);
-                        if (r == 4) { qhi = (qhi << 32) | (qlo >> 32); qlo <<= 32; }
-                        else { qhi = (qhi << (8 * r)) | (qlo >> (64 - 8 * r)); qlo <<= (8 * r); }
-                        qcnt = (nbytes - r) >> 2;
+                        qhi = (qhi << (8 * r)) | (r == 8 ? 0 : (qlo >> (64 - 8 * r)));
+                        qlo <<= (8 * r);
+                        uint32_t nw = (nbytes - r) >> 2;
+                        for (uint32_t k = 0; k < nw; k++) {
+                            ring[(wr & (HUF_RING - 1)) * 32] = (uint32_t)(qhi >> 32);
+                            wr++;
+                            qhi = (qhi << 32) | (qlo >> 32);
+                            qlo <<= 32;
+                        }
                         int skip = 8 - hb32(last);  // zero padding + the final-bit marker
                         buf <<= skip;
                         cnt -= skip;
+                        // prime the ring: 6 more blocks (reads below the stream start return bytes that are never consumed)
+#pragma unroll
+                        for (int k = 0; k < 6; k++) {
+                            if (blk > blk_min) blk--;
+                            uint4 b = *blk;
+                            ring[((wr + 0) & (HUF_RING - 1)) * 32] = b.w;
+                            ring[((wr + 1) & (HUF_RING - 1)) * 32] = b.z;
+                            ring[((wr + 2) & (HUF_RING - 1)) * 32] = b.y;
+                            ring[((wr + 3) & (HUF_RING - 1)) * 32] = b.x;
+                            wr += 4;
+                        }
                     }
+                    uint4 pendA = make_uint4(0, 0, 0, 0), pendB = make_uint4(0, 0, 0, 0);
+                    bool hasA = false, hasB = false;
+                    uint32_t cand = ring[(rd & (HUF_RING - 1)) * 32];
                     const int sh_idx = 64 - log;
+#define HUF_PHASE(pend, has)                                                               \
+    do {                                                                                   \
+        if (has) { /* block fetched two phases ago: now in registers for sure */           \
+            ring[((wr + 0) & (HUF_RING - 1)) * 32] = pend.w;                               \
+            ring[((wr + 1) & (HUF_RING - 1)) * 32] = pend.z;                               \
+            ring[((wr + 2) & (HUF_RING - 1)) * 32] = pend.y;                               \
+            ring[((wr + 3) & (HUF_RING - 1)) * 32] = pend.x;                               \
+            wr += 4;                                                                       \
+        }                                                                                  \
+        /* room for this block even when the other pending block lands first? */           \
+        has = (wr - rd) + 8u <= (uint32_t)HUF_RING;                                        \
+        if (has) {                                                                         \
+            if (blk > blk_min) blk--;                                                      \
+            pend = *blk;                                                                   \
+        }                                                                                  \
+    } while (0)
 #define HUF_REFILL()                                                                       \
     do {                                                                                   \
         if (cnt <= 32) {                                                                   \
-            if (qcnt == 0) {                                                               \
-                if (blk > blk_min) blk--;                                                  \
-                /* pull the data 64 bytes further down into L1 now (no register written, so the warp does not wait): */ \
-                /* the LDG below then hits L1 instead of exposing an HBM round trip to all 32 lanes */ \
-                prefetch_l1(blk - 4 > blk_min ? blk - 4 : blk_min);                        \
-                uint4 q_ = *blk;                                                           \
-                qlo = ((uint64_t)q_.y << 32) | q_.x;                                       \
-                qhi = ((uint64_t)q_.w << 32) | q_.z;                                       \
-                qcnt = 4;                                                                  \
-            }                                                                              \
-            uint32_t w_ = (uint32_t)(qhi >> 32);                                           \
-            qhi = (qhi << 32) | (qlo >> 32);                                               \
-            qlo <<= 32;                                                                    \
-            qcnt--;                                                                        \
-            buf |= (uint64_t)w_ << (32 - cnt);                                             \
+            buf |= (uint64_t)cand << (32 - cnt);                                           \
             cnt += 32;                                                                     \
+            rd++;                                                                          \
         }                                                                                  \
+        cand = ring[(rd & (HUF_RING - 1)) * 32];                                           \
     } while (0)
 #define HUF_SYM(outv, shift)                                                               \
     do {                                                                                   \
@@ -858,18 +885,30 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
         used_bits += nb_;                                                                  \
     } while (0)
                     uint32_t i = 0;
-                    // head: single bytes until dst is 16-byte aligned
+                    // head: single bytes until dst is 16-byte aligned (<= 15 symbols <= 6 words: covered by the primed ring)
                     while (i < count && (((uintptr_t)(dst + i)) & 15)) {
                         HUF_REFILL();
                         uint32_t o = 0;
                         HUF_SYM(o, 0);
                         dst[i++] = (uint8_t)o;
                     }
-                    // body: 16 symbols per aligned 128-bit store; one refill check per 2 symbols (<= 22 bits)
+                    // body: 16 symbols per aligned 128-bit store = two phases of 8 symbols (<= 88 bits <= 3 words each)
                     for (; i + 16 <= count; i += 16) {
                         uint32_t o[4];
+                        HUF_PHASE(pendA, hasA);
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
+                        for (int q = 0; q < 2; q++) {
+                            o[q] = 0;
+                            HUF_REFILL();
+                            HUF_SYM(o[q], 0);
+                            HUF_SYM(o[q], 8);
+                            HUF_REFILL();
+                            HUF_SYM(o[q], 16);
+                            HUF_SYM(o[q], 24);
+                        }
+                        HUF_PHASE(pendB, hasB);
+#pragma unroll
+                        for (int q = 2; q < 4; q++) {
                             o[q] = 0;
                             HUF_REFILL();
                             HUF_SYM(o[q], 0);
@@ -880,12 +919,19 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
                         }
                         *(uint4*)(dst + i) = make_uint4(o[0], o[1], o[2], o[3]);
                     }
+                    // tail (<= 15 symbols <= 6 words): what is already in the ring plus the pending blocks is enough
+                    if (i < count) {
+                        HUF_PHASE(pendA, hasA);
+                        HUF_PHASE(pendB, hasB);
+                        hasA = hasB = false;
+                    }
                     for (; i < count; i++) {
                         HUF_REFILL();
                         uint32_t o = 0;
                         HUF_SYM(o, 0);
                         dst[i] = (uint8_t)o;
                     }
+#undef HUF_PHASE
 #undef HUF_REFILL
 #undef HUF_SYM
                     ok = used_bits == total_bits;
@@ -944,7 +990,8 @@ void launch_zstd_prepare(const ZstdParams& P, cudaStream_t st) {
 static bool g_huf_attr_set = false;
 void launch_huf_decode(const ZstdParams& P, cudaStream_t st) {
     if (!P.count) return;
-    size_t smem = (size_t)HUF_WARPS * HUF_FRAMES_PER_WARP * HUF_TABLE_ENTRIES * sizeof(unsigned short);
+    size_t smem = (size_t)HUF_WARPS * HUF_FRAMES_PER_WARP * HUF_TABLE_ENTRIES * sizeof(unsigned short) +
+                  (size_t)HUF_WARPS * HUF_RING * 32 * sizeof(uint32_t);
     if (!g_huf_attr_set) {
         cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         g_huf_attr_set = true;
