@@ -717,35 +717,100 @@ __global__ void k_series_assemble(RollupParams P) {
     SeriesMeta m;
     m.start = 0;
     m.n = 0;
-    m._pad = 0;
+    m._pad = 0;  // bit 0: the series may hold Prometheus staleness markers (set by the decode kernel per block)
     m.max_prev_interval = 0;
     m.window = 0;
     bool failed = false;
-    for (uint32_t k = 0; k < nb; k++)
+    for (uint32_t k = 0; k < nb; k++) {
         if (P.blk_status[fb + k]) failed = true;
+        m._pad |= P.blk_hi[fb + k] >> 31;  // staleness-marker flag of the block (decode.cu ValEmit)
+    }
     if (!failed && nb) {
         // skip leading / trailing blocks that were trimmed away completely
         uint32_t a = 0, b = nb;
-        while (a < b && P.blk_hi[fb + a] == P.blk_lo[fb + a]) a++;
-        while (b > a && P.blk_hi[fb + b - 1] == P.blk_lo[fb + b - 1]) b--;
+        while (a < b && (P.blk_hi[fb + a] & 0x7fffffffu) == P.blk_lo[fb + a]) a++;
+        while (b > a && (P.blk_hi[fb + b - 1] & 0x7fffffffu) == P.blk_lo[fb + b - 1]) b--;
         if (a < b) {
             bool contiguous = true;
             for (uint32_t k = a; k < b; k++) {
                 if (k > a && P.blk_lo[fb + k] != 0) contiguous = false;
-                if (k + 1 < b && P.blk_hi[fb + k] != P.descs[fb + k].rows) contiguous = false;
+                if (k + 1 < b && (P.blk_hi[fb + k] & 0x7fffffffu) != P.descs[fb + k].rows) contiguous = false;
             }
             if (!contiguous) {
                 for (uint32_t k = 0; k < nb; k++) P.blk_status[fb + k] = VMB_ERR_BLOCK_ORDER;
                 failed = true;
             } else {
                 m.start = P.row_off[fb + a] + P.blk_lo[fb + a];
-                uint64_t end = P.row_off[fb + b - 1] + P.blk_hi[fb + b - 1];
+                uint64_t end = P.row_off[fb + b - 1] + (P.blk_hi[fb + b - 1] & 0x7fffffffu);
                 m.n = (uint32_t)(end - m.start);
             }
         }
     }
     P.meta[s] = m;
     if (failed && P.failed_blocks) atomicAdd(P.failed_blocks, 1u);
+}
+
+struct RcrState {
+    double corr, prev_raw, prev_out;
+    int64_t prev_ts;
+};
+
+// removeCounterResets (rollup.go:921) for one 32-row chunk held one row per lane.  Sequential float semantics are
+// preserved: corrections are accumulated in sample order by walking the (rare) reset / staleness-gap events of the chunk;
+// the final clamp `values[i] = max(values[i], values[i-1])` is a segmented prefix max (order-independent).  A chunk without
+// events (the common case) needs no scan at all: raw values are non-decreasing there, so the clamp is an elementwise max
+// with the last output of the previous chunk.
+__device__ __forceinline__ void rcr_chunk(RcrState& st, double* v, uint32_t cb, uint32_t n, double x, int64_t tt,
+                                          int64_t max_stale, int lane) {
+    const uint32_t i = cb + lane;
+    const bool valid = i < n;
+    double pv = shfl_up_f64(x, 1);
+    int64_t pt = max_stale > 0 ? (int64_t)shfl_up_u64((uint64_t)tt, 1) : 0;
+    if (lane == 0) {
+        pv = cb == 0 ? x : st.prev_raw;
+        pt = cb == 0 ? tt : st.prev_ts;
+    }
+    const double d = x - pv;
+    const bool is_reset = valid && d < 0;
+    const bool is_gap = valid && i > 0 && max_stale > 0 && (tt - pt) > max_stale;
+    uint32_t ev = __ballot_sync(VMB_FULL, is_reset || is_gap || (valid && (isnan(x) || i == 0)));
+    double outv;
+    if (ev == 0) {
+        double a = x + st.corr;
+        outv = (a < st.prev_out) ? st.prev_out : a;
+    } else {
+        double amt = 0.0;
+        if (is_reset) amt = ((-d * 8) < pv) ? (pv - x) : pv;
+        uint32_t evs = __ballot_sync(VMB_FULL, is_reset || is_gap);
+        double corr = st.corr, my_corr = st.corr;
+        while (evs) {
+            int b = __ffs((int)evs) - 1;
+            evs &= evs - 1;
+            double a = shfl_f64(amt, b);
+            int flags = __shfl_sync(VMB_FULL, (int)is_reset | ((int)is_gap << 1), b);
+            if (flags & 1) corr = corr + a;
+            if (flags & 2) corr = 0.0;
+            if (lane >= b) my_corr = corr;
+        }
+        st.corr = corr;
+        // element as a function of the previous output: Const(c) or MaxWith(m)
+        double mval = is_gap ? x : x + my_corr;
+        bool isc = is_gap || i == 0 || isnan(mval) || !valid;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            double am = shfl_up_f64(mval, off);
+            int ac = __shfl_up_sync(VMB_FULL, (int)isc, off);
+            if (lane >= off && !isc) {
+                mval = (mval < am) ? am : mval;
+                isc = ac != 0;
+            }
+        }
+        outv = isc ? mval : ((mval < st.prev_out) ? st.prev_out : mval);
+    }
+    if (valid) v[i] = outv;
+    st.prev_out = shfl_f64(outv, 31);
+    st.prev_raw = shfl_f64(x, 31);
+    if (max_stale > 0) st.prev_ts = (int64_t)shfl_u64((uint64_t)tt, 31);
 }
 
 // one warp per series
@@ -759,7 +824,7 @@ __global__ void __launch_bounds__(128) k_series_prepare(RollupParams P) {
         int64_t* t = P.ts + m.start;
         uint32_t n = m.n;
         // ---- dropStaleNaNs eval.go:1985
-        if ((rc.flags & VMB_RC_DROP_STALE_NANS) && n) {
+        if ((rc.flags & VMB_RC_DROP_STALE_NANS) && n && (m._pad & 1u)) {  // decoded batches know whether a marker exists
             bool has = false;
             for (uint32_t i = lane; i < n; i += 32) has |= is_stale_nan(v[i]);
             if (__any_sync(VMB_FULL, has)) {
@@ -785,52 +850,23 @@ __global__ void __launch_bounds__(128) k_series_prepare(RollupParams P) {
         //      sample order; the final clamp is a segmented prefix "max" which is order-independent)
         if ((rc.flags & VMB_RC_REMOVE_COUNTER_RESETS) && n) {
             const int64_t max_stale = rc.lookback_delta != 0 ? rc.lookback_delta + rc.window : 0;  // rollup.go:380-387
-            double corr = 0.0, prev_raw = 0.0, prev_out = 0.0;
-            int64_t prev_ts = 0;
-            for (uint32_t base = 0; base < n; base += 32) {
-                uint32_t i = base + lane;
-                bool valid = i < n;
-                double x = valid ? v[i] : 0.0;
-                int64_t tt = valid ? t[i] : 0;
-                double pv = shfl_up_f64(x, 1);
-                int64_t pt = (int64_t)shfl_up_u64((uint64_t)tt, 1);
-                if (lane == 0) {
-                    pv = base == 0 ? x : prev_raw;
-                    pt = base == 0 ? tt : prev_ts;
-                }
-                double d = x - pv;
-                bool is_reset = valid && d < 0;
-                double amt = 0.0;
-                if (is_reset) amt = ((-d * 8) < pv) ? (pv - x) : pv;
-                bool is_gap = valid && i > 0 && max_stale > 0 && (tt - pt) > max_stale;
-                uint32_t ev = __ballot_sync(VMB_FULL, is_reset || is_gap);
-                double my_corr = corr;
-                while (ev) {
-                    int b = __ffs((int)ev) - 1;
-                    ev &= ev - 1;
-                    double a = shfl_f64(amt, b);
-                    int flags = __shfl_sync(VMB_FULL, (int)is_reset | ((int)is_gap << 1), b);
-                    if (flags & 1) corr = corr + a;
-                    if (flags & 2) corr = 0.0;
-                    if (lane >= b) my_corr = corr;
-                }
-                // element as a function of the previous output: Const(c) or MaxWith(m)
-                double mval = is_gap ? x : x + my_corr;
-                bool isc = is_gap || i == 0 || isnan(mval) || !valid;
+            RcrState st;
+            st.corr = 0.0; st.prev_raw = 0.0; st.prev_out = 0.0; st.prev_ts = 0;
+            // four 32-row chunks per iteration: their loads are issued together (one HBM round trip per 128 rows)
+            for (uint32_t base = 0; base < n; base += 128) {
+                double x[4];
+                int64_t tt[4];
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    double am = shfl_up_f64(mval, off);
-                    int ac = __shfl_up_sync(VMB_FULL, (int)isc, off);
-                    if (lane >= off && !isc) {
-                        mval = (mval < am) ? am : mval;
-                        isc = ac != 0;
-                    }
+                for (int u = 0; u < 4; u++) {
+                    uint32_t i = base + 32u * u + lane;
+                    x[u] = i < n ? v[i] : 0.0;
+                    tt[u] = (max_stale > 0 && i < n) ? t[i] : 0;
                 }
-                double outv = isc ? mval : ((mval < prev_out) ? prev_out : mval);
-                if (valid) v[i] = outv;
-                prev_out = shfl_f64(outv, 31);
-                prev_raw = shfl_f64(x, 31);
-                prev_ts = (int64_t)shfl_u64((uint64_t)tt, 31);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    uint32_t cb = base + 32u * u;
+                    if (cb < n) rcr_chunk(st, v, cb, n, x[u], tt[u], max_stale, lane);
+                }
             }
         }
         // ---- maxPrevInterval / window  rollup.go:719-756

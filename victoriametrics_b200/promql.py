@@ -207,3 +207,35 @@ class IncrementalAggr:
         check(lib().vmb_aggr_finalize(ctx.h, self.aggr, C.c_void_p(self.values.ptr), C.c_void_p(self.counts.ptr), n,
                                       out.ctypes.data_as(_lib.f64p)))
         return out
+
+
+# ---- multi-GPU protocol for aggr(rollup(...)) by (...)   -------------------------------------------------
+# all-reduce operator and the identity vmb_aggr_prepare_allreduce writes into empty cells (count == 0), per aggregate
+ALLREDUCE_OP = {"sum": "sum", "avg": "sum", "count": "sum", "sum2": "sum", "group": "sum", "min": "min", "max": "max",
+                "geomean": "prod"}
+ALLREDUCE_IDENTITY = {"sum": 0.0, "avg": 0.0, "count": 0.0, "sum2": 0.0, "group": 0.0, "min": float("inf"),
+                      "max": float("-inf"), "geomean": 1.0}
+
+
+def shard_series(nseries, rank, world):
+    """series owned by `rank`: MetricID mod world (independent series => no exchange for decode + rollup)"""
+    return np.arange(rank, nseries, world)
+
+
+def dense_group_ids(group_keys):
+    """dense group ids from the marshaled group-by label sets (aggr_incremental.go:113 marshalMetricNameSorted);
+    every rank must call this on the SAME global key list so that ids agree across ranks -> (ids, ngroups)"""
+    uniq = {}
+    ids = np.empty(len(group_keys), dtype=np.uint32)
+    for i, k in enumerate(group_keys):
+        ids[i] = uniq.setdefault(k, len(uniq))
+    return ids, len(uniq)
+
+
+def torch_all_reduce(values_t, counts_t, op):
+    """the `all_reduce` callback for IncrementalAggr.finalize: NCCL (or gloo) all-reduce of values with the aggregate's
+    operator and of counts with sum"""
+    import torch.distributed as dist
+    ops = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX, "prod": dist.ReduceOp.PRODUCT}
+    dist.all_reduce(values_t, op=ops[op])
+    dist.all_reduce(counts_t, op=dist.ReduceOp.SUM)
