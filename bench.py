@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--window-ms", type=int, default=300_000)
     ap.add_argument("--step-ms", type=int, default=15_000)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=24.0, help="target CPU work of the cpu_baseline sample")
     return ap.parse_args()
 
 
@@ -173,7 +173,7 @@ def cpu_reference(descs, payload, func, start, end, step, window, target_seconds
     run(nb0, out0)  # warm-up
     dt0 = run(nb0, out0)
     rate0 = nb0 * rows / dt0
-    wall_target = max(1.0, target_seconds / cores)  # target_seconds of CPU work spread over all cores, >= 1 s of wall
+    wall_target = max(0.2, target_seconds / cores)  # target_seconds of CPU work spread over all cores, >= 0.2 s of wall
     nb = int(wall_target * rate0 / rows)
     nb = max(nb0, min(nb, len(descs)))
     out = np.empty((nb, P), dtype=np.float64)
@@ -342,6 +342,17 @@ def main():
             if ms_ > 0:
                 stages[n_] = {"ms": round(ms_, 4), "algorithmic_GB": round(b_ / 1e9, 3), "GBps": round(b_ / 1e9 / (ms_ / 1e3), 1)}
         dom = max(stages, key=lambda k: stages[k]["ms"]) if stages else None
+
+        def traffic_of(stage):
+            """dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernel from the committed `ncu --set full`
+            capture (profiles/r01/traffic.json: bytes per launch at 20 000 blocks, rate workload), scaled to this launch"""
+            try:
+                t = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))
+                if a.func != t["func"] or a.rows != t["rows"]:
+                    return None
+                return int(t["bytes_per_launch"][stage] * (a.blocks / t["blocks"]))
+            except Exception:
+                return None
         fused_bytes = compressed + a.blocks * points * 8
         out = dict(base)
         out.update({"value": value, "ms_per_step": ms_per_step, "gpu_launches": int(launches), "clocks": clocks,
@@ -349,7 +360,7 @@ def main():
         if dom:
             ach = stages[dom]["GBps"]
             out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                               "traffic": None, "peak_source": peak_src, "stages": stages,
+                               "traffic": traffic_of(dom), "peak_source": peak_src, "stages": stages,
                                "whole_step": {"fused_algorithmic_GB": round(fused_bytes / 1e9, 3),
                                               "GBps": round(fused_bytes / 1e9 / (ms_per_step / 1e3), 1),
                                               "frac": round(fused_bytes / 1e9 / (ms_per_step / 1e3) / peak, 4)}}

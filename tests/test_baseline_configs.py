@@ -1,0 +1,186 @@
+"""BASELINE.json `configs` as parity cases.
+  configs[0]  (CPU only)  encode+decode round trip, 10k series x 1k int64 samples, nearest-delta2, bit-exact plumbing
+  configs[1..4] (-m gpu)  the query shapes at reduced size against the oracle pipeline, plus size-independent properties
+                          at a larger size (host path == device path bit for bit, sampled series == oracle)."""
+import numpy as np
+import pytest
+
+import blockgen
+from rollup_names import AGGR, RF
+
+T0 = 1_700_000_000_000
+
+
+def f64bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+# ------------------------------------------------------------------------------------------------ configs[0] (CPU)
+def test_config0_encode_decode_roundtrip_10k_series(oracle):
+    """v[i] = v[i-1] + 30000 + round(N(0,1000)); precisionBits 64 => MarshalTypeNearestDelta2 (plain,
+    zstd does not reach the 0.9 ratio: SURVEY.md 7 table) ; product encoder bytes == oracle encoder bytes; round trip exact"""
+    from victoriametrics_b200 import encoding
+    rng = np.random.default_rng(100)
+    nser, n = 10_000, 1024
+    inc = 30000 + np.round(rng.normal(0, 1000, (nser, n))).astype(np.int64)
+    inc[:, 0] = rng.integers(0, 10 ** 9, nser)
+    vals = np.cumsum(inc, axis=1)
+    payload, offs, mts, firsts = encoding.marshal_columns(vals)
+    assert set(mts.tolist()) <= {1, 5}
+    assert (mts == 5).mean() > 0.9  # plain nearest-delta2, as the reference chooses for this data
+    have_ref = bool(oracle.lib().vmo_zstd_ref_available())
+    for s in list(range(0, nser, 97)) + [nser - 1]:
+        b = payload[int(offs[s]):int(offs[s + 1])]
+        assert int(firsts[s]) == int(vals[s, 0])
+        rc, out = oracle.unmarshal_int64_array(b, int(mts[s]), int(firsts[s]), n)
+        assert rc == 0 and np.array_equal(out, vals[s]), s
+        if have_ref:
+            ob, omt, ofirst = oracle.marshal_int64_array(vals[s])
+            if omt == 5 and mts[s] == 5:
+                assert np.array_equal(ob, b), s  # byte-identical marshaled form
+
+
+# ------------------------------------------------------------------------------------------------ GPU configs
+def _oracle_rollup_matrix(oracle, blocks, func, start, end, step, window, lookback=0, arg=None):
+    import victoriametrics_b200 as vm
+    rc = vm.promql.get_rollup_configs(func, start, end, step, window, lookback, args=arg)
+    out = []
+    for blk in blocks:
+        r, ts, fv, _ = blk.oracle_unmarshal()
+        assert r == 0
+        ts, fv = ts.copy(), fv.copy()
+        n = len(ts)
+        if rc.dropStaleNaNs and n:
+            n = oracle.lib().vmo_drop_stale_nans(fv.ctypes.data_as(oracle.f64p), ts.ctypes.data_as(oracle.i64p), n)
+        ts, fv = ts[:n].copy(), fv[:n].copy()
+        if rc.removeCounterResets and n:
+            oracle.lib().vmo_remove_counter_resets(fv.ctypes.data_as(oracle.f64p), ts.ctypes.data_as(oracle.i64p), n,
+                                                   lookback + window if lookback else 0)
+        o, _ = oracle.rollup_do(RF[func], fv, ts, start, end, step, window, lookback_delta=lookback,
+                                may_adjust_window=rc.MayAdjustWindow, is_default_rollup=rc.isDefaultRollup,
+                                samples_scanned_per_call=rc.samplesScannedPerCall, args=arg)
+        out.append(o)
+    return np.stack(out)
+
+
+def _mk(rng, n, kind, rows=2048, tkind="regular"):
+    return [blockgen.OBlock(blockgen.gen_timestamps(rng, tkind, rows, T0), blockgen.gen_values(rng, kind, rows), -2, 64, i)
+            for i in range(n)]
+
+
+@pytest.mark.gpu
+def test_config1_decode_plus_rate_5m_step15(oracle):
+    import victoriametrics_b200 as vm
+    rng = np.random.default_rng(101)
+    blocks = _mk(rng, 48, "counter_resets", rows=8192)
+    descs, payload = blockgen.to_blockset(blocks)
+    start, end, step, window = T0 + 300000, T0 + 15000 * 8191, 15000, 300000
+    got, scanned = vm.promql.eval_rollup_func_host("rate", descs, payload, start, end, step, window)
+    exp = _oracle_rollup_matrix(oracle, blocks, "rate", start, end, step, window)
+    assert got.shape == (48, 8172)
+    assert np.allclose(got, exp, rtol=1e-12, atol=0, equal_nan=True)
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+    assert scanned == 48 * (8192 + 2 * 8172)  # len(values) + samplesScannedPerCall(rate)=2 per point (rollup.go:238)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("func,arg", [("avg_over_time", None), ("max_over_time", None), ("quantile_over_time", 0.99)])
+def test_config2_gauge_over_time_functions(oracle, func, arg):
+    import victoriametrics_b200 as vm
+    rng = np.random.default_rng(102)
+    blocks = _mk(rng, 40, "gauge", rows=4096, tkind="jitter")
+    assert all(b.vmt in (4, 6) for b in blocks)
+    descs, payload = blockgen.to_blockset(blocks)
+    B = vm.storage.Blocks(descs, payload)
+    for step in (15000, 60000):
+        start, end, window = T0 + 300000, T0 + 15000 * 4000, 300000
+        got, _ = vm.promql.eval_rollup_func(func, B, start, end, step, window, args=arg)
+        exp = _oracle_rollup_matrix(oracle, blocks, func, start, end, step, window, arg=arg)
+        assert np.allclose(got, exp, rtol=1e-12, atol=0, equal_nan=True), (func, step)
+
+
+@pytest.mark.gpu
+def test_config3_sum_rate_by_label_single_rank(oracle):
+    """sum(rate(m[5m])) by (mode): the per-GPU partial of config 4 (the cross-rank all-reduce is covered by
+    tests/test_dist_aggr.py over gloo and by bench.py --gpus N over NCCL)"""
+    import torch
+    import victoriametrics_b200 as vm
+    rng = np.random.default_rng(103)
+    S, G = 64, 8
+    blocks = _mk(rng, S, "counter", rows=2048)
+    descs, payload = blockgen.to_blockset(blocks)
+    B = vm.storage.Blocks(descs, payload)
+    start, end, step, window = T0 + 300000, T0 + 15000 * 2000, 15000, 300000
+    rc = vm.promql.get_rollup_configs("rate", start, end, step, window)
+    groups = (np.arange(S) % G).astype(np.uint32)
+
+    class Buf:
+        def __init__(self, nbytes):
+            self.t = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+            self.ptr = self.t.data_ptr()
+
+    series, _ = vm.storage.decode_blocks(B)
+    ia = vm.promql.IncrementalAggr("sum", G, rc.points, Buf)
+    ia.update(series, rc, groups)
+    got = ia.finalize(vm.default_context())
+    rolled = _oracle_rollup_matrix(oracle, blocks, "rate", start, end, step, window)
+    exp_v, exp_c = np.zeros((G, rc.points)), np.zeros((G, rc.points))
+    for s in range(S):
+        row = np.ascontiguousarray(rolled[s])
+        g = int(groups[s])
+        oracle.lib().vmo_aggr_update(AGGR["sum"], exp_v[g].ctypes.data_as(oracle.f64p), exp_c[g].ctypes.data_as(oracle.f64p),
+                                     row.ctypes.data_as(oracle.f64p), rc.points)
+    for g in range(G):
+        oracle.lib().vmo_aggr_finalize(AGGR["sum"], exp_v[g].ctypes.data_as(oracle.f64p), exp_c[g].ctypes.data_as(oracle.f64p), rc.points)
+    assert np.allclose(got, exp_v, rtol=1e-12, atol=0, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_config4_mixed_codec_increase_1h_step60(oracle):
+    """40 % delta2 counters, 30 % gauges, 20 % const, 10 % delta-const -> increase(m[1h]) step 60 s"""
+    import victoriametrics_b200 as vm
+    rng = np.random.default_rng(104)
+    kinds = ["counter"] * 4 + ["counter_smooth"] * 2 + ["counter_big"] * 2 + ["gauge"] * 6 + ["const"] * 4 + ["delta_const"] * 2
+    blocks = [blockgen.OBlock(blockgen.gen_timestamps(rng, "regular", 4096, T0), blockgen.gen_values(rng, k, 4096), -2, 64, i)
+              for i, k in enumerate(kinds * 3)]
+    assert {b.vmt for b in blocks} >= {1, 2, 3, 4, 5}
+    descs, payload = blockgen.to_blockset(blocks)
+    start, end, step, window = T0 + 3600000, T0 + 15000 * 4095, 60000, 3600000
+    got, _ = vm.promql.eval_rollup_func_host("increase", descs, payload, start, end, step, window)
+    exp = _oracle_rollup_matrix(oracle, blocks, "increase", start, end, step, window)
+    assert np.allclose(got, exp, rtol=1e-12, atol=0, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_full_block_size_properties_20k_blocks(oracle):
+    """size-independent properties at a bench-like size (20 000 blocks x 8192 rows through the product's own encoder):
+    (1) host pipeline == device path bit for bit; (2) rate >= 0 wherever defined (counter resets removed);
+    (3) 16 sampled series == oracle within 1e-12; (4) samplesScanned closed form"""
+    import torch
+    import victoriametrics_b200 as vm
+    import bench
+    nb, rows = 20_000, 8192
+    descs, payload = bench.gen_blocks(nb, rows, seed=77)
+    start, end, step = bench.query_range(rows, 300000, 15000)
+    P = 1 + (end - start) // step
+    B = vm.storage.Blocks(descs, payload)
+    dev = torch.empty((nb, P), dtype=torch.float64, device="cuda")
+    _, sc1 = vm.promql.eval_rollup_func("rate", B, start, end, step, 300000, out_dev_ptr=dev.data_ptr())
+    torch.cuda.synchronize()
+    host, sc2 = vm.promql.eval_rollup_func_host("rate", descs, payload, start, end, step, 300000)
+    assert sc1 == sc2 == nb * (rows + 2 * P)
+    d = dev.cpu().numpy()
+    assert np.array_equal(f64bits(d), f64bits(host))
+    assert not np.isnan(d).any() and (d >= 0).all() and np.isfinite(d).all()
+    # sampled series against the oracle (decode with the oracle's own zstd decoder)
+    rc = vm.promql.get_rollup_configs("rate", start, end, step, 300000)
+    ts = bench.T0 + bench.SCRAPE_MS * np.arange(rows, dtype=np.int64)
+    for s in np.linspace(0, nb - 1, 16).astype(int):
+        dd = descs[s]
+        src = payload[int(dd["val_off"]):int(dd["val_off"]) + int(dd["val_size"])]
+        r, iv = oracle.unmarshal_int64_array(src, int(dd["val_mt"]), int(dd["first_value"]), rows)
+        assert r == 0
+        fv = oracle.decimal_to_float(iv, int(dd["scale"]))
+        oracle.lib().vmo_remove_counter_resets(fv.ctypes.data_as(oracle.f64p), ts.ctypes.data_as(oracle.i64p), rows, 0)
+        exp, _ = oracle.rollup_do(RF["rate"], fv, ts, start, end, step, 300000, may_adjust_window=True, samples_scanned_per_call=2)
+        assert np.allclose(d[s], exp, rtol=1e-12, atol=0), s

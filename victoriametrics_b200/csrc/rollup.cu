@@ -933,11 +933,17 @@ __global__ void __launch_bounds__(128) k_series_prepare(RollupParams P) {
 #define ROLLUP_CAP 2048    /* rows of one series resident in shared memory */
 #define ROLLUP_SEEKS 1024  /* grid times whose row index is shared by a tile */
 
-// first index with ts[idx] > x: interpolation guess + short walk, binary search when the walk does not converge
-__device__ __forceinline__ uint32_t seek_after(const int64_t* __restrict__ ts, uint32_t n, int64_t x, double inv_dt) {
-    if (n == 0 || ts[0] > x) return 0;
+// first index with ts[idx] > x: interpolation guess + short walk, binary search when the walk does not converge.
+// The guess is computed in fp32 from 32-bit offsets when the resident rows span < 2^31 ms (inv_dt > 0 signals that):
+// a guess only has to land near the answer, the walk makes it exact.
+__device__ __forceinline__ uint32_t seek_after(const int64_t* __restrict__ ts, uint32_t n, int64_t x, float inv_dt) {
+    if (n == 0) return 0;
+    const int64_t t0 = ts[0];
+    if (t0 > x) return 0;
     if (ts[n - 1] <= x) return n;
-    uint32_t g = (uint32_t)((double)(x - ts[0]) * inv_dt);
+    uint32_t g;
+    if (inv_dt > 0.0f) g = (uint32_t)(__uint2float_rn((uint32_t)(x - t0)) * inv_dt);
+    else g = n >> 1;
     if (g >= n) g = n - 1;
     if (ts[g] <= x) {
         uint32_t lim = g + 6 < n ? g + 6 : n;
@@ -951,29 +957,65 @@ __device__ __forceinline__ uint32_t seek_after(const int64_t* __restrict__ ts, u
     return g;
 }
 
-// one output point: rollup.go:769-819.  v/t are indexed by the row number inside the series; rows [i-1, j] must be readable.
+// (double)dt_ms / 1e3 exactly as IEEE division would round it: q = RN(x * RN(1/1000)), rem = x - q * 1000 (exact, FMA),
+// RN(q + rem * RN(1/1000)) -- Markstein's division step, valid for every finite x here (1000 is exact, no under/overflow
+// for |x| < 2^64).  Same trick as decimal->float in decode.cu; 3 flops instead of a ~25-instruction division sequence.
+__device__ __forceinline__ double ms_to_s(int64_t dt_ms) {
+    const double x = (double)dt_ms;
+    const double r = 1e-3;  // RN(1/1000)
+    double q = __dmul_rn(x, r);
+    double rem = __fma_rn(-q, 1e3, x);
+    return __fma_rn(rem, r, q);
+}
+
+// one output point: rollup.go:769-819.  v/t hold the rows [off, ...) of the series (shared-memory window or the whole
+// series with off == 0); rows [i-1, j] must be resident.
 template <int F>
 __device__ __forceinline__ double rollup_point(const vmb_rollup_cfg& rc, const SeriesMeta& m, const double* v, const int64_t* t,
-                                               uint32_t n, uint32_t i, uint32_t j, uint32_t p, unsigned long long& scanned) {
+                                               uint32_t off, uint32_t n, uint32_t i, uint32_t j, uint32_t p,
+                                               unsigned long long& scanned) {
     const int64_t tEnd = rc.start + (int64_t)p * rc.step;
     const int64_t tStart = tEnd - m.window;
     if (j < i) j = i;
+    const uint32_t ri = i - off, rj = j - off;  // indices into v / t
+    if (F == VMB_RF_RATE) {
+        // rollupDerivFast rollup.go:1954 on the rollupFuncArg doInternal would build (rollup.go:779-784), hand-flattened
+        scanned += rc.samples_scanned_per_call > 0 ? (unsigned long long)rc.samples_scanned_per_call : (unsigned long long)(j - i);
+        double pv = D_NAN;
+        int64_t pt = 0;
+        if (i < n && i > 0) {
+            int64_t tp = t[ri - 1];
+            if (tp > tStart - m.max_prev_interval) {
+                pv = v[ri - 1];
+                pt = tp;
+            }
+        }
+        const uint32_t nw = j - i;
+        if (isnan(pv)) {
+            if (nw < 2) return D_NAN;
+            pv = v[ri];
+            pt = t[ri];
+        } else if (nw == 0) {
+            return 0.0;
+        }
+        return (v[rj - 1] - pv) / ms_to_s(t[rj - 1] - pt);
+    }
     Win r;
     r.prevValue = D_NAN;
     r.prevTimestamp = tStart - m.max_prev_interval;
-    if (i < n && i > 0 && t[i - 1] > r.prevTimestamp) {
-        r.prevValue = v[i - 1];
-        r.prevTimestamp = t[i - 1];
+    if (i < n && i > 0 && t[ri - 1] > r.prevTimestamp) {
+        r.prevValue = v[ri - 1];
+        r.prevTimestamp = t[ri - 1];
     }
-    r.values = v + i;
-    r.timestamps = t + i;
+    r.values = v + ri;
+    r.timestamps = t + ri;
     r.n = j - i;
     r.realPrevValue = D_NAN;
     if (i > 0) {
-        int64_t curr = r.n > 0 ? t[i] : tStart;
-        if (rc.lookback_delta == 0 || (curr - t[i - 1]) < rc.lookback_delta) r.realPrevValue = v[i - 1];
+        int64_t curr = r.n > 0 ? t[ri] : tStart;
+        if (rc.lookback_delta == 0 || (curr - t[ri - 1]) < rc.lookback_delta) r.realPrevValue = v[ri - 1];
     }
-    r.realNextValue = j < n ? v[j] : D_NAN;
+    r.realNextValue = j < n ? v[rj] : D_NAN;
     r.currTimestamp = tEnd;
     r.idx = p;
     r.window = m.window;
@@ -1029,8 +1071,11 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
                 int64_t tl = s_ts[cnt - 1] - 1 - rc.start;
                 p_end = tl < 0 ? 0u : (uint32_t)min((int64_t)P.npoints, tl / rc.step + 1);
             }
-            double inv_dt = 0.0;
-            if (cnt > 1 && s_ts[cnt - 1] > s_ts[0]) inv_dt = (double)(cnt - 1) / (double)(s_ts[cnt - 1] - s_ts[0]);
+            float inv_dt = 0.0f;  // rows per millisecond over the resident range (0: no usable slope => bisect)
+            {
+                const int64_t span = cnt > 1 ? s_ts[cnt - 1] - s_ts[0] : 0;
+                if (span > 0 && span < (int64_t)0x7fffffff) inv_dt = __fdividef((float)(cnt - 1), (float)span);
+            }
             if (p_end <= p) {
                 // the window of point p needs more than CAP rows: do one tile from global memory
                 p_end = min(p + ROLLUP_THREADS, P.npoints);
@@ -1039,7 +1084,7 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
                     int64_t tEnd = rc.start + (int64_t)q * rc.step;
                     uint32_t i = upper_bound_ts(tg, n, tEnd - m.window);
                     uint32_t j = upper_bound_ts(tg, n, tEnd);
-                    out[q] = rollup_point<F>(rc, m, vg, tg, n, i, j, q, scanned);
+                    out[q] = rollup_point<F>(rc, m, vg, tg, 0u, n, i, j, q, scanned);
                 }
                 p = p_end;
                 if (p < P.npoints) {  // restart the resident range at the first row the next point needs
@@ -1050,8 +1095,6 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
                 continue;
             }
             // ---- tiles of ROLLUP_THREADS points
-            const double* v = s_val - base;  // so that v[row] / t[row] index by the row number inside the series
-            const int64_t* t = s_ts - base;
             for (uint32_t p0 = p; p0 < p_end; p0 += ROLLUP_THREADS) {
                 if (shared_seeks) {
                     __syncthreads();  // previous tile done with s_seek
@@ -1073,7 +1116,7 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
                         j = base + seek_after(s_ts, cnt, tEnd, inv_dt);
                     }
                     // rows before `base` are not resident: the slide rule below keeps row i-1 of the first point resident
-                    out[q] = rollup_point<F>(rc, m, v, t, n, i, j, q, scanned);
+                    out[q] = rollup_point<F>(rc, m, s_val, s_ts, base, n, i, j, q, scanned);
                 }
             }
             p = p_end;

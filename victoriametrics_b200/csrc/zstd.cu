@@ -721,15 +721,20 @@ __global__ void k_zstd_prepare(ZstdParams P) {
 #define HUF_FRAMES_PER_WARP 8
 #define HUF_TABLE_ENTRIES 2048
 #define HUF_RING 32 /* words of compressed input resident in shared memory per lane (power of two) */
+#define HUF_WARP_TABLE_BYTES (HUF_FRAMES_PER_WARP * (HUF_TABLE_ENTRIES + 256))
 
 __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
-    extern __shared__ unsigned short s_tab[];  // [HUF_WARPS * 8][2048]
+    // shared memory: per warp 8 x (2048-entry symbol table, u8) + 8 x (code length by symbol, 256 x u8), then the input rings.
+    // Splitting (symbol, length) into two byte tables costs a second dependent LDS per symbol but halves the footprint
+    // (2.25 KB instead of 4 KB per frame), so two CTAs fit an SM: two warps per scheduler hide each other's latency.
+    extern __shared__ __align__(16) uint8_t s_smem[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const uint32_t groups = (P.count + HUF_FRAMES_PER_WARP - 1) / HUF_FRAMES_PER_WARP;
-    unsigned short* wtab = s_tab + (size_t)warp * HUF_FRAMES_PER_WARP * HUF_TABLE_ENTRIES;
+    uint8_t* wtab = s_smem + (size_t)warp * HUF_WARP_TABLE_BYTES;
+    uint8_t* wnbs = wtab + HUF_FRAMES_PER_WARP * HUF_TABLE_ENTRIES;
     // per-warp input rings behind the tables: HUF_RING words per lane, word-interleaved across lanes
-    uint32_t* wring = (uint32_t*)(s_tab + (size_t)HUF_WARPS * HUF_FRAMES_PER_WARP * HUF_TABLE_ENTRIES) + (size_t)warp * HUF_RING * 32;
+    uint32_t* wring = (uint32_t*)(s_smem + (size_t)HUF_WARPS * HUF_WARP_TABLE_BYTES) + (size_t)warp * HUF_RING * 32;
     for (uint32_t g = blockIdx.x * HUF_WARPS + warp; g < groups; g += gridDim.x * HUF_WARPS) {
         // ---- build the 8 decode tables cooperatively: for frame f, entries are filled in (nbits desc, symbol asc) order
         for (int f = 0; f < HUF_FRAMES_PER_WARP; f++) {
@@ -738,10 +743,11 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
             const HufJob* job = &P.jobs[ji];
             if (job->nstreams == 0) continue;
             const int log = job->table_log;
-            unsigned short* tab = wtab + f * HUF_TABLE_ENTRIES;
+            uint8_t* tab = wtab + f * HUF_TABLE_ENTRIES;
             // each lane owns 8 symbols; start position of a symbol = sum over symbols that sort before it of 2^(log-nbits)
             uint32_t nb[8];
             uint64_t packed = *(const uint64_t*)(job->nbits + lane * 8);
+            *(uint64_t*)(wnbs + f * 256 + lane * 8) = packed;
 #pragma unroll
             for (int k = 0; k < 8; k++) nb[k] = (uint32_t)(packed >> (8 * k)) & 0xff;
             uint32_t start = 0;  // running table position
@@ -761,8 +767,8 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     if (nb[k] == (uint32_t)len) {
-                        unsigned short ent = (unsigned short)((len << 8) | (lane * 8 + k));
-                        for (uint32_t q = 0; q < span; q++) tab[(p + q) & (HUF_TABLE_ENTRIES - 1)] = ent;
+                        const uint8_t sym = (uint8_t)(lane * 8 + k);
+                        for (uint32_t q = 0; q < span; q++) tab[(p + q) & (HUF_TABLE_ENTRIES - 1)] = sym;
                         p += span;
                     }
                 }
@@ -780,7 +786,8 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
             bool ok = true;
             if (active) {
                 const int log = job->table_log;
-                const unsigned short* tab = wtab + f * HUF_TABLE_ENTRIES;
+                const uint8_t* tab = wtab + f * HUF_TABLE_ENTRIES;
+                const uint8_t* nbs = wnbs + f * 256;
                 uint32_t regen = job->regen_size;
                 uint32_t seg = job->nstreams == 1 ? regen : (regen + 3) / 4;
                 uint32_t count = job->nstreams == 1 ? regen : (s < 3 ? seg : regen - 3 * seg);
@@ -877,9 +884,9 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
     } while (0)
 #define HUF_SYM(outv, shift)                                                               \
     do {                                                                                   \
-        unsigned short ent_ = tab[(uint32_t)(buf >> sh_idx)];                              \
-        uint32_t nb_ = ent_ >> 8;                                                          \
-        outv |= (uint32_t)(ent_ & 0xff) << (shift);                                        \
+        uint32_t sym_ = tab[(uint32_t)(buf >> sh_idx)];                                    \
+        uint32_t nb_ = nbs[sym_];                                                          \
+        outv |= sym_ << (shift);                                                           \
         buf <<= nb_;                                                                       \
         cnt -= (int)nb_;                                                                   \
         used_bits += nb_;                                                                  \
@@ -990,15 +997,14 @@ void launch_zstd_prepare(const ZstdParams& P, cudaStream_t st) {
 static bool g_huf_attr_set = false;
 void launch_huf_decode(const ZstdParams& P, cudaStream_t st) {
     if (!P.count) return;
-    size_t smem = (size_t)HUF_WARPS * HUF_FRAMES_PER_WARP * HUF_TABLE_ENTRIES * sizeof(unsigned short) +
-                  (size_t)HUF_WARPS * HUF_RING * 32 * sizeof(uint32_t);
+    size_t smem = (size_t)HUF_WARPS * HUF_WARP_TABLE_BYTES + (size_t)HUF_WARPS * HUF_RING * 32 * sizeof(uint32_t);
     if (!g_huf_attr_set) {
         cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         g_huf_attr_set = true;
     }
     uint32_t groups = (P.count + HUF_FRAMES_PER_WARP - 1) / HUF_FRAMES_PER_WARP;
     uint32_t grid = (groups + HUF_WARPS - 1) / HUF_WARPS;
-    if (grid > 148u * 4u) grid = 148u * 4u;
+    if (grid > 148u * 8u) grid = 148u * 8u;
     k_huf_decode<<<grid, HUF_WARPS * 32, smem, st>>>(P);
 }
 
