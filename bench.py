@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--window-ms", type=int, default=300_000)
     ap.add_argument("--step-ms", type=int, default=15_000)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--aggr", default="", help="configs[4] variant: aggr(func(m[d])) by (label) with an NCCL all-reduce of the "
+                                               "per-GPU partial states, e.g. --aggr sum (kernel-only numbers; no e2e leg)")
+    ap.add_argument("--groups", type=int, default=1000, help="label groups for --aggr")
     ap.add_argument("--cpu-seconds", type=float, default=24.0, help="target CPU work of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -255,6 +258,30 @@ def main():
 
     def dev_step():
         return promql.eval_rollup_func(a.func, blocks, start, end, step, a.window_ms, out_dev_ptr=out_dev.data_ptr())
+
+    if a.aggr:
+        # sum(rate(m[5m])) by (label): every rank folds its own series into [groups x points] partial states, one NCCL
+        # all-reduce of values and one of counts merges them, every rank finalizes
+        a.no_e2e = True
+        rc_aggr = promql.get_rollup_configs(a.func, start, end, step, a.window_ms)
+        group_ids = ((np.arange(a.blocks, dtype=np.int64) * world + rank) % a.groups).astype(np.uint32)
+
+        class Buf:
+            def __init__(self, nbytes):
+                self.t = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+                self.ptr = self.t.data_ptr()
+        ia = promql.IncrementalAggr(a.aggr, a.groups, points, Buf)
+        reduce_cb = (lambda v, c, op: promql.torch_all_reduce(v.t, c.t, op)) if world > 1 else None
+        aggr_out = [None]
+
+        def dev_step():  # noqa: F811
+            scanned_ = ia.update_blocks(blocks, rc_aggr, group_ids)
+            aggr_out[0] = ia.finalize(ctx, all_reduce=reduce_cb)
+            return None, scanned_
+        base["metric"] = "rollup samples/sec (block decode + %s(%s) by label, raw samples decoded and scanned per second)" % (a.aggr, a.func)
+        base["config"]["workload"] = workload.replace("configs[1]", "configs[4]-style") + "; %s by %d groups" % (a.aggr, a.groups)
+        base["config"]["parallelism"] = ("series sharded by TSID across %d GPU(s); per-GPU partial [groups x points] states merged by "
+                                         "NCCL all-reduce (values: %s, counts: sum)" % (a.gpus, promql.ALLREDUCE_OP[a.aggr]))
 
     # ---- kernel-only: compressed blocks resident in HBM
     for _ in range(a.warmup):

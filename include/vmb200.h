@@ -208,6 +208,12 @@ int vmb_eval_rollup_host(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nbloc
 int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* blocks, int64_t tr_min, int64_t tr_max,
                            const vmb_rollup_cfg* cfg, double* d_out, uint64_t* samples_scanned);
 
+/* aggregate variant of the device-resident path: decode + preamble + rollup + vmb_rollup_aggr_partial in one call, decoded
+ * columns cached in the library (per-rank step of `aggr(rollup(m[d])) by (...)`, eval.go:1804) */
+int vmb_eval_rollup_aggr_device(vmb_ctx* ctx, const vmb_blocks* blocks, int64_t tr_min, int64_t tr_max,
+                                const vmb_rollup_cfg* cfg, int aggr_id, const uint32_t* group_ids, uint32_t ngroups,
+                                double* d_values, double* d_counts, uint64_t* samples_scanned);
+
 /* pinned host memory helpers (cudaHostAlloc) for callers that want full PCIe speed */
 void* vmb_host_alloc(size_t bytes);
 void vmb_host_free(void* p);

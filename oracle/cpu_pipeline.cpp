@@ -78,8 +78,6 @@ int vmo_cpu_eval_rollup(const vmo_block_desc* descs, size_t nblocks, const uint8
                 }
             }
             int64_t first_ts_save = d.min_ts;
-            vmo_block_header bh2 = bh;
-            bh2.min_ts = bh.min_ts;
             // UnmarshalTimestamps needs the real first timestamp even when the bounds check is disabled
             int64_t n;
             if (bh.min_ts == INT64_MIN) {

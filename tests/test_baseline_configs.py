@@ -133,6 +133,12 @@ def test_config3_sum_rate_by_label_single_rank(oracle):
     for g in range(G):
         oracle.lib().vmo_aggr_finalize(AGGR["sum"], exp_v[g].ctypes.data_as(oracle.f64p), exp_c[g].ctypes.data_as(oracle.f64p), rc.points)
     assert np.allclose(got, exp_v, rtol=1e-12, atol=0, equal_nan=True)
+    # the one-call variant on compressed device blocks (vmb_eval_rollup_aggr_device) yields the same bits
+    ia2 = vm.promql.IncrementalAggr("sum", G, rc.points, Buf)
+    scanned = ia2.update_blocks(B, rc, groups)
+    got2 = ia2.finalize(vm.default_context())
+    assert np.array_equal(got, got2, equal_nan=True)
+    assert scanned > 0
 
 
 @pytest.mark.gpu

@@ -87,6 +87,8 @@ def lib():
         "vmb_eval_rollup_host": (C.c_int, [vp, C.POINTER(BlockDesc), sz, u8p, sz, C.c_int64, C.c_int64,
                                            C.POINTER(RollupCfg), f64p, i32p, u64p]),
         "vmb_eval_rollup_device": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.POINTER(RollupCfg), vp, u64p]),
+        "vmb_eval_rollup_aggr_device": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.POINTER(RollupCfg), C.c_int, u32p, C.c_uint32,
+                                                  vp, vp, u64p]),
         "vmb_host_alloc": (vp, [sz]),
         "vmb_host_free": (None, [vp]),
         "vmb_ctx_last_stage_ms": (C.c_float, [vp, C.c_int]),

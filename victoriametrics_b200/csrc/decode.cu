@@ -8,10 +8,10 @@
 //   lib/storage/block.go:324-349   AppendRowsWithTimeRangeFilter / filterTimestamps
 //   lib/decimal/decimal.go:100     AppendDecimalToFloat
 //
-// Layout: a warp walks the varint byte stream in 512-byte tiles, 16 bytes per lane.  A value belongs to the lane
-// that holds its terminating byte; the bytes it starts with in the previous lane's chunk arrive by shuffle.  Per-lane
-// partial sums are combined with one warp scan per tile ((count, sum, sum-of-prefix-sums) is an associative triple
-// under wrapping int64 arithmetic), so the result is bit-identical to the sequential Go loop.
+// Layout: a warp walks the varint byte stream in 512-byte tiles (decode_stream.cuh): terminators are found byte-major,
+// the values are then dealt out value-major, and per-lane partial sums are combined with one warp scan per tile
+// ((count, sum, sum-of-prefix-sums) is an associative triple under wrapping int64 arithmetic), so the result is
+// bit-identical to the sequential Go loop.
 #include "common.cuh"
 
 namespace {
@@ -102,171 +102,6 @@ struct ValEmit {
 __device__ __forceinline__ uint32_t term_mask4(uint32_t w) {
     uint32_t t = ~w & 0x80808080u;
     return ((t >> 7) & 1u) | ((t >> 14) & 2u) | ((t >> 21) & 4u) | ((t >> 28) & 8u);
-}
-
-// Decodes a nearest-delta (delta2 == false) or nearest-delta2 stream of n-1 varints into n values.
-// Returns 0 or a VMB_ERR_* (uniform across the warp).
-template <class E>
-__device__ int decode_delta_stream(const uint8_t* __restrict__ src, uint32_t len, uint32_t n, int64_t first, bool delta2,
-                                   E& em) {
-    const int lane = lane_id();
-    if (n < (delta2 ? 2u : 1u)) return VMB_ERR_ROWS;  // Go: logger.Panicf("BUG: itemsCount ...")
-    const uint32_t nvar = n - 1;
-    if (len < nvar) return VMB_ERR_SHORT_SRC;  // int.go:183
-    if (lane == 0) em.emit(0, first, first);
-    uint32_t N = 0;           // varints consumed so far
-    uint64_t D1 = 0;          // running first-order delta (delta2 only)
-    uint64_t V = (uint64_t)first;
-    uint32_t cc1 = 0, cc2 = 0, cc3 = 0;  // last 9 bytes of the previous tile's lane 31
-    uint32_t carry_len_tile = 0;
-    int err = 0;  // lane-local error code (0 / negative)
-
-    for (uint32_t tile = 0; tile < len; tile += 512) {
-        const uint32_t o = tile + (uint32_t)lane * 16u;
-        const uint32_t valid = o >= len ? 0u : (len - o >= 16u ? 16u : len - o);
-        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        if (valid) {
-            uintptr_t a = (uintptr_t)(src + o);
-            const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
-            uint32_t sh = (uint32_t)(a & 3) * 8;
-            uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-            if (sh) {
-                uint32_t w4 = w[4];
-                c0 = __funnelshift_r(w0, w1, sh);
-                c1 = __funnelshift_r(w1, w2, sh);
-                c2 = __funnelshift_r(w2, w3, sh);
-                c3 = __funnelshift_r(w3, w4, sh);
-            } else {
-                c0 = w0; c1 = w1; c2 = w2; c3 = w3;
-            }
-        }
-        uint32_t m = term_mask4(c0) | (term_mask4(c1) << 4) | (term_mask4(c2) << 8) | (term_mask4(c3) << 12);
-        m &= valid >= 16 ? 0xffffu : ((1u << valid) - 1u);
-        // bytes after my last terminator carry over into the next lane
-        uint32_t tail_len;
-        if (m) tail_len = valid - 1u - (31u - (uint32_t)__clz((int)m));
-        else {
-            tail_len = valid;  // no terminator at all in a non-empty chunk is always an error (varints are <= 10 bytes)
-            if (valid == 16) err = VMB_ERR_VARINT_TOO_LONG;
-        }
-        uint32_t p1 = __shfl_up_sync(VMB_FULL, c1, 1), p2 = __shfl_up_sync(VMB_FULL, c2, 1), p3 = __shfl_up_sync(VMB_FULL, c3, 1);
-        uint32_t carry_len = __shfl_up_sync(VMB_FULL, tail_len, 1);
-        if (lane == 0) { p1 = cc1; p2 = cc2; p3 = cc3; carry_len = carry_len_tile; }
-        if (carry_len > 9) { err = VMB_ERR_VARINT_TOO_LONG; carry_len = 9; }
-        if (!valid) carry_len = 0;
-
-        // ---- parse: value k ends at byte k of my chunk
-        int64_t val[16];
-        uint64_t acc = 0;
-        uint32_t shift = 0;
-        {
-            // previous chunk bytes 7..15 == (p1 >> 24), p2[0..3], p3[0..3]
-            const uint32_t skip = 9u - carry_len;
-#pragma unroll
-            for (int k = 0; k < 9; k++) {
-                uint32_t b = k == 0 ? (p1 >> 24) : (k <= 4 ? (p2 >> (8 * (k - 1))) : (p3 >> (8 * (k - 5))));
-                b &= 0x7fu;
-                if ((uint32_t)k >= skip) {
-                    acc |= (uint64_t)b << shift;
-                    shift += 7;
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            uint32_t wsel = k < 4 ? c0 : (k < 8 ? c1 : (k < 12 ? c2 : c3));
-            uint32_t b = (wsel >> (8 * (k & 3))) & 0xffu;
-            val[k] = 0;
-            if ((uint32_t)k < valid) {
-                if (shift >= 63) {  // 10th byte: int.go:269-275
-                    if (b >= 0x80u) err = VMB_ERR_VARINT_TOO_LONG;
-                    else {
-                        if (b > 1u) err = VMB_ERR_VARINT_TOO_BIG;
-                        acc |= (uint64_t)1 << 63;
-                    }
-                } else {
-                    acc |= (uint64_t)(b & 0x7fu) << shift;
-                }
-                if (b < 0x80u) {
-                    val[k] = (int64_t)(acc >> 1) ^ -(int64_t)(acc & 1);  // zig-zag decode int.go:82
-                    acc = 0;
-                    shift = 0;
-                } else {
-                    shift = shift >= 56 ? 63 : shift + 7;
-                }
-            }
-        }
-        // ---- per-lane aggregates
-        uint32_t cnt = (uint32_t)__popc(m);
-        uint64_t s1 = 0, s2 = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if ((m >> k) & 1u) {
-                s1 += (uint64_t)val[k];
-                s2 += s1;
-            }
-        }
-        // ---- inclusive warp scan of (cnt, s1, s2); combine(A then B): s2 = s2A + s2B + cntB * s1A
-        uint32_t icnt = cnt;
-        uint64_t is1 = s1, is2 = s2;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            uint32_t acnt = __shfl_up_sync(VMB_FULL, icnt, off);
-            uint64_t as1 = shfl_up_u64(is1, off);
-            uint64_t as2 = shfl_up_u64(is2, off);
-            if (lane >= off) {
-                if (delta2) is2 = as2 + is2 + (uint64_t)icnt * as1;
-                is1 += as1;
-                icnt += acnt;
-            }
-        }
-        uint32_t ecnt = __shfl_up_sync(VMB_FULL, icnt, 1);
-        uint64_t es1 = shfl_up_u64(is1, 1), es2 = shfl_up_u64(is2, 1);
-        if (lane == 0) { ecnt = 0; es1 = 0; es2 = 0; }
-        // ---- emit
-        uint32_t pos = 1u + N + ecnt;
-        uint64_t d1 = D1 + es1;
-        uint64_t v = delta2 ? (V + es2 + (uint64_t)ecnt * D1) : (V + es1);
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if ((m >> k) & 1u) {
-                uint64_t pv = v;
-                if (delta2) {
-                    d1 += (uint64_t)val[k];
-                    v += d1;
-                } else {
-                    v += (uint64_t)val[k];
-                }
-                if (pos < n) em.emit(pos, (int64_t)v, (int64_t)pv);
-                pos++;
-            }
-        }
-        // ---- tile carries
-        uint32_t tcnt = __shfl_sync(VMB_FULL, icnt, 31);
-        uint64_t ts1 = shfl_u64(is1, 31), ts2 = shfl_u64(is2, 31);
-        if (delta2) {
-            V += ts2 + (uint64_t)tcnt * D1;
-            D1 += ts1;
-        } else {
-            V += ts1;
-        }
-        N += tcnt;
-        cc1 = __shfl_sync(VMB_FULL, c1, 31);
-        cc2 = __shfl_sync(VMB_FULL, c2, 31);
-        cc3 = __shfl_sync(VMB_FULL, c3, 31);
-        carry_len_tile = __shfl_sync(VMB_FULL, tail_len, 31);
-    }
-    // ---- stream-level checks (uniform)
-    int werr = 0;
-#pragma unroll
-    for (int off = 16; off; off >>= 1) err = min(err, __shfl_xor_sync(VMB_FULL, err, off));  // most negative wins
-    werr = err;
-    if (werr == 0) {
-        bool ends_ok = len == 0 || src[len - 1] < 0x80;
-        if (N < nvar) werr = VMB_ERR_SHORT_SRC;        // int.go:199 "cannot unmarshal varint from empty data"
-        else if (N > nvar || !ends_ok) werr = VMB_ERR_TAIL;  // nearest_delta.go:65 unexpected tail
-    }
-    return werr;
 }
 
 // UnmarshalVarInt64 int.go:173 (binary.Uvarint + zig-zag) on <= 11 bytes, executed redundantly by every lane

@@ -9,8 +9,9 @@
 //   k_zstd_prepare : one thread per frame of the common shape (one Compressed block, Huffman-coded literals):
 //                    parses headers + the Huffman tree description into a HufJob.
 //   k_huf_decode   : the hot one. Lane-packed: every lane owns ONE Huffman bitstream (4 per frame => 8 frames per
-//                    warp), decode tables live in shared memory, streams are read backwards through a 64-bit
-//                    register window refilled with aligned 32-bit loads, output is written as aligned 32-bit words.
+//                    warp); decode tables (symbol by code prefix, length by symbol) live in shared memory; the
+//                    compressed stream reaches the lane through a private shared-memory ring that is filled by
+//                    warp-uniform 16-byte loads issued two phases ahead; output leaves as aligned 16-byte stores.
 //   k_zstd_serial  : one thread per frame: (a) executes the sequences section of prepared frames, (b) decodes any
 //                    frame of another shape (raw/RLE blocks, multi-block, raw/RLE/treeless literals) completely.
 #include "common.cuh"
@@ -19,7 +20,6 @@
 namespace {
 
 __device__ __forceinline__ int hb32(uint32_t v) { return 31 - __clz((int)v); }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // backward bitstream (RFC 8878 4.1): MSB-aligned 64-bit window
 struct BitR {

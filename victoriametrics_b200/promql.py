@@ -195,6 +195,17 @@ class IncrementalAggr:
                                             C.c_void_p(rolled_scratch_ptr or 0), C.byref(scanned)))
         return scanned.value
 
+    def update_blocks(self, blocks, rc, group_ids, tr_min=storage.INT64_MIN, tr_max=storage.INT64_MAX):
+        """decode + preamble + rollup + fold of device-resident compressed blocks in one library call
+        (vmb_eval_rollup_aggr_device); the decoded columns stay in a library-side cache"""
+        g = np.ascontiguousarray(group_ids, dtype=np.uint32)
+        cfg = rc._cfg()
+        scanned = C.c_uint64(0)
+        check(lib().vmb_eval_rollup_aggr_device(blocks.ctx.h, blocks.h, tr_min, tr_max, C.byref(cfg), self.aggr,
+                                                g.ctypes.data_as(_lib.u32p), self.ngroups, C.c_void_p(self.values.ptr),
+                                                C.c_void_p(self.counts.ptr), C.byref(scanned)))
+        return scanned.value
+
     def finalize(self, ctx, all_reduce=None):
         """all_reduce(values_buf, counts_buf, op) is called between prepare and finalize when given"""
         n = self.ngroups * self.points
