@@ -272,11 +272,13 @@ def main():
                 self.ptr = self.t.data_ptr()
         ia = promql.IncrementalAggr(a.aggr, a.groups, points, Buf)
         reduce_cb = (lambda v, c, op: promql.torch_all_reduce(v.t, c.t, op)) if world > 1 else None
-        aggr_out = [None]
+        h_aggr = _lib.lib().vmb_host_alloc(a.groups * points * 8)
+        assert h_aggr, "pinned host allocation failed"
+        aggr_host = np.ctypeslib.as_array(C.cast(h_aggr, C.POINTER(C.c_double)), shape=(a.groups, points))
 
         def dev_step():  # noqa: F811
             scanned_ = ia.update_blocks(blocks, rc_aggr, group_ids)
-            aggr_out[0] = ia.finalize(ctx, all_reduce=reduce_cb)
+            ia.finalize(ctx, all_reduce=reduce_cb, out=aggr_host)  # D2H of the [groups x points] query result included
             return None, scanned_
         base["metric"] = "rollup samples/sec (block decode + %s(%s) by label, raw samples decoded and scanned per second)" % (a.aggr, a.func)
         base["config"]["workload"] = workload.replace("configs[1]", "configs[4]-style") + "; %s by %d groups" % (a.aggr, a.groups)

@@ -206,15 +206,18 @@ class IncrementalAggr:
                                                 C.c_void_p(self.counts.ptr), C.byref(scanned)))
         return scanned.value
 
-    def finalize(self, ctx, all_reduce=None):
-        """all_reduce(values_buf, counts_buf, op) is called between prepare and finalize when given"""
+    def finalize(self, ctx, all_reduce=None, out=None):
+        """all_reduce(values_buf, counts_buf, op) is called between prepare and finalize when given; `out` may be a
+        preallocated (ideally pinned, vmb_host_alloc) [ngroups x points] float64 array"""
         n = self.ngroups * self.points
         if all_reduce is not None:
             check(lib().vmb_aggr_prepare_allreduce(ctx.h, self.aggr, C.c_void_p(self.values.ptr), C.c_void_p(self.counts.ptr), n))
             ctx.synchronize()
             op = {"min": "min", "max": "max", "geomean": "prod"}.get(self.name, "sum")
             all_reduce(self.values, self.counts, op)
-        out = np.empty((self.ngroups, self.points), dtype=np.float64)
+        if out is None:
+            out = np.empty((self.ngroups, self.points), dtype=np.float64)
+        assert out.dtype == np.float64 and out.size == n and out.flags.c_contiguous
         check(lib().vmb_aggr_finalize(ctx.h, self.aggr, C.c_void_p(self.values.ptr), C.c_void_p(self.counts.ptr), n,
                                       out.ctypes.data_as(_lib.f64p)))
         return out
