@@ -931,7 +931,7 @@ __global__ void __launch_bounds__(128) k_series_prepare(RollupParams P) {
 
 #define ROLLUP_THREADS 256
 #define ROLLUP_CAP 2048    /* rows of one series resident in shared memory */
-#define ROLLUP_SEEKS 1024  /* grid times whose row index is shared by a tile */
+#define ROLLUP_SEEKS 2560  /* window edges of one fill: up to ROLLUP_CAP points + window/step shared left edges */
 
 // first index with ts[idx] > x: interpolation guess + short walk, binary search when the walk does not converge.
 // The guess is computed in fp32 from 32-bit offsets when the resident rows span < 2^31 ms (inv_dt > 0 signals that):
@@ -955,6 +955,25 @@ __device__ __forceinline__ uint32_t seek_after(const int64_t* __restrict__ ts, u
     while (g > lim && ts[g - 1] > x) g--;
     if (g > 0 && ts[g - 1] > x) g = upper_bound_ts(ts, g, x);
     return g;
+}
+
+// seek_after over the resident rows with the first / last resident timestamps already in registers and the common case
+// (regular scrape interval: the guess is the answer or one off) decided from three independent loads.
+__device__ __forceinline__ uint32_t seek_resident(const int64_t* __restrict__ ts, uint32_t n, int64_t x, float inv_dt,
+                                                  int64_t t_first, int64_t t_last) {
+    if (n == 0 || t_first > x) return 0;
+    if (t_last <= x) return n;
+    if (inv_dt > 0.0f) {  // here n >= 2 and t_first <= x < t_last
+        uint32_t g = (uint32_t)(__uint2float_rn((uint32_t)(x - t_first)) * inv_dt) + 1u;
+        if (g > n - 1) g = n - 1;
+        const uint32_t g2 = g + 1 < n ? g + 1 : g;
+        const int64_t a = ts[g - 1], b = ts[g], c = ts[g2];
+        if (a <= x) {
+            if (x < b) return g;
+            if (x < c) return g2;
+        }
+    }
+    return seek_after(ts, n, x, inv_dt);
 }
 
 // (double)dt_ms / 1e3 exactly as IEEE division would round it: q = RN(x * RN(1/1000)), rem = x - q * 1000 (exact, FMA),
@@ -1027,11 +1046,11 @@ __device__ __forceinline__ double rollup_point(const vmb_rollup_cfg& rc, const S
 
 // Streaming rollup: one CTA walks one series front to back.  Rows are pulled into shared memory once, in order, with
 // coalesced loads (no per-tile searches in global memory); the CTA computes every output point whose window lies inside the
-// resident rows (one thread per point, tiles of ROLLUP_THREADS points), then slides the resident range forward keeping only
+// resident rows (threads stride over the points of the fill), then slides the resident range forward keeping only
 // the rows the next point still needs.  Both the samples and the output grid are time-ordered, so this visits each row once.
 //
 // Window seeks: when the window is a multiple of the step (rate(m[5m]) at step 15 s: 20 steps), the left edge of point p is
-// the right edge of point p - window/step, so a tile computes ONE seek per grid time (s_seek[]) instead of two per point.
+// the right edge of point p - window/step, so a fill computes ONE seek per grid time (s_seek[]) instead of two per point.
 //
 // A window that does not fit ROLLUP_CAP rows (huge windows / very dense series) is handled for that tile by reading global
 // memory directly.  F >= 0 instantiates the kernel for one rollup function (the switch in call_func folds away).
@@ -1051,7 +1070,8 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
         double* out = P.out + (size_t)s * P.npoints;
         if (tid == 0) scanned += n;  // samplesScanned starts at len(values) rollup.go:766
         const uint32_t wsteps = (uint32_t)(m.window / rc.step);
-        const bool shared_seeks = (m.window % rc.step) == 0 && wsteps + ROLLUP_THREADS <= ROLLUP_SEEKS;
+        const bool shared_seeks = (m.window % rc.step) == 0 && wsteps <= ROLLUP_SEEKS - ROLLUP_CAP;
+        const uint32_t wsteps_cap = shared_seeks ? wsteps : 0u;
         uint32_t base = 0, cnt = 0, p = 0;
         while (p < P.npoints) {
             // ---- fill: rows [base + cnt, min(n, base + CAP))
@@ -1094,29 +1114,28 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
                 }
                 continue;
             }
-            // ---- tiles of ROLLUP_THREADS points
-            for (uint32_t p0 = p; p0 < p_end; p0 += ROLLUP_THREADS) {
-                if (shared_seeks) {
-                    __syncthreads();  // previous tile done with s_seek
-                    for (uint32_t q = tid; q < ROLLUP_THREADS + wsteps; q += ROLLUP_THREADS) {
-                        int64_t x = rc.start + ((int64_t)p0 + (int64_t)q - (int64_t)wsteps) * rc.step;
-                        s_seek[q] = base + seek_after(s_ts, cnt, x, inv_dt);
-                    }
-                    __syncthreads();
-                }
-                const uint32_t q = p0 + tid;
-                if (q < p_end) {
-                    uint32_t i, j;
-                    if (shared_seeks) {
-                        i = s_seek[tid];
-                        j = s_seek[tid + wsteps];
-                    } else {
-                        int64_t tEnd = rc.start + (int64_t)q * rc.step;
-                        i = base + seek_after(s_ts, cnt, tEnd - m.window, inv_dt);
-                        j = base + seek_after(s_ts, cnt, tEnd, inv_dt);
-                    }
+            // ---- the points of this fill, in two passes without barriers inside: every window edge first (shared by the
+            //      points when the window is a whole number of steps), then the points.  Iterations are independent, so
+            //      the shared-memory latencies of several points of one thread overlap.
+            if (p_end - p > ROLLUP_SEEKS - wsteps_cap) p_end = p + (ROLLUP_SEEKS - wsteps_cap);
+            const uint32_t np = p_end - p;
+            const int64_t t_first = cnt ? s_ts[0] : 0, t_last = cnt ? s_ts[cnt - 1] : 0;
+            if (shared_seeks) {
+                const int64_t x0 = rc.start + ((int64_t)p - (int64_t)wsteps) * rc.step;
+#pragma unroll 2
+                for (uint32_t q = tid; q < np + wsteps; q += ROLLUP_THREADS)
+                    s_seek[q] = base + seek_resident(s_ts, cnt, x0 + (int64_t)q * rc.step, inv_dt, t_first, t_last);
+                __syncthreads();
+#pragma unroll 2
+                for (uint32_t q = tid; q < np; q += ROLLUP_THREADS)
+                    out[p + q] = rollup_point<F>(rc, m, s_val, s_ts, base, n, s_seek[q], s_seek[q + wsteps], p + q, scanned);
+            } else {
+                for (uint32_t q = tid; q < np; q += ROLLUP_THREADS) {
+                    const int64_t tEnd = rc.start + (int64_t)(p + q) * rc.step;
+                    const uint32_t i = base + seek_resident(s_ts, cnt, tEnd - m.window, inv_dt, t_first, t_last);
+                    const uint32_t j = base + seek_resident(s_ts, cnt, tEnd, inv_dt, t_first, t_last);
                     // rows before `base` are not resident: the slide rule below keeps row i-1 of the first point resident
-                    out[q] = rollup_point<F>(rc, m, s_val, s_ts, base, n, i, j, q, scanned);
+                    out[p + q] = rollup_point<F>(rc, m, s_val, s_ts, base, n, i, j, p + q, scanned);
                 }
             }
             p = p_end;
