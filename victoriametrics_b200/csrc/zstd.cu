@@ -717,42 +717,49 @@ __global__ void k_zstd_prepare(ZstdParams P) {
 }
 
 // ---- lane-packed Huffman decode: 8 frames x 4 streams per warp
-#define HUF_WARPS 4
+#define HUF_WARPS 2
 #define HUF_FRAMES_PER_WARP 8
-#define HUF_TABLE_ENTRIES 2048
+#define HUF_MAX_LOG 11
 #define HUF_RING 32 /* words of compressed input resident in shared memory per lane (power of two) */
-#define HUF_WARP_TABLE_BYTES (HUF_FRAMES_PER_WARP * (HUF_TABLE_ENTRIES + 256))
+#define HUF_FRAME_BYTES (256 + 64) /* per frame: symbols in canonical order, then 10 thresholds (f32) + 12 index offsets (i16) */
+#define HUF_WARP_TABLE_BYTES (HUF_FRAMES_PER_WARP * HUF_FRAME_BYTES)
+#define HUF_FBIAS 0x4B000000u /* bits of 2^23: (HUF_FBIAS | v) is the float 2^23 + v for v < 2^23 */
 
 __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
-    // shared memory: per warp 8 x (2048-entry symbol table, u8) + 8 x (code length by symbol, 256 x u8), then the input rings.
-    // Splitting (symbol, length) into two byte tables costs a second dependent LDS per symbol but halves the footprint
-    // (2.25 KB instead of 4 KB per frame), so two CTAs fit an SM: two warps per scheduler hide each other's latency.
+    // Canonical decode without a 2^log-entry lookup table.  zstd lays a frame's codes out by descending length over the
+    // 11-bit (left-aligned) code space, so the length of the next code is 1 + #{k : v < S_k} where S_k is the position
+    // where the k-bit codes start: ten register-resident thresholds, ten compares, an add tree -- arithmetic only, no
+    // shared-memory access on the loop-carried path (the bit buffer advances as soon as the length is known).  The symbol
+    // is perm[(v >> (11 - L)) + adj[L]]: two small lookups off the critical path.  Per frame that is 320 bytes of shared
+    // memory instead of a 2048-entry table, so the SM holds every warp the grid has instead of two per scheduler.
     extern __shared__ __align__(16) uint8_t s_smem[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const uint32_t groups = (P.count + HUF_FRAMES_PER_WARP - 1) / HUF_FRAMES_PER_WARP;
     uint8_t* wtab = s_smem + (size_t)warp * HUF_WARP_TABLE_BYTES;
-    uint8_t* wnbs = wtab + HUF_FRAMES_PER_WARP * HUF_TABLE_ENTRIES;
     // per-warp input rings behind the tables: HUF_RING words per lane, word-interleaved across lanes
     uint32_t* wring = (uint32_t*)(s_smem + (size_t)HUF_WARPS * HUF_WARP_TABLE_BYTES) + (size_t)warp * HUF_RING * 32;
     for (uint32_t g = blockIdx.x * HUF_WARPS + warp; g < groups; g += gridDim.x * HUF_WARPS) {
-        // ---- build the 8 decode tables cooperatively: for frame f, entries are filled in (nbits desc, symbol asc) order
+        // ---- build the 8 canonical tables cooperatively: symbols in (nbits desc, symbol asc) order
         for (int f = 0; f < HUF_FRAMES_PER_WARP; f++) {
             uint32_t ji = g * HUF_FRAMES_PER_WARP + f;
             if (ji >= P.count) break;
             const HufJob* job = &P.jobs[ji];
             if (job->nstreams == 0) continue;
             const int log = job->table_log;
-            uint8_t* tab = wtab + f * HUF_TABLE_ENTRIES;
-            // each lane owns 8 symbols; start position of a symbol = sum over symbols that sort before it of 2^(log-nbits)
+            uint8_t* perm = wtab + f * HUF_FRAME_BYTES;
+            float* thr = (float*)(perm + 256);   // thr[k-1] = 2^23 + S_k, k = 1..10
+            short* adj = (short*)(perm + 256 + 40);  // adj[L], L = 1..11
+            // each lane owns 8 symbols
             uint32_t nb[8];
             uint64_t packed = *(const uint64_t*)(job->nbits + lane * 8);
-            *(uint64_t*)(wnbs + f * 256 + lane * 8) = packed;
 #pragma unroll
             for (int k = 0; k < 8; k++) nb[k] = (uint32_t)(packed >> (8 * k)) & 0xff;
-            uint32_t start = 0;  // running table position
+            uint32_t start = 0;  // S_len in the 11-bit code space
+            uint32_t rank = 0;   // symbols with longer codes
+            if (lane < 10) thr[lane] = __uint_as_float(HUF_FBIAS);  // k >= log: no k-bit codes above v, never counted
+            __syncwarp();
             for (int len = log; len >= 1; len--) {
-                uint32_t span = 1u << (log - len);
                 uint32_t mine = 0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) mine += (nb[k] == (uint32_t)len);
@@ -763,16 +770,17 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
                     if (lane >= off) inc += t;
                 }
                 uint32_t tot = __shfl_sync(VMB_FULL, inc, 31);
-                uint32_t p = start + (inc - mine) * span;
+                if (lane == 0) {
+                    if (len <= 10) thr[len - 1] = __uint_as_float(HUF_FBIAS | start);
+                    adj[len] = (short)((int)rank - (int)(start >> (HUF_MAX_LOG - len)));
+                }
+                uint32_t r = rank + inc - mine;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    if (nb[k] == (uint32_t)len) {
-                        const uint8_t sym = (uint8_t)(lane * 8 + k);
-                        for (uint32_t q = 0; q < span; q++) tab[(p + q) & (HUF_TABLE_ENTRIES - 1)] = sym;
-                        p += span;
-                    }
+                    if (nb[k] == (uint32_t)len) perm[r++ & 255u] = (uint8_t)(lane * 8 + k);
                 }
-                start += tot * span;
+                rank += tot;
+                start += tot << (HUF_MAX_LOG - len);
             }
         }
         __syncwarp();
@@ -785,9 +793,16 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
             if (active && (job->nstreams == 0 || s >= job->nstreams)) active = false;
             bool ok = true;
             if (active) {
-                const int log = job->table_log;
-                const uint8_t* tab = wtab + f * HUF_TABLE_ENTRIES;
-                const uint8_t* nbs = wnbs + f * 256;
+                const uint8_t* perm = wtab + f * HUF_FRAME_BYTES;
+                const short* adj = (const short*)(perm + 256 + 40);
+                float th[10];
+                {
+                    const float4 a4 = *(const float4*)(perm + 256), b4 = *(const float4*)(perm + 272);
+                    const float2 c2 = *(const float2*)(perm + 288);
+                    th[0] = a4.x; th[1] = a4.y; th[2] = a4.z; th[3] = a4.w;
+                    th[4] = b4.x; th[5] = b4.y; th[6] = b4.z; th[7] = b4.w;
+                    th[8] = c2.x; th[9] = c2.y;
+                }
                 uint32_t regen = job->regen_size;
                 uint32_t seg = job->nstreams == 1 ? regen : (regen + 3) / 4;
                 uint32_t count = job->nstreams == 1 ? regen : (s < 3 ? seg : regen - 3 * seg);
@@ -856,7 +871,6 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
                     uint4 pendA = make_uint4(0, 0, 0, 0), pendB = make_uint4(0, 0, 0, 0);
                     bool hasA = false, hasB = false;
                     uint32_t cand = ring[(rd & (HUF_RING - 1)) * 32];
-                    const int sh_idx = 64 - log;
 #define HUF_PHASE(pend, has)                                                               \
     do {                                                                                   \
         if (has) { /* block fetched two phases ago: now in registers for sure */           \
@@ -882,14 +896,21 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
         }                                                                                  \
         cand = ring[(rd & (HUF_RING - 1)) * 32];                                           \
     } while (0)
+#define HUF_LT(k) (vf_ < th[k] ? 1.0f : 0.0f)
 #define HUF_SYM(outv, shift)                                                               \
     do {                                                                                   \
-        uint32_t sym_ = tab[(uint32_t)(buf >> sh_idx)];                                    \
-        uint32_t nb_ = nbs[sym_];                                                          \
-        outv |= sym_ << (shift);                                                           \
+        const uint32_t v_ = (uint32_t)(buf >> 53);                                         \
+        const float vf_ = __uint_as_float(HUF_FBIAS | v_);                                 \
+        /* 2^23 + 1 + #{k : v < S_k}: the code length sits in the low mantissa bits */     \
+        const float s_ = ((HUF_LT(0) + HUF_LT(1)) + (HUF_LT(2) + HUF_LT(3))) +             \
+                         ((HUF_LT(4) + HUF_LT(5)) + (HUF_LT(6) + HUF_LT(7))) +             \
+                         ((HUF_LT(8) + HUF_LT(9)) + 8388609.0f);                           \
+        const uint32_t nb_ = __float_as_uint(s_) & 15u;                                    \
         buf <<= nb_;                                                                       \
         cnt -= (int)nb_;                                                                   \
         used_bits += nb_;                                                                  \
+        const uint32_t sym_ = perm[((v_ >> (HUF_MAX_LOG - nb_)) + (uint32_t)(int)adj[nb_]) & 255u]; \
+        outv |= sym_ << (shift);                                                           \
     } while (0)
                     uint32_t i = 0;
                     // head: single bytes until dst is 16-byte aligned (<= 15 symbols <= 6 words: covered by the primed ring)
@@ -941,6 +962,7 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
 #undef HUF_PHASE
 #undef HUF_REFILL
 #undef HUF_SYM
+#undef HUF_LT
                     ok = used_bits == total_bits;
                 }
             }
@@ -1004,7 +1026,7 @@ void launch_huf_decode(const ZstdParams& P, cudaStream_t st) {
     }
     uint32_t groups = (P.count + HUF_FRAMES_PER_WARP - 1) / HUF_FRAMES_PER_WARP;
     uint32_t grid = (groups + HUF_WARPS - 1) / HUF_WARPS;
-    if (grid > 148u * 8u) grid = 148u * 8u;
+    if (grid > 148u * 16u) grid = 148u * 16u;
     k_huf_decode<<<grid, HUF_WARPS * 32, smem, st>>>(P);
 }
 
