@@ -142,6 +142,51 @@ def test_config3_sum_rate_by_label_single_rank(oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("lookback,window_rows", [(0, 20), (45000, 20), (0, 3000)])
+def test_streamed_counter_resets_bit_exact(oracle, lookback, window_rows):
+    """the one-call paths run removeCounterResets inside the rollup kernel (rows corrected in shared memory as they stream
+    through, state carried from fill to fill; window_rows=3000 forces the correct-in-global-memory fallback):
+    last_over_time at step = scrape interval exposes every corrected value -> compare bit for bit"""
+    import torch
+    import victoriametrics_b200 as vm
+    rng = np.random.default_rng(77 + window_rows)
+    blocks = []
+    for i in range(24):
+        kind = ("counter_resets", "counter", "gauge", "counter_big")[i % 4]
+        tkind = ("regular", "jitter", "irregular")[i % 3]
+        blocks.append(blockgen.OBlock(blockgen.gen_timestamps(rng, tkind, 8192, T0), np.abs(blockgen.gen_values(rng, kind, 8192)),
+                                      -2, 64, i))
+    descs, payload = blockgen.to_blockset(blocks)
+    start, end, step, window = T0 + 15000, T0 + 15000 * 8300, 15000, 15000 * window_rows
+    rc = vm.promql.RollupConfig("last_over_time", start, end, step, window, LookbackDelta=lookback, removeCounterResets=True)
+    exp = []
+    for blk in blocks:
+        r, ts, fv, _ = blk.oracle_unmarshal()
+        assert r == 0
+        ts, fv = ts.copy(), fv.copy()
+        oracle.lib().vmo_remove_counter_resets(fv.ctypes.data_as(oracle.f64p), ts.ctypes.data_as(oracle.i64p), len(fv),
+                                               lookback + window if lookback else 0)
+        o, _ = oracle.rollup_do(RF["last_over_time"], fv, ts, start, end, step, window, lookback_delta=lookback)
+        exp.append(o)
+    exp = np.stack(exp)
+
+    def same_bits(a, b):  # NaN (an empty window) matches any NaN; everything else bit for bit
+        both_nan = np.isnan(a) & np.isnan(b)
+        return bool(np.all(both_nan | (a.view(np.uint64) == b.view(np.uint64))))
+    got_h, _ = vm.promql.eval_rollup_func_host("last_over_time", descs, payload, start, end, step, window, rc=rc)
+    assert same_bits(got_h, exp)
+    B = vm.storage.Blocks(descs, payload)
+    out = torch.empty(exp.shape, dtype=torch.float64, device="cuda")
+    vm.promql.eval_rollup_func("last_over_time", B, start, end, step, window, out_dev_ptr=out.data_ptr(), rc=rc)
+    assert same_bits(out.cpu().numpy(), exp)
+    # and the two-step API (stand-alone preamble kernel mutating the batch) agrees
+    series, _ = vm.storage.decode_blocks(B)
+    got2 = rc.do_series(series)[0]
+    series.close()
+    assert same_bits(got2, exp)
+
+
+@pytest.mark.gpu
 def test_config4_mixed_codec_increase_1h_step60(oracle):
     """40 % delta2 counters, 30 % gauges, 20 % const, 10 % delta-const -> increase(m[1h]) step 60 s"""
     import victoriametrics_b200 as vm

@@ -529,7 +529,7 @@ __global__ void k_meta_from_offsets(SeriesMeta* meta, const uint64_t* offsets, u
     SeriesMeta m;
     m.start = offsets[s];
     m.n = (uint32_t)(offsets[s + 1] - offsets[s]);
-    m._pad = 1;  // host-built batch: staleness markers unknown => dropStaleNaNs scans
+    m._pad = 3;  // host-built batch: staleness markers / value drops unknown => dropStaleNaNs and removeCounterResets scan
     m.max_prev_interval = 0;
     m.window = 0;
     meta[s] = m;

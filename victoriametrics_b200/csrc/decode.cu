@@ -84,6 +84,7 @@ struct TsEmit {
         if (v >= tr_min && pos < lo) lo = pos;
         if (v <= tr_max && pos + 1 > hi1) hi1 = pos + 1;
     }
+    __device__ __forceinline__ void note_decrease() {}
 };
 
 struct ValEmit {
@@ -91,9 +92,15 @@ struct ValEmit {
     Dec dec;
     bool as_int;
     bool saw_stale;  // a Prometheus staleness marker (decimal.go:406 vStaleNaN) was emitted: dropStaleNaNs has work to do
-    __device__ void init(void* o, int16_t scale, bool ai) { out = o; as_int = ai; saw_stale = false; dec.init(scale); }
-    __device__ __forceinline__ void emit(uint32_t pos, int64_t v, int64_t) {
+    bool saw_drop;   // some mantissa is below its predecessor: the only way removeCounterResets (rollup.go:921) can change
+                     // this block (decimal -> float is monotone inside a block: one scale), besides NaNs (saw_stale)
+    __device__ void init(void* o, int16_t scale, bool ai) {
+        out = o; as_int = ai; saw_stale = false; saw_drop = false; dec.init(scale);
+    }
+    __device__ __forceinline__ void note_decrease() { saw_drop = true; }
+    __device__ __forceinline__ void emit(uint32_t pos, int64_t v, int64_t pv) {
         saw_stale |= (v == VMB_V_STALE_NAN);
+        saw_drop |= (v < pv);
         if (as_int) ((int64_t*)out)[pos] = v;
         else ((double*)out)[pos] = dec.conv(v);
     }
@@ -153,6 +160,7 @@ __device__ int decode_column(const uint8_t* src, uint32_t len, int mt, int64_t f
                 int64_t v = (int64_t)((uint64_t)first + (uint64_t)i * (uint64_t)d);
                 em.emit(i, v, v);
             }
+            if (d < 0 && n > 1) em.note_decrease();
             return 0;
         }
         default:
@@ -255,7 +263,9 @@ __global__ void __launch_bounds__(128) k_decode_columns(DecodeParams P) {
             const bool as_int = (P.flags & VMB_DECODE_VALUES_AS_INT64) != 0;
             ve.init(as_int ? (void*)((int64_t*)P.val_out + ro) : (void*)((double*)P.val_out + ro), d.scale, as_int);
             rc = decode_column(src, len, d.val_mt, d.first_value, d.rows, ve, sm);
-            if (__any_sync(VMB_FULL, ve.saw_stale)) hi |= 0x80000000u;  // flag carried in the top bit of blk_hi
+            // flags carried in the top bits of blk_hi (rows <= 16384)
+            if (__any_sync(VMB_FULL, ve.saw_stale)) hi |= 0x80000000u;
+            if (__any_sync(VMB_FULL, ve.saw_stale || ve.saw_drop)) hi |= 0x40000000u;
         }
         if (lane == 0) {
             P.status[b] = rc;

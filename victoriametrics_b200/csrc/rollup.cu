@@ -717,31 +717,33 @@ __global__ void k_series_assemble(RollupParams P) {
     SeriesMeta m;
     m.start = 0;
     m.n = 0;
-    m._pad = 0;  // bit 0: the series may hold Prometheus staleness markers (set by the decode kernel per block)
+    // bit 0: the series may hold Prometheus staleness markers; bit 1: the series may hold a value below its predecessor
+    // (or a NaN), i.e. removeCounterResets may have something to do.  Both come from the decode kernel, per block.
+    m._pad = nb > 1 ? 2u : 0u;  // (a drop across a block boundary is not looked for: any multi-block series is a candidate)
     m.max_prev_interval = 0;
     m.window = 0;
     bool failed = false;
     for (uint32_t k = 0; k < nb; k++) {
         if (P.blk_status[fb + k]) failed = true;
-        m._pad |= P.blk_hi[fb + k] >> 31;  // staleness-marker flag of the block (decode.cu ValEmit)
+        m._pad |= (P.blk_hi[fb + k] >> 31) | ((P.blk_hi[fb + k] >> 29) & 2u);  // decode.cu ValEmit
     }
     if (!failed && nb) {
         // skip leading / trailing blocks that were trimmed away completely
         uint32_t a = 0, b = nb;
-        while (a < b && (P.blk_hi[fb + a] & 0x7fffffffu) == P.blk_lo[fb + a]) a++;
-        while (b > a && (P.blk_hi[fb + b - 1] & 0x7fffffffu) == P.blk_lo[fb + b - 1]) b--;
+        while (a < b && (P.blk_hi[fb + a] & 0x3fffffffu) == P.blk_lo[fb + a]) a++;
+        while (b > a && (P.blk_hi[fb + b - 1] & 0x3fffffffu) == P.blk_lo[fb + b - 1]) b--;
         if (a < b) {
             bool contiguous = true;
             for (uint32_t k = a; k < b; k++) {
                 if (k > a && P.blk_lo[fb + k] != 0) contiguous = false;
-                if (k + 1 < b && (P.blk_hi[fb + k] & 0x7fffffffu) != P.descs[fb + k].rows) contiguous = false;
+                if (k + 1 < b && (P.blk_hi[fb + k] & 0x3fffffffu) != P.descs[fb + k].rows) contiguous = false;
             }
             if (!contiguous) {
                 for (uint32_t k = 0; k < nb; k++) P.blk_status[fb + k] = VMB_ERR_BLOCK_ORDER;
                 failed = true;
             } else {
                 m.start = P.row_off[fb + a] + P.blk_lo[fb + a];
-                uint64_t end = P.row_off[fb + b - 1] + (P.blk_hi[fb + b - 1] & 0x7fffffffu);
+                uint64_t end = P.row_off[fb + b - 1] + (P.blk_hi[fb + b - 1] & 0x3fffffffu);
                 m.n = (uint32_t)(end - m.start);
             }
         }
@@ -848,8 +850,10 @@ __global__ void __launch_bounds__(128) k_series_prepare(RollupParams P) {
         }
         // ---- removeCounterResets rollup.go:921 (sequential float semantics preserved: corrections are accumulated in
         //      sample order; the final clamp is a segmented prefix "max" which is order-independent)
-        if ((rc.flags & VMB_RC_REMOVE_COUNTER_RESETS) && n) {
-            const int64_t max_stale = rc.lookback_delta != 0 ? rc.lookback_delta + rc.window : 0;  // rollup.go:380-387
+        // A series whose values never decrease (and hold no NaN) comes out of removeCounterResets unchanged unless the
+        // staleness-gap rule is on: the pass over its rows is skipped (decoded columns never hold -0.0, so "+ 0.0" is void)
+        const int64_t max_stale = rc.lookback_delta != 0 ? rc.lookback_delta + rc.window : 0;  // rollup.go:380-387
+        if ((rc.flags & VMB_RC_REMOVE_COUNTER_RESETS) && n && ((m._pad & 2u) || max_stale > 0)) {
             RcrState st;
             st.corr = 0.0; st.prev_raw = 0.0; st.prev_out = 0.0; st.prev_ts = 0;
             // four 32-row chunks per iteration: their loads are issued together (one HBM round trip per 128 rows)

@@ -131,11 +131,12 @@ def get_rollup_configs(func_name, start, end, step, window=0, lookback_delta=0, 
 
 
 def eval_rollup_func(func_name, blocks, start, end, step, window=0, lookback_delta=0, args=None, args2=None,
-                     tr_min=storage.INT64_MIN, tr_max=storage.INT64_MAX, out_dev_ptr=None):
+                     tr_min=storage.INT64_MIN, tr_max=storage.INT64_MAX, out_dev_ptr=None, rc=None):
     """evalRollupFuncNoCache eval.go:1680 -> evalRollupNoIncrementalAggregate eval.go:1845 on device-resident blocks:
     decode, per-series preamble, rollupConfig.Do for every series.
-    -> ([nseries x points] np.float64 or None, samplesScanned)"""
-    rc = get_rollup_configs(func_name, start, end, step, window, lookback_delta, args, args2)
+    -> ([nseries x points] np.float64 or None, samplesScanned).  `rc`: a RollupConfig to use instead of the one
+    getRollupConfigs derives from func_name."""
+    rc = rc or get_rollup_configs(func_name, start, end, step, window, lookback_delta, args, args2)
     cfg = rc._cfg()
     scanned = C.c_uint64(0)
     if out_dev_ptr is not None:
@@ -150,10 +151,10 @@ def eval_rollup_func(func_name, blocks, start, end, step, window=0, lookback_del
 
 
 def eval_rollup_func_host(func_name, descs, payload, start, end, step, window=0, lookback_delta=0, args=None, args2=None,
-                          tr_min=storage.INT64_MIN, tr_max=storage.INT64_MAX, out=None, nseries=None, ctx=None):
+                          tr_min=storage.INT64_MIN, tr_max=storage.INT64_MAX, out=None, nseries=None, ctx=None, rc=None):
     """the whole path with HOST buffers in one call (vmb_eval_rollup_host): H2D, decode, rollup, D2H."""
     ctx = ctx or _lib.default_context()
-    rc = get_rollup_configs(func_name, start, end, step, window, lookback_delta, args, args2)
+    rc = rc or get_rollup_configs(func_name, start, end, step, window, lookback_delta, args, args2)
     cfg = rc._cfg()
     if isinstance(descs, np.ndarray):
         dptr, n = descs.ctypes.data_as(C.POINTER(_lib.BlockDesc)), descs.shape[0]
