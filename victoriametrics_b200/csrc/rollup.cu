@@ -1058,11 +1058,50 @@ __device__ __forceinline__ double rollup_point(const vmb_rollup_cfg& rc, const S
 //
 // A window that does not fit ROLLUP_CAP rows (huge windows / very dense series) is handled for that tile by reading global
 // memory directly.  F >= 0 instantiates the kernel for one rollup function (the switch in call_func folds away).
+// shared memory of k_rollup at file scope: the device functions below index it directly (plain LDS with constant bases)
+__shared__ int64_t rs_ts[ROLLUP_CAP];     // timestamps of the resident rows
+__shared__ double rs_val[ROLLUP_CAP];     // their values
+__shared__ int32_t rs_rt[ROLLUP_CAP];     // timestamps relative to the first row of the series (32-bit fast path)
+__shared__ unsigned short rs_seek[ROLLUP_SEEKS];  // window edges of the fill as resident-row indices (<= ROLLUP_CAP)
+
+// first resident row with timestamp > x, timestamps as 32-bit offsets: the interpolation guess is the answer or one off for
+// regularly scraped series, decided from three independent loads; anything else falls back to seek_after
+__device__ __forceinline__ uint32_t seek32(uint32_t n, int32_t xr, float inv_dt, int32_t r_first, int32_t r_last, int64_t t_org) {
+    const int32_t off = xr > r_first ? xr - r_first : 0;
+    uint32_t g = (uint32_t)(__int2float_rn(off) * inv_dt) + 1u;
+    if (g > n - 1) g = n - 1;
+    const uint32_t gm = g ? g - 1 : 0, g2 = g + 1 < n ? g + 1 : g;
+    const int32_t a = rs_rt[gm], b = rs_rt[g], c = rs_rt[g2];
+    uint32_t res = xr < b ? g : g2;
+    const bool ok = a <= xr && (xr < b || xr < c);
+    const bool inside = xr >= r_first && xr < r_last;
+    if (inside && !ok) res = seek_after(rs_ts, n, t_org + xr, inv_dt);
+    res = xr < r_first ? 0u : res;
+    res = xr >= r_last ? n : res;
+    return res;
+}
+
+// rollupDerivFast (rollup.go:1954) for one point from the window edges i, j (absolute rows); tsp = tStart - maxPrevInterval
+// as an offset from the first row of the series.  Selects instead of branches; same operations as the generic path.
+__device__ __forceinline__ double rate_point32(uint32_t i, uint32_t j, uint32_t base, uint32_t n, uint32_t cnt, int32_t tsp) {
+    const uint32_t ri = i - base, rj = j - base, nw = j - i;
+    const bool have_prev = i > 0 && i < n;
+    const uint32_t ip = have_prev ? ri - 1 : 0u;
+    const uint32_t i0 = ri < cnt ? ri : cnt - 1;
+    const uint32_t il = rj ? rj - 1 : 0u;
+    const int32_t tp = rs_rt[ip], t0 = rs_rt[i0], tl = rs_rt[il];
+    const double vp = rs_val[ip], v0 = rs_val[i0], vl = rs_val[il];
+    const bool prev_ok = have_prev && tp > tsp && !isnan(vp);
+    const bool fixed = prev_ok ? nw == 0 : nw < 2;  // no division: 0 with a previous sample, NaN without
+    const double a = prev_ok ? vp : v0;
+    int32_t dt = tl - (prev_ok ? tp : t0);
+    dt = fixed ? 1000 : dt;
+    const double qv = (vl - a) / ms_to_s((int64_t)dt);
+    return fixed ? (prev_ok ? 0.0 : D_NAN) : qv;
+}
+
 template <int F>
 __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
-    __shared__ int64_t s_ts[ROLLUP_CAP];
-    __shared__ double s_val[ROLLUP_CAP];
-    __shared__ uint32_t s_seek[ROLLUP_SEEKS];
     const vmb_rollup_cfg& rc = P.cfg;
     const uint32_t tid = threadIdx.x;
     unsigned long long scanned = 0;
@@ -1076,14 +1115,30 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
         const uint32_t wsteps = (uint32_t)(m.window / rc.step);
         const bool shared_seeks = (m.window % rc.step) == 0 && wsteps <= ROLLUP_SEEKS - ROLLUP_CAP;
         const uint32_t wsteps_cap = shared_seeks ? wsteps : 0u;
+        // 32-bit fast path (rate): timestamps relative to the first row of the series, when everything fits 2^30 ms
+        const int64_t t_org = n ? tg[0] : 0;
+        bool fast = false;
+        int32_t start_r = 0, step32 = 0, win32 = 0, mpi32 = 0;
+        if (F == VMB_RF_RATE && shared_seeks && n) {
+            const int64_t lim = (int64_t)1 << 30;
+            const int64_t a0 = rc.start - (int64_t)wsteps * rc.step - t_org, a1 = rc.end - t_org;
+            fast = (tg[n - 1] - t_org) < lim && a0 > -lim && a0 < lim && a1 > -lim && a1 < lim && m.window < lim &&
+                   m.max_prev_interval < lim && rc.step < lim && rc.samples_scanned_per_call < 4096;
+            start_r = (int32_t)(rc.start - t_org);
+            step32 = (int32_t)rc.step;
+            win32 = (int32_t)m.window;
+            mpi32 = (int32_t)m.max_prev_interval;
+        }
         uint32_t base = 0, cnt = 0, p = 0;
         while (p < P.npoints) {
             // ---- fill: rows [base + cnt, min(n, base + CAP))
             __syncthreads();
             const uint32_t want = min(n - base, (uint32_t)ROLLUP_CAP);
             for (uint32_t k = cnt + tid; k < want; k += ROLLUP_THREADS) {
-                s_ts[k] = tg[base + k];
-                s_val[k] = vg[base + k];
+                const int64_t t = tg[base + k];
+                rs_ts[k] = t;
+                rs_val[k] = vg[base + k];
+                if (fast) rs_rt[k] = (int32_t)(t - t_org);
             }
             cnt = want;
             __syncthreads();
@@ -1092,12 +1147,12 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
             uint32_t p_end;
             if (base + cnt == n) p_end = P.npoints;
             else {
-                int64_t tl = s_ts[cnt - 1] - 1 - rc.start;
+                int64_t tl = rs_ts[cnt - 1] - 1 - rc.start;
                 p_end = tl < 0 ? 0u : (uint32_t)min((int64_t)P.npoints, tl / rc.step + 1);
             }
             float inv_dt = 0.0f;  // rows per millisecond over the resident range (0: no usable slope => bisect)
             {
-                const int64_t span = cnt > 1 ? s_ts[cnt - 1] - s_ts[0] : 0;
+                const int64_t span = cnt > 1 ? rs_ts[cnt - 1] - rs_ts[0] : 0;
                 if (span > 0 && span < (int64_t)0x7fffffff) inv_dt = __fdividef((float)(cnt - 1), (float)span);
             }
             if (p_end <= p) {
@@ -1118,35 +1173,64 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
                 }
                 continue;
             }
+            // ---- while this fill is being evaluated, pull the rows of the next one into L2: the next fill starts at most
+            //      ROLLUP_CAP rows after the last resident row.  One 128-byte line per thread (first half of the CTA:
+            //      timestamps, second half: values), so the next fill waits for L2 instead of HBM.
+            {
+                const uint32_t r = base + cnt + (tid & (ROLLUP_THREADS / 2 - 1)) * 16u;
+                if (r < n) {
+                    const void* a = tid < ROLLUP_THREADS / 2 ? (const void*)(tg + r) : (const void*)(vg + r);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                }
+            }
             // ---- the points of this fill, in two passes without barriers inside: every window edge first (shared by the
             //      points when the window is a whole number of steps), then the points.  Iterations are independent, so
             //      the shared-memory latencies of several points of one thread overlap.
             if (p_end - p > ROLLUP_SEEKS - wsteps_cap) p_end = p + (ROLLUP_SEEKS - wsteps_cap);
             const uint32_t np = p_end - p;
-            const int64_t t_first = cnt ? s_ts[0] : 0, t_last = cnt ? s_ts[cnt - 1] : 0;
-            if (shared_seeks) {
+            const int64_t t_first = cnt ? rs_ts[0] : 0, t_last = cnt ? rs_ts[cnt - 1] : 0;
+            if (fast) {
+                // branch-free 32-bit edges and rate() points (same arithmetic as rollup_point<VMB_RF_RATE>)
+                const int32_t r_first = rs_rt[0], r_last = rs_rt[cnt - 1];
+                const int32_t x0r = start_r + ((int32_t)p - (int32_t)wsteps) * step32;
+#pragma unroll 2
+                for (uint32_t q = tid; q < np + wsteps; q += ROLLUP_THREADS)
+                    rs_seek[q] = (unsigned short)seek32(cnt, x0r + (int32_t)q * step32, inv_dt, r_first, r_last, t_org);
+                __syncthreads();
+                const int32_t ts0 = start_r + (int32_t)p * step32 - win32 - mpi32;  // tStart - maxPrevInterval of point p
+                const uint32_t spc = (uint32_t)rc.samples_scanned_per_call;
+                uint32_t sc32 = 0;
+#pragma unroll 2
+                for (uint32_t q = tid; q < np; q += ROLLUP_THREADS) {
+                    const uint32_t i = base + rs_seek[q];
+                    const uint32_t j = max(i, base + rs_seek[q + wsteps]);
+                    sc32 += spc ? spc : j - i;
+                    out[p + q] = rate_point32(i, j, base, n, cnt, ts0 + (int32_t)q * step32);
+                }
+                scanned += sc32;
+            } else if (shared_seeks) {
                 const int64_t x0 = rc.start + ((int64_t)p - (int64_t)wsteps) * rc.step;
 #pragma unroll 2
                 for (uint32_t q = tid; q < np + wsteps; q += ROLLUP_THREADS)
-                    s_seek[q] = base + seek_resident(s_ts, cnt, x0 + (int64_t)q * rc.step, inv_dt, t_first, t_last);
+                    rs_seek[q] = (unsigned short)seek_resident(rs_ts, cnt, x0 + (int64_t)q * rc.step, inv_dt, t_first, t_last);
                 __syncthreads();
 #pragma unroll 2
                 for (uint32_t q = tid; q < np; q += ROLLUP_THREADS)
-                    out[p + q] = rollup_point<F>(rc, m, s_val, s_ts, base, n, s_seek[q], s_seek[q + wsteps], p + q, scanned);
+                    out[p + q] = rollup_point<F>(rc, m, rs_val, rs_ts, base, n, base + rs_seek[q], base + rs_seek[q + wsteps], p + q, scanned);
             } else {
                 for (uint32_t q = tid; q < np; q += ROLLUP_THREADS) {
                     const int64_t tEnd = rc.start + (int64_t)(p + q) * rc.step;
-                    const uint32_t i = base + seek_resident(s_ts, cnt, tEnd - m.window, inv_dt, t_first, t_last);
-                    const uint32_t j = base + seek_resident(s_ts, cnt, tEnd, inv_dt, t_first, t_last);
+                    const uint32_t i = base + seek_resident(rs_ts, cnt, tEnd - m.window, inv_dt, t_first, t_last);
+                    const uint32_t j = base + seek_resident(rs_ts, cnt, tEnd, inv_dt, t_first, t_last);
                     // rows before `base` are not resident: the slide rule below keeps row i-1 of the first point resident
-                    out[p + q] = rollup_point<F>(rc, m, s_val, s_ts, base, n, i, j, p + q, scanned);
+                    out[p + q] = rollup_point<F>(rc, m, rs_val, rs_ts, base, n, i, j, p + q, scanned);
                 }
             }
             p = p_end;
             if (p >= P.npoints) break;
             // ---- slide: keep rows from (first row after tStart(p)) - 1
             __syncthreads();
-            uint32_t lo = base + seek_after(s_ts, cnt, rc.start + (int64_t)p * rc.step - m.window, inv_dt);
+            uint32_t lo = base + seek_after(rs_ts, cnt, rc.start + (int64_t)p * rc.step - m.window, inv_dt);
             uint32_t nb = lo > base ? lo - 1 : base;
             if (nb > base + cnt - 1) nb = base + cnt - 1;
             const uint32_t shift = nb - base;
@@ -1156,14 +1240,17 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
                     uint32_t k = c + tid;
                     int64_t a = 0;
                     double b = 0.0;
+                    int32_t c32 = 0;
                     if (k < keep) {
-                        a = s_ts[k + shift];
-                        b = s_val[k + shift];
+                        a = rs_ts[k + shift];
+                        b = rs_val[k + shift];
+                        if (fast) c32 = rs_rt[k + shift];
                     }
                     __syncthreads();
                     if (k < keep) {
-                        s_ts[k] = a;
-                        s_val[k] = b;
+                        rs_ts[k] = a;
+                        rs_val[k] = b;
+                        if (fast) rs_rt[k] = c32;
                     }
                 }
                 base = nb;
