@@ -44,26 +44,32 @@ __device__ int decode_delta_stream_v2(const uint8_t* __restrict__ src, uint32_t 
     if (lane < 4) sm->bytes[lane] = 0;
     __syncwarp();
 
+    // the 16 bytes of a lane are fetched one tile ahead (aligned words + funnel shift): the HBM round trip of tile t+1
+    // overlaps the parse of tile t
+    uint32_t nw0 = 0, nw1 = 0, nw2 = 0, nw3 = 0, nw4 = 0;
+    auto fetch = [&](uint32_t tile) {
+        const uint32_t o = tile + (uint32_t)lane * 16u;
+        if (o < len) {
+            uintptr_t a = (uintptr_t)(src + o);
+            const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+            nw0 = w[0]; nw1 = w[1]; nw2 = w[2]; nw3 = w[3];
+            nw4 = (a & 3) ? w[4] : 0u;
+        }
+    };
+    fetch(0);
     for (uint32_t tile = 0; tile < len; tile += DS_TILE) {
-        // ---- 1. load 16 bytes per lane, stage them, find terminators
+        // ---- 1. this lane's 16 bytes (already in flight), stage them, find terminators
         const uint32_t o = tile + (uint32_t)lane * 16u;
         const uint32_t valid = o >= len ? 0u : (len - o >= 16u ? 16u : len - o);
         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
         if (valid) {
-            uintptr_t a = (uintptr_t)(src + o);
-            const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
-            uint32_t sh = (uint32_t)(a & 3) * 8;
-            uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-            if (sh) {
-                uint32_t w4 = w[4];
-                c0 = __funnelshift_r(w0, w1, sh);
-                c1 = __funnelshift_r(w1, w2, sh);
-                c2 = __funnelshift_r(w2, w3, sh);
-                c3 = __funnelshift_r(w3, w4, sh);
-            } else {
-                c0 = w0; c1 = w1; c2 = w2; c3 = w3;
-            }
+            const uint32_t sh = (uint32_t)((uintptr_t)(src + o) & 3) * 8;
+            c0 = __funnelshift_r(nw0, nw1, sh);
+            c1 = __funnelshift_r(nw1, nw2, sh);
+            c2 = __funnelshift_r(nw2, nw3, sh);
+            c3 = __funnelshift_r(nw3, nw4, sh);
         }
+        if (tile + DS_TILE < len) fetch(tile + DS_TILE);
         uint32_t* sb = sm->bytes + 4 + lane * 4;
         sb[0] = c0; sb[1] = c1; sb[2] = c2; sb[3] = c3;
         uint32_t m = term_mask4(c0) | (term_mask4(c1) << 4) | (term_mask4(c2) << 8) | (term_mask4(c3) << 12);
