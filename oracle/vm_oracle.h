@@ -133,6 +133,12 @@ void vmo_remove_counter_resets(double* values, const int64_t* timestamps, size_t
 void vmo_delta_values(double* values, size_t n);
 void vmo_deriv_values(double* values, const int64_t* timestamps, size_t n);
 size_t vmo_drop_stale_nans(double* values, int64_t* timestamps, size_t n);
+/* series assembly: netstorage.go:566 mergeSortBlocks (blocks = row ranges [offsets[b], offsets[b+1]) of ts/vals, each sorted),
+ * lib/storage/dedup.go:30 DeduplicateSamples (in place, returns the new length), :158 needsDedup */
+size_t vmo_merge_sort_blocks(const int64_t* ts, const double* vals, const uint64_t* offsets, size_t nblocks,
+                             int64_t dedup_interval, int64_t* out_ts, double* out_vals);
+size_t vmo_deduplicate_samples(int64_t* ts, double* vals, size_t n, int64_t interval);
+int vmo_needs_dedup(const int64_t* ts, size_t n, int64_t interval);
 int64_t vmo_get_scrape_interval(const int64_t* timestamps, size_t n, int64_t default_interval);
 int64_t vmo_get_max_prev_interval(int64_t scrape_interval);
 double vmo_quantile(double phi, const double* values, size_t n);

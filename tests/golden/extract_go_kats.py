@@ -287,6 +287,45 @@ def main():
             })
     K["rollup_do"] = do_tests
 
+    # ------------------------------------------------------------------ lib/storage/dedup.go, netstorage.mergeSortBlocks
+    def dur_ms(expr):
+        e = expr.replace("time.Millisecond", "1").replace("time.Second", "1000")
+        return as_int(e)
+    src = read("lib/storage/dedup_test.go")
+    K["needs_dedup"] = [{"interval": as_int(a[0]), "timestamps": parse_slice(a[1], as_int), "expected": a[2] == "true"}
+                        for a in calls(func_body(src, "TestNeedsDedup"), "f")]
+    dd = []
+    for a in calls(func_body(src, "TestDeduplicateSamples"), "f"):
+        ts = parse_slice(a[1], as_int)
+        dd.append({"interval": dur_ms(a[0]), "timestamps": ts, "values": [float(i).hex() for i in range(len(ts))],
+                   "timestamps_expected": parse_slice(a[2], as_int), "values_expected": parse_slice(a[3], as_float)})
+    for tname in ("TestDeduplicateSamplesWithIdenticalTimestamps", "TestDeduplicateSamples_KeepsFirstAndLast"):
+        for a in calls(func_body(src, tname), "f"):
+            dd.append({"interval": dur_ms(a[0]), "timestamps": parse_slice(a[1], as_int), "values": parse_slice(a[2], as_float),
+                       "timestamps_expected": parse_slice(a[3], as_int), "values_expected": parse_slice(a[4], as_float)})
+    K["dedup_samples"] = dd
+
+    def parse_struct(expr):  # {Timestamps: []int64{..}, Values: []float64{..}} (either may be missing)
+        body = expr.strip()
+        body = body[body.index("{") + 1:body.rindex("}")]
+        d = {"Timestamps": [], "Values": []}
+        for fld in split_top(body):
+            k, v = fld.split(":", 1)
+            d[k.strip()] = parse_slice(v, as_int if k.strip() == "Timestamps" else as_float)
+        return d
+    src = read("app/vmselect/netstorage/netstorage_test.go")
+    mm = []
+    for a in calls(func_body(src, "TestMergeSortBlocks"), "f"):
+        blocks = []
+        if a[0].strip() != "nil":
+            inner = a[0].strip()
+            inner = inner[inner.index("{") + 1:inner.rindex("}")]
+            blocks = [parse_struct(b) for b in split_top(inner)]
+        exp = parse_struct(a[2])
+        mm.append({"blocks": [{"timestamps": b["Timestamps"], "values": b["Values"]} for b in blocks], "dedup_interval": as_int(a[1]),
+                   "timestamps_expected": exp["Timestamps"], "values_expected": exp["Values"]})
+    K["merge_sort_blocks"] = mm
+
     with open(OUT, "w") as f:
         json.dump(K, f, indent=0, separators=(",", ":"))
     print("wrote", OUT, {k: (len(v) if isinstance(v, list) else 1) for k, v in K.items()})

@@ -16,6 +16,7 @@ _SO = os.path.join(_ORACLE_DIR, "libvmoracle.so")
 u8p = C.POINTER(C.c_uint8)
 i64p = C.POINTER(C.c_int64)
 f64p = C.POINTER(C.c_double)
+u64p = C.POINTER(C.c_uint64)
 
 
 def build():
@@ -84,6 +85,9 @@ def lib():
                                               C.c_int64, sz, C.c_int64, f64p, f64p]),
         "vmo_rollup_points": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
         "vmo_remove_counter_resets": (None, [f64p, i64p, sz, C.c_int64]),
+        "vmo_merge_sort_blocks": (sz, [i64p, f64p, u64p, sz, C.c_int64, i64p, f64p]),
+        "vmo_deduplicate_samples": (sz, [i64p, f64p, sz, C.c_int64]),
+        "vmo_needs_dedup": (C.c_int, [i64p, sz, C.c_int64]),
         "vmo_delta_values": (None, [f64p, sz]),
         "vmo_deriv_values": (None, [f64p, i64p, sz]),
         "vmo_drop_stale_nans": (sz, [f64p, i64p, sz]),
@@ -247,3 +251,25 @@ def rollup_do(func_id, values, timestamps, start, end, step, window, lookback_de
         cfg.args2 = _f64(a2)
     scanned = lib().vmo_rollup_do(C.byref(cfg), _f64(out), _f64(values), _i64(timestamps), len(values))
     return out, scanned
+
+
+def merge_sort_blocks(ts_list, val_list, dedup_interval=0):
+    """netstorage.go:566 mergeSortBlocks over per-block (timestamps, values) arrays -> (timestamps, values)"""
+    offs = np.zeros(len(ts_list) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(t) for t in ts_list])
+    n = int(offs[-1])
+    ts = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int64) for t in ts_list]) if n else np.zeros(0, np.int64))
+    vals = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in val_list]) if n else np.zeros(0, np.float64))
+    ots, ovals = np.zeros(max(n, 1), dtype=np.int64), np.zeros(max(n, 1), dtype=np.float64)
+    m = lib().vmo_merge_sort_blocks(ts.ctypes.data_as(i64p), vals.ctypes.data_as(f64p), offs.ctypes.data_as(u64p), len(ts_list),
+                                    int(dedup_interval), ots.ctypes.data_as(i64p), ovals.ctypes.data_as(f64p))
+    return ots[:m].copy(), ovals[:m].copy()
+
+
+def deduplicate_samples(ts, vals, interval):
+    ts = np.array(ts, dtype=np.int64)
+    vals = np.array(vals, dtype=np.float64)
+    if len(ts) == 0:
+        return ts, vals
+    m = lib().vmo_deduplicate_samples(ts.ctypes.data_as(i64p), vals.ctypes.data_as(f64p), len(ts), int(interval))
+    return ts[:m].copy(), vals[:m].copy()
