@@ -54,6 +54,9 @@ int vmb_ctx_create(int device, vmb_ctx** out);
 void vmb_ctx_destroy(vmb_ctx* ctx);
 /* stream = a cudaStream_t (0 = legacy default stream). */
 int vmb_ctx_set_stream(vmb_ctx* ctx, void* stream);
+/* storage.SetDedupInterval lib/storage/dedup.go:15 (-dedup.minScrapeInterval), in ms; 0 (default) = off.  Applied by every
+ * block-decoding entry point after the series are assembled (netstorage.go:611 DeduplicateSamples). */
+int vmb_ctx_set_dedup_interval(vmb_ctx* ctx, int64_t interval_ms);
 int vmb_ctx_synchronize(vmb_ctx* ctx);
 const char* vmb_last_error(void);
 int vmb_version(void);

@@ -89,6 +89,7 @@ def lib():
         "vmb_eval_rollup_device": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.POINTER(RollupCfg), vp, u64p]),
         "vmb_eval_rollup_aggr_device": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.POINTER(RollupCfg), C.c_int, u32p, C.c_uint32,
                                                   vp, vp, u64p]),
+        "vmb_ctx_set_dedup_interval": (C.c_int, [vp, C.c_int64]),
         "vmb_host_alloc": (vp, [sz]),
         "vmb_host_free": (None, [vp]),
         "vmb_ctx_last_stage_ms": (C.c_float, [vp, C.c_int]),
@@ -131,6 +132,10 @@ class Context:
 
     def set_stream(self, stream):
         check(lib().vmb_ctx_set_stream(self.h, C.c_void_p(int(stream))))
+
+    def set_dedup_interval(self, interval_ms):
+        """storage.SetDedupInterval (lib/storage/dedup.go:15): -dedup.minScrapeInterval in ms, 0 = off"""
+        check(lib().vmb_ctx_set_dedup_interval(self.h, int(interval_ms)))
 
     def synchronize(self):
         check(lib().vmb_ctx_synchronize(self.h))

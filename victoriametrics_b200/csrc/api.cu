@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -66,7 +67,8 @@ struct vmb_ctx {
     float stage_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[6] = {0, 0, 0, 0, 0, 0};
     // scratch (reused across calls)
-    DevBuf zscratch, zlit, zstatus, zjobs, zws, args1, args2, rolled, counters, tmp_out, grp;
+    DevBuf zscratch, zlit, zstatus, zjobs, zws, args1, args2, rolled, counters, tmp_out, grp, mheap, mnext;
+    int64_t dedup_interval = 0;  // storage.SetDedupInterval (lib/storage/dedup.go:15), ms; 0 = deduplication off
     void* h_pinned = nullptr;  // small pinned staging area for counters
     void* pipe = nullptr;      // pipeline.inc: streams, events and double-buffered slots of vmb_eval_rollup_host
     void (*pipe_destroy)(void*) = nullptr;
@@ -76,8 +78,10 @@ struct vmb_blocks {
     vmb_ctx* ctx = nullptr;
     size_t nblocks = 0, nseries = 0;
     uint64_t rows = 0, compressed = 0, scratch_total = 0;
+    uint64_t merge_rows = 0;  // rows of the series whose blocks overlap in time: size of the merge area behind the blocks
     bool needs_lit = false;
     uint32_t n_huf = 0, n_gen = 0, n_bad = 0;
+    uint64_t* d_ser_merge_off = nullptr;  // per series: offset into the merge area, UINT64_MAX = none
     vmb_block_desc* d_descs = nullptr;
     uint8_t* d_payload = nullptr;        // = d_payload_alloc + 64
     uint8_t* d_payload_alloc = nullptr;
@@ -138,7 +142,7 @@ extern "C" void vmb_ctx_destroy(vmb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->zscratch, &c->zlit, &c->zstatus, &c->zjobs, &c->zws, &c->args1, &c->args2, &c->rolled,
-                      &c->counters, &c->tmp_out, &c->grp};
+                      &c->counters, &c->tmp_out, &c->grp, &c->mheap, &c->mnext};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 6; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -149,6 +153,11 @@ extern "C" void vmb_ctx_destroy(vmb_ctx* c) {
 extern "C" int vmb_ctx_set_stream(vmb_ctx* c, void* stream) {
     if (!c) return VMB_ERR_INVALID_ARG;
     c->stream = (cudaStream_t)stream;
+    return VMB_OK;
+}
+extern "C" int vmb_ctx_set_dedup_interval(vmb_ctx* c, int64_t interval_ms) {
+    if (!c || interval_ms < 0) return VMB_ERR_INVALID_ARG;
+    c->dedup_interval = interval_ms;
     return VMB_OK;
 }
 extern "C" int vmb_ctx_synchronize(vmb_ctx* c) {
@@ -226,6 +235,7 @@ extern "C" void vmb_blocks_free(vmb_blocks* b) {
     cudaFree(b->d_payload_alloc);
     cudaFree(b->d_cols);
     cudaFree(b->d_row_off);
+    cudaFree(b->d_ser_merge_off);
     cudaFree(b->d_huf_list);
     cudaFree(b->d_gen_list);
     cudaFree(b->d_bad_list);
@@ -242,7 +252,8 @@ struct BlocksPlan {
     std::vector<ColInfo> cols;
     std::vector<uint64_t> row_off;
     std::vector<uint32_t> huf, gen, bad, ser_first, ser_nblocks;
-    uint64_t rows = 0, compressed = 0, scratch_total = 0;
+    std::vector<uint64_t> ser_merge_off;
+    uint64_t rows = 0, compressed = 0, scratch_total = 0, merge_rows = 0;
     bool needs_lit = false;
 };
 static int plan_blocks(BlocksPlan& pl, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload, size_t payload_len) {
@@ -289,6 +300,32 @@ static int plan_blocks(BlocksPlan& pl, const vmb_block_desc* descs, size_t nbloc
     }
     pl.row_off[nblocks] = pl.rows;
     pl.scratch_total = scratch;
+    // Multi-block series (netstorage.go:566 mergeSortBlocks): lay the decoded blocks of a series out in min-timestamp order,
+    // whatever order they arrived in.  When consecutive blocks are strictly disjoint in time the series is then the plain
+    // concatenation of its blocks; otherwise (overlap, touching ranges, replicas) it is merged on the GPU into the merge
+    // area behind the decoded blocks.
+    pl.ser_merge_off.assign(pl.ser_first.size(), UINT64_MAX);
+    std::vector<uint32_t> order;
+    for (size_t s = 0; s < pl.ser_first.size(); s++) {
+        const uint32_t fb = pl.ser_first[s], nb = pl.ser_nblocks[s];
+        if (nb < 2) continue;
+        order.resize(nb);
+        for (uint32_t k = 0; k < nb; k++) order[k] = fb + k;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return descs[a].min_ts < descs[b].min_ts; });
+        uint64_t r = pl.row_off[fb], total = 0;
+        bool overlap = false;
+        for (uint32_t k = 0; k < nb; k++) {
+            const vmb_block_desc& d = descs[order[k]];
+            const uint64_t rows = d.rows <= 16384 ? d.rows : 0;
+            pl.row_off[order[k]] = r + total;
+            total += rows;
+            if (k + 1 < nb && d.max_ts >= descs[order[k + 1]].min_ts) overlap = true;
+        }
+        if (overlap) {
+            pl.ser_merge_off[s] = pl.merge_rows;
+            pl.merge_rows += total;
+        }
+    }
     return 0;
 }
 
@@ -314,6 +351,7 @@ extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size
     b->rows = pl.rows;
     b->compressed = pl.compressed;
     b->scratch_total = pl.scratch_total;
+    b->merge_rows = pl.merge_rows;
     b->needs_lit = pl.needs_lit;
     b->n_huf = (uint32_t)pl.huf.size();
     b->n_gen = (uint32_t)pl.gen.size();
@@ -342,6 +380,7 @@ extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size
     TRY(upload_vec(&b->d_bad_list, pl.bad, st));
     TRY(upload_vec(&b->d_ser_first, pl.ser_first, st));
     TRY(upload_vec(&b->d_ser_nblocks, pl.ser_nblocks, st));
+    TRY(upload_vec(&b->d_ser_merge_off, pl.ser_merge_off, st));
 #undef TRY
     CU(cudaStreamSynchronize(st));  // the host vectors go out of scope
     *out = b;
@@ -452,8 +491,30 @@ static int run_decode(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, int64_t 
     R.descs = b->d_descs;
     R.blk_status = s->d_blk_status;
     R.failed_blocks = d_failed;
+    R.ser_merge_off = b->d_ser_merge_off;
+    R.rows_total = b->rows;
+    R.ts = s->d_ts;
+    R.vals = s->d_vals;
+    R.dedup_interval = (flags & VMB_DECODE_VALUES_AS_INT64) ? 0 : ctx->dedup_interval;
     launch_series_assemble(R, st);
     count_launch(ctx);
+    if (b->merge_rows) {
+        if (flags & VMB_DECODE_VALUES_AS_INT64) {
+            vmb_set_error("series with overlapping blocks cannot be assembled from VMB_DECODE_VALUES_AS_INT64 columns");
+            return VMB_ERR_INVALID_ARG;
+        }
+        int rc;
+        if ((rc = ctx->mheap.reserve(b->nblocks * sizeof(uint32_t)))) return rc;
+        if ((rc = ctx->mnext.reserve(b->nblocks * sizeof(uint32_t)))) return rc;
+        R.merge_heap = (uint32_t*)ctx->mheap.p;
+        R.merge_next = (uint32_t*)ctx->mnext.p;
+        launch_series_merge(R, st);
+        count_launch(ctx);
+    }
+    if (R.dedup_interval > 0) {
+        launch_series_dedup(R, st);
+        count_launch(ctx);
+    }
     if (ctx->timing) CU(cudaEventRecord(ctx->ev[2], st));
     CU(cudaGetLastError());
     return 0;
@@ -464,10 +525,10 @@ static int alloc_series_for(vmb_ctx* ctx, const vmb_blocks* b, vmb_series** out)
     s->ctx = ctx;
     s->nseries = b->nseries;
     s->nblocks = b->nblocks;
-    s->rows = b->rows;
+    s->rows = b->rows + b->merge_rows;  // decoded blocks, then the merge area
     int rc = 0;
-    if (!rc) rc = dev_alloc(&s->d_ts, b->rows + 8);
-    if (!rc) rc = dev_alloc(&s->d_vals, b->rows + 8);
+    if (!rc) rc = dev_alloc(&s->d_ts, s->rows + 8);
+    if (!rc) rc = dev_alloc(&s->d_vals, s->rows + 8);
     if (!rc) rc = dev_alloc(&s->d_meta, b->nseries);
     if (!rc) rc = dev_alloc(&s->d_blk_lo, b->nblocks);
     if (!rc) rc = dev_alloc(&s->d_blk_hi, b->nblocks);
@@ -886,7 +947,7 @@ extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t
     CU(cudaSetDevice(ctx->device));
     // the decoded columns are a per-ctx cache sized for the largest batch seen
     static thread_local vmb_series* cache = nullptr;
-    if (cache && (cache->ctx != ctx || cache->rows < b->rows || cache->nseries < b->nseries || cache->nblocks < b->nblocks)) {
+    if (cache && (cache->ctx != ctx || cache->rows < b->rows + b->merge_rows || cache->nseries < b->nseries || cache->nblocks < b->nblocks)) {
         vmb_series_free(cache);
         cache = nullptr;
     }
@@ -897,7 +958,7 @@ extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t
     vmb_series view = *cache;  // shallow view with this batch's logical sizes
     view.nseries = b->nseries;
     view.nblocks = b->nblocks;
-    view.rows = b->rows;
+    view.rows = b->rows + b->merge_rows;
     if ((rc = ctx->counters.reserve(64))) return rc;
     unsigned int* d_failed = (unsigned int*)ctx->counters.p;
     unsigned long long* d_scanned = (unsigned long long*)((char*)ctx->counters.p + 8);

@@ -706,10 +706,18 @@ struct RollupParams {
     const vmb_block_desc* descs;
     int32_t* blk_status;
     unsigned int* failed_blocks;  // device counter: blocks with a non-zero status
+    // series whose blocks overlap in time (or touch): merged into [rows_total + ser_merge_off[s], ...) of ts/vals
+    const uint64_t* ser_merge_off;  // per series, UINT64_MAX = blocks are disjoint (plain concatenation); may be nullptr
+    uint64_t rows_total;            // rows of the decoded blocks = start of the merge area
+    uint32_t* merge_heap;           // scratch, one entry per block: the sortBlocksHeap of the series
+    uint32_t* merge_next;           // scratch, one entry per block: sortBlock.NextIdx
+    int64_t dedup_interval;         // storage.GetDedupInterval(), ms; 0 = off
 };
 
-// one thread per series: [start, n) from the kept row ranges of its blocks (netstorage.go:444 unpackTo for blocks
-// that are already time-ordered and disjoint -- the mergeSortBlocks fast path netstorage.go:585)
+// one thread per series: [start, n) from the kept row ranges of its blocks (netstorage.go:444 unpackTo + the part of
+// mergeSortBlocks netstorage.go:566 that needs no data movement: blocks that are disjoint in time were laid out in time order
+// by the host plan, so the series is the concatenation of their kept rows).  Series with overlapping blocks get their start
+// in the merge area and are filled by k_series_merge.
 __global__ void k_series_assemble(RollupParams P) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.nseries) return;
@@ -719,6 +727,7 @@ __global__ void k_series_assemble(RollupParams P) {
     m.n = 0;
     // bit 0: the series may hold Prometheus staleness markers; bit 1: the series may hold a value below its predecessor
     // (or a NaN), i.e. removeCounterResets may have something to do.  Both come from the decode kernel, per block.
+    // bit 2: the series is assembled by k_series_merge.
     m._pad = nb > 1 ? 2u : 0u;  // (a drop across a block boundary is not looked for: any multi-block series is a candidate)
     m.max_prev_interval = 0;
     m.window = 0;
@@ -727,29 +736,262 @@ __global__ void k_series_assemble(RollupParams P) {
         if (P.blk_status[fb + k]) failed = true;
         m._pad |= (P.blk_hi[fb + k] >> 31) | ((P.blk_hi[fb + k] >> 29) & 2u);  // decode.cu ValEmit
     }
+    const uint64_t moff = P.ser_merge_off ? P.ser_merge_off[s] : ~0ull;
     if (!failed && nb) {
-        // skip leading / trailing blocks that were trimmed away completely
-        uint32_t a = 0, b = nb;
-        while (a < b && (P.blk_hi[fb + a] & 0x3fffffffu) == P.blk_lo[fb + a]) a++;
-        while (b > a && (P.blk_hi[fb + b - 1] & 0x3fffffffu) == P.blk_lo[fb + b - 1]) b--;
-        if (a < b) {
-            bool contiguous = true;
-            for (uint32_t k = a; k < b; k++) {
-                if (k > a && P.blk_lo[fb + k] != 0) contiguous = false;
-                if (k + 1 < b && (P.blk_hi[fb + k] & 0x3fffffffu) != P.descs[fb + k].rows) contiguous = false;
+        if (moff != ~0ull) {
+            m.start = P.rows_total + moff;
+            m._pad |= 4u;
+        } else {
+            uint64_t lo = ~0ull, hi = 0, kept = 0;
+            for (uint32_t k = 0; k < nb; k++) {
+                const uint32_t a = P.blk_lo[fb + k], b = P.blk_hi[fb + k] & 0x3fffffffu;
+                if (b <= a) continue;  // trimmed away completely
+                const uint64_t r = P.row_off[fb + k];
+                lo = r + a < lo ? r + a : lo;
+                hi = r + b > hi ? r + b : hi;
+                kept += b - a;
             }
-            if (!contiguous) {
-                for (uint32_t k = 0; k < nb; k++) P.blk_status[fb + k] = VMB_ERR_BLOCK_ORDER;
-                failed = true;
-            } else {
-                m.start = P.row_off[fb + a] + P.blk_lo[fb + a];
-                uint64_t end = P.row_off[fb + b - 1] + (P.blk_hi[fb + b - 1] & 0x3fffffffu);
-                m.n = (uint32_t)(end - m.start);
+            if (kept) {
+                if (hi - lo != kept) {  // a hole inside the series: cannot happen for time-disjoint blocks and one time range
+                    for (uint32_t k = 0; k < nb; k++) P.blk_status[fb + k] = VMB_ERR_BLOCK_ORDER;
+                    failed = true;
+                } else {
+                    m.start = lo;
+                    m.n = (uint32_t)kept;
+                }
             }
         }
     }
     P.meta[s] = m;
     if (failed && P.failed_blocks) atomicAdd(P.failed_blocks, 1u);
+}
+
+// ---- mergeSortBlocks netstorage.go:566 for the series whose blocks overlap: one warp per series replays the reference's
+// loop -- container/heap over the blocks ordered by their next timestamp (Init / Fix / Pop with Go's exact sift rules, so
+// that samples with equal timestamps come out in the reference's order), "copy from the top block everything not after the
+// next block's head" -- with the copies, the binary search and equalSamplesPrefix done by the 32 lanes together.
+// All lanes run the control flow redundantly on the same values; lane 0 writes the heap, __syncwarp() orders it.
+struct MergeHeap {
+    volatile uint32_t* h;     // block ids
+    volatile uint32_t* next;  // NextIdx per block (row inside the block)
+    const int64_t* ts;
+    const uint64_t* row_off;
+    int lane;
+    __device__ __forceinline__ int64_t head(uint32_t b) const { return ts[row_off[b] + next[b]]; }
+    __device__ __forceinline__ bool less(uint32_t i, uint32_t j) const { return head(h[i]) < head(h[j]); }
+    __device__ __forceinline__ void swap(uint32_t i, uint32_t j) {
+        uint32_t a = h[i], b = h[j];
+        __syncwarp();
+        if (lane == 0) { h[i] = b; h[j] = a; }
+        __syncwarp();
+    }
+    __device__ bool down(uint32_t i0, uint32_t n) {
+        uint32_t i = i0;
+        for (;;) {
+            uint32_t j1 = 2 * i + 1;
+            if (j1 >= n) break;
+            uint32_t j = j1;
+            if (j1 + 1 < n && less(j1 + 1, j1)) j = j1 + 1;
+            if (!less(j, i)) break;
+            swap(i, j);
+            i = j;
+        }
+        return i > i0;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_series_merge(RollupParams P) {
+    const int lane = lane_id();
+    const uint32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < P.nseries; s += warps_per_grid) {
+        if (P.ser_merge_off[s] == ~0ull) continue;
+        SeriesMeta m = P.meta[s];
+        if (!(m._pad & 4u)) continue;  // failed series
+        const uint32_t fb = P.ser_first_block[s], nb = P.ser_nblocks[s];
+        MergeHeap H;
+        H.h = P.merge_heap + fb;
+        H.next = P.merge_next;
+        H.ts = P.ts;
+        H.row_off = P.row_off;
+        H.lane = lane;
+        uint32_t hn = 0;
+        for (uint32_t k = 0; k < nb; k++) {  // empty blocks never enter the heap (netstorage.go:568)
+            const uint32_t b = fb + k, lo = P.blk_lo[b], hi = P.blk_hi[b] & 0x3fffffffu;
+            if (hi > lo) {
+                if (lane == 0) { H.h[hn] = b; H.next[b] = lo; }
+                hn++;
+            }
+        }
+        __syncwarp();
+        for (uint32_t i = hn / 2; i-- > 0;) H.down(i, hn);  // heap.Init
+        uint64_t o = m.start;
+        while (hn) {
+            const uint32_t top = H.h[0];
+            const uint32_t idx = H.next[top], end = P.blk_hi[top] & 0x3fffffffu;
+            const uint64_t trow = P.row_off[top];
+            uint32_t adv, ncopy;
+            if (hn == 1) {
+                adv = ncopy = end - idx;
+            } else {
+                uint32_t nx = H.h[1];
+                if (hn >= 3 && !(H.head(H.h[1]) <= H.head(H.h[2]))) nx = H.h[2];  // getNextBlock netstorage.go:689
+                const int64_t ts_next = H.head(nx);
+                uint32_t eq = 0;
+                if (P.dedup_interval > 0) {  // equalSamplesPrefix netstorage.go:622: timestamps first, then value bits
+                    const uint64_t nrow = P.row_off[nx] + H.next[nx];
+                    const uint32_t lim = min(end - idx, (P.blk_hi[nx] & 0x3fffffffu) - H.next[nx]);
+                    uint32_t nt = 0;
+                    for (; nt < lim; nt += 32) {
+                        const uint32_t k = nt + lane;
+                        const bool same = k < lim && P.ts[trow + idx + k] == P.ts[nrow + k];
+                        const uint32_t bad = ~__ballot_sync(VMB_FULL, same);
+                        if (bad) { nt += __ffs((int)bad) - 1; break; }
+                    }
+                    nt = min(nt, lim);
+                    for (; eq < nt; eq += 32) {
+                        const uint32_t k = eq + lane;
+                        const bool same = k < nt && __double_as_longlong(P.vals[trow + idx + k]) == __double_as_longlong(P.vals[nrow + k]);
+                        const uint32_t bad = ~__ballot_sync(VMB_FULL, same);
+                        if (bad) { eq += __ffs((int)bad) - 1; break; }
+                    }
+                    eq = min(eq, nt);
+                }
+                if (eq > 0) {
+                    adv = eq;  // replicated samples at the top are skipped when deduplication is on
+                    ncopy = 0;
+                } else {
+                    // binarySearchTimestamps netstorage.go:646: rows of the top block with timestamp <= ts_next
+                    uint32_t c = 0;
+                    const uint32_t rem = end - idx;
+                    if (P.ts[trow + end - 1] <= ts_next) c = rem;
+                    else {
+                        for (; c < rem; c += 32) {
+                            const uint32_t k = c + lane;
+                            const bool le = k < rem && P.ts[trow + idx + k] <= ts_next;
+                            const uint32_t gt = ~__ballot_sync(VMB_FULL, le);
+                            if (gt) { c += __ffs((int)gt) - 1; break; }
+                        }
+                        c = min(c, rem);
+                    }
+                    adv = ncopy = c;
+                }
+            }
+            for (uint32_t k = lane; k < ncopy; k += 32) {
+                P.ts[o + k] = P.ts[trow + idx + k];
+                P.vals[o + k] = P.vals[trow + idx + k];
+            }
+            o += ncopy;
+            __syncwarp();
+            if (lane == 0) H.next[top] = idx + adv;
+            __syncwarp();
+            if (hn == 1) break;
+            if (idx + adv < end) {
+                H.down(0, hn);  // heap.Fix(0): up(0) is a no-op
+            } else {            // heap.Pop
+                H.swap(0, hn - 1);
+                H.down(0, hn - 1);
+                hn--;
+            }
+        }
+        if (lane == 0) {
+            m.n = (uint32_t)(o - m.start);
+            P.meta[s] = m;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- storage.DeduplicateSamples lib/storage/dedup.go:30, in place, one warp per series.  For non-negative timestamps the
+// reference's running tsNext is always the smallest multiple of the interval >= the first timestamp of the current bucket,
+// so a row is kept iff it is the last one of its bucket ceil(ts / interval); its value is the maximum over the rows with
+// the same timestamp, never a staleness marker when anything else exists (:50-64).  Series with a negative timestamp (Go's %
+// truncates toward zero there) replay the sequential loop on lane 0.
+__device__ __forceinline__ int64_t dedup_bucket(int64_t t, int64_t d) { return (t + d - 1) / d; }
+
+__device__ double dedup_pick(const int64_t* t, const double* v, uint32_t j) {
+    const int64_t tp = t[j];
+    double vp = v[j];
+    while (j > 0 && t[j - 1] == tp) {
+        j--;
+        const double x = v[j];
+        if (is_stale_nan(x)) continue;
+        if (is_stale_nan(vp)) { vp = x; continue; }
+        if (x > vp) vp = x;
+    }
+    return vp;
+}
+
+__global__ void __launch_bounds__(128) k_series_dedup(RollupParams P) {
+    const int lane = lane_id();
+    const int64_t D = P.dedup_interval;
+    const uint32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < P.nseries; s += warps_per_grid) {
+        SeriesMeta m = P.meta[s];
+        const uint32_t n = m.n;
+        if (n < 2) continue;
+        int64_t* t = P.ts + m.start;
+        double* v = P.vals + m.start;
+        uint32_t o = 0;
+        if (t[0] < 0) {  // timestamps are sorted: the first one decides
+            if (lane == 0) {
+                int64_t ts_next = t[0] + D - 1;
+                ts_next -= ts_next % D;
+                bool need = false;  // needsDedup dedup.go:158
+                for (uint32_t i = 1; i < n && !need; i++) {
+                    if (t[i] <= ts_next) need = true;
+                    ts_next += D;
+                    if (ts_next < t[i]) { ts_next = t[i] + D - 1; ts_next -= ts_next % D; }
+                }
+                o = n;
+                if (need) {
+                    o = 0;
+                    ts_next = t[0] + D - 1;
+                    ts_next -= ts_next % D;
+                    for (uint32_t i = 1; i < n; i++) {
+                        const int64_t ti = t[i];
+                        if (ti <= ts_next) continue;
+                        const double pv = dedup_pick(t, v, i - 1);
+                        const int64_t pt = t[i - 1];
+                        t[o] = pt; v[o] = pv; o++;
+                        ts_next += D;
+                        if (ts_next < ti) { ts_next = ti + D - 1; ts_next -= ts_next % D; }
+                    }
+                    const double pv = dedup_pick(t, v, n - 1);
+                    const int64_t pt = t[n - 1];
+                    t[o] = pt; v[o] = pv; o++;
+                }
+            }
+            o = __shfl_sync(VMB_FULL, o, 0);
+        } else {
+            bool need = false;
+            for (uint32_t i = 1 + lane; i < n; i += 32) need |= dedup_bucket(t[i], D) == dedup_bucket(t[i - 1], D);
+            if (!__any_sync(VMB_FULL, need)) continue;
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t i = base + lane;
+                bool keep = false;
+                int64_t ti = 0;
+                double vi = 0.0;
+                if (i < n) {
+                    ti = t[i];
+                    keep = i == n - 1 || dedup_bucket(t[i + 1], D) != dedup_bucket(ti, D);
+                    if (keep) vi = dedup_pick(t, v, i);
+                }
+                const uint32_t bal = __ballot_sync(VMB_FULL, keep);  // also orders the reads above before the writes below
+                if (keep) {
+                    const uint32_t r = o + __popc(bal & ((1u << lane) - 1u));
+                    t[r] = ti;
+                    v[r] = vi;
+                }
+                o += __popc(bal);
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            m.n = o;
+            P.meta[s] = m;
+        }
+        __syncwarp();
+    }
 }
 
 struct RcrState {
@@ -1425,6 +1667,18 @@ __global__ void k_aggr_finalize(int aggr, double* dv, const double* dc, size_t n
 void launch_series_assemble(const RollupParams& P, cudaStream_t st) {
     if (!P.nseries) return;
     k_series_assemble<<<(P.nseries + 127) / 128, 128, 0, st>>>(P);
+}
+void launch_series_merge(const RollupParams& P, cudaStream_t st) {
+    if (!P.nseries) return;
+    uint32_t grid = (P.nseries + 3) / 4;
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    k_series_merge<<<grid, 128, 0, st>>>(P);
+}
+void launch_series_dedup(const RollupParams& P, cudaStream_t st) {
+    if (!P.nseries) return;
+    uint32_t grid = (P.nseries + 3) / 4;
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    k_series_dedup<<<grid, 128, 0, st>>>(P);
 }
 void launch_series_prepare(const RollupParams& P, cudaStream_t st) {
     if (!P.nseries) return;
