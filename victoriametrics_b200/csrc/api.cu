@@ -448,7 +448,7 @@ static int run_decode(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, int64_t 
             launch_huf_decode(Z, st);
             count_launch(ctx, 2);
             if (b->needs_lit) {
-                launch_zstd_serial(Z, 0, st);
+                launch_zstd_sequences(Z, st);
                 count_launch(ctx);
             }
         }

@@ -974,6 +974,153 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
     }
 }
 
+// ---- sequences of prepared frames, one warp per frame.  The FSE bitstream is inherently serial: all 32 lanes decode it
+// redundantly (uniform control flow, broadcast loads; the three decoding tables sit in shared memory), and every literal run /
+// match copy is then carried out by the 32 lanes together -- 128 bytes per step for the common non-overlapping case, the
+// periodic pattern out[o+k] = out[o-offset + k % offset] when a match overlaps itself.
+#define SEQ_WARPS 4
+struct SeqTables {
+    uint32_t ll[512];
+    uint32_t ml[512];
+    uint32_t of[256];
+};
+
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+    uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
+    if (head > n) head = n;
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    const uint32_t words = (n - head) >> 2;
+    for (uint32_t w = lane; w < words; w += 32) *(uint32_t*)(dst + head + 4 * w) = load_u32_unaligned(src + head + 4 * w);
+    const uint32_t done = head + 4 * words;
+    if (done + lane < n) dst[done + lane] = src[done + lane];  // <= 3 tail bytes
+}
+
+// returns the number of bytes produced or -1 (same on every lane)
+__device__ long long run_sequences_warp(SeqTables* T, SerialWs* ws, uint8_t* out, long long out_cap, const uint8_t* lits,
+                                        uint32_t lit_len, const uint8_t* src, uint32_t len, int lane) {
+    if (len < 1) return -1;
+    uint32_t pos = 0, nseq;
+    const uint32_t b0 = src[0];
+    if (b0 == 0) { nseq = 0; pos = 1; }
+    else if (b0 < 128) { nseq = b0; pos = 1; }
+    else if (b0 < 255) {
+        if (len < 2) return -1;
+        nseq = ((b0 - 128) << 8) + src[1];
+        pos = 2;
+    } else {
+        if (len < 3) return -1;
+        nseq = (uint32_t)src[1] + ((uint32_t)src[2] << 8) + 0x7F00u;
+        pos = 3;
+    }
+    long long o = 0;
+    uint32_t lit_pos = 0;
+    if (nseq > 0) {
+        if (pos >= len) return -1;
+        const uint32_t modes = src[pos++];
+        if (modes & 3) return -1;
+        int ll_log = 0, of_log = 0, ml_log = 0, okw = 1;
+        if (lane == 0) {  // table descriptions are expanded by one lane; `ws` is this warp's scratch for the builder
+            bool ok;
+            int have = 0;
+            pos += read_seq_table(T->ll, &ll_log, &have, (modes >> 6) & 3, c_ll_default, 36, 6, 35, 9, src + pos, len - pos, ws, &ok);
+            if (ok) {
+                have = 0;
+                pos += read_seq_table(T->of, &of_log, &have, (modes >> 4) & 3, c_of_default, 29, 5, 31, 8, src + pos, len - pos, ws, &ok);
+            }
+            if (ok) {
+                have = 0;
+                pos += read_seq_table(T->ml, &ml_log, &have, (modes >> 2) & 3, c_ml_default, 53, 6, 52, 9, src + pos, len - pos, ws, &ok);
+            }
+            okw = ok && pos < len;
+        }
+        okw = __shfl_sync(VMB_FULL, okw, 0);
+        pos = __shfl_sync(VMB_FULL, pos, 0);
+        ll_log = __shfl_sync(VMB_FULL, ll_log, 0);
+        of_log = __shfl_sync(VMB_FULL, of_log, 0);
+        ml_log = __shfl_sync(VMB_FULL, ml_log, 0);
+        __syncwarp();
+        if (!okw) return -1;
+        BitR bb;
+        if (!bb.init(src + pos, len - pos)) return -1;
+        unsigned long long rep0 = 1, rep1 = 4, rep2 = 8;  // one block per prepared frame: the repeat offsets start fresh
+        uint32_t sll = bb.read(ll_log), sof = bb.read(of_log), sml = bb.read(ml_log);
+        for (uint32_t i = 0; i < nseq; i++) {
+            const uint32_t ell = T->ll[sll], eof = T->of[sof], eml = T->ml[sml];
+            const uint32_t ofc = FSE_SYM(eof), mlc = FSE_SYM(eml), llc = FSE_SYM(ell);
+            if (ofc > 31 || mlc > 52 || llc > 35) return -1;
+            const unsigned long long ofv = (1ull << ofc) + bb.read((int)ofc);
+            const uint32_t mlen = c_ml_base[mlc] + bb.read(c_ml_bits[mlc]);
+            const uint32_t llen = c_ll_base[llc] + bb.read(c_ll_bits[llc]);
+            if (i + 1 < nseq) {
+                sll = FSE_BASE(ell) + bb.read((int)FSE_NB(ell));
+                sml = FSE_BASE(eml) + bb.read((int)FSE_NB(eml));
+                sof = FSE_BASE(eof) + bb.read((int)FSE_NB(eof));
+            }
+            if (bb.left < 0) return -1;
+            unsigned long long offset;
+            if (ofv > 3) {
+                offset = ofv - 3;
+                rep2 = rep1; rep1 = rep0; rep0 = offset;
+            } else {
+                const unsigned long long idx = ofv - 1 + (llen == 0 ? 1 : 0);
+                if (idx == 0) offset = rep0;
+                else {
+                    offset = idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1);
+                    if (offset == 0) return -1;
+                    if (idx > 1) rep2 = rep1;
+                    rep1 = rep0;
+                    rep0 = offset;
+                }
+            }
+            if (lit_pos + llen > lit_len) return -1;
+            if (o + llen + mlen > out_cap) return -1;
+            if (llen) warp_copy(out + o, lits + lit_pos, llen, lane);
+            o += llen;
+            lit_pos += llen;
+            if ((long long)offset > o) return -1;
+            __syncwarp();  // the match may read what the literal run (or an earlier sequence) just wrote
+            if (offset >= mlen) {
+                warp_copy(out + o, out + o - (long long)offset, mlen, lane);
+            } else {
+                const uint8_t* pat = out + o - (long long)offset;
+                const uint32_t off32 = (uint32_t)offset;
+                for (uint32_t k = lane; k < mlen; k += 32) out[o + k] = pat[k % off32];
+            }
+            o += mlen;
+            __syncwarp();
+        }
+        if (bb.left != 0) return -1;
+    } else if (pos != len) {
+        return -1;
+    }
+    const uint32_t rest = lit_len - lit_pos;
+    if (o + rest > out_cap) return -1;
+    warp_copy(out + o, lits + lit_pos, rest, lane);
+    return o + rest;
+}
+
+__global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_sequences(ZstdParams P) {
+    __shared__ SeqTables s_tab[SEQ_WARPS];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * SEQ_WARPS + warp, nw = gridDim.x * SEQ_WARPS;
+    if (gw >= P.ws_count) return;
+    SerialWs* ws = (SerialWs*)P.ws + gw;
+    for (uint32_t i = gw; i < P.count; i += nw) {
+        const HufJob* job = &P.jobs[i];
+        if (job->nstreams == 0 || !job->dst_is_lit) continue;
+        const uint32_t col = job->col;
+        if (P.status[col]) continue;
+        const ColInfo ci = P.cols[col];
+        const uint8_t* src;
+        uint32_t len;
+        col_src(P, col, &src, &len);
+        long long o = run_sequences_warp(&s_tab[warp], ws, P.scratch + ci.scratch_off, ci.content_size, P.lit + ci.scratch_off,
+                                         job->regen_size, src + job->seq_off, job->seq_size, lane);
+        if (lane == 0 && o != (long long)ci.content_size) P.status[col] = VMB_ERR_ZSTD;
+        __syncwarp();
+    }
+}
+
 // ---- serial kernel: (mode 0) sequences of prepared frames, (mode 1) complete generic frames
 __global__ void k_zstd_serial(ZstdParams P, int mode) {
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1028,6 +1175,12 @@ void launch_huf_decode(const ZstdParams& P, cudaStream_t st) {
     uint32_t grid = (groups + HUF_WARPS - 1) / HUF_WARPS;
     if (grid > 148u * 16u) grid = 148u * 16u;
     k_huf_decode<<<grid, HUF_WARPS * 32, smem, st>>>(P);
+}
+
+void launch_zstd_sequences(const ZstdParams& P, cudaStream_t st) {
+    if (!P.count || !P.ws_count) return;
+    uint32_t warps = P.count < P.ws_count ? P.count : P.ws_count;
+    k_zstd_sequences<<<(warps + SEQ_WARPS - 1) / SEQ_WARPS, SEQ_WARPS * 32, 0, st>>>(P);
 }
 
 void launch_zstd_serial(const ZstdParams& P, int mode, cudaStream_t st) {
