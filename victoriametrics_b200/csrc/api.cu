@@ -67,6 +67,7 @@ struct vmb_ctx {
     float stage_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[6] = {0, 0, 0, 0, 0, 0};
     // scratch (reused across calls)
+    DevBuf zseq;  // decoded zstd sequences (8 B each) between k_zstd_seq_decode and k_zstd_seq_exec
     DevBuf zscratch, zlit, zstatus, zjobs, zws, args1, args2, rolled, counters, tmp_out, grp, mheap, mnext;
     int64_t dedup_interval = 0;  // storage.SetDedupInterval (lib/storage/dedup.go:15), ms; 0 = deduplication off
     void* h_pinned = nullptr;  // small pinned staging area for counters
@@ -79,6 +80,7 @@ struct vmb_blocks {
     size_t nblocks = 0, nseries = 0;
     uint64_t rows = 0, compressed = 0, scratch_total = 0;
     uint64_t merge_rows = 0;  // rows of the series whose blocks overlap in time: size of the merge area behind the blocks
+    uint64_t seq_total = 0;   // zstd sequences over all VMB_ZK_HUF columns (size of the record arena)
     bool needs_lit = false;
     uint32_t n_huf = 0, n_gen = 0, n_bad = 0;
     uint64_t* d_ser_merge_off = nullptr;  // per series: offset into the merge area, UINT64_MAX = none
@@ -142,7 +144,7 @@ extern "C" void vmb_ctx_destroy(vmb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->zscratch, &c->zlit, &c->zstatus, &c->zjobs, &c->zws, &c->args1, &c->args2, &c->rolled,
-                      &c->counters, &c->tmp_out, &c->grp, &c->mheap, &c->mnext};
+                      &c->counters, &c->tmp_out, &c->grp, &c->mheap, &c->mnext, &c->zseq};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 6; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -253,7 +255,7 @@ struct BlocksPlan {
     std::vector<uint64_t> row_off;
     std::vector<uint32_t> huf, gen, bad, ser_first, ser_nblocks;
     std::vector<uint64_t> ser_merge_off;
-    uint64_t rows = 0, compressed = 0, scratch_total = 0, merge_rows = 0;
+    uint64_t rows = 0, compressed = 0, scratch_total = 0, merge_rows = 0, seq_total = 0;
     bool needs_lit = false;
 };
 static int plan_blocks(BlocksPlan& pl, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload, size_t payload_len) {
@@ -284,7 +286,17 @@ static int plan_blocks(BlocksPlan& pl, const vmb_block_desc* descs, size_t nbloc
             uint32_t len = which ? d.val_size : d.ts_size;
             uint32_t cs = 0;
             bool needs_lit = false;
-            ci.kind = zstd_classify_host(src, len, d.rows <= 16384 ? d.rows : 0, &cs, &needs_lit);
+            uint32_t nseq = 0;
+            ci.kind = zstd_classify_host(src, len, d.rows <= 16384 ? d.rows : 0, &cs, &needs_lit, &nseq);
+            if (ci.kind == VMB_ZK_HUF && nseq) {
+                if (pl.seq_total + nseq > 0xffffffffull) {
+                    vmb_set_error("more than 2^32 zstd sequences in one batch: split it");
+                    return VMB_ERR_INVALID_ARG;
+                }
+                ci.nseq = nseq;
+                ci.seq_rec_off = (uint32_t)pl.seq_total;
+                pl.seq_total += nseq;
+            }
             ci.content_size = cs;
             uint32_t col = (uint32_t)(2 * b + which);
             if (ci.kind == VMB_ZK_BAD) {
@@ -352,6 +364,7 @@ extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size
     b->compressed = pl.compressed;
     b->scratch_total = pl.scratch_total;
     b->merge_rows = pl.merge_rows;
+    b->seq_total = pl.seq_total;
     b->needs_lit = pl.needs_lit;
     b->n_huf = (uint32_t)pl.huf.size();
     b->n_gen = (uint32_t)pl.gen.size();
@@ -428,6 +441,10 @@ static int run_decode(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, int64_t 
         Z.payload = b->d_payload;
         Z.scratch = (uint8_t*)ctx->zscratch.p;
         Z.lit = b->needs_lit ? (uint8_t*)ctx->zlit.p : nullptr;
+        if (b->seq_total) {
+            if ((rc = ctx->zseq.reserve(b->seq_total * 8))) return rc;
+            Z.seq_rec = (unsigned long long*)ctx->zseq.p;
+        }
         Z.status = d_zstatus;
         if (b->n_bad) {
             k_set_status<<<(b->n_bad + 127) / 128, 128, 0, st>>>(d_zstatus, b->d_bad_list, b->n_bad, VMB_ERR_ZSTD);
@@ -449,7 +466,7 @@ static int run_decode(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, int64_t 
             count_launch(ctx, 2);
             if (b->needs_lit) {
                 launch_zstd_sequences(Z, st);
-                count_launch(ctx);
+                count_launch(ctx, 2);
             }
         }
         if (b->n_gen) {

@@ -29,7 +29,11 @@ struct ColInfo {            // one per column (2 per block: [2*b] timestamps, [2
     uint32_t content_size;  // decompressed size (frame header)
     uint8_t kind;           // VMB_ZK_*
     uint8_t _pad[3];
+    uint32_t nseq;          // VMB_ZK_HUF: Number_of_Sequences of the block (read by the host plan from the section header)
+    uint32_t seq_rec_off;   // where this column's decoded sequence records start in the record arena
+    uint32_t _pad2;
 };
+static_assert(sizeof(ColInfo) == 32, "ColInfo layout");
 
 // job record written by the zstd prepare kernel for the lane-packed Huffman kernel
 struct HufJob {

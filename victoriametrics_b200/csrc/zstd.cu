@@ -615,6 +615,7 @@ struct ZstdParams {
     HufJob* jobs;          // one per list entry (prepare -> huf)
     void* ws;              // SerialWs array, one per resident thread of k_zstd_serial
     uint32_t ws_count;
+    unsigned long long* seq_rec;  // decoded sequences (literal length | match length | offset), ColInfo::seq_rec_off
 };
 
 __device__ __forceinline__ void col_src(const ZstdParams& P, uint32_t col, const uint8_t** src, uint32_t* len) {
@@ -974,16 +975,159 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
     }
 }
 
-// ---- sequences of prepared frames, one warp per frame.  The FSE bitstream is inherently serial: all 32 lanes decode it
-// redundantly (uniform control flow, broadcast loads; the three decoding tables sit in shared memory), and every literal run /
-// match copy is then carried out by the 32 lanes together -- 128 bytes per step for the common non-overlapping case, the
-// periodic pattern out[o+k] = out[o-offset + k % offset] when a match overlaps itself.
-#define SEQ_WARPS 4
+// ---- sequences of prepared frames, in two kernels.
+// k_zstd_seq_decode: the FSE bitstream of a frame is inherently serial, and its latency (table lookup -> extra bits -> next
+//   state) is what bounds the step; so it runs apart from the copies, SEQ_G lanes per frame (redundantly: same registers,
+//   broadcast loads, the three decoding tables in shared memory), 32 / SEQ_G frames per warp, and leaves one 8-byte record
+//   per sequence: literal length | match length | offset.
+// k_zstd_seq_exec: one warp per frame turns the records into bytes -- positions by warp scans, every literal run
+//   independent of the rest, the matches in order (32 lanes per copy; out[o+k] = out[o-offset + k % offset] when a match
+//   overlaps itself).
+#define SEQ_G 8
+#define SEQ_FPW (32 / SEQ_G)
+#define SEQ_WARPS 2
+#define SEQ_REC(ll, ml, of) (((unsigned long long)(ll) << 44) | ((unsigned long long)(ml) << 24) | (unsigned long long)(of))
+#define SEQ_REC_LL(r) ((uint32_t)((r) >> 44))
+#define SEQ_REC_ML(r) ((uint32_t)((r) >> 24) & 0xfffffu)
+#define SEQ_REC_OF(r) ((uint32_t)(r) & 0xffffffu)
 struct SeqTables {
     uint32_t ll[512];
     uint32_t ml[512];
     uint32_t of[256];
 };
+
+__global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P) {
+    __shared__ SeqTables s_tab[SEQ_WARPS * SEQ_FPW];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int grp = lane / SEQ_G, sub = lane % SEQ_G;
+    const uint32_t gslot = (blockIdx.x * SEQ_WARPS + warp) * SEQ_FPW + grp;  // this group's workspace slot
+    const uint32_t nslots = gridDim.x * SEQ_WARPS * SEQ_FPW;
+    SeqTables* T = &s_tab[warp * SEQ_FPW + grp];
+    SerialWs* ws = (SerialWs*)P.ws + gslot;  // scratch of the table builder (launch guarantees gslot < ws_count)
+    for (uint32_t i0 = (blockIdx.x * SEQ_WARPS + warp) * SEQ_FPW; i0 < P.count; i0 += nslots) {
+        const uint32_t i = i0 + grp;
+        // ---- per group: locate the frame, read the section header, expand the table descriptions (group leader)
+        bool act = i < P.count;
+        const HufJob* job = act ? &P.jobs[i] : nullptr;
+        if (act && (job->nstreams == 0 || !job->dst_is_lit)) act = false;
+        uint32_t col = 0;
+        if (act) {
+            col = job->col;
+            if (P.status[col]) act = false;
+        }
+        bool ok = true;
+        const uint8_t* src = nullptr;
+        uint32_t len = 0, lit_len = 0, nseq = 0, pos = 0;
+        long long out_cap = 0;
+        unsigned long long* rec = nullptr;
+        int ll_log = 0, of_log = 0, ml_log = 0;
+        if (act) {
+            const ColInfo ci = P.cols[col];
+            const uint8_t* fsrc;
+            uint32_t flen;
+            col_src(P, col, &fsrc, &flen);
+            src = fsrc + job->seq_off;
+            len = job->seq_size;
+            out_cap = ci.content_size;
+            lit_len = job->regen_size;
+            rec = P.seq_rec + ci.seq_rec_off;
+            if (len < 1) ok = false;
+            else {
+                const uint32_t b0 = src[0];
+                if (b0 < 128) { nseq = b0; pos = 1; }
+                else if (b0 < 255) {
+                    if (len < 2) ok = false;
+                    else { nseq = ((b0 - 128) << 8) + src[1]; pos = 2; }
+                } else {
+                    if (len < 3) ok = false;
+                    else { nseq = (uint32_t)src[1] + ((uint32_t)src[2] << 8) + 0x7F00u; pos = 3; }
+                }
+            }
+            if (ok && nseq != ci.nseq) ok = false;  // the record arena was sized by the host from the same byte(s)
+            if (ok && (nseq == 0 || pos >= len)) ok = false;
+            if (ok) {
+                const uint32_t modes = src[pos++];
+                if (modes & 3) ok = false;
+                if (ok && sub == 0) {
+                    bool tok;
+                    int have = 0;
+                    pos += read_seq_table(T->ll, &ll_log, &have, (modes >> 6) & 3, c_ll_default, 36, 6, 35, 9, src + pos, len - pos, ws, &tok);
+                    if (tok) {
+                        have = 0;
+                        pos += read_seq_table(T->of, &of_log, &have, (modes >> 4) & 3, c_of_default, 29, 5, 31, 8, src + pos, len - pos, ws, &tok);
+                    }
+                    if (tok) {
+                        have = 0;
+                        pos += read_seq_table(T->ml, &ml_log, &have, (modes >> 2) & 3, c_ml_default, 53, 6, 52, 9, src + pos, len - pos, ws, &tok);
+                    }
+                    if (!tok || pos >= len) ok = false;  // (leader only; the group learns it from the broadcast below)
+                }
+            }
+        }
+        {   // broadcast the leader's view inside each group (uniform code: all 32 lanes execute the shuffles)
+            const int leader = grp * SEQ_G;
+            ok = __shfl_sync(VMB_FULL, (int)ok, leader) != 0;
+            pos = __shfl_sync(VMB_FULL, pos, leader);
+            ll_log = __shfl_sync(VMB_FULL, ll_log, leader);
+            of_log = __shfl_sync(VMB_FULL, of_log, leader);
+            ml_log = __shfl_sync(VMB_FULL, ml_log, leader);
+        }
+        __syncwarp();
+        BitR bb;
+        bb.base = nullptr; bb.pos = 0; bb.buf = 0; bb.cnt = 0; bb.left = 0;
+        uint32_t sll = 0, sof = 0, sml = 0;
+        if (act && ok) {
+            if (!bb.init(src + pos, len - pos)) ok = false;
+            else {
+                sll = bb.read(ll_log);
+                sof = bb.read(of_log);
+                sml = bb.read(ml_log);
+            }
+        }
+        unsigned long long rep0 = 1, rep1 = 4, rep2 = 8;  // one block per prepared frame: the repeat offsets start fresh
+        long long o = 0;
+        uint32_t lit_pos = 0;
+        if (act && ok) {
+            for (uint32_t q = 0; q < nseq; q++) {
+                const uint32_t ell = T->ll[sll], eof = T->of[sof], eml = T->ml[sml];
+                const uint32_t ofc = FSE_SYM(eof), mlc = FSE_SYM(eml), llc = FSE_SYM(ell);
+                if (ofc > 31 || mlc > 52 || llc > 35) { ok = false; break; }
+                const unsigned long long ofv = (1ull << ofc) + bb.read((int)ofc);
+                const uint32_t mlen = c_ml_base[mlc] + bb.read(c_ml_bits[mlc]);
+                const uint32_t llen = c_ll_base[llc] + bb.read(c_ll_bits[llc]);
+                if (q + 1 < nseq) {
+                    sll = FSE_BASE(ell) + bb.read((int)FSE_NB(ell));
+                    sml = FSE_BASE(eml) + bb.read((int)FSE_NB(eml));
+                    sof = FSE_BASE(eof) + bb.read((int)FSE_NB(eof));
+                }
+                if (bb.left < 0) { ok = false; break; }
+                unsigned long long offset;
+                if (ofv > 3) {
+                    offset = ofv - 3;
+                    rep2 = rep1; rep1 = rep0; rep0 = offset;
+                } else {
+                    const unsigned long long idx = ofv - 1 + (llen == 0 ? 1 : 0);
+                    if (idx == 0) offset = rep0;
+                    else {
+                        offset = idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1);
+                        if (offset == 0) { ok = false; break; }
+                        if (idx > 1) rep2 = rep1;
+                        rep1 = rep0;
+                        rep0 = offset;
+                    }
+                }
+                if (lit_pos + llen > lit_len || o + llen + mlen > out_cap || (long long)offset > o + llen) { ok = false; break; }
+                o += (long long)llen + mlen;
+                lit_pos += llen;
+                if (sub == 0) rec[q] = SEQ_REC(llen, mlen, offset);  // all three < 2^20 here (out_cap <= 163840)
+            }
+            if (ok && bb.left != 0) ok = false;
+            if (ok && o + (long long)(lit_len - lit_pos) != out_cap) ok = false;
+        }
+        if (act && sub == 0 && !ok) P.status[col] = VMB_ERR_ZSTD;
+        __syncwarp();
+    }
+}
 
 __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
     uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
@@ -995,129 +1139,73 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint
     if (done + lane < n) dst[done + lane] = src[done + lane];  // <= 3 tail bytes
 }
 
-// returns the number of bytes produced or -1 (same on every lane)
-__device__ long long run_sequences_warp(SeqTables* T, SerialWs* ws, uint8_t* out, long long out_cap, const uint8_t* lits,
-                                        uint32_t lit_len, const uint8_t* src, uint32_t len, int lane) {
-    if (len < 1) return -1;
-    uint32_t pos = 0, nseq;
-    const uint32_t b0 = src[0];
-    if (b0 == 0) { nseq = 0; pos = 1; }
-    else if (b0 < 128) { nseq = b0; pos = 1; }
-    else if (b0 < 255) {
-        if (len < 2) return -1;
-        nseq = ((b0 - 128) << 8) + src[1];
-        pos = 2;
-    } else {
-        if (len < 3) return -1;
-        nseq = (uint32_t)src[1] + ((uint32_t)src[2] << 8) + 0x7F00u;
-        pos = 3;
-    }
-    long long o = 0;
-    uint32_t lit_pos = 0;
-    if (nseq > 0) {
-        if (pos >= len) return -1;
-        const uint32_t modes = src[pos++];
-        if (modes & 3) return -1;
-        int ll_log = 0, of_log = 0, ml_log = 0, okw = 1;
-        if (lane == 0) {  // table descriptions are expanded by one lane; `ws` is this warp's scratch for the builder
-            bool ok;
-            int have = 0;
-            pos += read_seq_table(T->ll, &ll_log, &have, (modes >> 6) & 3, c_ll_default, 36, 6, 35, 9, src + pos, len - pos, ws, &ok);
-            if (ok) {
-                have = 0;
-                pos += read_seq_table(T->of, &of_log, &have, (modes >> 4) & 3, c_of_default, 29, 5, 31, 8, src + pos, len - pos, ws, &ok);
-            }
-            if (ok) {
-                have = 0;
-                pos += read_seq_table(T->ml, &ml_log, &have, (modes >> 2) & 3, c_ml_default, 53, 6, 52, 9, src + pos, len - pos, ws, &ok);
-            }
-            okw = ok && pos < len;
-        }
-        okw = __shfl_sync(VMB_FULL, okw, 0);
-        pos = __shfl_sync(VMB_FULL, pos, 0);
-        ll_log = __shfl_sync(VMB_FULL, ll_log, 0);
-        of_log = __shfl_sync(VMB_FULL, of_log, 0);
-        ml_log = __shfl_sync(VMB_FULL, ml_log, 0);
-        __syncwarp();
-        if (!okw) return -1;
-        BitR bb;
-        if (!bb.init(src + pos, len - pos)) return -1;
-        unsigned long long rep0 = 1, rep1 = 4, rep2 = 8;  // one block per prepared frame: the repeat offsets start fresh
-        uint32_t sll = bb.read(ll_log), sof = bb.read(of_log), sml = bb.read(ml_log);
-        for (uint32_t i = 0; i < nseq; i++) {
-            const uint32_t ell = T->ll[sll], eof = T->of[sof], eml = T->ml[sml];
-            const uint32_t ofc = FSE_SYM(eof), mlc = FSE_SYM(eml), llc = FSE_SYM(ell);
-            if (ofc > 31 || mlc > 52 || llc > 35) return -1;
-            const unsigned long long ofv = (1ull << ofc) + bb.read((int)ofc);
-            const uint32_t mlen = c_ml_base[mlc] + bb.read(c_ml_bits[mlc]);
-            const uint32_t llen = c_ll_base[llc] + bb.read(c_ll_bits[llc]);
-            if (i + 1 < nseq) {
-                sll = FSE_BASE(ell) + bb.read((int)FSE_NB(ell));
-                sml = FSE_BASE(eml) + bb.read((int)FSE_NB(eml));
-                sof = FSE_BASE(eof) + bb.read((int)FSE_NB(eof));
-            }
-            if (bb.left < 0) return -1;
-            unsigned long long offset;
-            if (ofv > 3) {
-                offset = ofv - 3;
-                rep2 = rep1; rep1 = rep0; rep0 = offset;
-            } else {
-                const unsigned long long idx = ofv - 1 + (llen == 0 ? 1 : 0);
-                if (idx == 0) offset = rep0;
-                else {
-                    offset = idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1);
-                    if (offset == 0) return -1;
-                    if (idx > 1) rep2 = rep1;
-                    rep1 = rep0;
-                    rep0 = offset;
-                }
-            }
-            if (lit_pos + llen > lit_len) return -1;
-            if (o + llen + mlen > out_cap) return -1;
-            if (llen) warp_copy(out + o, lits + lit_pos, llen, lane);
-            o += llen;
-            lit_pos += llen;
-            if ((long long)offset > o) return -1;
-            __syncwarp();  // the match may read what the literal run (or an earlier sequence) just wrote
-            if (offset >= mlen) {
-                warp_copy(out + o, out + o - (long long)offset, mlen, lane);
-            } else {
-                const uint8_t* pat = out + o - (long long)offset;
-                const uint32_t off32 = (uint32_t)offset;
-                for (uint32_t k = lane; k < mlen; k += 32) out[o + k] = pat[k % off32];
-            }
-            o += mlen;
-            __syncwarp();
-        }
-        if (bb.left != 0) return -1;
-    } else if (pos != len) {
-        return -1;
-    }
-    const uint32_t rest = lit_len - lit_pos;
-    if (o + rest > out_cap) return -1;
-    warp_copy(out + o, lits + lit_pos, rest, lane);
-    return o + rest;
-}
-
-__global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_sequences(ZstdParams P) {
-    __shared__ SeqTables s_tab[SEQ_WARPS];
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t gw = blockIdx.x * SEQ_WARPS + warp, nw = gridDim.x * SEQ_WARPS;
-    if (gw >= P.ws_count) return;
-    SerialWs* ws = (SerialWs*)P.ws + gw;
+#define SEQX_WARPS 4
+__global__ void __launch_bounds__(SEQX_WARPS * 32) k_zstd_seq_exec(ZstdParams P) {
+    const int lane = lane_id();
+    const uint32_t gw = blockIdx.x * SEQX_WARPS + (threadIdx.x >> 5), nw = gridDim.x * SEQX_WARPS;
     for (uint32_t i = gw; i < P.count; i += nw) {
         const HufJob* job = &P.jobs[i];
         if (job->nstreams == 0 || !job->dst_is_lit) continue;
         const uint32_t col = job->col;
         if (P.status[col]) continue;
         const ColInfo ci = P.cols[col];
-        const uint8_t* src;
-        uint32_t len;
-        col_src(P, col, &src, &len);
-        long long o = run_sequences_warp(&s_tab[warp], ws, P.scratch + ci.scratch_off, ci.content_size, P.lit + ci.scratch_off,
-                                         job->regen_size, src + job->seq_off, job->seq_size, lane);
-        if (lane == 0 && o != (long long)ci.content_size) P.status[col] = VMB_ERR_ZSTD;
+        const unsigned long long* rec = P.seq_rec + ci.seq_rec_off;
+        const uint32_t nseq = ci.nseq;
+        uint8_t* out = P.scratch + ci.scratch_off;
+        const uint8_t* lits = P.lit + ci.scratch_off;
+        // ---- pass 1: literal runs (independent of everything else).  Positions: exclusive scans of (ll + ml) and ll.
+        uint32_t o_base = 0, l_base = 0;
+        for (uint32_t c = 0; c < nseq; c += 32) {
+            const uint32_t q = c + lane;
+            const unsigned long long r = q < nseq ? rec[q] : 0ull;
+            const uint32_t ll = SEQ_REC_LL(r), tot = ll + SEQ_REC_ML(r);
+            uint32_t so = tot, sl = ll;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t a = __shfl_up_sync(VMB_FULL, so, off), b = __shfl_up_sync(VMB_FULL, sl, off);
+                if (lane >= off) { so += a; sl += b; }
+            }
+            const uint32_t o = o_base + so - tot, lp = l_base + sl - ll;  // where this sequence's literals go / come from
+            const uint32_t maxll = __reduce_max_sync(VMB_FULL, ll);
+            if (maxll <= 16) {
+                for (uint32_t k = 0; k < ll; k++) out[o + k] = lits[lp + k];
+            } else {
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t n = __shfl_sync(VMB_FULL, ll, j);
+                    if (!n) continue;
+                    warp_copy(out + __shfl_sync(VMB_FULL, o, j), lits + __shfl_sync(VMB_FULL, lp, j), n, lane);
+                }
+            }
+            o_base += __shfl_sync(VMB_FULL, so, 31);
+            l_base += __shfl_sync(VMB_FULL, sl, 31);
+        }
+        warp_copy(out + o_base, lits + l_base, job->regen_size - l_base, lane);  // literals after the last sequence
         __syncwarp();
+        // ---- pass 2: the matches, in order
+        o_base = 0;
+        for (uint32_t c = 0; c < nseq; c += 32) {
+            const uint32_t q = c + lane;
+            const unsigned long long r = q < nseq ? rec[q] : 0ull;
+            const uint32_t ll = SEQ_REC_LL(r), ml = SEQ_REC_ML(r), of = SEQ_REC_OF(r);
+            uint32_t so = ll + ml;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t a = __shfl_up_sync(VMB_FULL, so, off);
+                if (lane >= off) so += a;
+            }
+            const uint32_t dst = o_base + so - ml;  // first byte of this sequence's match
+            const uint32_t cnt = min(32u, nseq - c);
+            for (uint32_t j = 0; j < cnt; j++) {
+                const uint32_t d = __shfl_sync(VMB_FULL, dst, j), m = __shfl_sync(VMB_FULL, ml, j), f = __shfl_sync(VMB_FULL, of, j);
+                if (f >= m) warp_copy(out + d, out + d - f, m, lane);
+                else {
+                    const uint8_t* pat = out + d - f;
+                    for (uint32_t k = lane; k < m; k += 32) out[d + k] = pat[k % f];
+                }
+                __syncwarp();
+            }
+            o_base += __shfl_sync(VMB_FULL, so, 31);
+        }
     }
 }
 
@@ -1178,9 +1266,16 @@ void launch_huf_decode(const ZstdParams& P, cudaStream_t st) {
 }
 
 void launch_zstd_sequences(const ZstdParams& P, cudaStream_t st) {
-    if (!P.count || !P.ws_count) return;
-    uint32_t warps = P.count < P.ws_count ? P.count : P.ws_count;
-    k_zstd_sequences<<<(warps + SEQ_WARPS - 1) / SEQ_WARPS, SEQ_WARPS * 32, 0, st>>>(P);
+    if (!P.count || !P.ws_count || !P.seq_rec) return;
+    const uint32_t per_cta = SEQ_WARPS * SEQ_FPW;
+    uint32_t groups = P.count < P.ws_count ? P.count : P.ws_count;  // one workspace slot per frame group
+    uint32_t grid = (groups + per_cta - 1) / per_cta;
+    if ((uint64_t)grid * per_cta > P.ws_count) grid = P.ws_count / per_cta;
+    if (grid == 0) grid = 1;
+    k_zstd_seq_decode<<<grid, SEQ_WARPS * 32, 0, st>>>(P);
+    uint32_t xgrid = (P.count + SEQX_WARPS - 1) / SEQX_WARPS;
+    if (xgrid > 148u * 16u) xgrid = 148u * 16u;
+    k_zstd_seq_exec<<<xgrid, SEQX_WARPS * 32, 0, st>>>(P);
 }
 
 void launch_zstd_serial(const ZstdParams& P, int mode, cudaStream_t st) {
@@ -1191,9 +1286,11 @@ void launch_zstd_serial(const ZstdParams& P, int mode, cudaStream_t st) {
 
 // ---- host-side classification at upload time: reads only the frame / block / literals headers
 // returns kind; fills content_size; *needs_lit = the literal arena is required for this column
-uint8_t zstd_classify_host(const uint8_t* src, uint32_t len, uint32_t rows, uint32_t* content_size, bool* needs_lit) {
+uint8_t zstd_classify_host(const uint8_t* src, uint32_t len, uint32_t rows, uint32_t* content_size, bool* needs_lit,
+                           uint32_t* nseq) {
     *needs_lit = false;
     *content_size = 0;
+    *nseq = 0;
     FrameHdr h;
     if (!parse_frame_header(&h, src, len)) return VMB_ZK_BAD;
     // a valid payload holds rows-1 varints of <= 10 bytes
@@ -1231,6 +1328,20 @@ uint8_t zstd_classify_host(const uint8_t* src, uint32_t len, uint32_t rows, uint
         hdr = 5;
     }
     if (hdr + csize >= bsize) return VMB_ZK_GENERIC;
-    *needs_lit = blk[hdr + csize] != 0;  // nbSeq byte
+    const uint8_t* sq = blk + hdr + csize;  // Number_of_Sequences (RFC 8878 3.1.1.3.2.1)
+    const uint32_t avail = bsize - hdr - csize;
+    uint32_t ns = sq[0];
+    if (ns >= 128) {
+        if (ns < 255) {
+            if (avail < 2) return VMB_ZK_GENERIC;
+            ns = ((ns - 128) << 8) + sq[1];
+        } else {
+            if (avail < 3) return VMB_ZK_GENERIC;
+            ns = (uint32_t)sq[1] + ((uint32_t)sq[2] << 8) + 0x7F00u;
+        }
+    }
+    if (ns == 0 && sq[0] != 0) return VMB_ZK_GENERIC;  // zero sequences spelled in the long form: leave it to the serial decoder
+    *nseq = ns;
+    *needs_lit = ns != 0;
     return VMB_ZK_HUF;
 }
