@@ -1092,13 +1092,39 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
                 const uint32_t ell = T->ll[sll], eof = T->of[sof], eml = T->ml[sml];
                 const uint32_t ofc = FSE_SYM(eof), mlc = FSE_SYM(eml), llc = FSE_SYM(ell);
                 if (ofc > 31 || mlc > 52 || llc > 35) { ok = false; break; }
-                const unsigned long long ofv = (1ull << ofc) + bb.read((int)ofc);
-                const uint32_t mlen = c_ml_base[mlc] + bb.read(c_ml_bits[mlc]);
-                const uint32_t llen = c_ll_base[llc] + bb.read(c_ll_bits[llc]);
-                if (q + 1 < nseq) {
-                    sll = FSE_BASE(ell) + bb.read((int)FSE_NB(ell));
-                    sml = FSE_BASE(eml) + bb.read((int)FSE_NB(eml));
-                    sof = FSE_BASE(eof) + bb.read((int)FSE_NB(eof));
+                // all the bits of this sequence in one go when the window holds them (it nearly always does): the six fields
+                // are cut out of the 64-bit window at precomputed offsets instead of six dependent read-and-shift steps
+                const bool more = q + 1 < nseq;
+                const uint32_t b_of = ofc, b_ml = c_ml_bits[mlc], b_ll = c_ll_bits[llc];
+                const uint32_t n_ll = more ? FSE_NB(ell) : 0u, n_ml = more ? FSE_NB(eml) : 0u, n_of = more ? FSE_NB(eof) : 0u;
+                const uint32_t o1 = b_of, o2 = o1 + b_ml, o3 = o2 + b_ll, o4 = o3 + n_ll, o5 = o4 + n_ml, need = o5 + n_of;
+                if (bb.cnt <= 32) bb.refill();
+                unsigned long long ofv;
+                uint32_t mlen, llen;
+                if ((int)need <= bb.cnt) {
+                    const uint64_t w = bb.buf;
+#define SEQ_CUT(off, nb) ((nb) ? (uint32_t)((w << (off)) >> (64u - (nb))) : 0u)
+                    ofv = (1ull << ofc) + SEQ_CUT(0u, b_of);
+                    mlen = c_ml_base[mlc] + SEQ_CUT(o1, b_ml);
+                    llen = c_ll_base[llc] + SEQ_CUT(o2, b_ll);
+                    if (more) {
+                        sll = FSE_BASE(ell) + SEQ_CUT(o3, n_ll);
+                        sml = FSE_BASE(eml) + SEQ_CUT(o4, n_ml);
+                        sof = FSE_BASE(eof) + SEQ_CUT(o5, n_of);
+                    }
+#undef SEQ_CUT
+                    bb.buf = need < 64u ? (w << need) : 0ull;
+                    bb.cnt -= (int)need;
+                    bb.left -= need;
+                } else {
+                    ofv = (1ull << ofc) + bb.read((int)ofc);
+                    mlen = c_ml_base[mlc] + bb.read(c_ml_bits[mlc]);
+                    llen = c_ll_base[llc] + bb.read(c_ll_bits[llc]);
+                    if (more) {
+                        sll = FSE_BASE(ell) + bb.read((int)FSE_NB(ell));
+                        sml = FSE_BASE(eml) + bb.read((int)FSE_NB(eml));
+                        sof = FSE_BASE(eof) + bb.read((int)FSE_NB(eof));
+                    }
                 }
                 if (bb.left < 0) { ok = false; break; }
                 unsigned long long offset;
@@ -1197,7 +1223,9 @@ __global__ void __launch_bounds__(SEQX_WARPS * 32) k_zstd_seq_exec(ZstdParams P)
             const uint32_t cnt = min(32u, nseq - c);
             for (uint32_t j = 0; j < cnt; j++) {
                 const uint32_t d = __shfl_sync(VMB_FULL, dst, j), m = __shfl_sync(VMB_FULL, ml, j), f = __shfl_sync(VMB_FULL, of, j);
-                if (f >= m) warp_copy(out + d, out + d - f, m, lane);
+                if (m <= 32) {  // the common case: one byte per lane, one step
+                    if ((uint32_t)lane < m) out[d + lane] = out[d - f + (f >= m ? (uint32_t)lane : (uint32_t)lane % f)];
+                } else if (f >= m) warp_copy(out + d, out + d - f, m, lane);
                 else {
                     const uint8_t* pat = out + d - f;
                     for (uint32_t k = lane; k < m; k += 32) out[d + k] = pat[k % f];
