@@ -1155,21 +1155,24 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
     }
 }
 
-__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+#define SEQX_WARPS 4
+#define SEQX_G 8  /* lanes per frame: matches are short (a dozen bytes), 32 lanes per copy would idle */
+__device__ __forceinline__ void groupx_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int sub) {
     uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
     if (head > n) head = n;
-    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    if ((uint32_t)sub < head) dst[sub] = src[sub];
     const uint32_t words = (n - head) >> 2;
-    for (uint32_t w = lane; w < words; w += 32) *(uint32_t*)(dst + head + 4 * w) = load_u32_unaligned(src + head + 4 * w);
+    for (uint32_t w = sub; w < words; w += SEQX_G) *(uint32_t*)(dst + head + 4 * w) = load_u32_unaligned(src + head + 4 * w);
     const uint32_t done = head + 4 * words;
-    if (done + lane < n) dst[done + lane] = src[done + lane];  // <= 3 tail bytes
+    if (done + sub < n) dst[done + sub] = src[done + sub];  // <= 3 tail bytes
 }
 
-#define SEQX_WARPS 4
 __global__ void __launch_bounds__(SEQX_WARPS * 32) k_zstd_seq_exec(ZstdParams P) {
-    const int lane = lane_id();
-    const uint32_t gw = blockIdx.x * SEQX_WARPS + (threadIdx.x >> 5), nw = gridDim.x * SEQX_WARPS;
-    for (uint32_t i = gw; i < P.count; i += nw) {
+    const int lane = lane_id(), sub = lane % SEQX_G;
+    const uint32_t gmask = ((1u << SEQX_G) - 1u) << (lane - sub);  // the lanes of this frame's group: all syncs are group-wide
+    const uint32_t gg = (blockIdx.x * SEQX_WARPS + (threadIdx.x >> 5)) * (32 / SEQX_G) + lane / SEQX_G;
+    const uint32_t ng = gridDim.x * SEQX_WARPS * (32 / SEQX_G);
+    for (uint32_t i = gg; i < P.count; i += ng) {
         const HufJob* job = &P.jobs[i];
         if (job->nstreams == 0 || !job->dst_is_lit) continue;
         const uint32_t col = job->col;
@@ -1181,58 +1184,58 @@ __global__ void __launch_bounds__(SEQX_WARPS * 32) k_zstd_seq_exec(ZstdParams P)
         const uint8_t* lits = P.lit + ci.scratch_off;
         // ---- pass 1: literal runs (independent of everything else).  Positions: exclusive scans of (ll + ml) and ll.
         uint32_t o_base = 0, l_base = 0;
-        for (uint32_t c = 0; c < nseq; c += 32) {
-            const uint32_t q = c + lane;
+        for (uint32_t c = 0; c < nseq; c += SEQX_G) {
+            const uint32_t q = c + sub;
             const unsigned long long r = q < nseq ? rec[q] : 0ull;
             const uint32_t ll = SEQ_REC_LL(r), tot = ll + SEQ_REC_ML(r);
             uint32_t so = tot, sl = ll;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t a = __shfl_up_sync(VMB_FULL, so, off), b = __shfl_up_sync(VMB_FULL, sl, off);
-                if (lane >= off) { so += a; sl += b; }
+            for (int off = 1; off < SEQX_G; off <<= 1) {
+                const uint32_t a = __shfl_up_sync(gmask, so, off, SEQX_G), b = __shfl_up_sync(gmask, sl, off, SEQX_G);
+                if (sub >= off) { so += a; sl += b; }
             }
             const uint32_t o = o_base + so - tot, lp = l_base + sl - ll;  // where this sequence's literals go / come from
-            const uint32_t maxll = __reduce_max_sync(VMB_FULL, ll);
-            if (maxll <= 16) {
+            if (__reduce_max_sync(gmask, ll) <= 8) {
                 for (uint32_t k = 0; k < ll; k++) out[o + k] = lits[lp + k];
             } else {
-                for (int j = 0; j < 32; j++) {
-                    const uint32_t n = __shfl_sync(VMB_FULL, ll, j);
-                    if (!n) continue;
-                    warp_copy(out + __shfl_sync(VMB_FULL, o, j), lits + __shfl_sync(VMB_FULL, lp, j), n, lane);
+                for (int j = 0; j < SEQX_G; j++) {
+                    const uint32_t n = __shfl_sync(gmask, ll, j, SEQX_G);
+                    const uint32_t oj = __shfl_sync(gmask, o, j, SEQX_G), lj = __shfl_sync(gmask, lp, j, SEQX_G);
+                    if (n) groupx_copy(out + oj, lits + lj, n, sub);
                 }
             }
-            o_base += __shfl_sync(VMB_FULL, so, 31);
-            l_base += __shfl_sync(VMB_FULL, sl, 31);
+            o_base += __shfl_sync(gmask, so, SEQX_G - 1, SEQX_G);
+            l_base += __shfl_sync(gmask, sl, SEQX_G - 1, SEQX_G);
         }
-        warp_copy(out + o_base, lits + l_base, job->regen_size - l_base, lane);  // literals after the last sequence
-        __syncwarp();
+        groupx_copy(out + o_base, lits + l_base, job->regen_size - l_base, sub);  // literals after the last sequence
+        __syncwarp(gmask);
         // ---- pass 2: the matches, in order
         o_base = 0;
-        for (uint32_t c = 0; c < nseq; c += 32) {
-            const uint32_t q = c + lane;
+        for (uint32_t c = 0; c < nseq; c += SEQX_G) {
+            const uint32_t q = c + sub;
             const unsigned long long r = q < nseq ? rec[q] : 0ull;
             const uint32_t ll = SEQ_REC_LL(r), ml = SEQ_REC_ML(r), of = SEQ_REC_OF(r);
             uint32_t so = ll + ml;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t a = __shfl_up_sync(VMB_FULL, so, off);
-                if (lane >= off) so += a;
+            for (int off = 1; off < SEQX_G; off <<= 1) {
+                const uint32_t a = __shfl_up_sync(gmask, so, off, SEQX_G);
+                if (sub >= off) so += a;
             }
             const uint32_t dst = o_base + so - ml;  // first byte of this sequence's match
-            const uint32_t cnt = min(32u, nseq - c);
+            const uint32_t cnt = min((uint32_t)SEQX_G, nseq - c);
             for (uint32_t j = 0; j < cnt; j++) {
-                const uint32_t d = __shfl_sync(VMB_FULL, dst, j), m = __shfl_sync(VMB_FULL, ml, j), f = __shfl_sync(VMB_FULL, of, j);
-                if (m <= 32) {  // the common case: one byte per lane, one step
-                    if ((uint32_t)lane < m) out[d + lane] = out[d - f + (f >= m ? (uint32_t)lane : (uint32_t)lane % f)];
-                } else if (f >= m) warp_copy(out + d, out + d - f, m, lane);
+                const uint32_t d = __shfl_sync(gmask, dst, j, SEQX_G), m = __shfl_sync(gmask, ml, j, SEQX_G);
+                const uint32_t f = __shfl_sync(gmask, of, j, SEQX_G);
+                if (m <= SEQX_G) {  // the common case: one byte per lane, one step
+                    if ((uint32_t)sub < m) out[d + sub] = out[d - f + (f >= m ? (uint32_t)sub : (uint32_t)sub % f)];
+                } else if (f >= m) groupx_copy(out + d, out + d - f, m, sub);
                 else {
                     const uint8_t* pat = out + d - f;
-                    for (uint32_t k = lane; k < m; k += 32) out[d + k] = pat[k % f];
+                    for (uint32_t k = sub; k < m; k += SEQX_G) out[d + k] = pat[k % f];
                 }
-                __syncwarp();
+                __syncwarp(gmask);
             }
-            o_base += __shfl_sync(VMB_FULL, so, 31);
+            o_base += __shfl_sync(gmask, so, SEQX_G - 1, SEQX_G);
         }
     }
 }
@@ -1301,7 +1304,8 @@ void launch_zstd_sequences(const ZstdParams& P, cudaStream_t st) {
     if ((uint64_t)grid * per_cta > P.ws_count) grid = P.ws_count / per_cta;
     if (grid == 0) grid = 1;
     k_zstd_seq_decode<<<grid, SEQ_WARPS * 32, 0, st>>>(P);
-    uint32_t xgrid = (P.count + SEQX_WARPS - 1) / SEQX_WARPS;
+    const uint32_t xper = SEQX_WARPS * (32 / SEQX_G);
+    uint32_t xgrid = (P.count + xper - 1) / xper;
     if (xgrid > 148u * 16u) xgrid = 148u * 16u;
     k_zstd_seq_exec<<<xgrid, SEQX_WARPS * 32, 0, st>>>(P);
 }
