@@ -998,6 +998,16 @@ struct SeqTables {
 
 __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P) {
     __shared__ SeqTables s_tab[SEQ_WARPS * SEQ_FPW];
+    // code -> (base value, extra bits): copies in shared memory, because the groups of a warp index them with different codes
+    // (constant memory would serve one address per pass)
+    __shared__ uint32_t s_ll_base[36], s_ml_base[53];
+    __shared__ uint8_t s_ll_bits[36], s_ml_bits[53];
+    for (uint32_t t = threadIdx.x; t < 53; t += blockDim.x) {
+        if (t < 36) { s_ll_base[t] = c_ll_base[t]; s_ll_bits[t] = c_ll_bits[t]; }
+        s_ml_base[t] = c_ml_base[t];
+        s_ml_bits[t] = c_ml_bits[t];
+    }
+    __syncthreads();
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int grp = lane / SEQ_G, sub = lane % SEQ_G;
     const uint32_t gslot = (blockIdx.x * SEQ_WARPS + warp) * SEQ_FPW + grp;  // this group's workspace slot
@@ -1084,71 +1094,84 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
                 sml = bb.read(ml_log);
             }
         }
-        unsigned long long rep0 = 1, rep1 = 4, rep2 = 8;  // one block per prepared frame: the repeat offsets start fresh
-        long long o = 0;
-        uint32_t lit_pos = 0;
-        if (act && ok) {
-            for (uint32_t q = 0; q < nseq; q++) {
+        uint32_t rep0 = 1, rep1 = 4, rep2 = 8;  // one block per prepared frame: the repeat offsets start fresh
+        uint32_t o = 0, lit_pos = 0;          // (everything fits 32 bits: content_size <= 163840)
+        // The loop is the same for every group of the warp (trip count = the longest frame, work predicated, no early
+        // exit): groups that left a loop at different times would never run in lockstep again, and the redundant
+        // instruction stream would be issued once per group instead of once per warp.
+        uint32_t nmax = (act && ok) ? nseq : 0u;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) nmax = max(nmax, __shfl_xor_sync(VMB_FULL, nmax, off));
+        for (uint32_t q = 0; q < nmax; q++) {
+            const bool run = act && ok && q < nseq;
+            if (run) {
                 const uint32_t ell = T->ll[sll], eof = T->of[sof], eml = T->ml[sml];
-                const uint32_t ofc = FSE_SYM(eof), mlc = FSE_SYM(eml), llc = FSE_SYM(ell);
-                if (ofc > 31 || mlc > 52 || llc > 35) { ok = false; break; }
+                const uint32_t ofc = min(FSE_SYM(eof), 31u), mlc = min(FSE_SYM(eml), 52u), llc = min(FSE_SYM(ell), 35u);
+                if (FSE_SYM(eof) > 31 || FSE_SYM(eml) > 52 || FSE_SYM(ell) > 35) ok = false;
                 // all the bits of this sequence in one go when the window holds them (it nearly always does): the six fields
                 // are cut out of the 64-bit window at precomputed offsets instead of six dependent read-and-shift steps
                 const bool more = q + 1 < nseq;
-                const uint32_t b_of = ofc, b_ml = c_ml_bits[mlc], b_ll = c_ll_bits[llc];
+                const uint32_t b_of = ofc, b_ml = s_ml_bits[mlc], b_ll = s_ll_bits[llc];
                 const uint32_t n_ll = more ? FSE_NB(ell) : 0u, n_ml = more ? FSE_NB(eml) : 0u, n_of = more ? FSE_NB(eof) : 0u;
                 const uint32_t o1 = b_of, o2 = o1 + b_ml, o3 = o2 + b_ll, o4 = o3 + n_ll, o5 = o4 + n_ml, need = o5 + n_of;
                 if (bb.cnt <= 32) bb.refill();
-                unsigned long long ofv;
-                uint32_t mlen, llen;
+                uint32_t x_of, x_ml, x_ll, x_sl, x_sm, x_so;
                 if ((int)need <= bb.cnt) {
                     const uint64_t w = bb.buf;
 #define SEQ_CUT(off, nb) ((nb) ? (uint32_t)((w << (off)) >> (64u - (nb))) : 0u)
-                    ofv = (1ull << ofc) + SEQ_CUT(0u, b_of);
-                    mlen = c_ml_base[mlc] + SEQ_CUT(o1, b_ml);
-                    llen = c_ll_base[llc] + SEQ_CUT(o2, b_ll);
-                    if (more) {
-                        sll = FSE_BASE(ell) + SEQ_CUT(o3, n_ll);
-                        sml = FSE_BASE(eml) + SEQ_CUT(o4, n_ml);
-                        sof = FSE_BASE(eof) + SEQ_CUT(o5, n_of);
-                    }
+                    x_of = SEQ_CUT(0u, b_of);
+                    x_ml = SEQ_CUT(o1, b_ml);
+                    x_ll = SEQ_CUT(o2, b_ll);
+                    x_sl = SEQ_CUT(o3, n_ll);
+                    x_sm = SEQ_CUT(o4, n_ml);
+                    x_so = SEQ_CUT(o5, n_of);
 #undef SEQ_CUT
                     bb.buf = need < 64u ? (w << need) : 0ull;
                     bb.cnt -= (int)need;
                     bb.left -= need;
                 } else {
-                    ofv = (1ull << ofc) + bb.read((int)ofc);
-                    mlen = c_ml_base[mlc] + bb.read(c_ml_bits[mlc]);
-                    llen = c_ll_base[llc] + bb.read(c_ll_bits[llc]);
-                    if (more) {
-                        sll = FSE_BASE(ell) + bb.read((int)FSE_NB(ell));
-                        sml = FSE_BASE(eml) + bb.read((int)FSE_NB(eml));
-                        sof = FSE_BASE(eof) + bb.read((int)FSE_NB(eof));
-                    }
+                    x_of = bb.read((int)b_of);
+                    x_ml = bb.read((int)b_ml);
+                    x_ll = bb.read((int)b_ll);
+                    x_sl = bb.read((int)n_ll);
+                    x_sm = bb.read((int)n_ml);
+                    x_so = bb.read((int)n_of);
                 }
-                if (bb.left < 0) { ok = false; break; }
-                unsigned long long offset;
+                const uint32_t ofv = (1u << ofc) + x_of;  // offset codes > 24 cannot be valid here and fail the range check
+                const uint32_t mlen = s_ml_base[mlc] + x_ml, llen = s_ll_base[llc] + x_ll;
+                if (more) {
+                    sll = FSE_BASE(ell) + x_sl;
+                    sml = FSE_BASE(eml) + x_sm;
+                    sof = FSE_BASE(eof) + x_so;
+                }
+                if (bb.left < 0) ok = false;
+                if (ofc > 24) ok = false;
+                uint32_t offset;
                 if (ofv > 3) {
                     offset = ofv - 3;
                     rep2 = rep1; rep1 = rep0; rep0 = offset;
                 } else {
-                    const unsigned long long idx = ofv - 1 + (llen == 0 ? 1 : 0);
+                    const uint32_t idx = ofv - 1 + (llen == 0 ? 1 : 0);
                     if (idx == 0) offset = rep0;
                     else {
                         offset = idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1);
-                        if (offset == 0) { ok = false; break; }
+                        if (offset == 0) ok = false;
                         if (idx > 1) rep2 = rep1;
                         rep1 = rep0;
                         rep0 = offset;
                     }
                 }
-                if (lit_pos + llen > lit_len || o + llen + mlen > out_cap || (long long)offset > o + llen) { ok = false; break; }
-                o += (long long)llen + mlen;
+                if (lit_pos + llen > lit_len || (unsigned long long)o + llen + mlen > (unsigned long long)out_cap || offset > o + llen ||
+                    offset == 0)
+                    ok = false;
+                o += llen + mlen;
                 lit_pos += llen;
-                if (sub == 0) rec[q] = SEQ_REC(llen, mlen, offset);  // all three < 2^20 here (out_cap <= 163840)
+                if (sub == 0 && ok) rec[q] = SEQ_REC(llen, mlen, offset);
             }
-            if (ok && bb.left != 0) ok = false;
-            if (ok && o + (long long)(lit_len - lit_pos) != out_cap) ok = false;
+        }
+        if (act && ok) {
+            if (bb.left != 0) ok = false;
+            if (ok && (long long)o + (long long)(lit_len - lit_pos) != out_cap) ok = false;
         }
         if (act && sub == 0 && !ok) P.status[col] = VMB_ERR_ZSTD;
         __syncwarp();
