@@ -37,7 +37,7 @@ extern "C" {
 #define VMB_ERR_DELTA_CONST (-8)      /* encoding.go:235 */
 #define VMB_ERR_TS_BOUNDS (-9)        /* lib/storage/block.go:298 checkTimestampsBounds */
 #define VMB_ERR_ROWS (-10)            /* block.go:263 RowsCount must be > 0; block_header.go:233 <= 16384 */
-#define VMB_ERR_BLOCK_ORDER (-11)     /* blocks of one series overlap in time: needs mergeSortBlocks */
+#define VMB_ERR_BLOCK_ORDER (-11)     /* internal consistency check of the series assembly (a hole between time-disjoint blocks) */
 /* API-level errors */
 #define VMB_ERR_INVALID_ARG (-50)     /* the Go code would logger.Panicf("BUG: ...") */
 #define VMB_ERR_CUDA (-51)
@@ -74,7 +74,7 @@ typedef struct {
     uint32_t ts_size;        /* TimestampsBlockSize */
     uint32_t val_size;       /* ValuesBlockSize */
     uint32_t rows;           /* RowsCount, 1..16384 */
-    uint32_t series_idx;     /* dense series index; the blocks of one series are consecutive and time-ordered */
+    uint32_t series_idx;     /* dense series index; the blocks of one series are consecutive, in any order (may overlap) */
     int16_t scale;           /* Scale: value = mantissa * 10^scale */
     uint8_t ts_mt;           /* TimestampsMarshalType 1..6 (lib/encoding/encoding.go:20-43) */
     uint8_t val_mt;          /* ValuesMarshalType */
