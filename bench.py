@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--blocks", type=int, default=100_000, help="blocks (= series) per GPU")
     ap.add_argument("--rows", type=int, default=8192)
     ap.add_argument("--func", default="rate")
+    ap.add_argument("--kind", default="counter", choices=["counter", "gauge", "mixed"],
+                    help="synthetic values: counter = configs[1] (default), gauge = configs[2]-style round(N(5000,300)) at "
+                         "scale -2, mixed = configs[4]-style 40%% counters / 30%% gauges / 20%% const / 10%% delta-const")
     ap.add_argument("--window-ms", type=int, default=300_000)
     ap.add_argument("--step-ms", type=int, default=15_000)
     ap.add_argument("--no-e2e", action="store_true")
@@ -55,7 +58,11 @@ def parse_args():
 
 
 # ------------------------------------------------------------------------------------------------ synthetic input
-def gen_blocks(nblocks, rows, seed, chunk=4000):
+GEN_STATS = {"series": 0, "series_with_drop": 0}
+RCR_FUNCS = ("rate", "increase", "irate", "increase_pure", "increase_prometheus", "rate_prometheus", "rollup_rate", "rollup_increase")
+
+
+def gen_blocks(nblocks, rows, seed, chunk=4000, kind="counter"):
     """node_cpu_seconds_total-like counters, marshaled by the product's own encoder
     (vmb_marshal_columns).  -> (descs structured array, payload np.uint8)"""
     from victoriametrics_b200 import encoding, storage
@@ -75,6 +82,17 @@ def gen_blocks(nblocks, rows, seed, chunk=4000):
         resets[:, 0] = False
         base = np.maximum.accumulate(np.where(resets, v, 0), axis=1)
         v -= base
+        if kind != "counter":
+            g = np.rint(rng.normal(5000.0, 300.0, (n, rows))).astype(np.int64)
+            if kind == "gauge":
+                v = g
+            else:  # mixed: series i takes its kind from i mod 10
+                k = (np.arange(c0, c0 + n) % 10)[:, None]
+                const = np.broadcast_to(rng.integers(0, 10 ** 6, (n, 1)), (n, rows))
+                dconst = rng.integers(0, 10 ** 6, (n, 1)) + rng.integers(1, 100, (n, 1)) * np.arange(rows, dtype=np.int64)[None, :]
+                v = np.where(k < 4, v, np.where(k < 7, g, np.where(k < 9, const, dconst)))
+        GEN_STATS["series"] += n
+        GEN_STATS["series_with_drop"] += int(np.count_nonzero((np.diff(v, axis=1) < 0).any(axis=1)))
         payload, offs, mts, firsts = encoding.marshal_columns(v)
         pieces.append(payload)
         cols["first_value"].append(firsts)
@@ -199,8 +217,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     start, end, step = query_range(a.rows, a.window_ms, a.step_ms)
     points = 1 + (end - start) // step
-    workload = "configs[1]: decode %d blocks x %d samples (ts delta-const, values zstd nearest-delta2 counters, scale %d) + %s()[%ds] step=%ds per GPU" % (
-        a.blocks, a.rows, SCALE, a.func, a.window_ms // 1000, a.step_ms // 1000)
+    what = {"counter": "configs[1]: decode %d blocks x %d samples (ts delta-const, values zstd nearest-delta2 counters, scale %d)",
+            "gauge": "configs[2]-style: decode %d blocks x %d samples (ts delta-const, values zstd nearest-delta gauges, scale %d)",
+            "mixed": "configs[4]-style: decode %d blocks x %d samples (40%% counters, 30%% gauges, 20%% const, 10%% delta-const, scale %d)"}[a.kind]
+    workload = (what + " + %s()[%ds] step=%ds per GPU") % (a.blocks, a.rows, SCALE, a.func, a.window_ms // 1000, a.step_ms // 1000)
     base = {"metric": "rollup samples/sec (block decode + %s, raw samples decoded and scanned per second)" % a.func,
             "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64 codec -> f64 rollup", "data": "synthetic",
@@ -211,7 +231,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        descs, payload = gen_blocks(min(a.blocks, 20000), a.rows, seed=1234)
+        descs, payload = gen_blocks(min(a.blocks, 20000), a.rows, seed=1234, kind=a.kind)
         vals = []
         for _ in range(a.warmup):
             cpu_reference(descs, payload, a.func, start, end, step, a.window_ms, 2.0)
@@ -242,7 +262,7 @@ def main():
     ctx.set_stream(stream.cuda_stream)
 
     t_gen = time.perf_counter()
-    descs, payload = gen_blocks(a.blocks, a.rows, seed=1234 + rank)
+    descs, payload = gen_blocks(a.blocks, a.rows, seed=1234 + rank, kind=a.kind)
     gen_s = time.perf_counter() - t_gen
     rows_total = int(a.blocks) * int(a.rows)
     compressed = int(descs["val_size"].sum()) + int(descs["ts_size"][0])
@@ -361,10 +381,12 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
         varint_bytes = int(2 * rows_total)  # ~2 B/sample zig-zag varints in this workload (measured: raw/zstd ratio 0.86)
+        drop_frac = (GEN_STATS["series_with_drop"] / max(GEN_STATS["series"], 1)) if a.func in RCR_FUNCS else 0.0
         stage_names = ["zstd", "column_decode", "series_preamble", "rollup", "aggregate"]
         stage_bytes = [compressed + varint_bytes,                          # zstd: read frames, write varint bytes
                        varint_bytes + 64 * a.blocks + rows_total * 16,     # decode: read varints + descs, write ts+val
-                       rows_total * 16,                                    # preamble: read+write values (removeCounterResets)
+                       int(rows_total * 16 * drop_frac),                   # preamble: read+write values of the series that
+                                                                           # hold a value drop (removeCounterResets), others skipped
                        rows_total * 16 + a.blocks * points * 8, 0]         # rollup: read ts+val, write result
         stages = {}
         for n_, ms_, b_ in zip(stage_names, stage_ms, stage_bytes):
@@ -402,6 +424,7 @@ def main():
         out["config"]["compressed_bytes_per_gpu"] = compressed
         out["config"]["bytes_per_sample_compressed"] = round(compressed / rows_total, 3)
         out["config"]["input_generation_s"] = round(gen_s, 1)
+        out["config"]["series_with_a_counter_reset"] = round(GEN_STATS["series_with_drop"] / max(GEN_STATS["series"], 1), 3)
         if world == 1 and a.cpu_seconds > 0:
             try:
                 cb, _ = cpu_reference(descs, payload, a.func, start, end, step, a.window_ms, a.cpu_seconds)
