@@ -168,8 +168,9 @@ def cpu_reference(descs, payload, func, start, end, step, window, target_seconds
     fn.argtypes = [C.c_void_p, C.c_size_t, O.u8p, C.c_int64, C.c_int64, C.POINTER(O.RollupCfg), C.c_int, C.c_int, O.f64p,
                    C.POINTER(C.c_uint64), C.c_int, C.c_int]
     rc = promql.get_rollup_configs(func, start, end, step, window)
+    phis = np.full(rc.points, 0.99) if func == "quantile_over_time" else None  # kept alive by this frame
     cfg = O.RollupCfg(RF[func], start, end, step, window, 0, 0, int(rc.MayAdjustWindow), int(rc.isDefaultRollup),
-                      rc.samplesScannedPerCall, None, None)
+                      rc.samplesScannedPerCall, phis.ctypes.data_as(O.f64p) if phis is not None else None, None)
     cores = os.cpu_count() or 1
     try:
         cores = len(os.sched_getaffinity(0))
@@ -276,8 +277,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    func_args = np.full(points, 0.99) if a.func == "quantile_over_time" else None  # quantile_over_time(0.99, m[d])
+
     def dev_step():
-        return promql.eval_rollup_func(a.func, blocks, start, end, step, a.window_ms, out_dev_ptr=out_dev.data_ptr())
+        return promql.eval_rollup_func(a.func, blocks, start, end, step, a.window_ms, args=func_args, out_dev_ptr=out_dev.data_ptr())
 
     if a.aggr:
         # sum(rate(m[5m])) by (label): every rank folds its own series into [groups x points] partial states, one NCCL
@@ -345,8 +348,8 @@ def main():
         h_out = np.ctypeslib.as_array(C.cast(ho, C.POINTER(C.c_double)), shape=(a.blocks, points))
 
         def host_step():
-            return promql.eval_rollup_func_host(a.func, h_descs, h_payload, start, end, step, a.window_ms, out=h_out,
-                                                nseries=a.blocks, ctx=ctx)
+            return promql.eval_rollup_func_host(a.func, h_descs, h_payload, start, end, step, a.window_ms, args=func_args,
+                                                out=h_out, nseries=a.blocks, ctx=ctx)
         for _ in range(max(1, min(a.warmup, 2))):
             host_step()
         barrier()

@@ -766,6 +766,15 @@ static int check_cfg(const vmb_rollup_cfg* cfg, int64_t* points) {
     }
     *points = 1 + (cfg->end - cfg->start) / cfg->step;
     if (*points > 0x7fffffff) return VMB_ERR_INVALID_ARG;
+    // functions with a per-point argument (rollup.go: newRollupQuantile, newRollupPredictLinear, ... newRollupHoltWinters)
+    if ((cfg->func_id == VMB_RF_QUANTILE || (cfg->func_id >= VMB_RF_PREDICT_LINEAR && cfg->func_id <= VMB_RF_SUM_EQ)) && !cfg->args) {
+        vmb_set_error("rollup func %d needs cfg.args (one value per output point)", cfg->func_id);
+        return VMB_ERR_INVALID_ARG;
+    }
+    if (cfg->func_id == VMB_RF_HOLT_WINTERS && (!cfg->args || !cfg->args2)) {
+        vmb_set_error("holt_winters needs cfg.args (sf) and cfg.args2 (tf)");
+        return VMB_ERR_INVALID_ARG;
+    }
     return 0;
 }
 
@@ -824,11 +833,6 @@ extern "C" int vmb_rollup(vmb_ctx* ctx, vmb_series* s, const vmb_rollup_cfg* cfg
     int64_t points;
     int rc = check_cfg(cfg, &points);
     if (rc) return rc;
-    if ((cfg->func_id == VMB_RF_QUANTILE || (cfg->func_id >= VMB_RF_PREDICT_LINEAR && cfg->func_id <= VMB_RF_SUM_EQ)) && !cfg->args) {
-        vmb_set_error("rollup func %d needs cfg.args", cfg->func_id);
-        return VMB_ERR_INVALID_ARG;
-    }
-    if (cfg->func_id == VMB_RF_HOLT_WINTERS && !cfg->args2) return VMB_ERR_INVALID_ARG;
     CU(cudaSetDevice(ctx->device));
     size_t total = (size_t)s->nseries * (size_t)points;
     double* d_out = out;
