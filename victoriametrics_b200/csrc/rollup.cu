@@ -55,8 +55,55 @@ __device__ double quantile_tf(double phi, const double* v, uint32_t n, T tf) {
     double lower = fmax(0.0, floor(rank));
     double upper = fmin(nn - 1, lower + 1);
     double weight = rank - floor(rank);
-    double vlo = kth_smallest(v, n, (uint32_t)(int)lower, tf);
-    double vhi = kth_smallest(v, n, (uint32_t)(int)upper, tf);
+    const uint32_t kl = (uint32_t)(int)lower, ku = (uint32_t)(int)upper;
+    double vlo, vhi;
+    if (m - 1 - kl <= 3) {
+        // both order statistics are among the four largest values (phi = 0.9 ... 1 for the usual 20-sample window):
+        // one pass with the four largest kept sorted in registers
+        double t0 = -D_INF, t1 = -D_INF, t2 = -D_INF, t3 = -D_INF;  // t0 >= t1 >= t2 >= t3
+        for (uint32_t a = 0; a < n; a++) {
+            double x = tf(v[a]);
+            if (isnan(x)) continue;
+            if (x > t3) {
+                t3 = x;
+                if (t3 > t2) { double s = t2; t2 = t3; t3 = s; }
+                if (t2 > t1) { double s = t1; t1 = t2; t2 = s; }
+                if (t1 > t0) { double s = t0; t0 = t1; t1 = s; }
+            }
+        }
+        const uint32_t dl = m - 1 - kl, du = m - 1 - ku;  // distance from the maximum
+        vlo = dl == 0 ? t0 : (dl == 1 ? t1 : (dl == 2 ? t2 : t3));
+        vhi = du == 0 ? t0 : (du == 1 ? t1 : (du == 2 ? t2 : t3));
+    } else if (ku <= 3) {
+        double t0 = D_INF, t1 = D_INF, t2 = D_INF, t3 = D_INF;  // t0 <= t1 <= t2 <= t3: the four smallest
+        for (uint32_t a = 0; a < n; a++) {
+            double x = tf(v[a]);
+            if (isnan(x)) continue;
+            if (x < t3) {
+                t3 = x;
+                if (t3 < t2) { double s = t2; t2 = t3; t3 = s; }
+                if (t2 < t1) { double s = t1; t1 = t2; t2 = s; }
+                if (t1 < t0) { double s = t0; t0 = t1; t1 = s; }
+            }
+        }
+        vlo = kl == 0 ? t0 : (kl == 1 ? t1 : (kl == 2 ? t2 : t3));
+        vhi = ku == 0 ? t0 : (ku == 1 ? t1 : (ku == 2 ? t2 : t3));
+    } else {
+        // general case: rank every value once, pick both neighbours of the rank in the same pass
+        vlo = vhi = D_NAN;
+        for (uint32_t a = 0; a < n; a++) {
+            double x = tf(v[a]);
+            if (isnan(x)) continue;
+            uint32_t less = 0, leq = 0;
+            for (uint32_t b = 0; b < n; b++) {
+                double y = tf(v[b]);
+                less += (y < x);
+                leq += (y <= x);
+            }
+            if (less <= kl && kl < leq) vlo = x;
+            if (less <= ku && ku < leq) vhi = x;
+        }
+    }
     return vlo * (1 - weight) + vhi * weight;
 }
 __device__ double quantile(double phi, const double* v, uint32_t n) { return quantile_tf(phi, v, n, Ident()); }
