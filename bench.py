@@ -116,43 +116,99 @@ def query_range(rows, window_ms, step_ms):
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
+    """SM clock / throttle reasons / power sampled DURING the timed region: NVML in-process every ~2 ms (the timed region of
+    the device-resident arm is < 100 ms), `nvidia-smi -lms` as the fallback"""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, pci_bus_id=None):
         self.gpu = gpu_index
-        self.rows = []
+        self.pci = pci_bus_id
+        self.rows = []   # (time, sm_mhz, max_mhz, power_w, [reasons])
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.pci:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByPciBusId(self.pci.encode() if isinstance(self.pci, str) else self.pci)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml = (pynvml, h)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nvml
+        R = (("hw_slowdown", getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+             ("hw_thermal_slowdown", getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+             ("sw_thermal_slowdown", getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+             ("sw_power_cap", getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = int(get_reasons(h))
+                try:
+                    pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = 0.0
+                self.rows.append((time.time(), sm, self.max_mhz, pw, [n for n, bit in R if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+            r = [x.strip() for x in line.split(",")]
+            if len(r) >= 9:
+                try:
+                    reasons = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9])
+                               if v.lower().startswith("active")]
+                    self.rows.append((time.time(), float(r[1]), float(r[2]), float(r[3]), reasons))
+                except ValueError:
+                    pass
 
-    def stop(self, t_begin, t_end):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t_begin - 0.05 <= t <= t_end + 0.15 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+    def window(self, t_begin, t_end):
+        rows = [r for r in self.rows if t_begin <= r[0] <= t_end]
+        src = "inside the timed region"
+        if not rows:
+            rows = [r for r in self.rows if t_begin - 0.2 <= r[0] <= t_end + 0.2]
+            src = "within 0.2 s of the timed region"
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows)
-        reasons = set()
-        for r in rows:
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows),
-                "power_w_max": max(float(r[3]) for r in rows)}
+        sm = sorted(r[1] for r in rows)
+        reasons = sorted({n for r in rows for n in r[4]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": rows[0][2], "reasons": reasons, "samples": len(rows),
+                "power_w_max": round(max(r[3] for r in rows), 1), "sampled": src,
+                "via": "nvml" if self.nvml else "nvidia-smi"}
+
+    def stop(self, t_begin=None, t_end=None):
+        self.stop_flag = True
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+        if t_begin is None:
+            return None
+        return self.window(t_begin, t_end)
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -311,7 +367,13 @@ def main():
     # ---- kernel-only: compressed blocks resident in HBM
     for _ in range(a.warmup):
         dev_step()
-    sampler = ClockSampler(local_rank)
+    pci = None
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        pci = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        pass
+    sampler = ClockSampler(local_rank, pci)
     sampler.start()
     barrier()
     l0 = ctx.launch_count
@@ -326,7 +388,7 @@ def main():
     te = time.time()
     launches = ctx.launch_count - l0
     dev_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(tb, te)
+    clocks = sampler.window(tb, te)
     # per-stage device times of one extra step (CUDA events inside the library, same stream)
     ctx.enable_stage_timing(True)
     dev_step()
@@ -355,18 +417,21 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tw = time.perf_counter()
+        tb2 = time.time()
         e0.record(stream)
         for _ in range(a.steps):
             host_step()
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - tw
+        e2e_clocks = sampler.window(tb2, time.time())
         e2e_ms = max(e0.elapsed_time(e1), 0.0)
         e2e = {"ms": e2e_ms, "wall_ms": wall * 1e3, "h2d": int(descs.nbytes + payload.size), "d2h": int(nbytes_out)}
         check = float(np.nansum(h_out[: min(a.blocks, 64)]))
         dcheck = float(torch.nansum(out_dev[: min(a.blocks, 64)]).item())
         assert abs(check - dcheck) <= 1e-9 * max(1.0, abs(dcheck)), (check, dcheck)
 
+    sampler.stop()
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e["ms"] if e2e else 0.0, e2e["wall_ms"] if e2e else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -423,7 +488,8 @@ def main():
             per = e2e_ms / a.steps
             out["e2e"] = {"value": world * rows_total / (per / 1e3), "unit": "samples/s", "ms_per_step": per,
                           "wall_ms_per_step": e2e_wall_ms / a.steps, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                          "api": "vmb_eval_rollup_host (pinned host descriptors+payload in, pinned host result out)"}
+                          "api": "vmb_eval_rollup_host (pinned host descriptors+payload in, pinned host result out)",
+                          "clocks": e2e_clocks}
         out["config"]["compressed_bytes_per_gpu"] = compressed
         out["config"]["bytes_per_sample_compressed"] = round(compressed / rows_total, 3)
         out["config"]["input_generation_s"] = round(gen_s, 1)
