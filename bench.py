@@ -373,6 +373,23 @@ def main():
         pci = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
     except Exception:
         pass
+    # NUMA placement: run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU's PCIe root, like any
+    # multi-GPU host process would be deployed; restored before the CPU baseline, which uses every core
+    affinity0 = None
+    numa_cpus = None
+    try:
+        affinity0 = os.sched_getaffinity(0)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % pci[4:]) as f:  # sysfs uses a 4-digit PCI domain
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= affinity0
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            numa_cpus = len(cpus)
+    except Exception:
+        pass
     sampler = ClockSampler(local_rank, pci)
     sampler.start()
     barrier()
@@ -494,6 +511,12 @@ def main():
         out["config"]["bytes_per_sample_compressed"] = round(compressed / rows_total, 3)
         out["config"]["input_generation_s"] = round(gen_s, 1)
         out["config"]["series_with_a_counter_reset"] = round(GEN_STATS["series_with_drop"] / max(GEN_STATS["series"], 1), 3)
+        out["config"]["host_affinity"] = ("GPU-local NUMA node, %d CPUs" % numa_cpus) if numa_cpus else "unchanged"
+        if affinity0:
+            try:
+                os.sched_setaffinity(0, affinity0)
+            except Exception:
+                pass
         if world == 1 and a.cpu_seconds > 0:
             try:
                 cb, _ = cpu_reference(descs, payload, a.func, start, end, step, a.window_ms, a.cpu_seconds)
