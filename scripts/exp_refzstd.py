@@ -10,9 +10,10 @@ from victoriametrics_b200 import storage, promql
 NB = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 ctx = vm.default_context()
 T0 = 1_700_000_000_000
+TKIND = sys.argv[2] if len(sys.argv) > 2 else "regular"
 for kind in ("counter", "counter_smooth", "gauge", "gauge_small"):
     rng = np.random.default_rng(1)
-    uniq = [blockgen.OBlock(blockgen.gen_timestamps(rng, "regular", 8192, T0), blockgen.gen_values(rng, kind, 8192), -2, 64, 0)
+    uniq = [blockgen.OBlock(blockgen.gen_timestamps(rng, TKIND, 8192, T0), blockgen.gen_values(rng, kind, 8192), -2, 64, 0)
             for _ in range(64)]
     blocks = []
     for i in range(NB):
@@ -23,9 +24,9 @@ for kind in ("counter", "counter_smooth", "gauge", "gauge_small"):
         blocks.append(c)
     descs, payload = blockgen.to_blockset(blocks)
     B = storage.Blocks(descs, payload)
-    mts = sorted(set(int(b.vmt) for b in uniq))
+    mts = sorted(set((int(b.tmt), int(b.vmt)) for b in uniq))
     ratio = sum(b.vdata.size for b in uniq) / (64 * 8192)
-    start, end, step = T0 + 300000, T0 + 15000 * 8191, 15000
+    start, end, step = T0 + 300000, int(uniq[0].ts[-1]), 15000
     points = 1 + (end - start) // step
     out = torch.empty((NB, points), dtype=torch.float64, device="cuda")
     for _ in range(2):

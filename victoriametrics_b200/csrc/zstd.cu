@@ -681,8 +681,11 @@ __global__ void k_zstd_prepare(ZstdParams P) {
         short norm[256];
         unsigned short next[256];
         int tlog = 0;
-        uint32_t used = huf_read_weights(job->nbits, &tlog, blk + hdr, csize, ftab, norm, next);
+        __align__(16) uint8_t nb_local[256];  // weights / code lengths are built on the thread's stack (L1), not in the job record
+        uint32_t used = huf_read_weights(nb_local, &tlog, blk + hdr, csize, ftab, norm, next);
         if (!used) break;
+#pragma unroll
+        for (int k = 0; k < 32; k++) ((uint64_t*)job->nbits)[k] = ((const uint64_t*)nb_local)[k];  // (records are 8-byte aligned)
         uint32_t lrem = csize - used;
         const uint8_t* lp = blk + hdr + used;
         if (streams == 1) {
