@@ -221,6 +221,55 @@ def test_zstd_golden_frames_through_gpu(vm, oracle):
     assert ok > 100
 
 
+def test_zstd_sequences_batched_stress(vm, oracle):
+    """many libzstd frames with very different sequence sections in ONE batch (frames share warps in k_zstd_seq_decode /
+    k_zstd_seq_exec): long literal runs, long matches, matches overlapping themselves (period 1..7), RLE / predefined /
+    FSE-described tables, repeat offsets, frames with 1 sequence next to frames with thousands"""
+    rng = np.random.default_rng(20240921)
+    blocks = []
+    for i in range(700):
+        n = int(rng.choice([2, 3, 17, 64, 129, 500, 1024, 3000, 8192]))
+        shape = i % 7
+        if shape == 0:      # straight line with rare kinks: delta2 is a run of zeros -> offset-1 matches
+            d = np.full(n, int(rng.integers(1, 1000)), dtype=np.int64)
+            d[rng.random(n) < 0.01] += rng.integers(1, 50)
+            v = np.cumsum(d)
+        elif shape == 1:    # periodic increments (period 2..7): self-overlapping matches
+            per = int(rng.integers(2, 8))
+            pat = rng.integers(0, 300, per)
+            v = np.cumsum(np.tile(pat, n // per + 1)[:n]).astype(np.int64)
+        elif shape == 2:    # noise with a long repeated segment: long matches at a large offset
+            seg = rng.integers(0, 5000, max(n // 4, 1))
+            d = np.concatenate([seg, rng.integers(0, 5000, max(n // 4, 1)), seg, seg])[:n]
+            d = np.resize(d, n)
+            v = np.cumsum(d).astype(np.int64)
+        elif shape == 3:    # mostly constant gauge with spikes
+            v = np.full(n, int(rng.integers(0, 10**6)), dtype=np.int64)
+            k = rng.random(n) < 0.02
+            v[k] += rng.integers(-1000, 1000, int(k.sum()))
+        elif shape == 4:    # smooth counter
+            v = blockgen.gen_values(rng, "counter_smooth", n)
+        elif shape == 5:    # small-alphabet gauge
+            v = blockgen.gen_values(rng, "gauge_small", n)
+        else:               # steps: long runs of one delta, then another
+            d = np.repeat(rng.integers(0, 100, n // 50 + 1), 50)[:n]
+            v = np.cumsum(d).astype(np.int64)
+        ts = blockgen.gen_timestamps(rng, str(rng.choice(["regular", "jitter", "irregular"])), n)
+        blocks.append(blockgen.OBlock(ts, np.asarray(v, dtype=np.int64), int(rng.choice([-2, 0, 2])), 64, i))
+    kinds = {b.vmt for b in blocks} | {b.tmt for b in blocks}
+    assert {1, 4} & kinds  # zstd columns are present
+    descs, payload = blockgen.to_blockset(blocks)
+    B = vm.storage.Blocks(descs, payload)
+    series, status = vm.storage.decode_blocks(B, values_as_int64=True)
+    assert not status.any()
+    got = series.to_lists(np.int64)
+    series.close()
+    for b, (gts, gv) in zip(blocks, got):
+        assert np.array_equal(gts, b.ts), (b.series_idx, b.tmt)
+        rc, ets, _, eiv = b.oracle_unmarshal()
+        assert rc == 0 and np.array_equal(gv, eiv), (b.series_idx, b.vmt)
+
+
 def test_blocks_written_by_the_product_encoder_decode_identically(vm, oracle):
     rng = np.random.default_rng(7)
     bs = vm.storage.BlockSet()
