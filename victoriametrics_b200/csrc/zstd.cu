@@ -986,18 +986,86 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
 // k_zstd_seq_exec: one warp per frame turns the records into bytes -- positions by warp scans, every literal run
 //   independent of the rest, the matches in order (32 lanes per copy; out[o+k] = out[o-offset + k % offset] when a match
 //   overlaps itself).
-#define SEQ_G 8
+#define SEQ_G 4
 #define SEQ_FPW (32 / SEQ_G)
-#define SEQ_WARPS 2
+#define SEQ_WARPS 1
 #define SEQ_REC(ll, ml, of) (((unsigned long long)(ll) << 44) | ((unsigned long long)(ml) << 24) | (unsigned long long)(of))
 #define SEQ_REC_LL(r) ((uint32_t)((r) >> 44))
 #define SEQ_REC_ML(r) ((uint32_t)((r) >> 24) & 0xfffffu)
 #define SEQ_REC_OF(r) ((uint32_t)(r) & 0xffffffu)
+// decoding tables of one frame, 3 bytes per state (16-bit nbits|base + 8-bit symbol) so that more frames fit an SM
 struct SeqTables {
-    uint32_t ll[512];
-    uint32_t ml[512];
-    uint32_t of[256];
+    unsigned short ll_nb[512], ml_nb[512], of_nb[256];  // (nbits << 12) | base, base < 512
+    uint8_t ll_sym[512], ml_sym[512], of_sym[256];
 };
+
+// fse_build for the packed layout (same spreading, RFC 8878 4.1.1)
+__device__ bool fse_build_packed(uint8_t* sym, unsigned short* nbbase, const short* norm, int nsym, int log, unsigned short* next) {
+    const int size = 1 << log;
+    int high = size - 1;
+    for (int s = 0; s < nsym; s++) {
+        if (norm[s] == -1) {
+            sym[high--] = (uint8_t)s;
+            next[s] = 1;
+        } else {
+            next[s] = (unsigned short)norm[s];
+        }
+    }
+    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+    int pos = 0;
+    for (int s = 0; s < nsym; s++) {
+        for (int i = 0; i < norm[s]; i++) {
+            sym[pos] = (uint8_t)s;
+            do {
+                pos = (pos + step) & mask;
+            } while (pos > high);
+        }
+    }
+    if (pos != 0) return false;
+    for (int i = 0; i < size; i++) {
+        const uint32_t s = sym[i];
+        const uint32_t ns = next[s]++;
+        const int nb = log - hb32(ns);
+        nbbase[i] = (unsigned short)(((uint32_t)nb << 12) | ((ns << nb) - (uint32_t)size));
+    }
+    return true;
+}
+
+// Symbol_Compression_Mode of one sequence table (RFC 8878 3.1.1.3.2.1) -> packed table; returns bytes consumed.
+// Repeat mode is invalid here: a prepared frame holds a single block.
+__device__ uint32_t read_seq_table_packed(uint8_t* sym, unsigned short* nbbase, int* tlog, int mode, const short* defnorm, int defn,
+                                          int deflog, int max_sym, int max_log, const uint8_t* src, uint32_t len, SerialWs* ws,
+                                          bool* ok) {
+    *ok = true;
+    if (mode == 0) {
+        for (int i = 0; i < defn; i++) ws->norm[i] = defnorm[i];
+        if (!fse_build_packed(sym, nbbase, ws->norm, defn, deflog, ws->next)) *ok = false;
+        *tlog = deflog;
+        return 0;
+    }
+    if (mode == 1) {
+        if (len < 1 || src[0] > max_sym) {
+            *ok = false;
+            return 0;
+        }
+        sym[0] = src[0];
+        nbbase[0] = 0;
+        *tlog = 0;
+        return 1;
+    }
+    if (mode == 2) {
+        int nsym, log;
+        const uint32_t used = fse_read_ncount(ws->norm, &nsym, &log, max_sym, max_log, src, len);
+        if (!used || !fse_build_packed(sym, nbbase, ws->norm, nsym, log, ws->next)) {
+            *ok = false;
+            return 0;
+        }
+        *tlog = log;
+        return used;
+    }
+    *ok = false;
+    return 0;
+}
 
 __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P) {
     __shared__ SeqTables s_tab[SEQ_WARPS * SEQ_FPW];
@@ -1063,16 +1131,14 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
                 if (modes & 3) ok = false;
                 if (ok && sub == 0) {
                     bool tok;
-                    int have = 0;
-                    pos += read_seq_table(T->ll, &ll_log, &have, (modes >> 6) & 3, c_ll_default, 36, 6, 35, 9, src + pos, len - pos, ws, &tok);
-                    if (tok) {
-                        have = 0;
-                        pos += read_seq_table(T->of, &of_log, &have, (modes >> 4) & 3, c_of_default, 29, 5, 31, 8, src + pos, len - pos, ws, &tok);
-                    }
-                    if (tok) {
-                        have = 0;
-                        pos += read_seq_table(T->ml, &ml_log, &have, (modes >> 2) & 3, c_ml_default, 53, 6, 52, 9, src + pos, len - pos, ws, &tok);
-                    }
+                    pos += read_seq_table_packed(T->ll_sym, T->ll_nb, &ll_log, (modes >> 6) & 3, c_ll_default, 36, 6, 35, 9, src + pos,
+                                                 len - pos, ws, &tok);
+                    if (tok)
+                        pos += read_seq_table_packed(T->of_sym, T->of_nb, &of_log, (modes >> 4) & 3, c_of_default, 29, 5, 31, 8,
+                                                     src + pos, len - pos, ws, &tok);
+                    if (tok)
+                        pos += read_seq_table_packed(T->ml_sym, T->ml_nb, &ml_log, (modes >> 2) & 3, c_ml_default, 53, 6, 52, 9,
+                                                     src + pos, len - pos, ws, &tok);
                     if (!tok || pos >= len) ok = false;  // (leader only; the group learns it from the broadcast below)
                 }
             }
@@ -1108,14 +1174,15 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
         for (uint32_t q = 0; q < nmax; q++) {
             const bool run = act && ok && q < nseq;
             if (run) {
-                const uint32_t ell = T->ll[sll], eof = T->of[sof], eml = T->ml[sml];
-                const uint32_t ofc = min(FSE_SYM(eof), 31u), mlc = min(FSE_SYM(eml), 52u), llc = min(FSE_SYM(ell), 35u);
-                if (FSE_SYM(eof) > 31 || FSE_SYM(eml) > 52 || FSE_SYM(ell) > 35) ok = false;
+                const uint32_t ell = T->ll_nb[sll], eof = T->of_nb[sof], eml = T->ml_nb[sml];  // (nbits << 12) | base
+                const uint32_t yll = T->ll_sym[sll], yof = T->of_sym[sof], yml = T->ml_sym[sml];
+                const uint32_t ofc = min(yof, 31u), mlc = min(yml, 52u), llc = min(yll, 35u);
+                if (yof > 31 || yml > 52 || yll > 35) ok = false;
                 // all the bits of this sequence in one go when the window holds them (it nearly always does): the six fields
                 // are cut out of the 64-bit window at precomputed offsets instead of six dependent read-and-shift steps
                 const bool more = q + 1 < nseq;
                 const uint32_t b_of = ofc, b_ml = s_ml_bits[mlc], b_ll = s_ll_bits[llc];
-                const uint32_t n_ll = more ? FSE_NB(ell) : 0u, n_ml = more ? FSE_NB(eml) : 0u, n_of = more ? FSE_NB(eof) : 0u;
+                const uint32_t n_ll = more ? (ell >> 12) : 0u, n_ml = more ? (eml >> 12) : 0u, n_of = more ? (eof >> 12) : 0u;
                 const uint32_t o1 = b_of, o2 = o1 + b_ml, o3 = o2 + b_ll, o4 = o3 + n_ll, o5 = o4 + n_ml, need = o5 + n_of;
                 if (bb.cnt <= 32) bb.refill();
                 uint32_t x_of, x_ml, x_ll, x_sl, x_sm, x_so;
@@ -1143,9 +1210,9 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
                 const uint32_t ofv = (1u << ofc) + x_of;  // offset codes > 24 cannot be valid here and fail the range check
                 const uint32_t mlen = s_ml_base[mlc] + x_ml, llen = s_ll_base[llc] + x_ll;
                 if (more) {
-                    sll = FSE_BASE(ell) + x_sl;
-                    sml = FSE_BASE(eml) + x_sm;
-                    sof = FSE_BASE(eof) + x_so;
+                    sll = (ell & 0xfffu) + x_sl;
+                    sml = (eml & 0xfffu) + x_sm;
+                    sof = (eof & 0xfffu) + x_so;
                 }
                 if (bb.left < 0) ok = false;
                 if (ofc > 24) ok = false;
