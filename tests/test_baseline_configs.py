@@ -187,6 +187,52 @@ def test_streamed_counter_resets_bit_exact(oracle, lookback, window_rows):
 
 
 @pytest.mark.gpu
+def test_regular_timestamp_mode_edges(oracle):
+    """series with MarshalTypeDeltaConst timestamps take the rollup path that derives timestamps from the row index:
+    tiny and huge scrape intervals, 2-row series, staleness markers (rows removed -> mode off), time-range trimming,
+    query ranges that start before / end after the data, steps that do not divide the scrape interval"""
+    import torch
+    import victoriametrics_b200 as vm
+    rng = np.random.default_rng(311)
+    blocks = []
+    for i, (n, dt) in enumerate([(2, 15000), (3, 1), (100, 7), (8192, 15000), (8192, 1000), (5000, 60000), (64, 999),
+                                 (8192, 15000), (777, 15000), (16, 10**6)]):
+        ts = (T0 + dt * np.arange(n)).astype(np.int64)
+        kind = "special" if i in (7, 8) else ("counter_resets" if i % 2 else "counter")
+        vals = np.abs(blockgen.gen_values(rng, kind, n)) if kind != "special" else blockgen.gen_values(rng, kind, n)
+        blocks.append(blockgen.OBlock(ts, vals, -2, 64, i))
+    assert all(b.tmt == 2 for b in blocks)
+    descs, payload = blockgen.to_blockset(blocks)
+    B = vm.storage.Blocks(descs, payload)
+    for (start, end, step, window, tr) in [
+            (T0 + 300000, T0 + 15000 * 8191, 15000, 300000, None),
+            (T0 - 600000, T0 + 15000 * 9000, 15000, 60000, None),          # grid wider than the data on both sides
+            (T0 + 1000, T0 + 200000, 7000, 21000, None),                    # step unrelated to any scrape interval
+            (T0 + 300000, T0 + 15000 * 4000, 30000, 300000, (T0 + 15000 * 100 + 1, T0 + 15000 * 3000)),  # trimmed blocks
+            (T0, T0 + 5000, 1, 5, None)]:                                   # millisecond grid over the 1 ms / 7 ms series
+        kw = {} if tr is None else dict(tr_min=tr[0], tr_max=tr[1])
+        exp = []
+        for b in blocks:
+            r, ts, fv, _ = b.oracle_unmarshal(*(tr or (-(1 << 63), (1 << 63) - 1)))
+            assert r == 0
+            ts, fv = ts.copy(), fv.copy()
+            n = oracle.lib().vmo_drop_stale_nans(fv.ctypes.data_as(oracle.f64p), ts.ctypes.data_as(oracle.i64p), len(ts)) if len(ts) else 0
+            ts, fv = ts[:n].copy(), fv[:n].copy()
+            if n:
+                oracle.lib().vmo_remove_counter_resets(fv.ctypes.data_as(oracle.f64p), ts.ctypes.data_as(oracle.i64p), n, 0)
+            o, _ = oracle.rollup_do(RF["rate"], fv, ts, start, end, step, window, samples_scanned_per_call=2)
+            exp.append(o)
+        exp = np.stack(exp)
+        out = torch.empty(exp.shape, dtype=torch.float64, device="cuda")
+        vm.promql.eval_rollup_func("rate", B, start, end, step, window, out_dev_ptr=out.data_ptr(), **kw)
+        got = out.cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(exp)), (start, step)
+        assert np.allclose(got, exp, rtol=1e-12, atol=0, equal_nan=True), (start, step)
+        got_h, _ = vm.promql.eval_rollup_func_host("rate", descs, payload, start, end, step, window, **kw)
+        assert np.allclose(got_h, exp, rtol=1e-12, atol=0, equal_nan=True), (start, step)
+
+
+@pytest.mark.gpu
 def test_config4_mixed_codec_increase_1h_step60(oracle):
     """40 % delta2 counters, 30 % gauges, 20 % const, 10 % delta-const -> increase(m[1h]) step 60 s"""
     import victoriametrics_b200 as vm

@@ -775,6 +775,8 @@ __global__ void k_series_assemble(RollupParams P) {
     // bit 0: the series may hold Prometheus staleness markers; bit 1: the series may hold a value below its predecessor
     // (or a NaN), i.e. removeCounterResets may have something to do.  Both come from the decode kernel, per block.
     // bit 2: the series is assembled by k_series_merge.
+    // bit 3: the timestamps are an arithmetic progression (one block, MarshalTypeDeltaConst timestamps, no deduplication):
+    //        the rollup kernel derives them from the row index instead of reading them.
     m._pad = nb > 1 ? 2u : 0u;  // (a drop across a block boundary is not looked for: any multi-block series is a candidate)
     m.max_prev_interval = 0;
     m.window = 0;
@@ -805,6 +807,7 @@ __global__ void k_series_assemble(RollupParams P) {
                 } else {
                     m.start = lo;
                     m.n = (uint32_t)kept;
+                    if (nb == 1 && kept >= 2 && P.descs[fb].ts_mt == 2 && P.dedup_interval <= 0) m._pad |= 8u;
                 }
             }
         }
@@ -1134,6 +1137,7 @@ __global__ void __launch_bounds__(128) k_series_prepare(RollupParams P) {
                     o += __popc(bal);
                     __syncwarp();
                 }
+                if (o != n) m._pad &= ~8u;  // rows were removed: the timestamps are no arithmetic progression any more
                 n = o;
             }
         }
@@ -1347,6 +1351,37 @@ __device__ __forceinline__ double rollup_point(const vmb_rollup_cfg& rc, const S
 //
 // A window that does not fit ROLLUP_CAP rows (huge windows / very dense series) is handled for that tile by reading global
 // memory directly.  F >= 0 instantiates the kernel for one rollup function (the switch in call_func folds away).
+// rate() for one point of a series whose timestamps are t_org + row * dt (rows absolute): same selects as rate_point32 below
+// with the timestamps derived from the row indices
+__device__ __forceinline__ double rate_point_ap(uint32_t i, uint32_t j, uint32_t base, uint32_t n, uint32_t cnt, int32_t tsp,
+                                                int32_t dt_row, const double* __restrict__ val) {
+    const uint32_t ri = i - base, rj = j - base, nw = j - i;
+    const bool have_prev = i > 0 && i < n;
+    const uint32_t ip = have_prev ? ri - 1 : 0u;
+    const uint32_t i0 = ri < cnt ? ri : cnt - 1;
+    const uint32_t il = rj ? rj - 1 : 0u;
+    const double vp = val[ip], v0 = val[i0], vl = val[il];
+    const int32_t tp = (int32_t)(base + ip) * dt_row;
+    const bool prev_ok = have_prev && tp > tsp && !isnan(vp);
+    const bool fixed = prev_ok ? nw == 0 : nw < 2;
+    const double a = prev_ok ? vp : v0;
+    int32_t dt = (int32_t)(il - (prev_ok ? ip : i0)) * dt_row;
+    dt = fixed ? 1000 : dt;
+    const double qv = (vl - a) / ms_to_s((int64_t)dt);
+    return fixed ? (prev_ok ? 0.0 : D_NAN) : qv;
+}
+
+// rows with timestamp <= t_org + xr when row k sits at t_org + k * dt: exact floor division from a float estimate
+__device__ __forceinline__ uint32_t seek_ap(int32_t xr, int32_t dt_row, float inv_row, uint32_t n) {
+    if (xr < 0) return 0u;
+    if (xr >= (int32_t)(n - 1) * dt_row) return n;  // at or past the last row (also keeps the quotient below 2^14: n <= 16384)
+    uint32_t q = (uint32_t)(__int2float_rz(xr) * inv_row);
+    int32_t r = xr - (int32_t)q * dt_row;
+    if (r < 0) { q--; r += dt_row; }
+    if (r >= dt_row) q++;
+    return q + 1u < n ? q + 1u : n;
+}
+
 // shared memory of k_rollup at file scope: the device functions below index it directly (plain LDS with constant bases)
 __shared__ int64_t rs_ts[ROLLUP_CAP];     // timestamps of the resident rows
 __shared__ double rs_val[ROLLUP_CAP];     // their values
@@ -1418,16 +1453,32 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
             win32 = (int32_t)m.window;
             mpi32 = (int32_t)m.max_prev_interval;
         }
+        // arithmetic-progression mode: no timestamp is read at all (rows sit at t_org + row * dt_row)
+        int32_t dt_row = 0;
+        float inv_row = 0.0f;
+        bool ap = false;
+        if (fast && (m._pad & 8u) && n >= 2) {
+            const int64_t d = tg[1] - tg[0];
+            if (d > 0 && d < ((int64_t)1 << 30) && (int64_t)(n - 1) * d < ((int64_t)1 << 30)) {
+                ap = true;
+                dt_row = (int32_t)d;
+                inv_row = 1.0f / (float)dt_row;
+            }
+        }
         uint32_t base = 0, cnt = 0, p = 0;
         while (p < P.npoints) {
             // ---- fill: rows [base + cnt, min(n, base + CAP))
             __syncthreads();
             const uint32_t want = min(n - base, (uint32_t)ROLLUP_CAP);
-            for (uint32_t k = cnt + tid; k < want; k += ROLLUP_THREADS) {
-                const int64_t t = tg[base + k];
-                rs_ts[k] = t;
-                rs_val[k] = vg[base + k];
-                if (fast) rs_rt[k] = (int32_t)(t - t_org);
+            if (ap) {
+                for (uint32_t k = cnt + tid; k < want; k += ROLLUP_THREADS) rs_val[k] = vg[base + k];
+            } else {
+                for (uint32_t k = cnt + tid; k < want; k += ROLLUP_THREADS) {
+                    const int64_t t = tg[base + k];
+                    rs_ts[k] = t;
+                    rs_val[k] = vg[base + k];
+                    if (fast) rs_rt[k] = (int32_t)(t - t_org);
+                }
             }
             cnt = want;
             __syncthreads();
@@ -1436,12 +1487,12 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
             uint32_t p_end;
             if (base + cnt == n) p_end = P.npoints;
             else {
-                int64_t tl = rs_ts[cnt - 1] - 1 - rc.start;
+                int64_t tl = (ap ? t_org + (int64_t)(base + cnt - 1) * dt_row : rs_ts[cnt - 1]) - 1 - rc.start;
                 p_end = tl < 0 ? 0u : (uint32_t)min((int64_t)P.npoints, tl / rc.step + 1);
             }
             float inv_dt = 0.0f;  // rows per millisecond over the resident range (0: no usable slope => bisect)
             {
-                const int64_t span = cnt > 1 ? rs_ts[cnt - 1] - rs_ts[0] : 0;
+                const int64_t span = (cnt > 1 && !ap) ? rs_ts[cnt - 1] - rs_ts[0] : 0;
                 if (span > 0 && span < (int64_t)0x7fffffff) inv_dt = __fdividef((float)(cnt - 1), (float)span);
             }
             if (p_end <= p) {
@@ -1467,7 +1518,7 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
             //      timestamps, second half: values), so the next fill waits for L2 instead of HBM.
             {
                 const uint32_t r = base + cnt + (tid & (ROLLUP_THREADS / 2 - 1)) * 16u;
-                if (r < n) {
+                if (r < n && (!ap || tid >= ROLLUP_THREADS / 2)) {
                     const void* a = tid < ROLLUP_THREADS / 2 ? (const void*)(tg + r) : (const void*)(vg + r);
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
                 }
@@ -1477,8 +1528,29 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
             //      the shared-memory latencies of several points of one thread overlap.
             if (p_end - p > ROLLUP_SEEKS - wsteps_cap) p_end = p + (ROLLUP_SEEKS - wsteps_cap);
             const uint32_t np = p_end - p;
-            const int64_t t_first = cnt ? rs_ts[0] : 0, t_last = cnt ? rs_ts[cnt - 1] : 0;
-            if (fast) {
+            const int64_t t_first = (cnt && !ap) ? rs_ts[0] : 0, t_last = (cnt && !ap) ? rs_ts[cnt - 1] : 0;
+            if (ap) {
+                // edges from the row arithmetic (absolute rows, clamped to the resident range), then the points
+                const int32_t x0r = start_r + ((int32_t)p - (int32_t)wsteps) * step32;
+#pragma unroll 2
+                for (uint32_t q = tid; q < np + wsteps; q += ROLLUP_THREADS) {
+                    uint32_t e = seek_ap(x0r + (int32_t)q * step32, dt_row, inv_row, n);
+                    e = e < base ? base : (e > base + cnt ? base + cnt : e);
+                    rs_seek[q] = (unsigned short)(e - base);
+                }
+                __syncthreads();
+                const int32_t ts0 = start_r + (int32_t)p * step32 - win32 - mpi32;
+                const uint32_t spc = (uint32_t)rc.samples_scanned_per_call;
+                uint32_t sc32 = 0;
+#pragma unroll 2
+                for (uint32_t q = tid; q < np; q += ROLLUP_THREADS) {
+                    const uint32_t i = base + rs_seek[q];
+                    const uint32_t j = max(i, base + rs_seek[q + wsteps]);
+                    sc32 += spc ? spc : j - i;
+                    out[p + q] = rate_point_ap(i, j, base, n, cnt, ts0 + (int32_t)q * step32, dt_row, rs_val);
+                }
+                scanned += sc32;
+            } else if (fast) {
                 // branch-free 32-bit edges and rate() points (same arithmetic as rollup_point<VMB_RF_RATE>)
                 const int32_t r_first = rs_rt[0], r_last = rs_rt[cnt - 1];
                 const int32_t x0r = start_r + ((int32_t)p - (int32_t)wsteps) * step32;
@@ -1519,7 +1591,13 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
             if (p >= P.npoints) break;
             // ---- slide: keep rows from (first row after tStart(p)) - 1
             __syncthreads();
-            uint32_t lo = base + seek_after(rs_ts, cnt, rc.start + (int64_t)p * rc.step - m.window, inv_dt);
+            uint32_t lo;
+            if (ap) {
+                lo = seek_ap((int32_t)(rc.start + (int64_t)p * rc.step - m.window - t_org), dt_row, inv_row, n);
+                lo = lo < base ? base : (lo > base + cnt ? base + cnt : lo);
+            } else {
+                lo = base + seek_after(rs_ts, cnt, rc.start + (int64_t)p * rc.step - m.window, inv_dt);
+            }
             uint32_t nb = lo > base ? lo - 1 : base;
             if (nb > base + cnt - 1) nb = base + cnt - 1;
             const uint32_t shift = nb - base;
@@ -1531,15 +1609,19 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
                     double b = 0.0;
                     int32_t c32 = 0;
                     if (k < keep) {
-                        a = rs_ts[k + shift];
                         b = rs_val[k + shift];
-                        if (fast) c32 = rs_rt[k + shift];
+                        if (!ap) {
+                            a = rs_ts[k + shift];
+                            if (fast) c32 = rs_rt[k + shift];
+                        }
                     }
                     __syncthreads();
                     if (k < keep) {
-                        rs_ts[k] = a;
                         rs_val[k] = b;
-                        if (fast) rs_rt[k] = c32;
+                        if (!ap) {
+                            rs_ts[k] = a;
+                            if (fast) rs_rt[k] = c32;
+                        }
                     }
                 }
                 base = nb;
