@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--blocks", type=int, default=100_000, help="blocks (= series) per GPU")
     ap.add_argument("--rows", type=int, default=8192)
     ap.add_argument("--func", default="rate")
+    ap.add_argument("--ts", default="regular", choices=["regular", "jitter"],
+                    help="timestamps: regular = t0 + 15 s * i (one shared MarshalTypeDeltaConst payload, configs[1]); jitter = "
+                         "every series has its own +-50 ms scrape jitter (zstd nearest-delta2 timestamp columns)")
     ap.add_argument("--kind", default="counter", choices=["counter", "gauge", "mixed"],
                     help="synthetic values: counter = configs[1] (default), gauge = configs[2]-style round(N(5000,300)) at "
                          "scale -2, mixed = configs[4]-style 40%% counters / 30%% gauges / 20%% const / 10%% delta-const")
@@ -62,7 +65,7 @@ GEN_STATS = {"series": 0, "series_with_drop": 0}
 RCR_FUNCS = ("rate", "increase", "irate", "increase_pure", "increase_prometheus", "rate_prometheus", "rollup_rate", "rollup_increase")
 
 
-def gen_blocks(nblocks, rows, seed, chunk=4000, kind="counter"):
+def gen_blocks(nblocks, rows, seed, chunk=4000, kind="counter", ts_kind="regular"):
     """node_cpu_seconds_total-like counters, marshaled by the product's own encoder
     (vmb_marshal_columns).  -> (descs structured array, payload np.uint8)"""
     from victoriametrics_b200 import encoding, storage
@@ -72,7 +75,7 @@ def gen_blocks(nblocks, rows, seed, chunk=4000, kind="counter"):
     assert tmt == encoding.MarshalTypeDeltaConst
     pieces = [tdata]
     pos = tdata.size
-    cols = {k: [] for k in ("first_value", "val_off", "val_size", "val_mt")}
+    cols = {k: [] for k in ("first_value", "val_off", "val_size", "val_mt", "ts_off", "ts_size", "ts_mt", "min_ts", "max_ts")}
     for c0 in range(0, nblocks, chunk):
         n = min(chunk, nblocks - c0)
         inc = rng.integers(0, 1501, (n, rows), dtype=np.int64)
@@ -93,6 +96,16 @@ def gen_blocks(nblocks, rows, seed, chunk=4000, kind="counter"):
                 v = np.where(k < 4, v, np.where(k < 7, g, np.where(k < 9, const, dconst)))
         GEN_STATS["series"] += n
         GEN_STATS["series_with_drop"] += int(np.count_nonzero((np.diff(v, axis=1) < 0).any(axis=1)))
+        if ts_kind == "jitter":  # every series has its own scrape jitter of +-50 ms (SURVEY.md 8d config 2 variant)
+            tj = ts[None, :] + rng.integers(-50, 51, (n, rows))
+            tp_, toffs, tmts, tfirsts = encoding.marshal_columns(tj)
+            pieces.append(tp_)
+            cols["ts_off"].append(toffs[:-1] + pos)
+            cols["ts_size"].append(np.diff(toffs).astype(np.uint32))
+            cols["ts_mt"].append(tmts)
+            cols["min_ts"].append(tfirsts)
+            cols["max_ts"].append(tj[:, -1].copy())
+            pos += tp_.size
         payload, offs, mts, firsts = encoding.marshal_columns(v)
         pieces.append(payload)
         cols["first_value"].append(firsts)
@@ -100,11 +113,14 @@ def gen_blocks(nblocks, rows, seed, chunk=4000, kind="counter"):
         cols["val_size"].append(np.diff(offs).astype(np.uint32))
         cols["val_mt"].append(mts)
         pos += payload.size
+    tcols = dict(min_ts=tfirst, max_ts=int(ts[-1]), ts_off=0, ts_size=tdata.size, ts_mt=tmt)
+    if ts_kind == "jitter":
+        tcols = {k: np.concatenate(cols[k]) for k in ("min_ts", "max_ts", "ts_off", "ts_size", "ts_mt")}
     descs = storage.descs_from_arrays(
-        first_value=np.concatenate(cols["first_value"]), min_ts=tfirst, max_ts=int(ts[-1]), ts_off=0,
-        val_off=np.concatenate(cols["val_off"]), ts_size=tdata.size, val_size=np.concatenate(cols["val_size"]),
-        rows=np.full(nblocks, rows, dtype=np.uint32), series_idx=np.arange(nblocks, dtype=np.uint32), scale=SCALE,
-        ts_mt=tmt, val_mt=np.concatenate(cols["val_mt"]), precision_bits=64)
+        first_value=np.concatenate(cols["first_value"]), val_off=np.concatenate(cols["val_off"]),
+        val_size=np.concatenate(cols["val_size"]), rows=np.full(nblocks, rows, dtype=np.uint32),
+        series_idx=np.arange(nblocks, dtype=np.uint32), scale=SCALE, val_mt=np.concatenate(cols["val_mt"]), precision_bits=64,
+        **tcols)
     return descs, np.concatenate(pieces)
 
 
@@ -277,6 +293,8 @@ def main():
     what = {"counter": "configs[1]: decode %d blocks x %d samples (ts delta-const, values zstd nearest-delta2 counters, scale %d)",
             "gauge": "configs[2]-style: decode %d blocks x %d samples (ts delta-const, values zstd nearest-delta gauges, scale %d)",
             "mixed": "configs[4]-style: decode %d blocks x %d samples (40%% counters, 30%% gauges, 20%% const, 10%% delta-const, scale %d)"}[a.kind]
+    if a.ts == "jitter":
+        what = what.replace("ts delta-const", "ts zstd nearest-delta2 with +-50 ms jitter")
     workload = (what + " + %s()[%ds] step=%ds per GPU") % (a.blocks, a.rows, SCALE, a.func, a.window_ms // 1000, a.step_ms // 1000)
     base = {"metric": "rollup samples/sec (block decode + %s, raw samples decoded and scanned per second)" % a.func,
             "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True,
@@ -288,7 +306,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        descs, payload = gen_blocks(min(a.blocks, 20000), a.rows, seed=1234, kind=a.kind)
+        descs, payload = gen_blocks(min(a.blocks, 20000), a.rows, seed=1234, kind=a.kind, ts_kind=a.ts)
         vals = []
         for _ in range(a.warmup):
             cpu_reference(descs, payload, a.func, start, end, step, a.window_ms, 2.0)
@@ -319,10 +337,10 @@ def main():
     ctx.set_stream(stream.cuda_stream)
 
     t_gen = time.perf_counter()
-    descs, payload = gen_blocks(a.blocks, a.rows, seed=1234 + rank, kind=a.kind)
+    descs, payload = gen_blocks(a.blocks, a.rows, seed=1234 + rank, kind=a.kind, ts_kind=a.ts)
     gen_s = time.perf_counter() - t_gen
     rows_total = int(a.blocks) * int(a.rows)
-    compressed = int(descs["val_size"].sum()) + int(descs["ts_size"][0])
+    compressed = int(descs["val_size"].sum()) + (int(descs["ts_size"].sum()) if a.ts == "jitter" else int(descs["ts_size"][0]))
 
     blocks = storage.Blocks(descs, payload, ctx)
     out_dev = torch.empty((a.blocks, points), dtype=torch.float64, device="cuda")
@@ -465,7 +483,7 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
-        varint_bytes = int(2 * rows_total)  # ~2 B/sample zig-zag varints in this workload (measured: raw/zstd ratio 0.86)
+        varint_bytes = int(2 * rows_total) * (2 if a.ts == "jitter" else 1)  # ~2 B/sample zig-zag varints per zstd column
         drop_frac = (GEN_STATS["series_with_drop"] / max(GEN_STATS["series"], 1)) if a.func in RCR_FUNCS else 0.0
         stage_names = ["zstd", "column_decode", "series_preamble", "rollup", "aggregate"]
         stage_bytes = [compressed + varint_bytes,                          # zstd: read frames, write varint bytes
