@@ -60,7 +60,9 @@ struct Dec {  // decimal.AppendDecimalToFloat decimal.go:100 for one block (scal
             f = __fma_rn(rem, rcp, q);
         } else if (mode < 0) f = __ddiv_rn(f, e10);
         else if (mode > 0) f = __dmul_rn(f, e10);
-        if (v > VMB_V_MAX || v < VMB_V_MIN) {  // isSpecialValue decimal.go:417
+        // isSpecialValue decimal.go:417: v in {vStaleNaN = 2^63-2, vInfPos = 2^63-1, vInfNeg = -2^63}, three consecutive
+        // values in wrapping arithmetic: one unsigned range test instead of three 64-bit comparisons
+        if ((uint64_t)v - 0x7FFFFFFFFFFFFFFEull < 3ull) {
             if (v == VMB_V_INF_POS) f = __longlong_as_double(0x7ff0000000000000LL);
             else if (v == VMB_V_INF_NEG) f = __longlong_as_double((long long)0xfff0000000000000ULL);
             else f = __longlong_as_double((long long)VMB_STALE_NAN_BITS);
@@ -75,16 +77,27 @@ struct TsEmit {
     int64_t tr_min, tr_max;
     uint32_t lo, hi1;  // lane-local: min pos with ts >= tr_min ; 1 + max pos with ts <= tr_max
     bool validate, bad_order;
+    bool inside;       // every value of the column is known to lie inside [tr_min, tr_max]: nothing to track
     __device__ void init(int64_t* o, int64_t a, int64_t b, bool v) {
-        out = o; tr_min = a; tr_max = b; lo = 0xffffffffu; hi1 = 0; validate = v; bad_order = false;
+        out = o; tr_min = a; tr_max = b; lo = 0xffffffffu; hi1 = 0; validate = v; bad_order = false; inside = false;
     }
     __device__ __forceinline__ void emit(uint32_t pos, int64_t v, int64_t prev) {
         out[pos] = v;
         if (validate && v < prev) bad_order = true;
-        if (v >= tr_min && pos < lo) lo = pos;
-        if (v <= tr_max && pos + 1 > hi1) hi1 = pos + 1;
+        if (!inside) {
+            if (v >= tr_min && pos < lo) lo = pos;
+            if (v <= tr_max && pos + 1 > hi1) hi1 = pos + 1;
+        }
     }
     __device__ __forceinline__ void note_decrease() {}
+    // a non-decreasing arithmetic progression first..last with n values: inside the range as a whole?
+    __device__ __forceinline__ void note_progression(int64_t first, int64_t last, uint32_t n) {
+        if (first <= last && first >= tr_min && last <= tr_max) {
+            inside = true;
+            lo = 0;
+            hi1 = n;
+        }
+    }
 };
 
 struct ValEmit {
@@ -98,8 +111,9 @@ struct ValEmit {
         out = o; as_int = ai; saw_stale = false; saw_drop = false; dec.init(scale);
     }
     __device__ __forceinline__ void note_decrease() { saw_drop = true; }
+    __device__ __forceinline__ void note_progression(int64_t, int64_t, uint32_t) {}
     __device__ __forceinline__ void emit(uint32_t pos, int64_t v, int64_t pv) {
-        saw_stale |= (v == VMB_V_STALE_NAN);
+        if ((uint64_t)v - 0x7FFFFFFFFFFFFFFEull < 3ull) saw_stale |= (v == VMB_V_STALE_NAN);
         saw_drop |= (v < pv);
         if (as_int) ((int64_t*)out)[pos] = v;
         else ((double*)out)[pos] = dec.conv(v);
@@ -156,6 +170,8 @@ __device__ int decode_column(const uint8_t* src, uint32_t len, int mt, int64_t f
             int rc = read_single_varint(src, len, &d, &used);
             if (rc) return rc;
             if (used < len) return VMB_ERR_TAIL;
+            if (d >= 0 && (n == 1 || (uint64_t)d <= (uint64_t)0x7fffffffffffffffLL / (n - 1)))  // no wrap-around
+                em.note_progression(first, (int64_t)((uint64_t)first + (uint64_t)(n - 1) * (uint64_t)d), n);
             for (uint32_t i = lane; i < n; i += 32) {
                 int64_t v = (int64_t)((uint64_t)first + (uint64_t)i * (uint64_t)d);
                 em.emit(i, v, v);

@@ -96,9 +96,9 @@ __device__ int decode_delta_stream_v2(const uint8_t* __restrict__ src, uint32_t 
         c |= 1u;  // odd stride: conflict-free shared-memory access
         const uint32_t k0 = min(T, (uint32_t)lane * c), k1 = min(T, k0 + c);
         uint64_t s1 = 0, s2 = 0;
+        int s = (k0 == 0 || k0 >= T) ? start_rel : (int)sm->pos[k0 - 1] + 1;  // first byte of the lane's first varint
         for (uint32_t k = k0; k < k1; k++) {
             const int e = (int)sm->pos[k];
-            const int s = k == 0 ? start_rel : (int)sm->pos[k - 1] + 1;
             const int vl = e - s + 1;  // varint length in bytes
             uint64_t u;
             if (vl <= 4) {
@@ -124,6 +124,7 @@ __device__ int decode_delta_stream_v2(const uint8_t* __restrict__ src, uint32_t 
             sm->val[k] = v;
             s1 += (uint64_t)v;
             s2 += s1;
+            s = e + 1;
         }
         // ---- 3. scan (count, s1, s2); combine(A then B): s2 = s2A + s2B + cntB * s1A
         uint32_t icnt = k1 - k0;
