@@ -105,16 +105,20 @@ struct ValEmit {
     Dec dec;
     bool as_int;
     bool saw_stale;  // a Prometheus staleness marker (decimal.go:406 vStaleNaN) was emitted: dropStaleNaNs has work to do
+    uint32_t first_drop;  // first row whose mantissa is below its predecessor (lane-local minimum)
     bool saw_drop;   // some mantissa is below its predecessor: the only way removeCounterResets (rollup.go:921) can change
                      // this block (decimal -> float is monotone inside a block: one scale), besides NaNs (saw_stale)
     __device__ void init(void* o, int16_t scale, bool ai) {
-        out = o; as_int = ai; saw_stale = false; saw_drop = false; dec.init(scale);
+        out = o; as_int = ai; saw_stale = false; saw_drop = false; first_drop = 0xffffffffu; dec.init(scale);
     }
-    __device__ __forceinline__ void note_decrease() { saw_drop = true; }
+    __device__ __forceinline__ void note_decrease() { saw_drop = true; first_drop = 1; }
     __device__ __forceinline__ void note_progression(int64_t, int64_t, uint32_t) {}
     __device__ __forceinline__ void emit(uint32_t pos, int64_t v, int64_t pv) {
         if ((uint64_t)v - 0x7FFFFFFFFFFFFFFEull < 3ull) saw_stale |= (v == VMB_V_STALE_NAN);
-        saw_drop |= (v < pv);
+        if (v < pv) {
+            saw_drop = true;
+            first_drop = min(first_drop, pos);
+        }
         if (as_int) ((int64_t*)out)[pos] = v;
         else ((double*)out)[pos] = dec.conv(v);
     }
@@ -279,9 +283,15 @@ __global__ void __launch_bounds__(128) k_decode_columns(DecodeParams P) {
             const bool as_int = (P.flags & VMB_DECODE_VALUES_AS_INT64) != 0;
             ve.init(as_int ? (void*)((int64_t*)P.val_out + ro) : (void*)((double*)P.val_out + ro), d.scale, as_int);
             rc = decode_column(src, len, d.val_mt, d.first_value, d.rows, ve, sm);
-            // flags carried in the top bits of blk_hi (rows <= 16384)
+            // blk_hi: bits 0-14 end of the kept rows (<= 16384), bits 15-28 first row with a value drop, bit 30 "may change
+            // under removeCounterResets", bit 31 "holds a staleness marker"
             if (__any_sync(VMB_FULL, ve.saw_stale)) hi |= 0x80000000u;
-            if (__any_sync(VMB_FULL, ve.saw_stale || ve.saw_drop)) hi |= 0x40000000u;
+            if (__any_sync(VMB_FULL, ve.saw_stale || ve.saw_drop)) {
+                uint32_t fd = ve.first_drop;
+#pragma unroll
+                for (int off = 16; off; off >>= 1) fd = min(fd, __shfl_xor_sync(VMB_FULL, fd, off));
+                hi |= 0x40000000u | ((fd < 16384u ? fd : 0u) << 15);
+            }
         }
         if (lane == 0) {
             P.status[b] = rc;

@@ -793,7 +793,7 @@ __global__ void k_series_assemble(RollupParams P) {
         } else {
             uint64_t lo = ~0ull, hi = 0, kept = 0;
             for (uint32_t k = 0; k < nb; k++) {
-                const uint32_t a = P.blk_lo[fb + k], b = P.blk_hi[fb + k] & 0x3fffffffu;
+                const uint32_t a = P.blk_lo[fb + k], b = P.blk_hi[fb + k] & 0x7fffu;
                 if (b <= a) continue;  // trimmed away completely
                 const uint64_t r = P.row_off[fb + k];
                 lo = r + a < lo ? r + a : lo;
@@ -808,6 +808,11 @@ __global__ void k_series_assemble(RollupParams P) {
                     m.start = lo;
                     m.n = (uint32_t)kept;
                     if (nb == 1 && kept >= 2 && P.descs[fb].ts_mt == 2 && P.dedup_interval <= 0) m._pad |= 8u;
+                    if (nb == 1 && P.dedup_interval <= 0 && !(m._pad & 1u)) {
+                        // bits 8-23: the row removeCounterResets may start from (nothing before the first value drop changes)
+                        const uint32_t fd = (P.blk_hi[fb] >> 15) & 0x3fffu, a = P.blk_lo[fb];
+                        if (fd > a) m._pad |= (fd - a) << 8;
+                    }
                 }
             }
         }
@@ -866,7 +871,7 @@ __global__ void __launch_bounds__(128) k_series_merge(RollupParams P) {
         H.lane = lane;
         uint32_t hn = 0;
         for (uint32_t k = 0; k < nb; k++) {  // empty blocks never enter the heap (netstorage.go:568)
-            const uint32_t b = fb + k, lo = P.blk_lo[b], hi = P.blk_hi[b] & 0x3fffffffu;
+            const uint32_t b = fb + k, lo = P.blk_lo[b], hi = P.blk_hi[b] & 0x7fffu;
             if (hi > lo) {
                 if (lane == 0) { H.h[hn] = b; H.next[b] = lo; }
                 hn++;
@@ -877,7 +882,7 @@ __global__ void __launch_bounds__(128) k_series_merge(RollupParams P) {
         uint64_t o = m.start;
         while (hn) {
             const uint32_t top = H.h[0];
-            const uint32_t idx = H.next[top], end = P.blk_hi[top] & 0x3fffffffu;
+            const uint32_t idx = H.next[top], end = P.blk_hi[top] & 0x7fffu;
             const uint64_t trow = P.row_off[top];
             uint32_t adv, ncopy;
             if (hn == 1) {
@@ -889,7 +894,7 @@ __global__ void __launch_bounds__(128) k_series_merge(RollupParams P) {
                 uint32_t eq = 0;
                 if (P.dedup_interval > 0) {  // equalSamplesPrefix netstorage.go:622: timestamps first, then value bits
                     const uint64_t nrow = P.row_off[nx] + H.next[nx];
-                    const uint32_t lim = min(end - idx, (P.blk_hi[nx] & 0x3fffffffu) - H.next[nx]);
+                    const uint32_t lim = min(end - idx, (P.blk_hi[nx] & 0x7fffu) - H.next[nx]);
                     uint32_t nt = 0;
                     for (; nt < lim; nt += 32) {
                         const uint32_t k = nt + lane;
@@ -1137,20 +1142,29 @@ __global__ void __launch_bounds__(128) k_series_prepare(RollupParams P) {
                     o += __popc(bal);
                     __syncwarp();
                 }
-                if (o != n) m._pad &= ~8u;  // rows were removed: the timestamps are no arithmetic progression any more
+                if (o != n) m._pad &= 0xffu & ~8u;  // rows were removed: no arithmetic progression, no known first drop
                 n = o;
             }
         }
         // ---- removeCounterResets rollup.go:921 (sequential float semantics preserved: corrections are accumulated in
         //      sample order; the final clamp is a segmented prefix "max" which is order-independent)
-        // A series whose values never decrease (and hold no NaN) comes out of removeCounterResets unchanged unless the
-        // staleness-gap rule is on: the pass over its rows is skipped (decoded columns never hold -0.0, so "+ 0.0" is void)
+        // A series whose values never decrease (and hold no NaN) comes out of removeCounterResets unchanged -- the
+        // staleness-gap rule only ever zeroes the correction, and without a value drop there is none -- so the pass over its
+        // rows is skipped (decoded columns never hold -0.0, so "+ 0.0" is void).  For the same reason the rows before the
+        // first value drop of a series are not touched: the pass starts at the 128-row group that holds it, in the state the
+        // sequential loop has there (no correction yet, outputs == inputs).
         const int64_t max_stale = rc.lookback_delta != 0 ? rc.lookback_delta + rc.window : 0;  // rollup.go:380-387
-        if ((rc.flags & VMB_RC_REMOVE_COUNTER_RESETS) && n && ((m._pad & 2u) || max_stale > 0)) {
+        if ((rc.flags & VMB_RC_REMOVE_COUNTER_RESETS) && n && (m._pad & 2u)) {
             RcrState st;
             st.corr = 0.0; st.prev_raw = 0.0; st.prev_out = 0.0; st.prev_ts = 0;
+            const uint32_t r0 = (m._pad >> 8) & 0xffffu;
+            const uint32_t base0 = r0 >= n ? 0u : (r0 & ~127u);
+            if (base0) {
+                st.prev_raw = st.prev_out = v[base0 - 1];
+                st.prev_ts = max_stale > 0 ? t[base0 - 1] : 0;
+            }
             // four 32-row chunks per iteration: their loads are issued together (one HBM round trip per 128 rows)
-            for (uint32_t base = 0; base < n; base += 128) {
+            for (uint32_t base = base0; base < n; base += 128) {
                 double x[4];
                 int64_t tt[4];
 #pragma unroll
