@@ -61,7 +61,7 @@ def parse_args():
 
 
 # ------------------------------------------------------------------------------------------------ synthetic input
-GEN_STATS = {"series": 0, "series_with_drop": 0}
+GEN_STATS = {"series": 0, "series_with_drop": 0, "rows": 0, "rows_from_first_drop": 0}
 RCR_FUNCS = ("rate", "increase", "irate", "increase_pure", "increase_prometheus", "rate_prometheus", "rollup_rate", "rollup_increase")
 
 
@@ -95,7 +95,12 @@ def gen_blocks(nblocks, rows, seed, chunk=4000, kind="counter", ts_kind="regular
                 dconst = rng.integers(0, 10 ** 6, (n, 1)) + rng.integers(1, 100, (n, 1)) * np.arange(rows, dtype=np.int64)[None, :]
                 v = np.where(k < 4, v, np.where(k < 7, g, np.where(k < 9, const, dconst)))
         GEN_STATS["series"] += n
-        GEN_STATS["series_with_drop"] += int(np.count_nonzero((np.diff(v, axis=1) < 0).any(axis=1)))
+        dropped = np.diff(v, axis=1) < 0
+        has = dropped.any(axis=1)
+        GEN_STATS["series_with_drop"] += int(np.count_nonzero(has))
+        GEN_STATS["rows"] += n * rows
+        # removeCounterResets touches a series from the 128-row group of its first value drop on
+        GEN_STATS["rows_from_first_drop"] += int((rows - ((np.argmax(dropped, axis=1)[has] + 1) & ~127)).sum())
         if ts_kind == "jitter":  # every series has its own scrape jitter of +-50 ms (SURVEY.md 8d config 2 variant)
             tj = ts[None, :] + rng.integers(-50, 51, (n, rows))
             tp_, toffs, tmts, tfirsts = encoding.marshal_columns(tj)
@@ -484,12 +489,12 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
         varint_bytes = int(2 * rows_total) * (2 if a.ts == "jitter" else 1)  # ~2 B/sample zig-zag varints per zstd column
-        drop_frac = (GEN_STATS["series_with_drop"] / max(GEN_STATS["series"], 1)) if a.func in RCR_FUNCS else 0.0
+        drop_frac = (GEN_STATS["rows_from_first_drop"] / max(GEN_STATS["rows"], 1)) if a.func in RCR_FUNCS else 0.0
         stage_names = ["zstd", "column_decode", "series_preamble", "rollup", "aggregate"]
         stage_bytes = [compressed + varint_bytes,                          # zstd: read frames, write varint bytes
                        varint_bytes + 64 * a.blocks + rows_total * 16,     # decode: read varints + descs, write ts+val
-                       int(rows_total * 16 * drop_frac),                   # preamble: read+write values of the series that
-                                                                           # hold a value drop (removeCounterResets), others skipped
+                       int(rows_total * 16 * drop_frac),                   # preamble: read+write values from the first value drop
+                                                                           # of a series on (removeCounterResets); the rest is skipped
                        rows_total * 16 + a.blocks * points * 8, 0]         # rollup: read ts+val, write result
         stages = {}
         for n_, ms_, b_ in zip(stage_names, stage_ms, stage_bytes):
