@@ -1439,7 +1439,7 @@ __device__ __forceinline__ double rate_point32(uint32_t i, uint32_t j, uint32_t 
 }
 
 template <int F>
-__global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
+__global__ void __launch_bounds__(ROLLUP_THREADS, 4) k_rollup(RollupParams P) {
     const vmb_rollup_cfg& rc = P.cfg;
     const uint32_t tid = threadIdx.x;
     unsigned long long scanned = 0;
@@ -1450,8 +1450,19 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
         const uint32_t n = m.n;
         double* out = P.out + (size_t)s * P.npoints;
         if (tid == 0) scanned += n;  // samplesScanned starts at len(values) rollup.go:766
-        const uint32_t wsteps = (uint32_t)(m.window / rc.step);
-        const bool shared_seeks = (m.window % rc.step) == 0 && wsteps <= ROLLUP_SEEKS - ROLLUP_CAP;
+        // window / step and window % step: 32-bit arithmetic when both fit (a 64-bit division is ~100 instructions and every
+        // thread of the CTA computes this)
+        uint32_t wsteps;
+        bool window_is_steps;
+        if ((uint64_t)m.window < (1ull << 31) && (uint64_t)rc.step < (1ull << 31)) {
+            const uint32_t w32 = (uint32_t)m.window, s32 = (uint32_t)rc.step;
+            wsteps = w32 / s32;
+            window_is_steps = wsteps * s32 == w32;
+        } else {
+            wsteps = (uint32_t)(m.window / rc.step);
+            window_is_steps = (m.window % rc.step) == 0;
+        }
+        const bool shared_seeks = window_is_steps && wsteps <= ROLLUP_SEEKS - ROLLUP_CAP;
         const uint32_t wsteps_cap = shared_seeks ? wsteps : 0u;
         // 32-bit fast path (rate): timestamps relative to the first row of the series, when everything fits 2^30 ms
         const int64_t t_org = n ? tg[0] : 0;
@@ -1502,7 +1513,9 @@ __global__ void __launch_bounds__(ROLLUP_THREADS) k_rollup(RollupParams P) {
             if (base + cnt == n) p_end = P.npoints;
             else {
                 int64_t tl = (ap ? t_org + (int64_t)(base + cnt - 1) * dt_row : rs_ts[cnt - 1]) - 1 - rc.start;
-                p_end = tl < 0 ? 0u : (uint32_t)min((int64_t)P.npoints, tl / rc.step + 1);
+                if (tl < 0) p_end = 0u;
+                else if (fast) p_end = min(P.npoints, (uint32_t)tl / (uint32_t)step32 + 1u);  // tl < 2^31 here
+                else p_end = (uint32_t)min((int64_t)P.npoints, tl / rc.step + 1);
             }
             float inv_dt = 0.0f;  // rows per millisecond over the resident range (0: no usable slope => bisect)
             {
