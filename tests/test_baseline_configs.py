@@ -196,7 +196,7 @@ def test_regular_timestamp_mode_edges(oracle):
     rng = np.random.default_rng(311)
     blocks = []
     for i, (n, dt) in enumerate([(2, 15000), (3, 1), (100, 7), (8192, 15000), (8192, 1000), (5000, 60000), (64, 999),
-                                 (8192, 15000), (777, 15000), (16, 10**6)]):
+                                 (8192, 15000), (777, 15000), (16, 10**6), (8192, 1)]):
         ts = (T0 + dt * np.arange(n)).astype(np.int64)
         kind = "special" if i in (7, 8) else ("counter_resets" if i % 2 else "counter")
         vals = np.abs(blockgen.gen_values(rng, kind, n)) if kind != "special" else blockgen.gen_values(rng, kind, n)
@@ -209,7 +209,9 @@ def test_regular_timestamp_mode_edges(oracle):
             (T0 - 600000, T0 + 15000 * 9000, 15000, 60000, None),          # grid wider than the data on both sides
             (T0 + 1000, T0 + 200000, 7000, 21000, None),                    # step unrelated to any scrape interval
             (T0 + 300000, T0 + 15000 * 4000, 30000, 300000, (T0 + 15000 * 100 + 1, T0 + 15000 * 3000)),  # trimmed blocks
-            (T0, T0 + 5000, 1, 5, None)]:                                   # millisecond grid over the 1 ms / 7 ms series
+            (T0, T0 + 5000, 1, 5, None),                                    # millisecond grid over the 1 ms / 7 ms series
+            (T0 + 6000, T0 + 8100, 1000, 5000, None)]:                      # 5000-row windows on the 1 ms series: more rows
+                                                                            # than the shared-memory window holds
         kw = {} if tr is None else dict(tr_min=tr[0], tr_max=tr[1])
         exp = []
         for b in blocks:
