@@ -157,6 +157,12 @@ enum vmb_rollup_func { /* rollup.go:24-108; names in comments are the MetricsQL 
 #define VMB_RC_IS_DEFAULT_ROLLUP 2u     /* funcName == "default_rollup" rollup.go:408 */
 #define VMB_RC_REMOVE_COUNTER_RESETS 4u /* rollupFuncsRemoveCounterResets rollup.go:223: preFunc */
 #define VMB_RC_DROP_STALE_NANS 8u       /* eval.go:1985 (not for default_rollup / stale_samples_over_time) */
+/* value preFuncs of the multi-output rollups (getRollupConfigs rollup.go:440-476), applied after removeCounterResets,
+ * once per batch like it */
+#define VMB_RC_PRE_DELTA_VALUES 16u     /* rollup_increase / rollup_delta: deltaValues rollup.go:960 */
+#define VMB_RC_PRE_DERIV_VALUES 32u     /* rollup_rate / rollup_deriv: derivValues rollup.go:976 */
+#define VMB_RC_PRE_SCRAPE_INTERVAL 64u  /* rollup_scrape_interval: seconds between samples rollup.go:462-474 */
+#define VMB_RC_PRE_MASK 112u
 
 typedef struct { /* == rollupConfig rollup.go:574 + what getRollupConfigs (rollup.go:374) derives from the func name */
     int32_t func_id;          /* enum vmb_rollup_func */

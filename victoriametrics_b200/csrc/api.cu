@@ -107,6 +107,7 @@ struct vmb_series {
     uint32_t* d_blk_hi = nullptr;
     int32_t* d_blk_status = nullptr;
     bool stale_dropped = false, resets_removed = false;
+    uint32_t pre_applied = 0;  // VMB_RC_PRE_* already applied to the values (at most one of them, once)
     bool values_are_int = false;
 };
 
@@ -809,6 +810,19 @@ static int run_rollup(vmb_ctx* ctx, vmb_series* s, const vmb_rollup_cfg* cfg, in
     uint32_t flags = cfg->flags;
     if (s->stale_dropped) flags &= ~VMB_RC_DROP_STALE_NANS;
     if (s->resets_removed) flags &= ~VMB_RC_REMOVE_COUNTER_RESETS;
+    {
+        const uint32_t pre = flags & VMB_RC_PRE_MASK;
+        if (pre & (pre - 1)) {
+            vmb_set_error("at most one value preFunc (VMB_RC_PRE_*) per rollup config");
+            return VMB_ERR_INVALID_ARG;
+        }
+        if (s->pre_applied && pre != s->pre_applied) {
+            vmb_set_error("this batch already went through another value preFunc: decode it again");
+            return VMB_ERR_INVALID_ARG;
+        }
+        if (s->pre_applied) flags &= ~VMB_RC_PRE_MASK;
+        else s->pre_applied = pre;
+    }
     R.cfg.flags = flags;
     launch_series_prepare(R, st);
     count_launch(ctx);
@@ -954,6 +968,7 @@ static int eval_device_async(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, i
                              const vmb_rollup_cfg* cfg, int64_t points, double* d_out, unsigned int* d_failed,
                              unsigned long long* d_scanned) {
     s->stale_dropped = s->resets_removed = false;
+    s->pre_applied = 0;
     int rc = run_decode(ctx, b, s, tr_min, tr_max, 0, d_failed);
     if (rc) return rc;
     return run_rollup(ctx, s, cfg, points, d_out, d_scanned);

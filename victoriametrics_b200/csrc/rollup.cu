@@ -1180,6 +1180,70 @@ __global__ void __launch_bounds__(128) k_series_prepare(RollupParams P) {
                 }
             }
         }
+        // ---- value preFuncs of the multi-output rollups (rollup.go:440-476), in place.  Output i needs inputs i and i+1:
+        //      chunks run in ascending order, every lane reads before the chunk writes.
+        if ((rc.flags & VMB_RC_PRE_MASK) && n) {
+            __syncwarp();
+            if (rc.flags & VMB_RC_PRE_DERIV_VALUES) {
+                bool dup = false;  // duplicate timestamps make the loop carry state (rollup.go:987): rare, replayed by lane 0
+                for (uint32_t i = 1 + lane; i < n; i += 32) dup |= t[i] == t[i - 1];
+                if (__any_sync(VMB_FULL, dup)) {
+                    if (lane == 0) {
+                        double prevDeriv = 0.0, prevValue = v[0];
+                        int64_t prevTs = t[0];
+                        for (uint32_t i = 0; i + 1 < n; i++) {
+                            const double x = v[i + 1];
+                            const int64_t ts = t[i + 1];
+                            if (ts == prevTs) {
+                                v[i] = prevDeriv;
+                                continue;
+                            }
+                            prevDeriv = (x - prevValue) / ((double)(ts - prevTs) / 1e3);
+                            v[i] = prevDeriv;
+                            prevValue = x;
+                            prevTs = ts;
+                        }
+                        v[n - 1] = prevDeriv;
+                    }
+                } else {
+                    double last = 0.0;
+                    for (uint32_t base = 0; base + 1 < n; base += 32) {
+                        const uint32_t i = base + lane;
+                        double o = 0.0;
+                        const bool act = i + 1 < n;
+                        if (act) o = (v[i + 1] - v[i]) / ((double)(t[i + 1] - t[i]) / 1e3);
+                        __syncwarp();
+                        if (act) v[i] = o;
+                        if (i + 2 == n) last = o;
+                    }
+                    last = __shfl_sync(VMB_FULL, last, (int)((n - 2) & 31u));
+                    __syncwarp();
+                    if (lane == 0) v[n - 1] = n > 1 ? last : 0.0;  // prevDeriv (0 for a single sample)
+                }
+            } else if (rc.flags & VMB_RC_PRE_DELTA_VALUES) {
+                double last = 0.0;
+                for (uint32_t base = 0; base + 1 < n; base += 32) {
+                    const uint32_t i = base + lane;
+                    double o = 0.0;
+                    const bool act = i + 1 < n;
+                    if (act) o = v[i + 1] - v[i];
+                    __syncwarp();
+                    if (act) v[i] = o;
+                    if (i + 2 == n) last = o;
+                }
+                last = __shfl_sync(VMB_FULL, last, (int)((n - 2) & 31u));
+                __syncwarp();
+                if (lane == 0) v[n - 1] = n > 1 ? last : 0.0;  // prevDelta (0 for a single sample)
+            } else {  // VMB_RC_PRE_SCRAPE_INTERVAL: values[i] = ts[i]/1000 - ts[i-1]/1000, values[0] = values[1]
+                for (uint32_t i = lane; i < n; i += 32) {
+                    double o = D_NAN;
+                    if (i > 0) o = (double)t[i] / 1000 - (double)t[i - 1] / 1000;
+                    else if (n > 1) o = (double)t[1] / 1000 - (double)t[0] / 1000;
+                    v[i] = o;
+                }
+            }
+            __syncwarp();
+        }
         // ---- maxPrevInterval / window  rollup.go:719-756
         if (lane == 0) {
             int64_t maxPrev = rc.step;

@@ -44,6 +44,17 @@ ROLLUP_FUNCS_SAMPLES_SCANNED_PER_CALL = {
     "scrape_interval": 2, "tfirst_over_time": 1, "timestamp": 1, "timestamp_with_name": 1, "tlast_over_time": 1}
 
 RC_MAY_ADJUST_WINDOW, RC_IS_DEFAULT_ROLLUP, RC_REMOVE_COUNTER_RESETS, RC_DROP_STALE_NANS = 1, 2, 4, 8
+RC_PRE = {None: 0, "delta": 16, "deriv": 32, "scrape_interval": 64}  # value preFuncs of the multi-output rollups
+# rollup.go:147 rollupAggrFuncs: what aggr_over_time() accepts
+ROLLUP_AGGR_FUNCS = {"absent_over_time", "ascent_over_time", "avg_over_time", "changes", "count_over_time",
+                     "decreases_over_time", "default_rollup", "delta", "deriv", "deriv_fast", "descent_over_time",
+                     "distinct_over_time", "first_over_time", "geomean_over_time", "idelta", "ideriv", "increase",
+                     "increase_pure", "increases_over_time", "integrate", "irate", "iqr_over_time", "lag", "last_over_time",
+                     "lifetime", "mad_over_time", "max_over_time", "median_over_time", "min_over_time", "mode_over_time",
+                     "present_over_time", "range_over_time", "rate", "rate_over_sum", "resets", "scrape_interval",
+                     "stale_samples_over_time", "stddev_over_time", "stdvar_over_time", "sum_over_time", "sum2_over_time",
+                     "tfirst_over_time", "timestamp", "timestamp_with_name", "tlast_change_over_time", "tlast_over_time",
+                     "tmax_over_time", "tmin_over_time", "zscore_over_time"}
 AGGR_FUNCS = {"sum": 0, "min": 1, "max": 2, "avg": 3, "count": 4, "sum2": 5, "geomean": 6, "any": 7, "group": 8}
 
 
@@ -61,12 +72,13 @@ class RollupConfig:
 
     def __init__(self, Func, Start, End, Step, Window=0, LookbackDelta=0, MayAdjustWindow=False, isDefaultRollup=False,
                  samplesScannedPerCall=0, args=None, args2=None, removeCounterResets=False, dropStaleNaNs=False,
-                 minStalenessInterval=0):
+                 minStalenessInterval=0, TagValue="", preFunc=None):
         self.Func, self.Start, self.End, self.Step, self.Window = Func, int(Start), int(End), int(Step), int(Window)
         self.LookbackDelta, self.MayAdjustWindow, self.isDefaultRollup = int(LookbackDelta), MayAdjustWindow, isDefaultRollup
         self.samplesScannedPerCall, self.args, self.args2 = samplesScannedPerCall, args, args2
         self.removeCounterResets, self.dropStaleNaNs = removeCounterResets, dropStaleNaNs
         self.minStalenessInterval = int(minStalenessInterval)
+        self.TagValue, self.preFunc = TagValue, preFunc  # rollup.go:576 TagValue; preFunc in (None, "delta", "deriv", "scrape_interval")
         if self.Step <= 0 or self.Start > self.End or self.Window < 0:  # rollup.go:703-711 logger.Panicf("BUG: ...")
             raise ValueError("BUG: invalid rollupConfig: Step=%d Start=%d End=%d Window=%d" % (Step, Start, End, Window))
         self.Timestamps = get_timestamps(self.Start, self.End, self.Step)
@@ -78,7 +90,8 @@ class RollupConfig:
 
     def _cfg(self):
         flags = (RC_MAY_ADJUST_WINDOW if self.MayAdjustWindow else 0) | (RC_IS_DEFAULT_ROLLUP if self.isDefaultRollup else 0) \
-            | (RC_REMOVE_COUNTER_RESETS if self.removeCounterResets else 0) | (RC_DROP_STALE_NANS if self.dropStaleNaNs else 0)
+            | (RC_REMOVE_COUNTER_RESETS if self.removeCounterResets else 0) | (RC_DROP_STALE_NANS if self.dropStaleNaNs else 0) \
+            | RC_PRE[self.preFunc]
         cfg = RollupCfg(ROLLUP_FUNCS[self.Func], flags, self.Start, self.End, self.Step, self.Window, self.LookbackDelta,
                         self.minStalenessInterval, self.samplesScannedPerCall, 0, None, None)
         self._keep = []
@@ -254,3 +267,73 @@ def torch_all_reduce(values_t, counts_t, op):
     ops = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX, "prod": dist.ReduceOp.PRODUCT}
     dist.all_reduce(values_t, op=ops[op])
     dist.all_reduce(counts_t, op=dist.ReduceOp.SUM)
+
+
+# ---- multi-output rollups (getRollupConfigs rollup.go:416-504): one input series -> several output series --------------
+def get_rollup_configs_multi(func_name, start, end, step, window=0, lookback_delta=0, tag=None, aggr_funcs=None, phis=None,
+                             no_stale_markers=False, min_staleness_interval=0):
+    """getRollupConfigs rollup.go:374 for rollup(), rollup_rate/deriv/increase/delta(), rollup_scrape_interval(),
+    rollup_candlestick(), aggr_over_time() and quantiles_over_time(): -> [RollupConfig], one per output series, TagValue =
+    the value of the `rollup` (or phi) label.  The value preFunc (deltaValues / derivValues / intervals) and
+    removeCounterResets are shared by the configs and run once per decoded batch."""
+    name = func_name.lower()
+    rcr = name in ROLLUP_FUNCS_REMOVE_COUNTER_RESETS
+    pre = None
+    spc = ROLLUP_FUNCS_SAMPLES_SCANNED_PER_CALL.get(name, 0)
+    if name in ("rollup", "rollup_rate", "rollup_deriv", "rollup_increase", "rollup_delta", "rollup_scrape_interval"):
+        pre = {"rollup_rate": "deriv", "rollup_deriv": "deriv", "rollup_increase": "delta", "rollup_delta": "delta",
+               "rollup_scrape_interval": "scrape_interval"}.get(name)
+        funcs = {"min": "min_over_time", "max": "max_over_time", "avg": "avg_over_time"}
+        if tag in (None, ""):
+            pairs = [(funcs[t], t, None) for t in ("min", "max", "avg")]
+        elif tag in funcs:
+            pairs = [(funcs[tag], "", None)]
+        else:
+            raise ValueError("unexpected second arg for %s: %r; want `min`, `max` or `avg`" % (func_name, tag))
+    elif name == "rollup_candlestick":
+        funcs = {"open": "rollup_open", "close": "rollup_close", "low": "rollup_low", "high": "rollup_high"}
+        if tag in (None, ""):
+            pairs = [(funcs[t], t, None) for t in ("open", "close", "low", "high")]
+        elif tag in funcs:
+            pairs = [(funcs[tag], tag, None)]
+        else:
+            raise ValueError("unexpected second arg for %s: %r; want `open`, `close`, `low` or `high`" % (func_name, tag))
+    elif name == "aggr_over_time":
+        if not aggr_funcs:
+            raise ValueError("aggr_over_time() needs at least one aggregate function name")
+        pairs = []
+        for f in aggr_funcs:
+            f = f.lower()
+            if f not in ROLLUP_AGGR_FUNCS:
+                raise ValueError("%r cannot be used in `aggr_over_time` function" % f)
+            rcr = rcr or f in ROLLUP_FUNCS_REMOVE_COUNTER_RESETS
+            pairs.append((f, f, None))
+    elif name == "quantiles_over_time":
+        if not phis:
+            raise ValueError("quantiles_over_time() needs at least one phi")
+        pairs = [("quantile_over_time", repr(float(p)).rstrip("0").rstrip(".") if float(p) != int(p) else str(int(p)), float(p))
+                 for p in phis]
+    else:
+        raise KeyError("%r is not a multi-output rollup function" % func_name)
+    drop_stale = not no_stale_markers
+    return [RollupConfig(f, start, end, step, window, lookback_delta,
+                         MayAdjustWindow=name in ROLLUP_FUNCS_CAN_ADJUST_WINDOW, isDefaultRollup=False,
+                         samplesScannedPerCall=spc, args=arg, removeCounterResets=rcr, dropStaleNaNs=drop_stale,
+                         minStalenessInterval=min_staleness_interval, TagValue=t, preFunc=pre) for f, t, arg in pairs]
+
+
+def eval_rollup_func_multi(func_name, blocks, start, end, step, window=0, lookback_delta=0, tr_min=storage.INT64_MIN,
+                           tr_max=storage.INT64_MAX, **kw):
+    """evalRollupNoIncrementalAggregate eval.go:1845 for a multi-output rollup on device-resident blocks: decode once, run
+    the shared preFunc once, then one rollup per config -> ({TagValue: [nseries x points] np.float64}, samplesScanned)"""
+    rcs = get_rollup_configs_multi(func_name, start, end, step, window, lookback_delta, **kw)
+    series, _ = storage.decode_blocks(blocks, tr_min, tr_max)
+    try:
+        out, scanned = {}, 0
+        for rc in rcs:
+            m, sc = rc.do_series(series)
+            out[rc.TagValue] = m
+            scanned += sc
+        return out, scanned
+    finally:
+        series.close()
