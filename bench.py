@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--step-ms", type=int, default=15_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--aggr", default="", help="configs[4] variant: aggr(func(m[d])) by (label) with an NCCL all-reduce of the "
-                                               "per-GPU partial states, e.g. --aggr sum (kernel-only numbers; no e2e leg)")
+                                               "per-GPU partial states, e.g. --aggr sum (the host-buffer arm folds on the GPU too and returns [groups x points])")
     ap.add_argument("--groups", type=int, default=1000, help="label groups for --aggr")
     ap.add_argument("--cpu-seconds", type=float, default=24.0, help="target CPU work of the cpu_baseline sample")
     return ap.parse_args()
@@ -364,7 +364,8 @@ def main():
     if a.aggr:
         # sum(rate(m[5m])) by (label): every rank folds its own series into [groups x points] partial states, one NCCL
         # all-reduce of values and one of counts merges them, every rank finalizes
-        a.no_e2e = True
+        if world > 1:
+            a.no_e2e = True  # (the host-buffer arm of the aggregate is single-process: per-rank results are finalized)
         rc_aggr = promql.get_rollup_configs(a.func, start, end, step, a.window_ms)
         group_ids = ((np.arange(a.blocks, dtype=np.int64) * world + rank) % a.groups).astype(np.uint32)
 
@@ -438,7 +439,7 @@ def main():
     # ---- e2e: host buffers in, host result out
     e2e = None
     if not a.no_e2e:
-        nbytes_out = a.blocks * points * 8
+        nbytes_out = (a.groups if a.aggr else a.blocks) * points * 8
         hp = _lib.lib().vmb_host_alloc(payload.size + 64)
         ho = _lib.lib().vmb_host_alloc(nbytes_out)
         hd = _lib.lib().vmb_host_alloc(descs.nbytes)
@@ -447,9 +448,12 @@ def main():
         h_payload[:] = payload
         h_descs = np.ctypeslib.as_array(C.cast(hd, C.POINTER(C.c_uint8)), shape=(descs.nbytes,)).view(descs.dtype)
         h_descs[:] = descs
-        h_out = np.ctypeslib.as_array(C.cast(ho, C.POINTER(C.c_double)), shape=(a.blocks, points))
+        h_out = np.ctypeslib.as_array(C.cast(ho, C.POINTER(C.c_double)), shape=((a.groups if a.aggr else a.blocks), points))
 
         def host_step():
+            if a.aggr:
+                return promql.eval_rollup_aggr_host(a.aggr, a.func, h_descs, h_payload, group_ids, a.groups, start, end, step,
+                                                    a.window_ms, args=func_args, out=h_out, ctx=ctx)
             return promql.eval_rollup_func_host(a.func, h_descs, h_payload, start, end, step, a.window_ms, args=func_args,
                                                 out=h_out, nseries=a.blocks, ctx=ctx)
         for _ in range(max(1, min(a.warmup, 2))):
@@ -467,9 +471,12 @@ def main():
         e2e_clocks = sampler.window(tb2, time.time())
         e2e_ms = max(e0.elapsed_time(e1), 0.0)
         e2e = {"ms": e2e_ms, "wall_ms": wall * 1e3, "h2d": int(descs.nbytes + payload.size), "d2h": int(nbytes_out)}
-        check = float(np.nansum(h_out[: min(a.blocks, 64)]))
-        dcheck = float(torch.nansum(out_dev[: min(a.blocks, 64)]).item())
-        assert abs(check - dcheck) <= 1e-9 * max(1.0, abs(dcheck)), (check, dcheck)
+        if a.aggr:  # same query result as the device-resident arm (chunk-wise folding only reorders float additions)
+            assert np.allclose(h_out, aggr_host, rtol=1e-9, atol=0, equal_nan=True)
+        else:
+            check = float(np.nansum(h_out[: min(a.blocks, 64)]))
+            dcheck = float(torch.nansum(out_dev[: min(a.blocks, 64)]).item())
+            assert abs(check - dcheck) <= 1e-9 * max(1.0, abs(dcheck)), (check, dcheck)
 
     sampler.stop()
     # ---- max over ranks
@@ -528,7 +535,8 @@ def main():
             per = e2e_ms / a.steps
             out["e2e"] = {"value": world * rows_total / (per / 1e3), "unit": "samples/s", "ms_per_step": per,
                           "wall_ms_per_step": e2e_wall_ms / a.steps, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                          "api": "vmb_eval_rollup_host (pinned host descriptors+payload in, pinned host result out)",
+                          "api": ("vmb_eval_rollup_aggr_host (pinned host descriptors+payload in, [groups x points] result out)"
+                                  if a.aggr else "vmb_eval_rollup_host (pinned host descriptors+payload in, pinned host result out)"),
                           "clocks": e2e_clocks}
         out["config"]["compressed_bytes_per_gpu"] = compressed
         out["config"]["bytes_per_sample_compressed"] = round(compressed / rows_total, 3)

@@ -217,6 +217,14 @@ int vmb_eval_rollup_host(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nbloc
 int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* blocks, int64_t tr_min, int64_t tr_max,
                            const vmb_rollup_cfg* cfg, double* d_out, uint64_t* samples_scanned);
 
+/* aggregate variant of the host path (evalRollupWithIncrementalAggregate eval.go:1804 end to end): the same chunked
+ * pipeline as vmb_eval_rollup_host, but every chunk's [series x P] matrix is folded on the GPU into {values, counts}[G x P]
+ * and only the finalized [ngroups x P] result (host pointer) travels back.  group_ids: one dense id per series of the batch. */
+int vmb_eval_rollup_aggr_host(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload,
+                              size_t payload_len, int64_t tr_min, int64_t tr_max, const vmb_rollup_cfg* cfg, int aggr_id,
+                              const uint32_t* group_ids, uint32_t ngroups, double* out_host, int32_t* block_status,
+                              uint64_t* samples_scanned);
+
 /* aggregate variant of the device-resident path: decode + preamble + rollup + vmb_rollup_aggr_partial in one call, decoded
  * columns cached in the library (per-rank step of `aggr(rollup(m[d])) by (...)`, eval.go:1804) */
 int vmb_eval_rollup_aggr_device(vmb_ctx* ctx, const vmb_blocks* blocks, int64_t tr_min, int64_t tr_max,

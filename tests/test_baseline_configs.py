@@ -139,6 +139,24 @@ def test_config3_sum_rate_by_label_single_rank(oracle):
     got2 = ia2.finalize(vm.default_context())
     assert np.array_equal(got, got2, equal_nan=True)
     assert scanned > 0
+    # and the host path (chunked pipeline folding every chunk on the GPU): several chunks, every aggregate
+    import os
+    os.environ["VMB_PIPE_CHUNK_BLOCKS"] = "10"
+    try:
+        for aggr in ("sum", "min", "max", "avg", "count", "sum2", "geomean", "any", "group"):
+            got3, scanned3 = vm.promql.eval_rollup_aggr_host(aggr, "rate", descs, payload, groups, G, start, end, step, window)
+            e_v, e_c = np.zeros((G, rc.points)), np.zeros((G, rc.points))
+            for s_ in range(S):
+                row = np.ascontiguousarray(rolled[s_])
+                g = int(groups[s_])
+                oracle.lib().vmo_aggr_update(AGGR[aggr], e_v[g].ctypes.data_as(oracle.f64p), e_c[g].ctypes.data_as(oracle.f64p),
+                                             row.ctypes.data_as(oracle.f64p), rc.points)
+            for g in range(G):
+                oracle.lib().vmo_aggr_finalize(AGGR[aggr], e_v[g].ctypes.data_as(oracle.f64p), e_c[g].ctypes.data_as(oracle.f64p), rc.points)
+            assert np.allclose(got3, e_v, rtol=1e-12, atol=0, equal_nan=True), aggr
+            assert scanned3 == scanned
+    finally:
+        del os.environ["VMB_PIPE_CHUNK_BLOCKS"]
 
 
 @pytest.mark.gpu

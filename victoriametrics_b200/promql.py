@@ -186,6 +186,29 @@ def eval_rollup_func_host(func_name, descs, payload, start, end, step, window=0,
     return out, scanned.value
 
 
+def eval_rollup_aggr_host(aggr_name, func_name, descs, payload, group_ids, ngroups, start, end, step, window=0,
+                          lookback_delta=0, args=None, args2=None, tr_min=storage.INT64_MIN, tr_max=storage.INT64_MAX,
+                          out=None, ctx=None, rc=None):
+    """aggr(rollup(m[d])) by (...) with HOST buffers in one call (vmb_eval_rollup_aggr_host): H2D, decode, rollup and the
+    incremental aggregate on the GPU, D2H of the [ngroups x points] result only -> (np.float64[ngroups, points], samplesScanned)"""
+    ctx = ctx or _lib.default_context()
+    rc = rc or get_rollup_configs(func_name, start, end, step, window, lookback_delta, args, args2)
+    cfg = rc._cfg()
+    if isinstance(descs, np.ndarray):
+        dptr, n = descs.ctypes.data_as(C.POINTER(_lib.BlockDesc)), descs.shape[0]
+    else:
+        dptr, n = descs, len(descs)
+    if out is None:
+        out = np.empty((int(ngroups), rc.points), dtype=np.float64)
+    g = np.ascontiguousarray(group_ids, dtype=np.uint32)
+    payload = np.ascontiguousarray(payload, dtype=np.uint8)
+    scanned = C.c_uint64(0)
+    check(lib().vmb_eval_rollup_aggr_host(ctx.h, dptr, n, payload.ctypes.data_as(_lib.u8p), payload.size, tr_min, tr_max,
+                                          C.byref(cfg), AGGR_FUNCS[aggr_name.lower()], g.ctypes.data_as(_lib.u32p), int(ngroups),
+                                          out.ctypes.data_as(_lib.f64p), None, C.byref(scanned)))
+    return out, scanned.value
+
+
 class IncrementalAggr:
     """incrementalAggrFuncContext aggr_incremental.go:73: aggr(rollup(m[d])) by (...) without keeping [series x points]
     on the host.  update() == updateTimeseries for every series of a device batch (per-GPU partial state);
