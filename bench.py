@@ -364,8 +364,6 @@ def main():
     if a.aggr:
         # sum(rate(m[5m])) by (label): every rank folds its own series into [groups x points] partial states, one NCCL
         # all-reduce of values and one of counts merges them, every rank finalizes
-        if world > 1:
-            a.no_e2e = True  # (the host-buffer arm of the aggregate is single-process: per-rank results are finalized)
         rc_aggr = promql.get_rollup_configs(a.func, start, end, step, a.window_ms)
         group_ids = ((np.arange(a.blocks, dtype=np.int64) * world + rank) % a.groups).astype(np.uint32)
 
@@ -451,6 +449,10 @@ def main():
         h_out = np.ctypeslib.as_array(C.cast(ho, C.POINTER(C.c_double)), shape=((a.groups if a.aggr else a.blocks), points))
 
         def host_step():
+            if a.aggr and world > 1:  # per-rank partial from host buffers, NCCL all-reduce, finalize + D2H of the result
+                sc_ = ia.update_host(h_descs, h_payload, rc_aggr, group_ids, ctx)
+                ia.finalize(ctx, all_reduce=reduce_cb, out=h_out)
+                return h_out, sc_
             if a.aggr:
                 return promql.eval_rollup_aggr_host(a.aggr, a.func, h_descs, h_payload, group_ids, a.groups, start, end, step,
                                                     a.window_ms, args=func_args, out=h_out, ctx=ctx)
@@ -535,7 +537,8 @@ def main():
             per = e2e_ms / a.steps
             out["e2e"] = {"value": world * rows_total / (per / 1e3), "unit": "samples/s", "ms_per_step": per,
                           "wall_ms_per_step": e2e_wall_ms / a.steps, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                          "api": ("vmb_eval_rollup_aggr_host (pinned host descriptors+payload in, [groups x points] result out)"
+                          "api": (("vmb_eval_rollup_aggr_host_partial + NCCL all-reduce + vmb_aggr_finalize" if world > 1 else
+                                   "vmb_eval_rollup_aggr_host") + " (pinned host descriptors+payload in, [groups x points] result out)"
                                   if a.aggr else "vmb_eval_rollup_host (pinned host descriptors+payload in, pinned host result out)"),
                           "clocks": e2e_clocks}
         out["config"]["compressed_bytes_per_gpu"] = compressed

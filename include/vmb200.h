@@ -225,6 +225,13 @@ int vmb_eval_rollup_aggr_host(vmb_ctx* ctx, const vmb_block_desc* descs, size_t 
                               const uint32_t* group_ids, uint32_t ngroups, double* out_host, int32_t* block_status,
                               uint64_t* samples_scanned);
 
+/* ... without the final step: the partial state of this batch is left in the caller's DEVICE buffers {values, counts}
+ * [ngroups x P] (overwritten), for vmb_aggr_merge or vmb_aggr_prepare_allreduce + all-reduce + vmb_aggr_finalize (multi-GPU) */
+int vmb_eval_rollup_aggr_host_partial(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload,
+                                      size_t payload_len, int64_t tr_min, int64_t tr_max, const vmb_rollup_cfg* cfg, int aggr_id,
+                                      const uint32_t* group_ids, uint32_t ngroups, double* d_values, double* d_counts,
+                                      int32_t* block_status, uint64_t* samples_scanned);
+
 /* aggregate variant of the device-resident path: decode + preamble + rollup + vmb_rollup_aggr_partial in one call, decoded
  * columns cached in the library (per-rank step of `aggr(rollup(m[d])) by (...)`, eval.go:1804) */
 int vmb_eval_rollup_aggr_device(vmb_ctx* ctx, const vmb_blocks* blocks, int64_t tr_min, int64_t tr_max,

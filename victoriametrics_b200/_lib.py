@@ -89,6 +89,8 @@ def lib():
         "vmb_eval_rollup_device": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.POINTER(RollupCfg), vp, u64p]),
         "vmb_eval_rollup_aggr_host": (C.c_int, [vp, C.POINTER(BlockDesc), C.c_size_t, u8p, C.c_size_t, C.c_int64, C.c_int64,
                                                 C.POINTER(RollupCfg), C.c_int, u32p, C.c_uint32, f64p, i32p, u64p]),
+        "vmb_eval_rollup_aggr_host_partial": (C.c_int, [vp, C.POINTER(BlockDesc), C.c_size_t, u8p, C.c_size_t, C.c_int64, C.c_int64,
+                                                        C.POINTER(RollupCfg), C.c_int, u32p, C.c_uint32, vp, vp, i32p, u64p]),
         "vmb_eval_rollup_aggr_device": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.POINTER(RollupCfg), C.c_int, u32p, C.c_uint32,
                                                   vp, vp, u64p]),
         "vmb_ctx_set_dedup_interval": (C.c_int, [vp, C.c_int64]),

@@ -243,6 +243,23 @@ class IncrementalAggr:
                                                 C.c_void_p(self.counts.ptr), C.byref(scanned)))
         return scanned.value
 
+    def update_host(self, descs, payload, rc, group_ids, ctx, tr_min=storage.INT64_MIN, tr_max=storage.INT64_MAX):
+        """the same from HOST buffers through the chunked pipeline (vmb_eval_rollup_aggr_host_partial): the partial state of
+        the batch replaces this object's state"""
+        g = np.ascontiguousarray(group_ids, dtype=np.uint32)
+        cfg = rc._cfg()
+        scanned = C.c_uint64(0)
+        if isinstance(descs, np.ndarray):
+            dptr, n = descs.ctypes.data_as(C.POINTER(_lib.BlockDesc)), descs.shape[0]
+        else:
+            dptr, n = descs, len(descs)
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        check(lib().vmb_eval_rollup_aggr_host_partial(ctx.h, dptr, n, payload.ctypes.data_as(_lib.u8p), payload.size, tr_min,
+                                                      tr_max, C.byref(cfg), self.aggr, g.ctypes.data_as(_lib.u32p), self.ngroups,
+                                                      C.c_void_p(self.values.ptr), C.c_void_p(self.counts.ptr), None,
+                                                      C.byref(scanned)))
+        return scanned.value
+
     def finalize(self, ctx, all_reduce=None, out=None):
         """all_reduce(values_buf, counts_buf, op) is called between prepare and finalize when given; `out` may be a
         preallocated (ideally pinned, vmb_host_alloc) [ngroups x points] float64 array"""
