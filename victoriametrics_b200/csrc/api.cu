@@ -72,6 +72,7 @@ struct vmb_ctx {
     DevBuf zseq;  // decoded zstd sequences (8 B each) between k_zstd_seq_decode and k_zstd_seq_exec
     DevBuf zscratch, zlit, zstatus, zjobs, zws, args1, args2, rolled, counters, tmp_out, grp, mheap, mnext;
     int64_t dedup_interval = 0;  // storage.SetDedupInterval (lib/storage/dedup.go:15), ms; 0 = deduplication off
+    struct vmb_series* col_cache = nullptr;  // decoded columns of the one-call device paths, sized for the largest batch seen
     void* h_pinned = nullptr;  // small pinned staging area for counters
     void* pipe = nullptr;      // pipeline.inc: streams, events and double-buffered slots of vmb_eval_rollup_host
     void (*pipe_destroy)(void*) = nullptr;
@@ -142,10 +143,13 @@ extern "C" int vmb_ctx_create(int device, vmb_ctx** out) {
     *out = c;
     return VMB_OK;
 }
+extern "C" void vmb_series_free(vmb_series* s);
 extern "C" void vmb_ctx_destroy(vmb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->col_cache) vmb_series_free(c->col_cache);
+    c->col_cache = nullptr;
     DevBuf* bufs[] = {&c->zscratch, &c->zlit, &c->zstatus, &c->zjobs, &c->zws, &c->args1, &c->args2, &c->rolled,
                       &c->counters, &c->tmp_out, &c->grp, &c->mheap, &c->mnext, &c->zseq};
     for (DevBuf* b : bufs) b->release();
@@ -976,6 +980,22 @@ static int eval_device_async(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, i
     return run_rollup(ctx, s, cfg, points, d_out, d_scanned);
 }
 
+// the decoded columns of the one-call device paths: owned by the ctx, grown to the largest batch seen
+static int ctx_column_cache(vmb_ctx* ctx, const vmb_blocks* b, vmb_series** out) {
+    vmb_series* c = ctx->col_cache;
+    if (c && (c->rows < b->rows + b->merge_rows || c->nseries < b->nseries || c->nblocks < b->nblocks)) {
+        vmb_series_free(c);
+        ctx->col_cache = c = nullptr;
+    }
+    if (!c) {
+        int rc = alloc_series_for(ctx, b, &c);
+        if (rc) return rc;
+        ctx->col_cache = c;
+    }
+    *out = c;
+    return 0;
+}
+
 extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t tr_min, int64_t tr_max,
                                       const vmb_rollup_cfg* cfg, double* d_out, uint64_t* samples_scanned) {
     if (!ctx || !b || !d_out) return VMB_ERR_INVALID_ARG;
@@ -983,16 +1003,8 @@ extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t
     int rc = check_cfg(cfg, &points);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
-    // the decoded columns are a per-ctx cache sized for the largest batch seen
-    static thread_local vmb_series* cache = nullptr;
-    if (cache && (cache->ctx != ctx || cache->rows < b->rows + b->merge_rows || cache->nseries < b->nseries || cache->nblocks < b->nblocks)) {
-        vmb_series_free(cache);
-        cache = nullptr;
-    }
-    if (!cache) {
-        rc = alloc_series_for(ctx, b, &cache);
-        if (rc) return rc;
-    }
+    vmb_series* cache = nullptr;
+    if ((rc = ctx_column_cache(ctx, b, &cache))) return rc;
     vmb_series view = *cache;  // shallow view with this batch's logical sizes
     view.nseries = b->nseries;
     view.nblocks = b->nblocks;
