@@ -1375,14 +1375,11 @@ void launch_zstd_prepare(const ZstdParams& P, cudaStream_t st) {
     k_zstd_prepare<<<(P.count + 63) / 64, 64, 0, st>>>(P);
 }
 
-static bool g_huf_attr_set = false;
 void launch_huf_decode(const ZstdParams& P, cudaStream_t st) {
     if (!P.count) return;
-    size_t smem = (size_t)HUF_WARPS * HUF_WARP_TABLE_BYTES + (size_t)HUF_WARPS * HUF_RING * 32 * sizeof(uint32_t);
-    if (!g_huf_attr_set) {
-        cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        g_huf_attr_set = true;
-    }
+    // 13 KB per CTA: below the 48 KB that need no opt-in
+    constexpr size_t smem = (size_t)HUF_WARPS * HUF_WARP_TABLE_BYTES + (size_t)HUF_WARPS * HUF_RING * 32 * sizeof(uint32_t);
+    static_assert(smem <= 48 * 1024, "k_huf_decode would need cudaFuncAttributeMaxDynamicSharedMemorySize");
     uint32_t groups = (P.count + HUF_FRAMES_PER_WARP - 1) / HUF_FRAMES_PER_WARP;
     uint32_t grid = (groups + HUF_WARPS - 1) / HUF_WARPS;
     if (grid > 148u * 16u) grid = 148u * 16u;
