@@ -206,6 +206,22 @@ int vmb_aggr_prepare_allreduce(vmb_ctx* ctx, int aggr_id, double* d_values, cons
 /* finalizeAggr* (aggr_incremental.go:189,:368,:400...): in place on DEVICE pointers, then optional copy to out_host */
 int vmb_aggr_finalize(vmb_ctx* ctx, int aggr_id, double* d_values, const double* d_counts, size_t n, double* out_host);
 
+/* ---- topk(k, q) / bottomk(k, q)  ==  newAggrFuncTopK aggr.go:646 on a DEVICE matrix d_vals[nseries x P] (e.g. the output
+ * of vmb_rollup / vmb_eval_rollup_device): per group and point only the k best values survive, the others become NaN
+ * (fillNaNsAtIdx aggr.go:786); rows left without a value are reported so that the host drops them (removeEmptySeries).
+ * Values equal to the k-th best are all kept (the reference's unstable sort keeps an arbitrary subset of them).
+ *   1. vmb_topk_candidates: d_cand[ngroups x P x kmax] <- the kmax best non-NaN values of this process per (group, point), best
+ *      first, NaN padded; kmax = the largest k of the query, <= 64.  reverse != 0: bottomk.
+ *   2. several processes: all-gather the candidate arrays, then vmb_topk_merge([nparts x cells x kmax], cells = ngroups*P).
+ *   3. vmb_topk_apply: ks = one k per point (HOST, getIntK aggr.go:793: NaN / negative -> 0, capped by the group size);
+ *      group_sizes = series per group over ALL processes (HOST); row_nonempty = HOST array, 1 byte per series. */
+int vmb_topk_candidates(vmb_ctx* ctx, const double* d_vals, size_t nseries, size_t points, const uint32_t* group_ids,
+                        uint32_t ngroups, uint32_t kmax, int reverse, double* d_cand);
+int vmb_topk_merge(vmb_ctx* ctx, const double* d_parts, uint32_t nparts, size_t cells, uint32_t kmax, int reverse, double* d_cand);
+int vmb_topk_apply(vmb_ctx* ctx, double* d_vals, size_t nseries, size_t points, const uint32_t* group_ids, uint32_t ngroups,
+                   const uint32_t* group_sizes, const double* d_cand, uint32_t kmax, const double* ks, int reverse,
+                   unsigned char* row_nonempty);
+
 /* ---- whole path in one call with HOST buffers (what a patched evalRollupNoIncrementalAggregate, eval.go:1845,
  * would call): H2D of descriptors+payload, decode, preamble, rollup, D2H of the [nseries x P] result; processed in
  * chunks so copies overlap the kernels.  out_host: [nseries x P]. */

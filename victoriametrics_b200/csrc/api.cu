@@ -1031,6 +1031,7 @@ extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t
 
 #include "pipeline.inc"
 #include "aggr_eval.inc"
+#include "topk.inc"
 
 // ------------------------------------------------------------------------------------------------ batched host encoder
 #include <atomic>

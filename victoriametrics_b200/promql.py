@@ -377,3 +377,38 @@ def eval_rollup_func_multi(func_name, blocks, start, end, step, window=0, lookba
         return out, scanned
     finally:
         series.close()
+
+
+# ---- topk / bottomk over the [series x points] matrix (aggr.go:646 newAggrFuncTopK) -------------------------------------
+def topk(ks, vals_dev_ptr, nseries, points, device_alloc, group_ids=None, ngroups=1, reverse=False, ctx=None,
+         all_gather=None, group_sizes=None):
+    """topk(k, q) (reverse=True: bottomk) on a DEVICE matrix [nseries x points] of float64, masked in place: per group and
+    point only the k best values survive (fillNaNsAtIdx aggr.go:786).  ks: scalar or one k per point.
+    device_alloc(nbytes) -> object with .ptr.  Several processes (series sharded by rank): all_gather(buf, nbytes) ->
+    (gathered_buf, nparts) over the candidate lists, and group_sizes = series per group over ALL processes.
+    -> np.bool_[nseries]: rows that still hold a value (removeEmptySeries drops the others)"""
+    ctx = ctx or _lib.default_context()
+    g = np.zeros(nseries, dtype=np.uint32) if group_ids is None else np.ascontiguousarray(group_ids, dtype=np.uint32)
+    if group_sizes is None:
+        group_sizes = np.bincount(g, minlength=ngroups)
+    gs = np.ascontiguousarray(group_sizes, dtype=np.uint32)
+    kk = np.ascontiguousarray(np.broadcast_to(np.asarray(ks, dtype=np.float64), (points,)))
+    kclean = np.where(np.isnan(kk) | (kk < 0), 0.0, kk)
+    kmax = int(min(np.floor(kclean.max()) if points else 0, gs.max() if ngroups else 0))
+    kmax = max(kmax, 1)
+    if kmax > 64:
+        raise ValueError("topk on the GPU supports k <= 64 (got %d)" % kmax)
+    cells = int(ngroups) * int(points)
+    cand = device_alloc(cells * kmax * 8)
+    rev = 1 if reverse else 0
+    check(lib().vmb_topk_candidates(ctx.h, C.c_void_p(int(vals_dev_ptr)), nseries, points, g.ctypes.data_as(_lib.u32p), int(ngroups),
+                                    kmax, rev, C.c_void_p(cand.ptr)))
+    if all_gather is not None:
+        ctx.synchronize()
+        parts, nparts = all_gather(cand, cells * kmax * 8)
+        check(lib().vmb_topk_merge(ctx.h, C.c_void_p(parts.ptr), int(nparts), cells, kmax, rev, C.c_void_p(cand.ptr)))
+    flags = np.zeros(max(nseries, 1), dtype=np.uint8)
+    check(lib().vmb_topk_apply(ctx.h, C.c_void_p(int(vals_dev_ptr)), nseries, points, g.ctypes.data_as(_lib.u32p), int(ngroups),
+                               gs.ctypes.data_as(_lib.u32p), C.c_void_p(cand.ptr), kmax, kk.ctypes.data_as(_lib.f64p), rev,
+                               flags.ctypes.data_as(_lib.u8p)))
+    return flags[:nseries].astype(bool)
