@@ -1,6 +1,7 @@
 // libvmb200: C ABI (include/vmb200.h), device memory management and kernel orchestration.
 // Single translation unit: the kernel files are included below so that no relocatable device code is needed.
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>

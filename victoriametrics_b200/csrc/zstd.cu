@@ -799,13 +799,15 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
             if (active) {
                 const uint8_t* perm = wtab + f * HUF_FRAME_BYTES;
                 const short* adj = (const short*)(perm + 256 + 40);
-                float th[10];
+                // the ten thresholds S_k (0..2048, exact in fp16) as five half2 registers: two compares per instruction
+                __half2 th2[5];
                 {
-                    const float4 a4 = *(const float4*)(perm + 256), b4 = *(const float4*)(perm + 272);
-                    const float2 c2 = *(const float2*)(perm + 288);
-                    th[0] = a4.x; th[1] = a4.y; th[2] = a4.z; th[3] = a4.w;
-                    th[4] = b4.x; th[5] = b4.y; th[6] = b4.z; th[7] = b4.w;
-                    th[8] = c2.x; th[9] = c2.y;
+                    const float* tf = (const float*)(perm + 256);
+#pragma unroll
+                    for (int j = 0; j < 5; j++) {
+                        const uint32_t a = __float_as_uint(tf[2 * j]) & 0x7fffffu, b = __float_as_uint(tf[2 * j + 1]) & 0x7fffffu;
+                        th2[j] = __halves2half2(__ushort2half_rn((unsigned short)a), __ushort2half_rn((unsigned short)b));
+                    }
                 }
                 uint32_t regen = job->regen_size;
                 uint32_t seg = job->nstreams == 1 ? regen : (regen + 3) / 4;
@@ -900,16 +902,14 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
         }                                                                                  \
         cand = ring[(rd & (HUF_RING - 1)) * 32];                                           \
     } while (0)
-#define HUF_LT(k) (vf_ < th[k] ? 1.0f : 0.0f)
+#define HUF_LT(k) __hlt2(vv_, th2[k]) /* (1.0, 0.0) per half */
 #define HUF_SYM(outv, shift)                                                               \
     do {                                                                                   \
         const uint32_t v_ = (uint32_t)(buf >> 53);                                         \
-        const float vf_ = __uint_as_float(HUF_FBIAS | v_);                                 \
-        /* 2^23 + 1 + #{k : v < S_k}: the code length sits in the low mantissa bits */     \
-        const float s_ = ((HUF_LT(0) + HUF_LT(1)) + (HUF_LT(2) + HUF_LT(3))) +             \
-                         ((HUF_LT(4) + HUF_LT(5)) + (HUF_LT(6) + HUF_LT(7))) +             \
-                         ((HUF_LT(8) + HUF_LT(9)) + 8388609.0f);                           \
-        const uint32_t nb_ = __float_as_uint(s_) & 15u;                                    \
+        const __half2 vv_ = __half2half2(__ushort2half_rn((unsigned short)v_));            \
+        /* code length = 1 + #{k : v < S_k}; the count (<= 10) is exact in fp16 */          \
+        const __half2 c_ = __hadd2(__hadd2(__hadd2(HUF_LT(0), HUF_LT(1)), __hadd2(HUF_LT(2), HUF_LT(3))), HUF_LT(4)); \
+        const uint32_t nb_ = 1u + (uint32_t)__half2ushort_rz(__hadd(__low2half(c_), __high2half(c_))); \
         buf <<= nb_;                                                                       \
         cnt -= (int)nb_;                                                                   \
         used_bits += nb_;                                                                  \
