@@ -831,7 +831,6 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
                     //     re-read (LDS) at every refill check by all lanes, so that read is uniform too.
                     // The ring is word-interleaved across lanes (word w of lane l at [w*32 + l]): conflict-free.
                     const uint32_t total_bits = (slen - 1) * 8 + (uint32_t)hb32(last);
-                    uint32_t used_bits = 0;
                     const uint8_t* endp = base + slen - 1;                                 // byte holding the final-bit marker
                     const uint4* blk = (const uint4*)((uintptr_t)endp & ~(uintptr_t)15);   // aligned block that holds it
                     const uint4* blk_min = (const uint4*)(((uintptr_t)base & ~(uintptr_t)15) - 32);  // never read below this
@@ -874,6 +873,7 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
                             wr += 4;
                         }
                     }
+                    const int cnt_init = cnt;  // payload bits consumed so far = cnt_init + 32 * rd - cnt (no per-symbol counter)
                     uint4 pendA = make_uint4(0, 0, 0, 0), pendB = make_uint4(0, 0, 0, 0);
                     bool hasA = false, hasB = false;
                     uint32_t cand = ring[(rd & (HUF_RING - 1)) * 32];
@@ -912,7 +912,6 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
         const uint32_t nb_ = 1u + (uint32_t)__half2ushort_rz(__hadd(__low2half(c_), __high2half(c_))); \
         buf <<= nb_;                                                                       \
         cnt -= (int)nb_;                                                                   \
-        used_bits += nb_;                                                                  \
         const uint32_t sym_ = perm[((v_ >> (HUF_MAX_LOG - nb_)) + (uint32_t)(int)adj[nb_]) & 255u]; \
         outv |= sym_ << (shift);                                                           \
     } while (0)
@@ -967,7 +966,7 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
 #undef HUF_REFILL
 #undef HUF_SYM
 #undef HUF_LT
-                    ok = used_bits == total_bits;
+                    ok = (long long)cnt_init + 32ll * (long long)rd - (long long)cnt == (long long)total_bits;
                 }
             }
             // a frame fails if any of its streams failed
