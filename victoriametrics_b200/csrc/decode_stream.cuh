@@ -97,6 +97,7 @@ __device__ int decode_delta_stream_v2(const uint8_t* __restrict__ src, uint32_t 
         const uint32_t k0 = min(T, (uint32_t)lane * c), k1 = min(T, k0 + c);
         uint64_t s1 = 0, s2 = 0;
         int s = (k0 == 0 || k0 >= T) ? start_rel : (int)sm->pos[k0 - 1] + 1;  // first byte of the lane's first varint
+#pragma unroll 2
         for (uint32_t k = k0; k < k1; k++) {
             const int e = (int)sm->pos[k];
             const int vl = e - s + 1;  // varint length in bytes
