@@ -139,7 +139,10 @@ def _check_blocks(vm, blocks, tr_min=I64_MIN, tr_max=I64_MAX, as_int=False):
     assert len(per) == len(blocks)
     for i, blk in enumerate(blocks):
         rc, ts, fv, iv = blk.oracle_unmarshal(tr_min, tr_max)
-        assert int(status[i]) == rc, (i, blk.tmt, blk.vmt, blk.rows, int(status[i]), rc)
+        if rc == -102:  # the Go code would logger.Panicf("BUG: ..."): any error will do
+            assert int(status[i]) != 0, (i, blk.tmt, blk.vmt, blk.rows)
+        else:
+            assert int(status[i]) == rc, (i, blk.tmt, blk.vmt, blk.rows, int(status[i]), rc)
         if rc:
             continue
         gts, gv = per[i]
@@ -191,6 +194,42 @@ def test_decode_blocks_corrupt_blocks_are_reported_per_block(vm):
     if b.tmt in (5, 6):
         b.max_ts -= 1
         _check_blocks(vm, [b])
+
+
+def test_decode_blocks_fuzzed_payloads(vm):
+    """one random mutation per block -- flipped / inserted / dropped bytes anywhere in either column (varints, zstd frame
+    headers, Huffman trees, FSE tables, bitstreams), wrong row counts, swapped marshal types: the GPU path must neither crash
+    nor disagree with the oracle about which blocks are bad, and the good ones must still decode bit for bit"""
+    rng = np.random.default_rng(20240922)
+    blocks = blockgen.random_blocks(rng, 700, rows_choices=(2, 3, 33, 100, 512, 1000, 4096, 8192))
+    for i, b in enumerate(blocks):
+        kind = int(rng.integers(0, 8))
+        col = "vdata" if rng.random() < 0.7 else "tdata"
+        d = getattr(b, col).copy()
+        if kind <= 2 and d.size:            # flip 1..3 bytes
+            for _ in range(int(rng.integers(1, 4))):
+                d[int(rng.integers(0, d.size))] ^= int(rng.integers(1, 256))
+        elif kind == 3 and d.size > 1:      # truncate
+            d = d[: int(rng.integers(0, d.size))].copy()
+        elif kind == 4:                     # append garbage
+            d = np.concatenate([d, rng.integers(0, 256, int(rng.integers(1, 9)), dtype=np.uint8)])
+        elif kind == 5 and d.size > 2:      # drop a byte in the middle
+            k = int(rng.integers(0, d.size))
+            d = np.concatenate([d[:k], d[k + 1:]])
+        elif kind == 6:                     # claim another row count
+            b.rows = max(1, b.rows + int(rng.choice([-1, 1, 7, -5])))
+        else:                               # claim another marshal type
+            if col == "vdata":
+                b.vmt = int(rng.integers(1, 7))
+            else:
+                b.tmt = int(rng.integers(1, 7))
+        setattr(b, col, d)
+    bad = 0
+    for lo in range(0, len(blocks), 100):   # several batches: the mutations meet different warp / group neighbours
+        part = blocks[lo:lo + 100]
+        _check_blocks(vm, part)
+        bad += sum(1 for b in part if b.oracle_unmarshal()[0] != 0)
+    assert 150 < bad < 690  # the fuzz produces both broken and still-valid blocks
 
 
 def test_zstd_golden_frames_through_gpu(vm, oracle):

@@ -41,6 +41,8 @@ __device__ int decode_delta_stream_v2(const uint8_t* __restrict__ src, uint32_t 
     uint64_t V = (uint64_t)first;
     int start_rel = 0;         // where the value in progress starts, relative to the current tile start (<= 0)
     int err = 0;
+    uint32_t err_at = 0xffffffffu;  // index of the varint that raised err: the sequential Go loop reports the FIRST bad varint
+                                    // (int.go:196-284) and never looks past the nvar-th one
     if (lane < 4) sm->bytes[lane] = 0;
     __syncwarp();
 
@@ -111,14 +113,14 @@ __device__ int decode_delta_stream_v2(const uint8_t* __restrict__ src, uint32_t 
                 for (int b = 0; b < vl; b++) {
                     uint32_t byte = (sm->bytes[(s + b + 16) >> 2] >> (8 * ((s + b + 16) & 3))) & 0xffu;
                     if (b == 9) {  // 10th byte: int.go:269-275
-                        if (byte > 1u) err = VMB_ERR_VARINT_TOO_BIG;
+                        if (byte > 1u && N + k < err_at) { err = VMB_ERR_VARINT_TOO_BIG; err_at = N + k; }
                         u |= (uint64_t)1 << 63;
                     } else {
                         u |= (uint64_t)(byte & 0x7fu) << (7 * b);
                     }
                 }
             } else {
-                err = VMB_ERR_VARINT_TOO_LONG;  // int.go:277
+                if (N + k < err_at) { err = VMB_ERR_VARINT_TOO_LONG; err_at = N + k; }  // int.go:277
                 u = 0;
             }
             long long v = (long long)(u >> 1) ^ -(long long)(u & 1);  // zig-zag decode int.go:82
@@ -179,7 +181,7 @@ __device__ int decode_delta_stream_v2(const uint8_t* __restrict__ src, uint32_t 
             // truncated varint and is reported by the stream-level checks below
             start_rel -= DS_TILE;
             if (start_rel < -16) {
-                if (tile + DS_TILE <= len) err = VMB_ERR_VARINT_TOO_LONG;
+                if (tile + DS_TILE <= len && N < err_at) { err = VMB_ERR_VARINT_TOO_LONG; err_at = N; }
                 start_rel = -16;
             }
         }
@@ -187,8 +189,14 @@ __device__ int decode_delta_stream_v2(const uint8_t* __restrict__ src, uint32_t 
         __syncwarp();
     }
     // ---- stream-level checks (uniform)
+    if (err_at >= nvar) err = 0;  // a malformed varint behind the last one that is read is only "unexpected tail"
+    {
+        uint32_t first = err ? err_at : 0xffffffffu;
 #pragma unroll
-    for (int off = 16; off; off >>= 1) err = min(err, __shfl_xor_sync(VMB_FULL, err, off));  // most negative wins
+        for (int off = 16; off; off >>= 1) first = min(first, __shfl_xor_sync(VMB_FULL, first, off));
+        const uint32_t owner = __ballot_sync(VMB_FULL, err != 0 && err_at == first);
+        err = owner ? __shfl_sync(VMB_FULL, err, __ffs((int)owner) - 1) : 0;
+    }
     int werr = err;
     if (werr == 0) {
         bool ends_ok = len == 0 || src[len - 1] < 0x80;
