@@ -200,7 +200,7 @@ def test_decode_blocks_fuzzed_payloads(vm):
     """one random mutation per block -- flipped / inserted / dropped bytes anywhere in either column (varints, zstd frame
     headers, Huffman trees, FSE tables, bitstreams), wrong row counts, swapped marshal types: the GPU path must neither crash
     nor disagree with the oracle about which blocks are bad, and the good ones must still decode bit for bit"""
-    rng = np.random.default_rng(20240922)
+    rng = np.random.default_rng(int(os.environ.get("VMB_FUZZ_SEED", "20240922")))  # other seeds for ad-hoc campaigns
     blocks = blockgen.random_blocks(rng, 700, rows_choices=(2, 3, 33, 100, 512, 1000, 4096, 8192))
     for i, b in enumerate(blocks):
         kind = int(rng.integers(0, 8))
