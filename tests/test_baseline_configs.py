@@ -253,6 +253,54 @@ def test_regular_timestamp_mode_edges(oracle):
 
 
 @pytest.mark.gpu
+def test_random_query_grids_through_the_fast_paths(oracle):
+    """random (start, end, step, window, lookbackDelta) grids over regular / jittered / irregular series: whichever rollup path
+    the kernel picks per series (arithmetic timestamps, 32-bit relative timestamps, generic 64-bit, global-memory windows)
+    must agree with the oracle"""
+    import os
+    import torch
+    import victoriametrics_b200 as vm
+    rng = np.random.default_rng(int(os.environ.get("VMB_FUZZ_SEED", "5150")))
+    blocks = []
+    for i in range(30):
+        n = int(rng.choice([2, 17, 300, 2049, 5000, 8192]))
+        tkind = ("regular", "jitter", "irregular", "regular")[i % 4]
+        ts = blockgen.gen_timestamps(rng, tkind, n, T0)
+        if tkind == "regular" and i % 8 == 3:
+            ts = (T0 + int(rng.choice([1, 250, 1000, 60000])) * np.arange(n)).astype(np.int64)
+        blocks.append(blockgen.OBlock(ts, np.abs(blockgen.gen_values(rng, ("counter_resets", "counter", "gauge")[i % 3], n)), -2, 64, i))
+    descs, payload = blockgen.to_blockset(blocks)
+    B = vm.storage.Blocks(descs, payload)
+    span = 15000 * 8192
+    for trial in range(36):
+        step = int(rng.choice([1000, 7000, 15000, 30000, 60000, 300000, 3600000]))
+        window = int(rng.choice([0, step, 2 * step, 5 * step, 20 * step, 300000, 90001, 3600000, 15000 * 3000]))
+        start = T0 + int(rng.integers(-2 * step, span // 2))
+        npts = int(rng.integers(1, 1200))
+        end = start + step * npts
+        lookback = int(rng.choice([0, 0, 0, 300000, 45000]))
+        func = ("rate", "rate", "increase", "avg_over_time", "max_over_time", "irate")[trial % 6]
+        rc = vm.promql.get_rollup_configs(func, start, end, step, window, lookback)
+        exp = []
+        for b in blocks:
+            r, ts, fv, _ = b.oracle_unmarshal()
+            ts, fv = ts.copy(), fv.copy()
+            if rc.removeCounterResets:
+                oracle.lib().vmo_remove_counter_resets(fv.ctypes.data_as(oracle.f64p), ts.ctypes.data_as(oracle.i64p), len(fv),
+                                                       lookback + window if lookback else 0)
+            o, _ = oracle.rollup_do(RF[func], fv, ts, start, end, step, window, lookback_delta=lookback,
+                                    may_adjust_window=rc.MayAdjustWindow, samples_scanned_per_call=rc.samplesScannedPerCall)
+            exp.append(o)
+        exp = np.stack(exp)
+        out = torch.empty(exp.shape, dtype=torch.float64, device="cuda")
+        vm.promql.eval_rollup_func(func, B, start, end, step, window, lookback, out_dev_ptr=out.data_ptr())
+        got = out.cpu().numpy()
+        key = (trial, func, start - T0, step, window, lookback, npts)
+        assert np.array_equal(np.isnan(got), np.isnan(exp)), key
+        assert np.allclose(got, exp, rtol=1e-12, atol=0, equal_nan=True), key
+
+
+@pytest.mark.gpu
 def test_config4_mixed_codec_increase_1h_step60(oracle):
     """40 % delta2 counters, 30 % gauges, 20 % const, 10 % delta-const -> increase(m[1h]) step 60 s"""
     import victoriametrics_b200 as vm
