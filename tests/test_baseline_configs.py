@@ -218,7 +218,7 @@ def test_regular_timestamp_mode_edges(oracle):
         ts = (T0 + dt * np.arange(n)).astype(np.int64)
         kind = "special" if i in (7, 8) else ("counter_resets" if i % 2 else "counter")
         vals = np.abs(blockgen.gen_values(rng, kind, n)) if kind != "special" else blockgen.gen_values(rng, kind, n)
-        blocks.append(blockgen.OBlock(ts, vals, -2, 64, i))
+        blocks.append(blockgen.OBlock(ts, vals, -2, 24 if i == 4 else 64, i))  # one block with lossy precisionBits
     assert all(b.tmt == 2 for b in blocks)
     descs, payload = blockgen.to_blockset(blocks)
     B = vm.storage.Blocks(descs, payload)

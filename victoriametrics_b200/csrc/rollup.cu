@@ -807,7 +807,9 @@ __global__ void k_series_assemble(RollupParams P) {
                 } else {
                     m.start = lo;
                     m.n = (uint32_t)kept;
-                    if (nb == 1 && kept >= 2 && P.descs[fb].ts_mt == 2 && P.dedup_interval <= 0) m._pad |= 8u;
+                    // (precisionBits < 64 sends the timestamps through EnsureNonDecreasingSequence, which may move the last one)
+                    if (nb == 1 && kept >= 2 && P.descs[fb].ts_mt == 2 && P.descs[fb].precision_bits >= 64 && P.dedup_interval <= 0)
+                        m._pad |= 8u;
                     if (nb == 1 && P.dedup_interval <= 0 && !(m._pad & 1u)) {
                         // bits 8-23: the row removeCounterResets may start from (nothing before the first value drop changes)
                         const uint32_t fd = (P.blk_hi[fb] >> 15) & 0x3fffu, a = P.blk_lo[fb];
