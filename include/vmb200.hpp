@@ -244,6 +244,31 @@ inline uint64_t evalRollupFunc(Ctx& ctx, const rollupConfig& rc, const std::vect
     return scanned;
 }
 
+// evalRollupWithIncrementalAggregate eval.go:1804 (aggr_incremental.go): aggr(rollup(m[d])) by (...) for all blocks of the
+// query at once; groupIDs = one dense id per series (marshalMetricNameSorted of the group-by labels, assigned by the caller).
+// out: [ngroups x len(rc.Timestamps)] row-major; returns samplesScanned.
+inline int aggrFuncId(const std::string& name) {
+    static const std::unordered_map<std::string, int> ids = {{"sum", VMB_AGGR_SUM}, {"min", VMB_AGGR_MIN}, {"max", VMB_AGGR_MAX},
+                                                             {"avg", VMB_AGGR_AVG}, {"count", VMB_AGGR_COUNT}, {"sum2", VMB_AGGR_SUM2},
+                                                             {"geomean", VMB_AGGR_GEOMEAN}, {"any", VMB_AGGR_ANY},
+                                                             {"group", VMB_AGGR_GROUP}};
+    auto it = ids.find(name);
+    if (it == ids.end()) throw Error(VMB_ERR_INVALID_ARG, "aggregate without incremental form: " + name);
+    return it->second;
+}
+inline uint64_t evalRollupFuncWithIncrementalAggregate(Ctx& ctx, const std::string& aggrName, const rollupConfig& rc,
+                                                       const std::vector<vmb_block_desc>& descs, const std::vector<uint8_t>& payload,
+                                                       const std::vector<uint32_t>& groupIDs, uint32_t ngroups, int64_t trMin,
+                                                       int64_t trMax, std::vector<double>& out) {
+    vmb_rollup_cfg c = rc.cfg();
+    out.resize((size_t)ngroups * rc.Timestamps.size());
+    uint64_t scanned = 0;
+    int r = vmb_eval_rollup_aggr_host(ctx.get(), descs.data(), descs.size(), payload.data(), payload.size(), trMin, trMax, &c,
+                                      aggrFuncId(aggrName), groupIDs.data(), ngroups, out.data(), nullptr, &scanned);
+    if (r) throw Error(r, "evalRollupFuncWithIncrementalAggregate");
+    return scanned;
+}
+
 }  // namespace promql
 }  // namespace vmb
 #endif

@@ -101,6 +101,47 @@ int main() {
         CHECK(decimal::AppendFloatToDecimal(d, {-24, 0, 4.123, 0.3}) == -3);
         CHECK((d == std::vector<int64_t>{-24000, 0, 4123, 300}));
     }
+    {  // evalRollupFunc vs evalRollupFuncWithIncrementalAggregate (eval.go:1845 / :1804): sum(delta(m)) over two series made
+       // of the reference's test vectors (values scaled / shifted), marshaled into blocks by MarshalTimestamps / MarshalValues
+        std::vector<vmb_block_desc> descs;
+        std::vector<uint8_t> payload;
+        for (int s = 0; s < 2; s++) {
+            std::vector<int64_t> va;
+            for (double v : testValues) va.push_back((int64_t)v * (s + 1) + 7 * s);
+            vmb_block_desc d;
+            std::memset(&d, 0, sizeof(d));
+            d.ts_off = payload.size();
+            encoding::Marshaled mt = encoding::MarshalTimestamps(payload, testTimestamps, 64);
+            d.ts_size = (uint32_t)(payload.size() - d.ts_off);
+            d.val_off = payload.size();
+            encoding::Marshaled mv = encoding::MarshalValues(payload, va, 64);
+            d.val_size = (uint32_t)(payload.size() - d.val_off);
+            d.first_value = mv.firstValue;
+            d.min_ts = mt.firstValue;
+            d.max_ts = testTimestamps.back();
+            d.rows = (uint32_t)va.size();
+            d.series_idx = (uint32_t)s;
+            d.scale = 0;
+            d.ts_mt = (uint8_t)mt.mt;
+            d.val_mt = (uint8_t)mv.mt;
+            d.precision_bits = 64;
+            descs.push_back(d);
+        }
+        promql::rollupConfig rc = promql::getRollupConfigs("delta", 0, 160, 40, 0, 0);
+        std::vector<double> rolled, summed;
+        uint64_t sc1 = promql::evalRollupFunc(ctx, rc, descs, payload, INT64_MIN, INT64_MAX, rolled, 2);
+        uint64_t sc2 = promql::evalRollupFuncWithIncrementalAggregate(ctx, "sum", rc, descs, payload, {0, 0}, 1, INT64_MIN, INT64_MAX,
+                                                                      summed);
+        CHECK(sc1 == sc2 && sc1 == 2 * 24);
+        const size_t P = rc.Timestamps.size();
+        CHECK(rolled.size() == 2 * P && summed.size() == P);
+        CHECK(rowsEqual(std::vector<double>(rolled.begin(), rolled.begin() + P), {nan, 21, -9, 22, 0}));  // TestRollupFuncsNoWindow/delta
+        for (size_t p = 0; p < P; p++) {
+            double a = rolled[p], b = rolled[P + p];
+            double exp = std::isnan(a) ? b : (std::isnan(b) ? a : a + b);  // updateAggrSum skips NaN
+            CHECK(std::isnan(exp) ? std::isnan(summed[p]) : summed[p] == exp);
+        }
+    }
     std::printf(failures ? "host_mirror_test: %d FAILURES\n" : "host_mirror_test: OK\n", failures);
     return failures ? 1 : 0;
 }
