@@ -777,7 +777,7 @@ __global__ void k_series_assemble(RollupParams P) {
     // bit 2: the series is assembled by k_series_merge.
     // bit 3: the timestamps are an arithmetic progression (one block, MarshalTypeDeltaConst timestamps, no deduplication):
     //        the rollup kernel derives them from the row index instead of reading them.
-    m._pad = nb > 1 ? 2u : 0u;  // (a drop across a block boundary is not looked for: any multi-block series is a candidate)
+    m._pad = 0u;
     m.max_prev_interval = 0;
     m.window = 0;
     bool failed = false;
@@ -789,7 +789,7 @@ __global__ void k_series_assemble(RollupParams P) {
     if (!failed && nb) {
         if (moff != ~0ull) {
             m.start = P.rows_total + moff;
-            m._pad |= 4u;
+            m._pad |= 4u | 2u;  // (merged rows interleave blocks: always a candidate for removeCounterResets)
         } else {
             uint64_t lo = ~0ull, hi = 0, kept = 0;
             for (uint32_t k = 0; k < nb; k++) {
@@ -799,6 +799,22 @@ __global__ void k_series_assemble(RollupParams P) {
                 lo = r + a < lo ? r + a : lo;
                 hi = r + b > hi ? r + b : hi;
                 kept += b - a;
+            }
+            // a value drop across a block boundary (time-disjoint blocks, laid out in time order): compare the decoded values
+            // on both sides of every boundary.  Many blocks per series: no search, the series is simply a candidate.
+            if (nb > 1 && !(m._pad & 2u)) {
+                if (nb > 16) m._pad |= 2u;
+                else {
+                    for (uint32_t k = 0; k < nb && !(m._pad & 2u); k++) {
+                        const uint64_t endk = P.row_off[fb + k] + P.descs[fb + k].rows;  // first row of the next block in layout
+                        for (uint32_t j = 0; j < nb; j++) {
+                            if (j != k && P.row_off[fb + j] == endk && P.descs[fb + j].rows) {
+                                const double a = P.vals[endk - 1], b = P.vals[endk];
+                                if (!(b - a >= 0)) m._pad |= 2u;  // drop or NaN
+                            }
+                        }
+                    }
+                }
             }
             if (kept) {
                 if (hi - lo != kept) {  // a hole inside the series: cannot happen for time-disjoint blocks and one time range
