@@ -86,6 +86,33 @@ typedef struct {
  * (file offsets) -- the caller rebases them onto its payload arena.  series_idx is left 0. */
 int vmb_block_desc_from_header(vmb_block_desc* out, const uint8_t header[81], uint8_t tsid_out[24]);
 
+/* blockHeader.Marshal block_header.go:104 (inverse of the above; tsid may be NULL = zeros) */
+int vmb_block_header_marshal(uint8_t header[81], const vmb_block_desc* d, const uint8_t tsid[24]);
+/* unmarshalBlockHeaders block_header.go:261 (part_search.go:247): an uncompressed index block = `count` 81-byte headers
+ * sorted by TSID.  out[count]; tsids ([count * 24], may be NULL) receives the TSIDs.  Errors: wrong length
+ * (VMB_ERR_SHORT_SRC / VMB_ERR_ROWS), a header that fails blockHeader.validate (:230), unsorted TSIDs (VMB_ERR_INVALID_ARG). */
+int vmb_index_block_unmarshal(vmb_block_desc* out, uint8_t* tsids, size_t count, const uint8_t* data, size_t len);
+/* metaindexRow metaindex_row.go:12 (56-byte big-endian wire form :61) */
+typedef struct {
+    uint8_t tsid[24];
+    int64_t min_ts, max_ts;
+    uint64_t index_block_offset;
+    uint32_t block_headers_count, index_block_size;
+} vmb_metaindex_row; /* 56 bytes */
+/* unmarshalMetaindexRows metaindex_row.go:129 on the decompressed metaindex.bin (vmb_zstd_decompress_batch below);
+ * *n receives the number of rows (also when cap is too small: VMB_ERR_CAP).  Same checks as the Go code: at least one row,
+ * BlockHeadersCount > 0, IndexBlockSize <= 2*maxBlockSize, rows sorted by TSID. */
+int vmb_metaindex_rows_unmarshal(vmb_metaindex_row* out, size_t cap, size_t* n, const uint8_t* data, size_t len);
+int vmb_metaindex_row_marshal(uint8_t out[56], const vmb_metaindex_row* row); /* metaindexRow.Marshal :61 */
+/* encoding.DecompressZSTD (lib/encoding/compress.go:27) for n frames at once on the GPU -- index blocks (part_search.go:238)
+ * and metaindex.bin (metaindex_row.go:134) go through the same kernels as the block payloads.  frames + offs[n+1] = the
+ * compressed frames back to back; every frame must declare its content size (libzstd/gozstd always do) of <= 163840 bytes.
+ * Frame i is written to dst + dst_offs[i] (16-byte aligned), dst_lens[i] bytes; vmb_zstd_decompress_bound gives the dst size.
+ * statuses ([n], may be NULL): 0 or VMB_ERR_ZSTD per frame; returns VMB_ERR_ZSTD if any frame failed. */
+int vmb_zstd_decompress_bound(const uint8_t* frames, const uint64_t* offs, size_t n, uint64_t* out_bytes);
+int vmb_zstd_decompress_batch(vmb_ctx* ctx, const uint8_t* frames, const uint64_t* offs, size_t n, uint8_t* dst,
+                              size_t dst_cap, uint64_t* dst_offs, uint32_t* dst_lens, int32_t* statuses);
+
 /* ---- per-call drop-ins (single column; host buffers; run on the GPU) ------------------------------------- */
 /* encoding.UnmarshalValues / UnmarshalTimestamps  encoding.go:111 / :90 (unmarshalInt64Array :173) */
 int vmb_unmarshal_int64(vmb_ctx* ctx, int64_t* dst, size_t items_count, const uint8_t* src, size_t src_len, int mt,
@@ -106,6 +133,9 @@ int vmb_marshal_columns(uint8_t* dst, size_t cap, uint64_t* offs, uint8_t* mts, 
                         size_t ncols, size_t rows, uint8_t precision_bits, int nthreads);
 /* decimal.AppendFloatToDecimal decimal.go:173 (host-side, write path) */
 int vmb_float_to_decimal(int64_t* dst, int16_t* out_scale, const double* src, size_t n);
+/* decimal.CalibrateScale decimal.go:13 (host-side; block merge path lib/storage/merge.go): a and b are rescaled in place to
+ * the common exponent returned in *out_e. */
+int vmb_calibrate_scale(int64_t* a, size_t na, int16_t ae, int64_t* b, size_t nb, int16_t be, int16_t* out_e);
 
 /* ---- batched block decode  ==  Block.UnmarshalData (block.go:250) + AppendRowsWithTimeRangeFilter (:324)
  * for every block of a query at once (replaces netstorage.go:425 packedTimeseries.Unpack fan-out) ------------- */

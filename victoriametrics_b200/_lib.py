@@ -24,6 +24,15 @@ class BlockDesc(C.Structure):
 assert C.sizeof(BlockDesc) == 64
 
 
+class MetaindexRow(C.Structure):
+    """vmb_metaindex_row == lib/storage/metaindex_row.go:12 metaindexRow"""
+    _fields_ = [("tsid", C.c_uint8 * 24), ("min_ts", C.c_int64), ("max_ts", C.c_int64), ("index_block_offset", C.c_uint64),
+                ("block_headers_count", C.c_uint32), ("index_block_size", C.c_uint32)]
+
+
+assert C.sizeof(MetaindexRow) == 56
+
+
 class RollupCfg(C.Structure):
     """vmb_rollup_cfg == rollupConfig (rollup.go:574)"""
     _fields_ = [("func_id", C.c_int32), ("flags", C.c_uint32), ("start", C.c_int64), ("end", C.c_int64),
@@ -60,6 +69,13 @@ def lib():
         "vmb_version": (C.c_int, []),
         "vmb_ctx_launch_count": (C.c_uint64, [vp]),
         "vmb_block_desc_from_header": (C.c_int, [C.POINTER(BlockDesc), u8p, u8p]),
+        "vmb_block_header_marshal": (C.c_int, [u8p, C.POINTER(BlockDesc), u8p]),
+        "vmb_index_block_unmarshal": (C.c_int, [C.POINTER(BlockDesc), u8p, sz, u8p, sz]),
+        "vmb_metaindex_rows_unmarshal": (C.c_int, [C.POINTER(MetaindexRow), sz, C.POINTER(sz), u8p, sz]),
+        "vmb_metaindex_row_marshal": (C.c_int, [u8p, C.POINTER(MetaindexRow)]),
+        "vmb_zstd_decompress_bound": (C.c_int, [u8p, u64p, sz, u64p]),
+        "vmb_zstd_decompress_batch": (C.c_int, [vp, u8p, u64p, sz, u8p, sz, u64p, u32p, i32p]),
+        "vmb_calibrate_scale": (C.c_int, [i64p, sz, C.c_int16, i64p, sz, C.c_int16, C.POINTER(C.c_int16)]),
         "vmb_unmarshal_int64": (C.c_int, [vp, i64p, sz, u8p, sz, C.c_int, C.c_int64]),
         "vmb_decimal_to_float": (C.c_int, [vp, f64p, i64p, sz, C.c_int16]),
         "vmb_marshal_int64": (C.c_int, [u8p, sz, C.POINTER(sz), C.POINTER(C.c_int), i64p, i64p, sz, C.c_uint8]),

@@ -226,6 +226,102 @@ extern "C" int vmb_block_desc_from_header(vmb_block_desc* d, const uint8_t h[81]
     return VMB_OK;
 }
 
+static inline void be_put(uint8_t* d, uint64_t v, int n) {
+    for (int i = 0; i < n; i++) d[i] = (uint8_t)(v >> (8 * (n - 1 - i)));
+}
+// blockHeader.Marshal block_header.go:104
+extern "C" int vmb_block_header_marshal(uint8_t h[81], const vmb_block_desc* d, const uint8_t tsid[24]) {
+    if (!h || !d) return VMB_ERR_INVALID_ARG;
+    if (tsid) memcpy(h, tsid, 24);
+    else memset(h, 0, 24);
+    auto zz = [](int64_t v) { return (uint64_t)((v << 1) ^ (v >> 63)); };  // int.go:75
+    be_put(h + 24, zz(d->min_ts), 8);
+    be_put(h + 32, zz(d->max_ts), 8);
+    be_put(h + 40, zz(d->first_value), 8);
+    be_put(h + 48, d->ts_off, 8);
+    be_put(h + 56, d->val_off, 8);
+    be_put(h + 64, d->ts_size, 4);
+    be_put(h + 68, d->val_size, 4);
+    be_put(h + 72, d->rows, 4);
+    be_put(h + 76, (uint16_t)((d->scale << 1) ^ (d->scale >> 15)), 2);  // int.go:57
+    h[78] = d->ts_mt;
+    h[79] = d->val_mt;
+    h[80] = d->precision_bits;
+    return VMB_OK;
+}
+// unmarshalBlockHeaders block_header.go:261: `count` headers back to back, sorted by TSID (TSID.Less tsid.go:89 == memcmp of
+// the big-endian wire form)
+extern "C" int vmb_index_block_unmarshal(vmb_block_desc* out, uint8_t* tsids, size_t count, const uint8_t* data, size_t len) {
+    if (!out || !data || count == 0) return VMB_ERR_INVALID_ARG;
+    if (len != count * 81) {
+        vmb_set_error("invalid number of block headers found: %zu bytes; want %zu block headers", len, count);
+        return len % 81 ? VMB_ERR_SHORT_SRC : VMB_ERR_ROWS;
+    }
+    for (size_t i = 0; i < count; i++) {
+        int rc = vmb_block_desc_from_header(&out[i], data + i * 81, tsids ? tsids + i * 24 : nullptr);
+        if (rc) {
+            vmb_set_error("cannot unmarshal block header %zu: error %d", i, rc);
+            return rc;
+        }
+        if (i && memcmp(data + (i - 1) * 81, data + i * 81, 24) > 0) {
+            vmb_set_error("block headers must be sorted by tsid (header %zu)", i);
+            return VMB_ERR_INVALID_ARG;
+        }
+    }
+    return VMB_OK;
+}
+// metaindexRow.Unmarshal + unmarshalMetaindexRows metaindex_row.go:72 / :129 (on the decompressed bytes): 56-byte rows
+extern "C" int vmb_metaindex_rows_unmarshal(vmb_metaindex_row* out, size_t cap, size_t* n_out, const uint8_t* data, size_t len) {
+    if (!n_out || (len && !data)) return VMB_ERR_INVALID_ARG;
+    *n_out = 0;
+    if (len == 0) {
+        vmb_set_error("expecting non-zero metaindex rows; got zero");
+        return VMB_ERR_SHORT_SRC;
+    }
+    if (len % 56) {
+        vmb_set_error("cannot unmarshal metaindexRow #%zu: %zu trailing bytes", len / 56, len % 56);
+        return VMB_ERR_SHORT_SRC;
+    }
+    const size_t n = len / 56;
+    *n_out = n;
+    if (n > cap || !out) return VMB_ERR_CAP;
+    auto unzz = [](uint64_t u) { return (int64_t)(u >> 1) ^ -(int64_t)(u & 1); };
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t* r = data + i * 56;
+        vmb_metaindex_row& m = out[i];
+        memcpy(m.tsid, r, 24);
+        m.block_headers_count = (uint32_t)be_get(r + 24, 4);
+        m.min_ts = unzz(be_get(r + 28, 8));
+        m.max_ts = unzz(be_get(r + 36, 8));
+        m.index_block_offset = be_get(r + 44, 8);
+        m.index_block_size = (uint32_t)be_get(r + 52, 4);
+        if (m.block_headers_count == 0) {
+            vmb_set_error("metaindexRow #%zu: BlockHeadersCount must be greater than 0", i);
+            return VMB_ERR_ROWS;
+        }
+        if (m.index_block_size > 131072) {
+            vmb_set_error("metaindexRow #%zu: too big IndexBlockSize %u", i, m.index_block_size);
+            return VMB_ERR_INVALID_ARG;
+        }
+        if (i && memcmp(r - 56, r, 24) > 0) {
+            vmb_set_error("metaindexRow values must be sorted by TSID (row %zu)", i);
+            return VMB_ERR_INVALID_ARG;
+        }
+    }
+    return VMB_OK;
+}
+extern "C" int vmb_metaindex_row_marshal(uint8_t out[56], const vmb_metaindex_row* m) {  // metaindex_row.go:61
+    if (!out || !m) return VMB_ERR_INVALID_ARG;
+    auto zz = [](int64_t v) { return (uint64_t)((v << 1) ^ (v >> 63)); };
+    memcpy(out, m->tsid, 24);
+    be_put(out + 24, m->block_headers_count, 4);
+    be_put(out + 28, zz(m->min_ts), 8);
+    be_put(out + 36, zz(m->max_ts), 8);
+    be_put(out + 44, m->index_block_offset, 8);
+    be_put(out + 52, m->index_block_size, 4);
+    return VMB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ upload
 template <class T>
 static int dev_alloc(T** p, size_t n) {
@@ -428,61 +524,72 @@ __global__ void k_set_status(int32_t* status, const uint32_t* list, uint32_t n, 
     if (i < n) status[list[i]] = v;
 }
 
+// zstd stage: every compressed column of `b` is decompressed into ctx->zscratch (at ColInfo::scratch_off); per-column status
+// in ctx->zstatus ([2 * nblocks] int32).  *d_zstatus_out = nullptr when the batch holds no zstd column.
+static int run_zstd(vmb_ctx* ctx, const vmb_blocks* b, int32_t** d_zstatus_out) {
+    cudaStream_t st = ctx->stream;
+    *d_zstatus_out = nullptr;
+    if (b->n_huf + b->n_gen + b->n_bad == 0) return VMB_OK;
+    int rc;
+    if ((rc = ctx->zscratch.reserve(b->scratch_total + 64))) return rc;
+    if ((rc = ctx->zstatus.reserve(2 * b->nblocks * sizeof(int32_t)))) return rc;
+    int32_t* d_zstatus = (int32_t*)ctx->zstatus.p;
+    CU(cudaMemsetAsync(d_zstatus, 0, 2 * b->nblocks * sizeof(int32_t), st));
+    if (b->needs_lit && (rc = ctx->zlit.reserve(b->scratch_total + 64))) return rc;
+    ZstdParams Z;
+    memset(&Z, 0, sizeof(Z));
+    Z.descs = b->d_descs;
+    Z.cols = b->d_cols;
+    Z.payload = b->d_payload;
+    Z.scratch = (uint8_t*)ctx->zscratch.p;
+    Z.lit = b->needs_lit ? (uint8_t*)ctx->zlit.p : nullptr;
+    if (b->seq_total) {
+        if ((rc = ctx->zseq.reserve(b->seq_total * 8))) return rc;
+        Z.seq_rec = (unsigned long long*)ctx->zseq.p;
+    }
+    Z.status = d_zstatus;
+    if (b->n_bad) {
+        k_set_status<<<(b->n_bad + 127) / 128, 128, 0, st>>>(d_zstatus, b->d_bad_list, b->n_bad, VMB_ERR_ZSTD);
+        count_launch(ctx);
+    }
+    const uint32_t ws_threads = 148u * 2u * 32u;
+    if (b->needs_lit || b->n_gen) {
+        if ((rc = ctx->zws.reserve((size_t)ws_threads * zstd_serial_ws_bytes()))) return rc;
+        Z.ws = ctx->zws.p;
+        Z.ws_count = ws_threads;
+    }
+    if (b->n_huf) {
+        if ((rc = ctx->zjobs.reserve((size_t)b->n_huf * sizeof(HufJob)))) return rc;
+        Z.jobs = (HufJob*)ctx->zjobs.p;
+        Z.list = b->d_huf_list;
+        Z.count = b->n_huf;
+        launch_zstd_prepare(Z, st);
+        launch_huf_decode(Z, st);
+        count_launch(ctx, 2);
+        if (b->needs_lit) {
+            launch_zstd_sequences(Z, st);
+            count_launch(ctx, 2);
+        }
+    }
+    if (b->n_gen) {
+        Z.list = b->d_gen_list;
+        Z.count = b->n_gen;
+        launch_zstd_serial(Z, 1, st);
+        count_launch(ctx);
+    }
+    *d_zstatus_out = d_zstatus;
+    return VMB_OK;
+}
+
 // runs zstd + column decode + series assembly into `s` (whose buffers are already allocated)
 static int run_decode(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, int64_t tr_min, int64_t tr_max, uint32_t flags,
                       unsigned int* d_failed) {
     cudaStream_t st = ctx->stream;
-    const bool has_zstd = b->n_huf + b->n_gen + b->n_bad > 0;
     if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
     int32_t* d_zstatus = nullptr;
-    if (has_zstd) {
-        int rc;
-        if ((rc = ctx->zscratch.reserve(b->scratch_total + 64))) return rc;
-        if ((rc = ctx->zstatus.reserve(2 * b->nblocks * sizeof(int32_t)))) return rc;
-        d_zstatus = (int32_t*)ctx->zstatus.p;
-        CU(cudaMemsetAsync(d_zstatus, 0, 2 * b->nblocks * sizeof(int32_t), st));
-        if (b->needs_lit && (rc = ctx->zlit.reserve(b->scratch_total + 64))) return rc;
-        ZstdParams Z;
-        memset(&Z, 0, sizeof(Z));
-        Z.descs = b->d_descs;
-        Z.cols = b->d_cols;
-        Z.payload = b->d_payload;
-        Z.scratch = (uint8_t*)ctx->zscratch.p;
-        Z.lit = b->needs_lit ? (uint8_t*)ctx->zlit.p : nullptr;
-        if (b->seq_total) {
-            if ((rc = ctx->zseq.reserve(b->seq_total * 8))) return rc;
-            Z.seq_rec = (unsigned long long*)ctx->zseq.p;
-        }
-        Z.status = d_zstatus;
-        if (b->n_bad) {
-            k_set_status<<<(b->n_bad + 127) / 128, 128, 0, st>>>(d_zstatus, b->d_bad_list, b->n_bad, VMB_ERR_ZSTD);
-            count_launch(ctx);
-        }
-        const uint32_t ws_threads = 148u * 2u * 32u;
-        if (b->needs_lit || b->n_gen) {
-            if ((rc = ctx->zws.reserve((size_t)ws_threads * zstd_serial_ws_bytes()))) return rc;
-            Z.ws = ctx->zws.p;
-            Z.ws_count = ws_threads;
-        }
-        if (b->n_huf) {
-            if ((rc = ctx->zjobs.reserve((size_t)b->n_huf * sizeof(HufJob)))) return rc;
-            Z.jobs = (HufJob*)ctx->zjobs.p;
-            Z.list = b->d_huf_list;
-            Z.count = b->n_huf;
-            launch_zstd_prepare(Z, st);
-            launch_huf_decode(Z, st);
-            count_launch(ctx, 2);
-            if (b->needs_lit) {
-                launch_zstd_sequences(Z, st);
-                count_launch(ctx, 2);
-            }
-        }
-        if (b->n_gen) {
-            Z.list = b->d_gen_list;
-            Z.count = b->n_gen;
-            launch_zstd_serial(Z, 1, st);
-            count_launch(ctx);
-        }
+    {
+        int rc = run_zstd(ctx, b, &d_zstatus);
+        if (rc) return rc;
     }
     if (ctx->timing) CU(cudaEventRecord(ctx->ev[1], st));
     DecodeParams D;
@@ -757,6 +864,86 @@ extern "C" int vmb_zstd_compress(uint8_t* dst, size_t cap, size_t* out_len, cons
     *out_len = out.size();
     if (out.size() > cap) return VMB_ERR_CAP;
     memcpy(dst, out.data(), out.size());
+    return VMB_OK;
+}
+
+extern "C" int vmb_calibrate_scale(int64_t* a, size_t na, int16_t ae, int64_t* b, size_t nb, int16_t be, int16_t* out_e) {
+    if (!out_e || (na && !a) || (nb && !b)) return VMB_ERR_INVALID_ARG;
+    *out_e = vmb_host::calibrate_scale(a, na, ae, b, nb, be);
+    return VMB_OK;
+}
+
+// encoding.DecompressZSTD (compress.go:27) for a batch of frames, on the GPU.  Every frame travels as the values column of a
+// pseudo block (MarshalTypeZSTDNearestDelta over the frame's bytes) through the same kernels as the block payloads; only the
+// zstd stage runs.  Layout of dst: frame i at dst_offs[i] (16-byte aligned, in frame order), dst_lens[i] bytes.
+static const uint32_t kZstdBatchRows = 16384;  // content bound = 10 bytes x rows = 163840 >= 2*maxBlockSize (part.go index blocks)
+extern "C" int vmb_zstd_decompress_bound(const uint8_t* frames, const uint64_t* offs, size_t n, uint64_t* out_bytes) {
+    if (!out_bytes || (n && (!frames || !offs))) return VMB_ERR_INVALID_ARG;
+    uint64_t tot = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (offs[i + 1] < offs[i] || offs[i + 1] - offs[i] > 0xffffffffull) return VMB_ERR_INVALID_ARG;
+        uint32_t cs = 0, nseq = 0;
+        bool lit = false;
+        const uint8_t kind = zstd_classify_host(frames + offs[i], (uint32_t)(offs[i + 1] - offs[i]), kZstdBatchRows, &cs, &lit, &nseq);
+        if (kind != VMB_ZK_BAD) tot += ((uint64_t)cs + 15) & ~(uint64_t)15;
+    }
+    *out_bytes = tot;
+    return VMB_OK;
+}
+extern "C" int vmb_zstd_decompress_batch(vmb_ctx* ctx, const uint8_t* frames, const uint64_t* offs, size_t n, uint8_t* dst,
+                                         size_t dst_cap, uint64_t* dst_offs, uint32_t* dst_lens, int32_t* statuses) {
+    if (!ctx || !frames || !offs || !dst_offs || !dst_lens || n == 0 || n > 0x7fffffffull) return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<vmb_block_desc> descs(n);
+    for (size_t i = 0; i < n; i++) {
+        if (offs[i + 1] < offs[i] || offs[i + 1] - offs[i] > 0xffffffffull) return VMB_ERR_INVALID_ARG;
+        vmb_block_desc& d = descs[i];
+        memset(&d, 0, sizeof(d));
+        d.ts_mt = 3;
+        d.val_mt = 4;
+        d.val_off = offs[i];
+        d.val_size = (uint32_t)(offs[i + 1] - offs[i]);
+        d.rows = kZstdBatchRows;
+        d.precision_bits = 64;
+        d.series_idx = (uint32_t)i;
+    }
+    vmb_blocks* b = nullptr;
+    int rc = vmb_blocks_upload(ctx, descs.data(), n, frames, (size_t)offs[n], &b);
+    if (rc) return rc;
+    std::vector<ColInfo> cols(2 * n);
+    std::vector<int32_t> st(2 * n, 0);
+    int32_t* d_zstatus = nullptr;
+    cudaError_t e = cudaSuccess;
+    rc = run_zstd(ctx, b, &d_zstatus);
+    if (rc == VMB_OK) {
+        e = cudaMemcpyAsync(cols.data(), b->d_cols, cols.size() * sizeof(ColInfo), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && d_zstatus)
+            e = cudaMemcpyAsync(st.data(), d_zstatus, st.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && b->scratch_total) {
+            if (b->scratch_total > dst_cap || !dst) rc = VMB_ERR_CAP;
+            else e = cudaMemcpyAsync(dst, ctx->zscratch.p, b->scratch_total, cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            vmb_set_error("vmb_zstd_decompress_batch: %s", cudaGetErrorString(e));
+            rc = VMB_ERR_CUDA;
+        }
+    }
+    vmb_blocks_free(b);
+    if (rc) return rc;
+    int bad = 0;
+    for (size_t i = 0; i < n; i++) {
+        const ColInfo& ci = cols[2 * i + 1];
+        const int32_t s = st[2 * i + 1];
+        dst_offs[i] = ci.scratch_off;
+        dst_lens[i] = s ? 0u : ci.content_size;
+        if (statuses) statuses[i] = s;
+        bad += s != 0;
+    }
+    if (bad) {
+        vmb_set_error("%d of %zu zstd frames failed to decompress", bad, n);
+        return VMB_ERR_ZSTD;
+    }
     return VMB_OK;
 }
 

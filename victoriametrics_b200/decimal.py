@@ -23,3 +23,13 @@ def append_float_to_decimal(src):
     e = C.c_int16(0)
     check(lib().vmb_float_to_decimal(dst.ctypes.data_as(_lib.i64p), C.byref(e), f.ctypes.data_as(_lib.f64p), f.size))
     return dst, e.value
+
+
+def calibrate_scale(a, ae, b, be):
+    """decimal.CalibrateScale decimal.go:13 (host, merge path) -> (a', b', e): both arrays rescaled to the common exponent e"""
+    a = np.array(a, dtype=np.int64)
+    b = np.array(b, dtype=np.int64)
+    e = C.c_int16(0)
+    check(lib().vmb_calibrate_scale(a.ctypes.data_as(_lib.i64p), a.size, int(ae), b.ctypes.data_as(_lib.i64p), b.size, int(be),
+                                    C.byref(e)))
+    return a, b, e.value

@@ -54,6 +54,32 @@ def zstd_compress(src):
     return dst[:n.value].copy()
 
 
+def decompress_zstd_batch(frames, ctx=None):
+    """encoding.DecompressZSTD compress.go:27 for a list of frames at once (GPU) -> list of np.uint8 arrays.
+    Raises VmbError(VMB_ERR_ZSTD) if a frame is corrupt, like the Go error return."""
+    ctx = ctx or _lib.default_context()
+    frames = [np.ascontiguousarray(np.frombuffer(f, dtype=np.uint8) if isinstance(f, (bytes, bytearray)) else f, dtype=np.uint8)
+              for f in frames]
+    n = len(frames)
+    if n == 0:
+        return []
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([f.size for f in frames])
+    arena = np.concatenate(frames) if n else np.zeros(0, dtype=np.uint8)
+    if arena.size == 0:
+        arena = np.zeros(1, dtype=np.uint8)
+    bound = C.c_uint64(0)
+    check(lib().vmb_zstd_decompress_bound(arena.ctypes.data_as(_lib.u8p), offs.ctypes.data_as(_lib.u64p), n, C.byref(bound)))
+    dst = np.empty(max(bound.value, 1), dtype=np.uint8)
+    doffs = np.zeros(n, dtype=np.uint64)
+    dlens = np.zeros(n, dtype=np.uint32)
+    st = np.zeros(n, dtype=np.int32)
+    check(lib().vmb_zstd_decompress_batch(ctx.h, arena.ctypes.data_as(_lib.u8p), offs.ctypes.data_as(_lib.u64p), n,
+                                          dst.ctypes.data_as(_lib.u8p), dst.size, doffs.ctypes.data_as(_lib.u64p),
+                                          dlens.ctypes.data_as(_lib.u32p), st.ctypes.data_as(_lib.i32p)))
+    return [dst[int(o):int(o) + int(l)] for o, l in zip(doffs, dlens)]
+
+
 def marshal_columns(vals2d, precision_bits=64, nthreads=None):
     """batched MarshalValues for equal-length columns: vals2d [ncols x rows] int64
     -> (payload np.uint8, offs np.uint64[ncols+1], mts np.uint8[ncols], firsts np.int64[ncols])"""

@@ -81,14 +81,111 @@ class BlockSet:
 def descs_from_arrays(**cols):
     """vectorised construction of a BlockDesc array from numpy columns (bench-sized inputs)"""
     n = len(cols["rows"])
-    dt = np.dtype([("first_value", "<i8"), ("min_ts", "<i8"), ("max_ts", "<i8"), ("ts_off", "<u8"), ("val_off", "<u8"),
-                   ("ts_size", "<u4"), ("val_size", "<u4"), ("rows", "<u4"), ("series_idx", "<u4"), ("scale", "<i2"),
-                   ("ts_mt", "u1"), ("val_mt", "u1"), ("precision_bits", "u1"), ("_pad", "u1", (3,))])
-    assert dt.itemsize == 64
-    a = np.zeros(n, dtype=dt)
+    a = np.zeros(n, dtype=DESC_DTYPE)
     for k, v in cols.items():
         a[k] = v
     return a
+
+
+DESC_DTYPE = np.dtype([("first_value", "<i8"), ("min_ts", "<i8"), ("max_ts", "<i8"), ("ts_off", "<u8"), ("val_off", "<u8"),
+                       ("ts_size", "<u4"), ("val_size", "<u4"), ("rows", "<u4"), ("series_idx", "<u4"), ("scale", "<i2"),
+                       ("ts_mt", "u1"), ("val_mt", "u1"), ("precision_bits", "u1"), ("_pad", "u1", (3,))])
+METAINDEX_DTYPE = np.dtype([("tsid", "u1", (24,)), ("min_ts", "<i8"), ("max_ts", "<i8"), ("index_block_offset", "<u8"),
+                            ("block_headers_count", "<u4"), ("index_block_size", "<u4")])
+assert DESC_DTYPE.itemsize == 64 and METAINDEX_DTYPE.itemsize == 56
+
+
+def marshal_block_header(desc, tsid=None):
+    """blockHeader.Marshal block_header.go:104 -> 81 bytes.  desc: BlockDesc or one record of a DESC_DTYPE array"""
+    if not isinstance(desc, BlockDesc):
+        desc = BlockDesc.from_buffer_copy(np.asarray(desc).tobytes())
+    out = (C.c_uint8 * 81)()
+    t = None
+    if tsid is not None:
+        t = (C.c_uint8 * 24).from_buffer_copy(bytes(tsid))
+    check(lib().vmb_block_header_marshal(out, C.byref(desc), t))
+    return bytes(out)
+
+
+def unmarshal_block_headers(data, count):
+    """unmarshalBlockHeaders block_header.go:261 on an uncompressed index block -> (DESC_DTYPE array, tsids np.uint8[count, 24])"""
+    d = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+    out = np.zeros(max(count, 1), dtype=DESC_DTYPE)
+    tsids = np.zeros((max(count, 1), 24), dtype=np.uint8)
+    src = d if d.size else np.zeros(1, dtype=np.uint8)
+    check(lib().vmb_index_block_unmarshal(out.ctypes.data_as(C.POINTER(BlockDesc)), tsids.ctypes.data_as(_lib.u8p), count,
+                                          src.ctypes.data_as(_lib.u8p), d.size))
+    return out[:count], tsids[:count]
+
+
+def unmarshal_metaindex_rows(data):
+    """unmarshalMetaindexRows metaindex_row.go:129 on the decompressed metaindex.bin -> METAINDEX_DTYPE array"""
+    d = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+    cap = d.size // 56 + 1
+    out = np.zeros(cap, dtype=METAINDEX_DTYPE)
+    n = C.c_size_t(0)
+    src = d if d.size else np.zeros(1, dtype=np.uint8)
+    check(lib().vmb_metaindex_rows_unmarshal(out.ctypes.data_as(C.POINTER(_lib.MetaindexRow)), cap, C.byref(n),
+                                             src.ctypes.data_as(_lib.u8p), d.size))
+    return out[:n.value]
+
+
+def marshal_metaindex_row(row):
+    """metaindexRow.Marshal metaindex_row.go:61 -> 56 bytes"""
+    r = _lib.MetaindexRow.from_buffer_copy(np.asarray(row).tobytes())
+    out = (C.c_uint8 * 56)()
+    check(lib().vmb_metaindex_row_marshal(out, C.byref(r)))
+    return bytes(out)
+
+
+class Part:
+    """The four data files of one part directory (lib/storage/part.go:34: metaindex.bin, index.bin, timestamps.bin, values.bin)
+    as byte strings.  collect_blocks() == what partSearch (part_search.go:160 nextBHS -> :238 readIndexBlock) and
+    netstorage hand to the query path, for every block of the part at once: metaindex.bin and all the index blocks are
+    decompressed on the GPU in two batched calls, the headers become vmb_block_desc records whose offsets point into one
+    payload arena [timestamps.bin | values.bin] -- the layout a storage node would DMA the two files into."""
+
+    def __init__(self, metaindex_bin, index_bin, timestamps_bin, values_bin):
+        as_u8 = lambda b: np.frombuffer(b, dtype=np.uint8) if isinstance(b, (bytes, bytearray)) else np.asarray(b, dtype=np.uint8)
+        self.metaindex_bin, self.index_bin = as_u8(metaindex_bin), as_u8(index_bin)
+        self.timestamps_bin, self.values_bin = as_u8(timestamps_bin), as_u8(values_bin)
+
+    def metaindex_rows(self, ctx=None):
+        return unmarshal_metaindex_rows(encoding.decompress_zstd_batch([self.metaindex_bin], ctx)[0])
+
+    def collect_blocks(self, ctx=None, tsids=None, tr_min=INT64_MIN, tr_max=INT64_MAX):
+        """-> (DESC_DTYPE array with dense series_idx, payload np.uint8, tsids of the series np.uint8[nseries, 24]).
+        tsids (optional, iterable of 24-byte TSIDs) and [tr_min, tr_max] filter blocks like partSearch.Init (part_search.go:64)."""
+        rows = self.metaindex_rows(ctx)
+        frames = []
+        for r in rows:
+            o, sz = int(r["index_block_offset"]), int(r["index_block_size"])
+            if o + sz > self.index_bin.size:
+                raise _lib.VmbError(-1, "index block [%d, %d) outside index.bin (%d bytes)" % (o, o + sz, self.index_bin.size))
+            frames.append(self.index_bin[o:o + sz])
+        blocks = encoding.decompress_zstd_batch(frames, ctx)
+        descs, ids = [], []
+        for r, ib in zip(rows, blocks):
+            d, t = unmarshal_block_headers(ib, int(r["block_headers_count"]))
+            descs.append(d)
+            ids.append(t)
+        descs = np.concatenate(descs)
+        ids = np.concatenate(ids)
+        keep = (descs["max_ts"] >= tr_min) & (descs["min_ts"] <= tr_max)
+        if tsids is not None:
+            want = {bytes(t) for t in tsids}
+            keep &= np.fromiter((ids[i].tobytes() in want for i in range(len(ids))), dtype=bool, count=len(ids))
+        descs, ids = descs[keep], ids[keep]
+        if (descs["ts_off"] + descs["ts_size"] > self.timestamps_bin.size).any() or \
+                (descs["val_off"] + descs["val_size"] > self.values_bin.size).any():
+            raise _lib.VmbError(-1, "block payload outside timestamps.bin / values.bin")
+        descs["val_off"] += np.uint64(self.timestamps_bin.size)
+        new_series = np.ones(len(descs), dtype=bool)
+        if len(descs) > 1:
+            new_series[1:] = (ids[1:] != ids[:-1]).any(axis=1)
+        descs["series_idx"] = (np.cumsum(new_series) - 1).astype(np.uint32)
+        payload = np.concatenate([self.timestamps_bin, self.values_bin])
+        return descs, payload, ids[new_series]
 
 
 class Blocks:
