@@ -13,6 +13,10 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+# ad-hoc differential campaigns on the GPU box: VMB_SEED_OFFSET=k shifts every seeded generator of the GPU tests
+# (the committed expectations are for offset 0; a few structural assertions, e.g. "at least 50 index blocks", may not hold elsewhere)
+SEED0 = int(os.environ.get("VMB_SEED_OFFSET", "0"))
+
 STALE_NAN = struct.unpack("<d", struct.pack("<Q", 0x7FF0000000000002))[0]
 
 

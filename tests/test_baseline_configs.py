@@ -3,6 +3,8 @@
   configs[1..4] (-m gpu)  the query shapes at reduced size against the oracle pipeline, plus size-independent properties
                           at a larger size (host path == device path bit for bit, sampled series == oracle)."""
 import numpy as np
+
+from conftest import SEED0
 import pytest
 
 import blockgen
@@ -20,7 +22,7 @@ def test_config0_encode_decode_roundtrip_10k_series(oracle):
     """v[i] = v[i-1] + 30000 + round(N(0,1000)); precisionBits 64 => MarshalTypeNearestDelta2 (plain,
     zstd does not reach the 0.9 ratio: SURVEY.md 7 table) ; product encoder bytes == oracle encoder bytes; round trip exact"""
     from victoriametrics_b200 import encoding
-    rng = np.random.default_rng(100)
+    rng = np.random.default_rng(SEED0 + 100)
     nser, n = 10_000, 1024
     inc = 30000 + np.round(rng.normal(0, 1000, (nser, n))).astype(np.int64)
     inc[:, 0] = rng.integers(0, 10 ** 9, nser)
@@ -71,7 +73,7 @@ def _mk(rng, n, kind, rows=2048, tkind="regular"):
 @pytest.mark.gpu
 def test_config1_decode_plus_rate_5m_step15(oracle):
     import victoriametrics_b200 as vm
-    rng = np.random.default_rng(101)
+    rng = np.random.default_rng(SEED0 + 101)
     blocks = _mk(rng, 48, "counter_resets", rows=8192)
     descs, payload = blockgen.to_blockset(blocks)
     start, end, step, window = T0 + 300000, T0 + 15000 * 8191, 15000, 300000
@@ -87,7 +89,7 @@ def test_config1_decode_plus_rate_5m_step15(oracle):
 @pytest.mark.parametrize("func,arg", [("avg_over_time", None), ("max_over_time", None), ("quantile_over_time", 0.99)])
 def test_config2_gauge_over_time_functions(oracle, func, arg):
     import victoriametrics_b200 as vm
-    rng = np.random.default_rng(102)
+    rng = np.random.default_rng(SEED0 + 102)
     blocks = _mk(rng, 40, "gauge", rows=4096, tkind="jitter")
     assert all(b.vmt in (4, 6) for b in blocks)
     descs, payload = blockgen.to_blockset(blocks)
@@ -105,7 +107,7 @@ def test_config3_sum_rate_by_label_single_rank(oracle):
     tests/test_dist_aggr.py over gloo and by bench.py --gpus N over NCCL)"""
     import torch
     import victoriametrics_b200 as vm
-    rng = np.random.default_rng(103)
+    rng = np.random.default_rng(SEED0 + 103)
     S, G = 64, 8
     blocks = _mk(rng, S, "counter", rows=2048)
     descs, payload = blockgen.to_blockset(blocks)
@@ -167,7 +169,7 @@ def test_streamed_counter_resets_bit_exact(oracle, lookback, window_rows):
     last_over_time at step = scrape interval exposes every corrected value -> compare bit for bit"""
     import torch
     import victoriametrics_b200 as vm
-    rng = np.random.default_rng(77 + window_rows)
+    rng = np.random.default_rng(SEED0 + 77 + window_rows)
     blocks = []
     for i in range(24):
         kind = ("counter_resets", "counter", "gauge", "counter_big")[i % 4]
@@ -211,7 +213,7 @@ def test_regular_timestamp_mode_edges(oracle):
     query ranges that start before / end after the data, steps that do not divide the scrape interval"""
     import torch
     import victoriametrics_b200 as vm
-    rng = np.random.default_rng(311)
+    rng = np.random.default_rng(SEED0 + 311)
     blocks = []
     for i, (n, dt) in enumerate([(2, 15000), (3, 1), (100, 7), (8192, 15000), (8192, 1000), (5000, 60000), (64, 999),
                                  (8192, 15000), (777, 15000), (16, 10**6), (8192, 1)]):
@@ -260,7 +262,7 @@ def test_random_query_grids_through_the_fast_paths(oracle):
     import os
     import torch
     import victoriametrics_b200 as vm
-    rng = np.random.default_rng(int(os.environ.get("VMB_FUZZ_SEED", "5150")))
+    rng = np.random.default_rng(SEED0 + int(os.environ.get("VMB_FUZZ_SEED", "5150")))
     blocks = []
     for i in range(30):
         n = int(rng.choice([2, 17, 300, 2049, 5000, 8192]))
@@ -304,7 +306,7 @@ def test_random_query_grids_through_the_fast_paths(oracle):
 def test_config4_mixed_codec_increase_1h_step60(oracle):
     """40 % delta2 counters, 30 % gauges, 20 % const, 10 % delta-const -> increase(m[1h]) step 60 s"""
     import victoriametrics_b200 as vm
-    rng = np.random.default_rng(104)
+    rng = np.random.default_rng(SEED0 + 104)
     kinds = ["counter"] * 4 + ["counter_smooth"] * 2 + ["counter_big"] * 2 + ["gauge"] * 6 + ["const"] * 4 + ["delta_const"] * 2
     blocks = [blockgen.OBlock(blockgen.gen_timestamps(rng, "regular", 4096, T0), blockgen.gen_values(rng, k, 4096), -2, 64, i)
               for i, k in enumerate(kinds * 3)]

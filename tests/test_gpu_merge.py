@@ -2,6 +2,8 @@
 Reference vectors (netstorage_test.go:11, dedup_test.go) through the CUDA path, then randomized differentials against the
 oracle: overlapping / touching / replicated blocks in any arrival order, several scales, time-range trimming, dedup on/off."""
 import numpy as np
+
+from conftest import SEED0
 import pytest
 
 import blockgen
@@ -119,7 +121,7 @@ def _oracle_series(oracle, blocks, dedup, tr_min=-(1 << 63), tr_max=(1 << 63) - 
 @pytest.mark.parametrize("dedup", [0, 1, 1000, 30000])
 def test_merge_random_differential(vmctx, oracle, dedup):
     vm, ctx = vmctx
-    rng = np.random.default_rng(1000 + dedup)
+    rng = np.random.default_rng(SEED0 + 1000 + dedup)
     ctx.set_dedup_interval(dedup)
     per_series = [_random_series_blocks(rng, s) for s in range(120)]
     flat = [b for blocks in per_series for b in blocks]
@@ -142,7 +144,7 @@ def test_dedup_negative_timestamps_and_long_runs(vmctx, oracle):
     """negative timestamps take the sequential replay (Go's % truncates toward zero); long runs of equal timestamps
     cross the 32-row chunks of the parallel path"""
     vm, ctx = vmctx
-    rng = np.random.default_rng(77)
+    rng = np.random.default_rng(SEED0 + 77)
     cases = []
     for n, lo in ((500, -100_000), (3000, -5_000), (8192, 0), (8192, 10**12)):
         ts = lo + np.sort(rng.integers(0, n * 40, n)).astype(np.int64)
@@ -163,7 +165,7 @@ def test_rate_over_merged_series_all_entry_points(vmctx, oracle):
     import torch
     from rollup_names import RF
     vm, ctx = vmctx
-    rng = np.random.default_rng(4242)
+    rng = np.random.default_rng(SEED0 + 4242)
     per_series = [_random_series_blocks(rng, s) for s in range(40)]
     flat = [b for blocks in per_series for b in blocks]
     descs, payload = blockgen.to_blockset(flat)

@@ -2,6 +2,8 @@
 rollup_scrape_interval(), rollup_candlestick(), aggr_over_time(), quantiles_over_time() through the CUDA path (shared value
 preFunc: deltaValues rollup.go:960, derivValues :976, scrape intervals :462) against the oracle"""
 import numpy as np
+
+from conftest import SEED0
 import pytest
 
 import blockgen
@@ -35,7 +37,7 @@ def _pre_oracle(oracle, name, ts, fv):
 def test_multi_output_rollups(oracle, name, kw):
     import victoriametrics_b200 as vm
     import zlib
-    rng = np.random.default_rng(zlib.crc32(name.encode()) % 1000 + len(kw))
+    rng = np.random.default_rng(SEED0 + zlib.crc32(name.encode()) % 1000 + len(kw))
     blocks = []
     for i in range(36):
         n = int(rng.choice([1, 2, 3, 40, 600, 4096]))

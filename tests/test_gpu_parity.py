@@ -9,6 +9,8 @@ import os
 import struct
 
 import numpy as np
+
+from conftest import SEED0
 import pytest
 
 import blockgen
@@ -61,7 +63,7 @@ def assert_allclose_nan(got, exp, rel, what=""):
 
 # ------------------------------------------------------------------------------------------------ codec: per-call
 def test_unmarshal_values_per_call_all_types(vm, oracle):
-    rng = np.random.default_rng(1)
+    rng = np.random.default_rng(SEED0 + 1)
     seen = set()
     for kind in blockgen.VALUE_KINDS:
         for n in (1, 2, 3, 33, 512, 513, 8192):
@@ -121,7 +123,7 @@ def test_decimal_to_float_kats_bit_exact(vm, kats, oracle):
             continue
         got = vm.decimal.append_decimal_to_float(va, e)
         assert f64bits(got).tolist() == [struct.unpack("<Q", struct.pack("<d", gofloat(s)))[0] for s in exp], (va, e)
-    rng = np.random.default_rng(2)
+    rng = np.random.default_rng(SEED0 + 2)
     for e in list(range(-30, 31)) + [-300, -323, -324, 308, 309, -40, 35]:
         va = np.concatenate([rng.integers(-(1 << 62), 1 << 62, 500), rng.integers(-100000, 100000, 500),
                              np.array([0, 1, -1, I64_MAX, I64_MIN, I64_MAX - 1, I64_MAX - 2, I64_MIN + 1])]).astype(np.int64)
@@ -156,7 +158,7 @@ def _check_blocks(vm, blocks, tr_min=I64_MIN, tr_max=I64_MAX, as_int=False):
 
 
 def test_decode_blocks_mixed_types_bit_exact(vm):
-    rng = np.random.default_rng(3)
+    rng = np.random.default_rng(SEED0 + 3)
     blocks = blockgen.random_blocks(rng, 400)
     types = {(b.tmt, b.vmt) for b in blocks}
     assert {t for t, _ in types} >= {2, 5} and {v for _, v in types} >= {1, 2, 3, 4, 5, 6}
@@ -165,13 +167,13 @@ def test_decode_blocks_mixed_types_bit_exact(vm):
 
 
 def test_decode_blocks_lossy_precision_bits(vm):
-    rng = np.random.default_rng(4)
+    rng = np.random.default_rng(SEED0 + 4)
     blocks = blockgen.random_blocks(rng, 120, pbs=(1, 4, 12, 24, 40, 63), ts_kinds=["jitter", "irregular", "regular"])
     _check_blocks(vm, blocks)  # exercises EnsureNonDecreasingSequence encoding.go:258
 
 
 def test_decode_blocks_time_range_filter(vm):
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(SEED0 + 5)
     blocks = blockgen.random_blocks(rng, 120, ts_kinds=["regular", "jitter", "dups"])
     t0 = 1_700_000_000_000
     for tr in ((t0 + 15000 * 100, t0 + 15000 * 3000), (t0 - 5, t0 + 3), (t0 + 10 ** 12, t0 + 2 * 10 ** 12), (I64_MIN, t0 + 1000)):
@@ -179,7 +181,7 @@ def test_decode_blocks_time_range_filter(vm):
 
 
 def test_decode_blocks_corrupt_blocks_are_reported_per_block(vm):
-    rng = np.random.default_rng(6)
+    rng = np.random.default_rng(SEED0 + 6)
     blocks = blockgen.random_blocks(rng, 60, value_kinds=["counter", "gauge", "counter_big", "counter_smooth"], ts_kinds=["jitter"])
     for i in range(0, 60, 3):
         b = blocks[i]
@@ -200,7 +202,7 @@ def test_decode_blocks_fuzzed_payloads(vm):
     """one random mutation per block -- flipped / inserted / dropped bytes anywhere in either column (varints, zstd frame
     headers, Huffman trees, FSE tables, bitstreams), wrong row counts, swapped marshal types: the GPU path must neither crash
     nor disagree with the oracle about which blocks are bad, and the good ones must still decode bit for bit"""
-    rng = np.random.default_rng(int(os.environ.get("VMB_FUZZ_SEED", "20240922")))  # other seeds for ad-hoc campaigns
+    rng = np.random.default_rng(SEED0 + int(os.environ.get("VMB_FUZZ_SEED", "20240922")))  # other seeds for ad-hoc campaigns
     blocks = blockgen.random_blocks(rng, 700, rows_choices=(2, 3, 33, 100, 512, 1000, 4096, 8192))
     for i, b in enumerate(blocks):
         kind = int(rng.integers(0, 8))
@@ -264,7 +266,7 @@ def test_zstd_sequences_batched_stress(vm, oracle):
     """many libzstd frames with very different sequence sections in ONE batch (frames share warps in k_zstd_seq_decode /
     k_zstd_seq_exec): long literal runs, long matches, matches overlapping themselves (period 1..7), RLE / predefined /
     FSE-described tables, repeat offsets, frames with 1 sequence next to frames with thousands"""
-    rng = np.random.default_rng(20240921)
+    rng = np.random.default_rng(SEED0 + 20240921)
     blocks = []
     for i in range(700):
         n = int(rng.choice([2, 3, 17, 64, 129, 500, 1024, 3000, 8192]))
@@ -310,7 +312,7 @@ def test_zstd_sequences_batched_stress(vm, oracle):
 
 
 def test_blocks_written_by_the_product_encoder_decode_identically(vm, oracle):
-    rng = np.random.default_rng(7)
+    rng = np.random.default_rng(SEED0 + 7)
     bs = vm.storage.BlockSet()
     raw = []
     for i in range(64):
@@ -383,7 +385,7 @@ ARG_FUNCS = {"quantile_over_time": 0.9, "predict_linear": 60.0, "holt_winters": 
 @pytest.mark.parametrize("name", RF_IDS)
 def test_rollup_function_differential_vs_oracle(vm, oracle, name):
     import zlib
-    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    rng = np.random.default_rng(SEED0 + zlib.crc32(name.encode()))
     fid = RF[name]
     configs = [(300000, 15000, 0), (60000, 60000, 0), (0, 15000, 0), (3600000, 300000, 300000), (45000, 7000, 120000)]
     for kind in ("counter", "gauge", "gaps", "stale", "dups"):
@@ -421,7 +423,7 @@ def test_rollup_function_differential_vs_oracle(vm, oracle, name):
 
 def test_remove_counter_resets_bit_exact(vm, oracle):
     """the preFunc of rate()/increase(): sequential float semantics must survive the warp-parallel formulation"""
-    rng = np.random.default_rng(8)
+    rng = np.random.default_rng(SEED0 + 8)
     ts_list, v_list = [], []
     for n in (1, 2, 31, 32, 33, 64, 1000, 8192):
         for kind in ("counter", "gauge", "gaps"):
@@ -444,7 +446,7 @@ def test_remove_counter_resets_bit_exact(vm, oracle):
 
 def test_incremental_aggregates(vm, oracle):
     import torch
-    rng = np.random.default_rng(9)
+    rng = np.random.default_rng(SEED0 + 9)
     S, P, G = 97, 50, 5
     ts_list, v_list = [], []
     for s in range(S):
@@ -509,7 +511,7 @@ def _oracle_pipeline(oracle, blocks, func, start, end, step, window, lookback, t
                                               ("default_rollup", 0, 30000)])
 def test_eval_rollup_whole_path_host_and_device(vm, oracle, func, window, step):
     import torch
-    rng = np.random.default_rng(10)
+    rng = np.random.default_rng(SEED0 + 10)
     blocks = blockgen.random_blocks(rng, 150, rows_choices=(2, 100, 1000, 8192),
                                     value_kinds=["counter", "counter_resets", "gauge", "const", "delta_const", "counter_smooth"],
                                     ts_kinds=["regular", "jitter"], scales=(-2,))
@@ -525,3 +527,27 @@ def test_eval_rollup_whole_path_host_and_device(vm, oracle, func, window, step):
     torch.cuda.synchronize()
     assert np.array_equal(f64bits(out.cpu().numpy()), f64bits(got_host))
     assert scanned == scanned2
+
+
+def test_delta_const_value_columns_that_wrap_are_counter_reset_candidates(vm, oracle):
+    """A values column stored as MarshalTypeDeltaConst can decrease although its delta is positive: first + i*d wraps in
+    int64 exactly like the Go loop (encoding.go:240), e.g. the two-row column {5216, MinInt64+1}.  removeCounterResets must
+    still run on such a series (found by the seed-shifted campaign, VMB_SEED_OFFSET=1000)."""
+    t0 = 1_700_000_000_000
+    cols = [np.array([5216, -(1 << 63) + 1], dtype=np.int64),                       # positive wrapped delta, value drops
+            np.array([(1 << 62) + 5, -(1 << 63) + 1005, -(1 << 62) + 2005], dtype=np.int64),  # delta 2^62+1000: wraps after row 0
+            np.array([10, 7, 4, 1], dtype=np.int64),                                  # plain negative delta
+            np.array([-5, 0, 5, 10], dtype=np.int64),                                 # increasing: no candidate
+            np.array([(1 << 63) - 3, -(1 << 63) + 1], dtype=np.int64)]               # increasing delta that wraps to a drop
+    blocks = []
+    for i, v in enumerate(cols):
+        ts = t0 + 15_000 * np.arange(len(v), dtype=np.int64)
+        b = blockgen.OBlock(ts, v, -2, 64, i)
+        assert b.vmt == 2, (i, b.vmt)  # MarshalTypeDeltaConst
+        blocks.append(b)
+    start, end, step, window = t0 + 15_000, t0 + 120_000, 15_000, 60_000
+    descs, payload = blockgen.to_blockset(blocks)
+    for func in ("rate", "increase", "irate"):
+        exp = _oracle_pipeline(oracle, blocks, func, start, end, step, window, 0)
+        got, _ = vm.promql.eval_rollup_func_host(func, descs, payload, start, end, step, window)
+        assert_allclose_nan(got, exp, 1e-12, func)

@@ -5,6 +5,8 @@
 import ctypes as C
 
 import numpy as np
+
+from conftest import SEED0
 import pytest
 
 import blockgen
@@ -41,7 +43,7 @@ def test_zstd_decompress_batch_matches_reference_libzstd(oracle):
     import victoriametrics_b200 as vm
     if not oracle.lib().vmo_zstd_ref_available():
         pytest.skip("oracle/_ref (the reference's libzstd) was not built")
-    rng = np.random.default_rng(20)
+    rng = np.random.default_rng(SEED0 + 20)
     raws = _payloads(rng)
     frames = [oracle.zstd_ref_compress(r, int(lvl)) for r, lvl in zip(raws, rng.choice([1, 3, 5], len(raws)))]
     got = vm.encoding.decompress_zstd_batch(frames)
@@ -58,7 +60,7 @@ def test_zstd_decompress_batch_reports_bad_frames(oracle):
     from victoriametrics_b200 import _lib
     if not oracle.lib().vmo_zstd_ref_available():
         pytest.skip("oracle/_ref (the reference's libzstd) was not built")
-    rng = np.random.default_rng(21)
+    rng = np.random.default_rng(SEED0 + 21)
     raws = [rng.integers(0, 7, 5000).astype(np.uint8) for _ in range(6)]
     frames = [oracle.zstd_ref_compress(r, 3) for r in raws]
     frames[1] = frames[1][: len(frames[1]) // 2].copy()        # truncated
@@ -109,7 +111,7 @@ def test_part_collect_blocks_decode_and_rollup(oracle, max_index_block):
     from rollup_names import RF
     if not oracle.lib().vmo_zstd_ref_available():
         pytest.skip("oracle/_ref (the reference's libzstd) was not built")
-    rng = np.random.default_rng(300 + max_index_block)
+    rng = np.random.default_rng(SEED0 + 300 + max_index_block)
     series, files = _make_part(rng, 260, max_index_block)
     assert files["index_blocks"] >= (1 if max_index_block > 1000 else 50)
     part = vm.storage.Part(files["metaindex_bin"], files["index_bin"], files["timestamps_bin"], files["values_bin"])

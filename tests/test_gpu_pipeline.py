@@ -4,6 +4,8 @@ contiguous) payload layouts, multi-block series and corrupt blocks."""
 import os
 
 import numpy as np
+
+from conftest import SEED0
 import pytest
 
 import blockgen
@@ -35,7 +37,7 @@ def _device_reference(vm, descs, payload, func, start, end, step, window, nserie
 
 @pytest.mark.parametrize("chunk", ["7", "64", "100000"])
 def test_pipeline_chunks_match_device_path(vm, chunk):
-    rng = np.random.default_rng(21)
+    rng = np.random.default_rng(SEED0 + 21)
     blocks = blockgen.random_blocks(rng, 300, rows_choices=(2, 50, 700, 8192),
                                     value_kinds=["counter", "counter_resets", "gauge", "const", "delta_const", "counter_smooth", "counter_big"],
                                     ts_kinds=["regular", "jitter"], scales=(-2, 0))
@@ -56,7 +58,7 @@ def test_pipeline_multiblock_series_and_scattered_payload(vm, oracle):
     """series of 3 consecutive blocks (concatenated like mergeSortBlocks' fast path) + a payload arena whose blocks are
     stored in reverse order (forces the host-side gather path)"""
     from rollup_names import RF
-    rng = np.random.default_rng(22)
+    rng = np.random.default_rng(SEED0 + 22)
     nser, per = 40, 3
     bs = vm.storage.BlockSet()
     series_ts, series_v = [], []
@@ -105,7 +107,7 @@ def test_pipeline_multiblock_series_and_scattered_payload(vm, oracle):
 
 
 def test_pipeline_reports_corrupt_blocks(vm):
-    rng = np.random.default_rng(23)
+    rng = np.random.default_rng(SEED0 + 23)
     blocks = blockgen.random_blocks(rng, 40, rows_choices=(100, 1000), value_kinds=["counter", "gauge"], ts_kinds=["jitter"])
     blocks[5].vdata = blocks[5].vdata[:-3].copy()
     descs, payload = blockgen.to_blockset(blocks)

@@ -2,6 +2,8 @@
 (exec_test.go:6592-6900) and randomized differentials against a direct restatement of the per-point sort; the multi-process
 protocol (candidate lists per shard -> merge -> apply per shard) is run with two shards on one GPU."""
 import numpy as np
+
+from conftest import SEED0
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -67,7 +69,7 @@ def test_topk_reference_query_vectors():
 @pytest.mark.parametrize("reverse", [False, True])
 def test_topk_random_differential(reverse):
     import victoriametrics_b200 as vm
-    rng = np.random.default_rng(17 + reverse)
+    rng = np.random.default_rng(SEED0 + 17 + reverse)
     S, P, G = 300, 257, 7
     vals = rng.normal(size=(S, P)) * 100
     vals[rng.random((S, P)) < 0.15] = NAN
@@ -92,7 +94,7 @@ def test_topk_two_shards_protocol():
     import ctypes as C
     import victoriametrics_b200 as vm
     from victoriametrics_b200 import _lib
-    rng = np.random.default_rng(99)
+    rng = np.random.default_rng(SEED0 + 99)
     S, P, G, K = 200, 100, 3, 5
     vals = rng.normal(size=(S, P))
     vals[rng.random((S, P)) < 0.1] = NAN

@@ -174,13 +174,16 @@ __device__ int decode_column(const uint8_t* src, uint32_t len, int mt, int64_t f
             int rc = read_single_varint(src, len, &d, &used);
             if (rc) return rc;
             if (used < len) return VMB_ERR_TAIL;
-            if (d >= 0 && (n == 1 || (uint64_t)d <= (uint64_t)0x7fffffffffffffffLL / (n - 1)))  // no wrap-around
-                em.note_progression(first, (int64_t)((uint64_t)first + (uint64_t)(n - 1) * (uint64_t)d), n);
+            // non-decreasing as a whole?  d >= 0 is not enough: first + i*d wraps like the Go loop (encoding.go:240 v += d), e.g.
+            // the two-row column {5216, MinInt64+1} is stored as delta-const with a positive (wrapped) delta
+            const int64_t last = (int64_t)((uint64_t)first + (uint64_t)(n - 1) * (uint64_t)d);
+            const bool monotone = d >= 0 && (n == 1 || (uint64_t)d <= (uint64_t)0x7fffffffffffffffLL / (n - 1)) && last >= first;
+            if (monotone) em.note_progression(first, last, n);
             for (uint32_t i = lane; i < n; i += 32) {
                 int64_t v = (int64_t)((uint64_t)first + (uint64_t)i * (uint64_t)d);
                 em.emit(i, v, v);
             }
-            if (d < 0 && n > 1) em.note_decrease();
+            if (!monotone) em.note_decrease();
             return 0;
         }
         default:
