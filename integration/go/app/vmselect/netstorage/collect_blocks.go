@@ -3,6 +3,7 @@
 package netstorage
 
 import (
+	"github.com/VictoriaMetrics/VictoriaMetrics/lib/storage"
 	"github.com/VictoriaMetrics/VictoriaMetrics/lib/vmb200"
 )
 
@@ -10,7 +11,9 @@ import (
 // metric name of each series. It replaces the per-series packedTimeseries.Unpack fan-out (netstorage.go:425) when the
 // rollup runs on the GPU: the time-range trim, mergeSortBlocks (:566) and DeduplicateSamples happen inside libvmb200
 // (blocks of one series may be appended in any order; pts.brs order is fine).
-func (rss *Results) CollectBlocks() (descs []vmb200.BlockDesc, payload []byte, metricNames []string) {
+//
+// tr is the search time range (Results.tr, netstorage.go:64) that Unpack passes to AppendRowsWithTimeRangeFilter.
+func (rss *Results) CollectBlocks() (descs []vmb200.BlockDesc, payload []byte, metricNames []string, tr storage.TimeRange) {
 	tbf := rss.tbf
 	for i := range rss.packedTimeseries {
 		pts := &rss.packedTimeseries[i]
@@ -20,5 +23,5 @@ func (rss *Results) CollectBlocks() (descs []vmb200.BlockDesc, payload []byte, m
 		}
 		metricNames = append(metricNames, pts.metricName)
 	}
-	return descs, payload, metricNames
+	return descs, payload, metricNames, rss.tr
 }

@@ -40,7 +40,7 @@ func newVMB200Cfg(funcName string, rc *rollupConfig, preFuncRemovesResets, dropS
 // library call for all series instead of rss.RunParallel + rc.Do per series.
 func evalRollupNoIncrementalAggregateGPU(funcName string, keepMetricNames bool, rss *netstorage.Results, rcs []*rollupConfig,
 	removesResets, dropStale bool, sharedTimestamps []int64) ([]*timeseries, uint64, error) {
-	descs, payload, names := rss.CollectBlocks()
+	descs, payload, names, tr := rss.CollectBlocks()
 	if len(descs) == 0 {
 		return nil, 0, nil
 	}
@@ -50,7 +50,7 @@ func evalRollupNoIncrementalAggregateGPU(funcName string, keepMetricNames bool, 
 	points := len(sharedTimestamps)
 	out := make([]float64, len(names)*points)
 	cfg := newVMB200Cfg(funcName, rcs[0], removesResets, dropStale)
-	scanned, err := c.EvalRollup(descs, payload, rcs[0].Start-rcs[0].Window-maxSilenceInterval(), rcs[0].End, cfg, out)
+	scanned, err := c.EvalRollup(descs, payload, tr.MinTimestamp, tr.MaxTimestamp, cfg, out)
 	if err != nil {
 		return nil, 0, err
 	}

@@ -24,13 +24,6 @@ func (br *BlockRef) AppendRawTo(descs []vmb200.BlockDesc, payload []byte, series
 	valOff := len(payload)
 	payload = bytesutil.ResizeWithCopyMayOverallocate(payload, valOff+int(br.bh.ValuesBlockSize))
 	br.p.valuesFile.MustReadAt(payload[valOff:], int64(br.bh.ValuesBlockOffset))
-	d.ts_off = C_uint64(tsOff)
-	d.val_off = C_uint64(valOff)
-	d.series_idx = C_uint32(seriesIdx)
+	vmb200.SetPlacement(&d, uint64(tsOff), uint64(valOff), seriesIdx)
 	return append(descs, d), payload
 }
-
-// C_uint64 / C_uint32 convert to the cgo field types of vmb200.BlockDesc (cgo types are package-local; the real patch
-// adds SetOffsets(tsOff, valOff uint64, seriesIdx uint32) to package vmb200 instead).
-func C_uint64(v int) uint64    { return uint64(v) }
-func C_uint32(v uint32) uint32 { return v }

@@ -145,6 +145,14 @@ func DescFromHeader(d *BlockDesc, header []byte) error {
 	return nil
 }
 
+// SetPlacement rebases a descriptor onto the caller's payload arena and assigns its dense series index (the cgo field
+// types are local to this package, so other packages go through this setter).
+func SetPlacement(d *BlockDesc, tsOff, valOff uint64, seriesIdx uint32) {
+	d.ts_off = C.uint64_t(tsOff)
+	d.val_off = C.uint64_t(valOff)
+	d.series_idx = C.uint32_t(seriesIdx)
+}
+
 // UnmarshalValues == encoding.UnmarshalValues (lib/encoding/encoding.go:111), one column per call (compat / tests).
 func (c *Ctx) UnmarshalValues(dst []int64, src []byte, mt byte, firstValue int64, itemsCount int) ([]int64, error) {
 	n := len(dst)
