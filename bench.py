@@ -257,11 +257,12 @@ def cpu_reference(descs, payload, func, start, end, step, window, target_seconds
     rows = int(descs["rows"][0])
     kind = "reference" if L.vmo_zstd_ref_available() else "port"
 
-    def run(nb, out):
+    def run(nb, out, nthreads=None):
         scanned = C.c_uint64(0)
         t = time.perf_counter()
         r = fn(descs.ctypes.data, nb, payload.ctypes.data_as(O.u8p), -(1 << 63), (1 << 63) - 1, C.byref(cfg),
-               int(rc.removeCounterResets), int(rc.dropStaleNaNs), out.ctypes.data_as(O.f64p), C.byref(scanned), cores, 1)
+               int(rc.removeCounterResets), int(rc.dropStaleNaNs), out.ctypes.data_as(O.f64p), C.byref(scanned),
+               nthreads or cores, 1)
         dt = time.perf_counter() - t
         assert r == 0, r
         return dt
@@ -277,14 +278,20 @@ def cpu_reference(descs, payload, func, start, end, step, window, target_seconds
     nb = max(nb0, min(nb, len(descs)))
     out = np.empty((nb, P), dtype=np.float64)
     out.fill(0.0)
-    best = None
-    for _ in range(max(repeats, 2)):
-        dt = run(nb, out)
-        best = dt if best is None else min(best, dt)
-    return {"value": nb * rows / best, "unit": "samples/s", "cores": cores, "kind": kind,
-            "sample": "%d of %d blocks x %d rows, %.2f s wall on %d threads (C++ restatement of the Go path%s)" %
-                      (nb, len(descs), rows, best, cores, "; zstd via the reference's libzstd 1.5.7" if kind == "reference" else ""),
-            "seconds": best, "blocks": nb}, out
+    # one software thread per hardware thread is not always the fastest on a hyper-threaded host: also try one per two and
+    # report whichever is faster (the baseline gets the benefit of the doubt)
+    tried = {}
+    for nt in ([cores, cores // 2] if cores >= 16 else [cores]):
+        for _ in range(max(repeats, 2)):
+            dt = run(nb, out, nt)
+            tried[nt] = min(tried.get(nt, dt), dt)
+    used = min(tried, key=tried.get)
+    best = tried[used]
+    return {"value": nb * rows / best, "unit": "samples/s", "cores": used, "kind": kind,
+            "sample": "%d of %d blocks x %d rows, %.2f s wall on %d threads (C++ restatement of the Go path%s)%s" %
+                      (nb, len(descs), rows, best, used, "; zstd via the reference's libzstd 1.5.7" if kind == "reference" else "",
+                       "; thread counts tried: " + ", ".join("%d -> %.2f s" % (k, v) for k, v in sorted(tried.items())) if len(tried) > 1 else ""),
+            "seconds": best, "blocks": nb, "host_threads_available": cores}, out
 
 
 # ------------------------------------------------------------------------------------------------ main
