@@ -81,3 +81,22 @@ def test_float_to_decimal_kats(kats):
     for fa, da_exp, e_exp in kats["append_float_to_decimal"]:
         da, e = vdecimal.append_float_to_decimal([gofloat(s) for s in fa])
         assert e == e_exp and da.tolist() == da_exp, fa
+
+
+def test_encoder_payloads_are_as_small_as_the_reference_encoders(oracle):
+    """MarshalValues through the library's writer (Huffman-only zstd frames) vs the reference algorithm with its own libzstd
+    at the reference's levels (encoding.go:371): same MarshalType, and no more than 3 % larger on any value kind"""
+    import blockgen
+    if not oracle.lib().vmo_zstd_ref_available():
+        pytest.skip("oracle/_ref (the reference's libzstd) was not built")
+    rng = np.random.default_rng(31)
+    for kind in ("counter", "counter_smooth", "gauge", "gauge_small", "counter_resets", "counter_big"):
+        ref = ours = 0
+        for _ in range(6):
+            v = blockgen.gen_values(rng, kind, 8192)
+            od, omt, ofirst = oracle.marshal_int64_array(v, 64)
+            pd, pmt, pfirst = encoding.marshal_values(v, 64)
+            assert (pmt, pfirst) == (omt, ofirst), kind
+            ref += od.size
+            ours += pd.size
+        assert ours <= 1.03 * ref, (kind, ours, ref)
