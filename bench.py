@@ -4,6 +4,9 @@
 Workload (BASELINE.json configs[1], the configuration `metric` is quoted on for one GPU):
   decode 100 000 blocks (8192 samples each; timestamps delta-const, values ZSTD nearest-delta2 counters at scale -2,
   rare resets) + rate(m[5m]) at step 15 s  ->  [100 000 x 8172] float64.
+The blocks are marshaled by the REFERENCE encoder (oracle restatement of marshalInt64Array + the reference's own libzstd
+1.5.7 at getCompressLevel): the bytes a vmstorage part holds.  `--encoder library` marshals the same values with the
+library's own encoder instead (reported beside the default as `alt_encoder`).
 One "step" = one pass of the hot path over that batch.  N > 1: every rank owns its own 100 000 blocks (series shard by
 TSID, no data-path collective) -> weak scaling.
 
@@ -12,7 +15,11 @@ TSID, no data-path collective) -> weak scaling.
           host memory, decode, rollup, D2H of the result, all inside the timed region
   roofline : the dominant kernel stage, algorithmic bytes / measured stage time vs MEASURED_PEAKS.json
   cpu_baseline : the oracle (C++ restatement of the Go path, zstd through the reference's own libzstd when
-          oracle/_ref is present) on all host cores over a bounded sample of the same blocks  (rank 0, N = 1)
+          oracle/_ref is present) on a persistent pool of host threads over the SAME blocks  (rank 0, N = 1)
+  aggr  : sum(rate(m[5m])) by (label) into 8 and 1024 groups; N > 1: the per-GPU partial states are merged by the
+          library's own NCCL all-reduce (vmb_comm_*), no Python in the data path
+  configs2 : (N = 1) BASELINE.json configs[2] and the north-star size: 1 M series x 8192 samples on one GPU --
+          rate() over counters, avg/max/quantile_over_time(0.99) over gauges
 
   --impl reference : times the reference's CPU implementation of the path (see cpu_baseline) on the same config.
 """
@@ -33,6 +40,7 @@ sys.path.insert(0, ROOT)
 T0 = 1_700_000_000_000
 SCRAPE_MS = 15000
 SCALE = -2
+KIND_ID = {"counter": 0, "gauge": 1, "mixed": 2}
 
 
 def parse_args():
@@ -50,83 +58,155 @@ def parse_args():
     ap.add_argument("--kind", default="counter", choices=["counter", "gauge", "mixed"],
                     help="synthetic values: counter = configs[1] (default), gauge = configs[2]-style round(N(5000,300)) at "
                          "scale -2, mixed = configs[4]-style 40%% counters / 30%% gauges / 20%% const / 10%% delta-const")
+    ap.add_argument("--encoder", default="reference", choices=["reference", "library"],
+                    help="who marshals the synthetic blocks: reference = oracle marshalInt64Array + the reference's libzstd 1.5.7 "
+                         "(what a vmstorage part holds); library = the product's own encoder (Huffman-only zstd frames)")
     ap.add_argument("--window-ms", type=int, default=300_000)
     ap.add_argument("--step-ms", type=int, default=15_000)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--aggr", default="", help="configs[4] variant: aggr(func(m[d])) by (label) with an NCCL all-reduce of the "
-                                               "per-GPU partial states, e.g. --aggr sum (the host-buffer arm folds on the GPU too and returns [groups x points])")
+    ap.add_argument("--no-aggr", action="store_true", help="skip the sum(rate) by (label) sub-record")
+    ap.add_argument("--no-alt-encoder", action="store_true", help="skip the library-encoded run reported beside the default")
+    ap.add_argument("--configs2-series", type=int, default=-1,
+                    help="series of the configs[2] sub-record (1 M x 8192 on one GPU); -1 = 1 000 000 at N = 1 with the default "
+                         "workload, 0 = off")
+    ap.add_argument("--parity-series", type=int, default=1000, help="series of the timed batch compared with the oracle (rank 0)")
+    ap.add_argument("--aggr", default="", help="run ONLY aggr(func(m[d])) by (label) as the main record, e.g. --aggr sum")
     ap.add_argument("--groups", type=int, default=1000, help="label groups for --aggr")
-    ap.add_argument("--cpu-seconds", type=float, default=24.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=2.0, help="minimum wall time of the cpu_baseline measurement (0 = skip)")
     return ap.parse_args()
 
 
+# ------------------------------------------------------------------------------------------------ oracle side (input + CPU arm)
+def oracle():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    L = O.lib()
+    if not getattr(L, "_bench_sigs", False):
+        vp, sz = C.c_void_p, C.c_size_t
+        L.vmo_pool_create.restype = vp
+        L.vmo_pool_create.argtypes = [C.c_int]
+        L.vmo_pool_destroy.restype = None
+        L.vmo_pool_destroy.argtypes = [vp]
+        L.vmo_pool_threads.argtypes = [vp]
+        L.vmo_pool_eval_rollup.restype = C.c_int
+        L.vmo_pool_eval_rollup.argtypes = [vp, vp, sz, O.u8p, C.c_int64, C.c_int64, C.POINTER(O.RollupCfg), C.c_int, C.c_int, O.f64p,
+                                           C.POINTER(C.c_uint64), C.c_int]
+        L.vmo_pool_gen_blocks.restype = C.c_int64
+        L.vmo_pool_gen_blocks.argtypes = [vp, C.c_int, C.c_int, sz, sz, C.c_uint64, C.c_int64, C.c_int64, C.c_int16, vp, O.u8p, sz,
+                                          C.POINTER(C.c_uint64)]
+        L.vmo_pool_gen_values.restype = C.c_int
+        L.vmo_pool_gen_values.argtypes = [vp, C.c_int, sz, sz, sz, C.c_uint64, O.i64p]
+        L._bench_sigs = True
+    return O, L
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def numa_layout():
+    out = []
+    try:
+        base = "/sys/devices/system/node"
+        for n in sorted(d for d in os.listdir(base) if d.startswith("node") and d[4:].isdigit()):
+            with open(os.path.join(base, n, "cpulist")) as f:
+                out.append("%s: cpus %s" % (n, f.read().strip()))
+    except Exception:
+        pass
+    return "; ".join(out) or "unknown"
+
+
+_POOLS = {}
+
+
+def get_pool(nthreads):
+    """persistent worker pool of the oracle (created once, outside every timed region)"""
+    O, L = oracle()
+    if nthreads not in _POOLS:
+        _POOLS[nthreads] = C.c_void_p(L.vmo_pool_create(nthreads))
+    return _POOLS[nthreads]
+
+
 # ------------------------------------------------------------------------------------------------ synthetic input
-GEN_STATS = {"series": 0, "series_with_drop": 0, "rows": 0, "rows_from_first_drop": 0}
-RCR_FUNCS = ("rate", "increase", "irate", "increase_pure", "increase_prometheus", "rate_prometheus", "rollup_rate", "rollup_increase")
-
-
-def gen_blocks(nblocks, rows, seed, chunk=4000, kind="counter", ts_kind="regular"):
-    """node_cpu_seconds_total-like counters, marshaled by the product's own encoder
-    (vmb_marshal_columns).  -> (descs structured array, payload np.uint8)"""
+def gen_blocks(nblocks, rows, seed, kind="counter", ts_kind="regular", encoder="reference"):
+    """node_cpu_seconds_total-like counters / gauges / the configs[4] mix, generated and marshaled
+    series by series on host threads (oracle/cpu_pipeline.cpp vmo_pool_gen_blocks).
+    -> (descs structured array, payload np.uint8, stats dict)"""
     from victoriametrics_b200 import encoding, storage
-    rng = np.random.default_rng(seed)
-    ts = T0 + SCRAPE_MS * np.arange(rows, dtype=np.int64)
-    tdata, tmt, tfirst = encoding.marshal_timestamps(ts)
-    assert tmt == encoding.MarshalTypeDeltaConst
-    pieces = [tdata]
-    pos = tdata.size
-    cols = {k: [] for k in ("first_value", "val_off", "val_size", "val_mt", "ts_off", "ts_size", "ts_mt", "min_ts", "max_ts")}
-    for c0 in range(0, nblocks, chunk):
-        n = min(chunk, nblocks - c0)
-        inc = rng.integers(0, 1501, (n, rows), dtype=np.int64)
-        inc[:, 0] += rng.integers(0, 10 ** 9, n)
-        v = np.cumsum(inc, axis=1)
-        resets = rng.random((n, rows)) < 1e-4
-        resets[:, 0] = False
-        base = np.maximum.accumulate(np.where(resets, v, 0), axis=1)
-        v -= base
-        if kind != "counter":
-            g = np.rint(rng.normal(5000.0, 300.0, (n, rows))).astype(np.int64)
-            if kind == "gauge":
-                v = g
-            else:  # mixed: series i takes its kind from i mod 10
-                k = (np.arange(c0, c0 + n) % 10)[:, None]
-                const = np.broadcast_to(rng.integers(0, 10 ** 6, (n, 1)), (n, rows))
-                dconst = rng.integers(0, 10 ** 6, (n, 1)) + rng.integers(1, 100, (n, 1)) * np.arange(rows, dtype=np.int64)[None, :]
-                v = np.where(k < 4, v, np.where(k < 7, g, np.where(k < 9, const, dconst)))
-        GEN_STATS["series"] += n
-        dropped = np.diff(v, axis=1) < 0
-        has = dropped.any(axis=1)
-        GEN_STATS["series_with_drop"] += int(np.count_nonzero(has))
-        GEN_STATS["rows"] += n * rows
-        # removeCounterResets touches a series from the 128-row group of its first value drop on
-        GEN_STATS["rows_from_first_drop"] += int((rows - ((np.argmax(dropped, axis=1)[has] + 1) & ~127)).sum())
-        if ts_kind == "jitter":  # every series has its own scrape jitter of +-50 ms (SURVEY.md 8d config 2 variant)
-            tj = ts[None, :] + rng.integers(-50, 51, (n, rows))
-            tp_, toffs, tmts, tfirsts = encoding.marshal_columns(tj)
-            pieces.append(tp_)
-            cols["ts_off"].append(toffs[:-1] + pos)
-            cols["ts_size"].append(np.diff(toffs).astype(np.uint32))
-            cols["ts_mt"].append(tmts)
-            cols["min_ts"].append(tfirsts)
-            cols["max_ts"].append(tj[:, -1].copy())
-            pos += tp_.size
-        payload, offs, mts, firsts = encoding.marshal_columns(v)
-        pieces.append(payload)
-        cols["first_value"].append(firsts)
-        cols["val_off"].append(offs[:-1] + pos)
-        cols["val_size"].append(np.diff(offs).astype(np.uint32))
-        cols["val_mt"].append(mts)
-        pos += payload.size
-    tcols = dict(min_ts=tfirst, max_ts=int(ts[-1]), ts_off=0, ts_size=tdata.size, ts_mt=tmt)
-    if ts_kind == "jitter":
-        tcols = {k: np.concatenate(cols[k]) for k in ("min_ts", "max_ts", "ts_off", "ts_size", "ts_mt")}
-    descs = storage.descs_from_arrays(
-        first_value=np.concatenate(cols["first_value"]), val_off=np.concatenate(cols["val_off"]),
-        val_size=np.concatenate(cols["val_size"]), rows=np.full(nblocks, rows, dtype=np.uint32),
-        series_idx=np.arange(nblocks, dtype=np.uint32), scale=SCALE, val_mt=np.concatenate(cols["val_mt"]), precision_bits=64,
-        **tcols)
-    return descs, np.concatenate(pieces)
+    O, L = oracle()
+    pool = get_pool(host_threads())
+    stats = (C.c_uint64 * 4)()
+    if encoder == "reference":
+        if not L.vmo_zstd_ref_available():
+            raise RuntimeError("oracle/_ref/libzstd_ref.so is missing: build it in the container that holds /root/reference "
+                               "(python -c 'import __graft_entry__ as g; g.build()'), or run with --encoder library")
+        descs = np.zeros(nblocks, dtype=storage.DESC_DTYPE)
+        per_row = 3 * (2 if ts_kind == "jitter" else 1)
+        while True:
+            cap = nblocks * rows * per_row + (1 << 20)
+            payload = np.empty(cap, dtype=np.uint8)
+            n = L.vmo_pool_gen_blocks(pool, KIND_ID[kind], 1 if ts_kind == "jitter" else 0, nblocks, rows, seed, T0, SCRAPE_MS, SCALE,
+                                      descs.ctypes.data, payload.ctypes.data_as(O.u8p), cap, stats)
+            if n == -101 and per_row < 40:  # VMO_ERR_CAP
+                per_row *= 2
+                continue
+            if n < 0:
+                raise RuntimeError("vmo_pool_gen_blocks failed: %d" % n)
+            break
+        payload = payload[:n]
+    else:
+        # the same values (same per-series RNG streams), marshaled by the product's own encoder through its C ABI
+        ts = T0 + SCRAPE_MS * np.arange(rows, dtype=np.int64)
+        tdata, tmt, tfirst = encoding.marshal_timestamps(ts)
+        pieces, pos = [tdata], tdata.size
+        cols = {k: [] for k in ("first_value", "val_off", "val_size", "val_mt", "ts_off", "ts_size", "ts_mt", "min_ts", "max_ts")}
+        rng = np.random.default_rng(seed)
+        chunk = 4000
+        for c0 in range(0, nblocks, chunk):
+            n = min(chunk, nblocks - c0)
+            v = np.empty((n, rows), dtype=np.int64)
+            rc = L.vmo_pool_gen_values(pool, KIND_ID[kind], c0, n, rows, seed, v.ctypes.data_as(O.i64p))
+            assert rc == 0, rc
+            if ts_kind == "jitter":
+                tj = ts[None, :] + rng.integers(-50, 51, (n, rows))
+                tp_, toffs, tmts, tfirsts = encoding.marshal_columns(tj)
+                pieces.append(tp_)
+                cols["ts_off"].append(toffs[:-1] + pos)
+                cols["ts_size"].append(np.diff(toffs).astype(np.uint32))
+                cols["ts_mt"].append(tmts)
+                cols["min_ts"].append(tfirsts)
+                cols["max_ts"].append(tj[:, -1].copy())
+                pos += tp_.size
+            p_, offs, mts, firsts = encoding.marshal_columns(v)
+            pieces.append(p_)
+            cols["first_value"].append(firsts)
+            cols["val_off"].append(offs[:-1] + pos)
+            cols["val_size"].append(np.diff(offs).astype(np.uint32))
+            cols["val_mt"].append(mts)
+            pos += p_.size
+            dropped = np.diff(v, axis=1) < 0
+            has = dropped.any(axis=1)
+            stats[1] += int(np.count_nonzero(has))
+            stats[3] += int((rows - ((np.argmax(dropped, axis=1)[has] + 1) & ~127)).sum())
+        stats[0], stats[2] = nblocks, nblocks * rows
+        tcols = dict(min_ts=tfirst, max_ts=int(ts[-1]), ts_off=0, ts_size=tdata.size, ts_mt=tmt)
+        if ts_kind == "jitter":
+            tcols = {k: np.concatenate(cols[k]) for k in ("min_ts", "max_ts", "ts_off", "ts_size", "ts_mt")}
+        descs = storage.descs_from_arrays(
+            first_value=np.concatenate(cols["first_value"]), val_off=np.concatenate(cols["val_off"]),
+            val_size=np.concatenate(cols["val_size"]), rows=np.full(nblocks, rows, dtype=np.uint32),
+            series_idx=np.arange(nblocks, dtype=np.uint32), scale=SCALE, val_mt=np.concatenate(cols["val_mt"]), precision_bits=64,
+            **tcols)
+        payload = np.concatenate(pieces)
+    st = {"series": int(stats[0]), "series_with_drop": int(stats[1]), "rows": int(stats[2]), "rows_from_first_drop": int(stats[3])}
+    return descs, payload, st
+
+
+def compressed_bytes(descs, ts_kind):
+    return int(descs["val_size"].sum()) + (int(descs["ts_size"].sum()) if ts_kind == "jitter" else int(descs["ts_size"][0]))
 
 
 def query_range(rows, window_ms, step_ms):
@@ -134,6 +214,8 @@ def query_range(rows, window_ms, step_ms):
     end = T0 + SCRAPE_MS * (rows - 1)
     return start, end, step_ms
 
+
+RCR_FUNCS = ("rate", "increase", "irate", "increase_pure", "increase_prometheus", "rate_prometheus", "rollup_rate", "rollup_increase")
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
@@ -233,66 +315,100 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference(descs, payload, func, start, end, step, window, target_seconds, repeats=1):
-    """the oracle's threaded per-series loop (oracle/cpu_pipeline.cpp) on a bounded sample -> dict"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    from rollup_names import RF
-    from victoriametrics_b200 import promql
-    L = O.lib()
-    fn = L.vmo_cpu_eval_rollup
-    fn.restype = C.c_int
-    fn.argtypes = [C.c_void_p, C.c_size_t, O.u8p, C.c_int64, C.c_int64, C.POINTER(O.RollupCfg), C.c_int, C.c_int, O.f64p,
-                   C.POINTER(C.c_uint64), C.c_int, C.c_int]
-    rc = promql.get_rollup_configs(func, start, end, step, window)
-    phis = np.full(rc.points, 0.99) if func == "quantile_over_time" else None  # kept alive by this frame
-    cfg = O.RollupCfg(RF[func], start, end, step, window, 0, 0, int(rc.MayAdjustWindow), int(rc.isDefaultRollup),
-                      rc.samplesScannedPerCall, phis.ctypes.data_as(O.f64p) if phis is not None else None, None)
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
-    P = rc.points
-    rows = int(descs["rows"][0])
-    kind = "reference" if L.vmo_zstd_ref_available() else "port"
+class CpuArm:
+    """the oracle's per-series loop (oracle/cpu_pipeline.cpp) over ALL blocks of the batch on a persistent pool of host
+    threads: Results.RunParallel + the closure of evalRollupNoIncrementalAggregate (netstorage.go:221, eval.go:1855)"""
 
-    def run(nb, out, nthreads=None):
+    def __init__(self, descs, payload, func, start, end, step, window):
+        from rollup_names import RF
+        from victoriametrics_b200 import promql
+        self.O, self.L = oracle()
+        O = self.O
+        self.descs, self.payload = descs, payload
+        self.rc = promql.get_rollup_configs(func, start, end, step, window)
+        self.phis = np.full(self.rc.points, 0.99) if func == "quantile_over_time" else None
+        self.cfg = O.RollupCfg(RF[func], start, end, step, window, 0, 0, int(self.rc.MayAdjustWindow), int(self.rc.isDefaultRollup),
+                               self.rc.samplesScannedPerCall, self.phis.ctypes.data_as(O.f64p) if self.phis is not None else None, None)
+        self.P = self.rc.points
+        self.rows = int(descs["rows"][0])
+        self.kind = "reference" if self.L.vmo_zstd_ref_available() else "port"
+        self.out = None
+
+    def alloc_out(self, nb):
+        if self.out is None or self.out.shape[0] < nb:
+            self.out = np.empty((nb, self.P), dtype=np.float64)
+            self.out.fill(0.0)  # touch the pages outside the timed region (the Go code reuses pooled buffers)
+        return self.out
+
+    def run(self, nthreads, nb=None, descs=None, out=None):
+        """one pass over the first nb blocks on the pool of `nthreads` threads -> seconds"""
+        d = self.descs if descs is None else descs
+        nb = len(d) if nb is None else nb
+        out = self.alloc_out(nb) if out is None else out
+        pool = get_pool(nthreads)
         scanned = C.c_uint64(0)
         t = time.perf_counter()
-        r = fn(descs.ctypes.data, nb, payload.ctypes.data_as(O.u8p), -(1 << 63), (1 << 63) - 1, C.byref(cfg),
-               int(rc.removeCounterResets), int(rc.dropStaleNaNs), out.ctypes.data_as(O.f64p), C.byref(scanned),
-               nthreads or cores, 1)
+        r = self.L.vmo_pool_eval_rollup(pool, d.ctypes.data, nb, self.payload.ctypes.data_as(self.O.u8p), -(1 << 63), (1 << 63) - 1,
+                                        C.byref(self.cfg), int(self.rc.removeCounterResets), int(self.rc.dropStaleNaNs),
+                                        out.ctypes.data_as(self.O.f64p), C.byref(scanned), 1)
         dt = time.perf_counter() - t
         assert r == 0, r
         return dt
 
-    nb0 = min(len(descs), max(cores * 8, 256))
-    out0 = np.empty((nb0, P), dtype=np.float64)
-    out0.fill(0.0)  # touch the pages outside the timed region (the Go code reuses pooled buffers)
-    run(nb0, out0)  # warm-up
-    dt0 = run(nb0, out0)
-    rate0 = nb0 * rows / dt0
-    wall_target = max(0.2, target_seconds / cores)  # target_seconds of CPU work spread over all cores, >= 0.2 s of wall
-    nb = int(wall_target * rate0 / rows)
-    nb = max(nb0, min(nb, len(descs)))
-    out = np.empty((nb, P), dtype=np.float64)
-    out.fill(0.0)
-    # one software thread per hardware thread is not always the fastest on a hyper-threaded host: also try one per two and
-    # report whichever is faster (the baseline gets the benefit of the doubt)
-    tried = {}
-    for nt in ([cores, cores // 2] if cores >= 16 else [cores]):
-        for _ in range(max(repeats, 2)):
-            dt = run(nb, out, nt)
-            tried[nt] = min(tried.get(nt, dt), dt)
-    used = min(tried, key=tried.get)
-    best = tried[used]
-    return {"value": nb * rows / best, "unit": "samples/s", "cores": used, "kind": kind,
-            "sample": "%d of %d blocks x %d rows, %.2f s wall on %d threads (C++ restatement of the Go path%s)%s" %
-                      (nb, len(descs), rows, best, used, "; zstd via the reference's libzstd 1.5.7" if kind == "reference" else "",
-                       "; thread counts tried: " + ", ".join("%d -> %.2f s" % (k, v) for k, v in sorted(tried.items())) if len(tried) > 1 else ""),
-            "seconds": best, "blocks": nb, "host_threads_available": cores}, out
+    def pick_threads(self):
+        """one software thread per hardware thread is not always the fastest on a hyper-threaded host: try one per two as well
+        (two untimed passes each, the second one counts) and keep the faster -- the baseline gets the benefit of the doubt"""
+        cores = host_threads()
+        tried = {}
+        for nt in ([cores, cores // 2] if cores >= 16 else [cores]):
+            self.run(nt)
+            tried[nt] = self.run(nt)
+        return min(tried, key=tried.get), tried
 
+    def measure(self, steps=None, min_wall=2.0, nthreads=None, tried=None):
+        """-> dict: `steps` whole passes (or as many as fill min_wall seconds, at least 2) timed back to back"""
+        if nthreads is None:
+            nthreads, tried = self.pick_threads()
+        nb = len(self.descs)
+        times = []
+        t_all = time.perf_counter()
+        while True:
+            times.append(self.run(nthreads))
+            if steps is not None and len(times) >= steps:
+                break
+            if steps is None and len(times) >= 2 and time.perf_counter() - t_all >= min_wall:
+                break
+        wall = time.perf_counter() - t_all
+        per = wall / len(times)
+        return {"value": nb * self.rows / per, "unit": "samples/s", "cores": nthreads, "kind": self.kind,
+                "sample": "all %d blocks x %d rows, %d passes back to back in %.2f s wall (%.3f s per pass; min %.3f, max %.3f) on a "
+                          "persistent pool of %d threads (C++ restatement of the Go path%s)" %
+                          (nb, self.rows, len(times), wall, per, min(times), max(times), nthreads,
+                           "; zstd via the reference's libzstd 1.5.7" if self.kind == "reference" else ""),
+                "seconds": wall, "passes": len(times), "ms_per_pass": per * 1e3, "blocks": nb,
+                "host_threads_available": host_threads(),
+                "thread_counts_tried_s_per_pass": {str(k): round(v, 4) for k, v in sorted((tried or {}).items())},
+                "numa": numa_layout()}
+
+
+def parity_check(arm, out_rows_fn, nseries, seed=7):
+    """full-size parity: `nseries` random series of the timed batch through the oracle (CPU) against the GPU result rows.
+    out_rows_fn(idx) -> np.float64[len(idx), P] (rows of the GPU result).  1e-12 relative like tests/ (north_star: 1e-9)."""
+    nb = len(arm.descs)
+    idx = np.sort(np.random.default_rng(seed).choice(nb, size=min(nseries, nb), replace=False))
+    sub = np.ascontiguousarray(arm.descs[idx])
+    exp = np.empty((len(idx), arm.P), dtype=np.float64)
+    arm.run(min(host_threads(), 32), descs=sub, out=exp)
+    got = out_rows_fn(idx)
+    both_nan = np.isnan(got) & np.isnan(exp)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rel = np.abs(got - exp) / np.maximum(np.abs(exp), 1e-300)
+    rel[both_nan] = 0.0
+    rel[(got == exp)] = 0.0
+    rel[np.isnan(rel)] = np.inf  # NaN on one side only
+    worst = float(rel.max()) if rel.size else 0.0
+    return {"series": int(len(idx)), "points": int(arm.P), "max_rel_err": worst, "tolerance": 1e-12, "ok": bool(worst <= 1e-12),
+            "nan_points": int(both_nan.sum())}
 
 # ------------------------------------------------------------------------------------------------ main
 def main():
@@ -308,32 +424,34 @@ def main():
     if a.ts == "jitter":
         what = what.replace("ts delta-const", "ts zstd nearest-delta2 with +-50 ms jitter")
     workload = (what + " + %s()[%ds] step=%ds per GPU") % (a.blocks, a.rows, SCALE, a.func, a.window_ms // 1000, a.step_ms // 1000)
+    enc_note = {"reference": "reference encoder: marshalInt64Array restated by the oracle + the reference's own libzstd 1.5.7 at "
+                             "getCompressLevel (what a vmstorage part holds)",
+                "library": "the library's own encoder (vmb_marshal_columns: Huffman-only zstd frames)"}[a.encoder]
     base = {"metric": "rollup samples/sec (block decode + %s, raw samples decoded and scanned per second)" % a.func,
             "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64 codec -> f64 rollup", "data": "synthetic",
             "config": {"workload": workload, "blocks_per_gpu": a.blocks, "rows_per_block": a.rows, "points_per_series": int(points),
+                       "encoder": enc_note,
                        "parallelism": "series sharded by TSID across %d GPU(s), no data-path collective" % a.gpus,
-                       "l2": "inputs (>=1.3 GB compressed, 13 GB decoded) exceed the 126 MB L2; no flush needed"}}
+                       "l2": "inputs (>=1.3 GB compressed, 6.5 GB result) exceed the 126 MB L2; no flush needed"}}
 
     if a.impl == "reference":
         if rank != 0:
             return 0
-        descs, payload = gen_blocks(min(a.blocks, 20000), a.rows, seed=1234, kind=a.kind, ts_kind=a.ts)
-        vals = []
-        for _ in range(a.warmup):
-            cpu_reference(descs, payload, a.func, start, end, step, a.window_ms, 2.0)
         t_all = time.perf_counter()
-        last = None
-        for _ in range(a.steps):
-            last, _ = cpu_reference(descs, payload, a.func, start, end, step, a.window_ms, a.cpu_seconds / max(a.steps, 1) + 1.0)
-            vals.append(last["value"])
-        v = float(np.median(vals))
+        descs, payload, _ = gen_blocks(a.blocks, a.rows, seed=1234, kind=a.kind, ts_kind=a.ts, encoder=a.encoder)
+        arm = CpuArm(descs, payload, a.func, start, end, step, a.window_ms)
+        nt, tried = arm.pick_threads()  # 2 untimed passes per thread count: they are warm-up passes too
+        for _ in range(max(0, a.warmup - 2 * len(tried))):
+            arm.run(nt)
+        m = arm.measure(steps=a.steps, nthreads=nt, tried=tried)
         out = dict(base)
-        out.update({"impl": "reference", "value": v, "ms_per_step": 1e3 * a.blocks * a.rows / v,
-                    "cpu_baseline": dict(last, value=v), "gpu_launches": 0,
-                    "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        out.update({"impl": "reference", "value": m["value"], "ms_per_step": m["ms_per_pass"],
+                    "cpu_baseline": m, "gpu_launches": 0,
+                    "e2e": {"value": m["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     "wall_s": time.perf_counter() - t_all})
-        out["config"]["note"] = "CPU reference arm: each step is a bounded sample of the workload; value = samples/s on all host cores"
+        out["config"]["note"] = ("CPU reference arm: every step is one whole pass over the same %d blocks on a persistent thread pool; "
+                                 "ms_per_step is measured (wall of the %d timed passes / %d)" % (a.blocks, a.steps, a.steps))
         print(json.dumps(out))
         return 0
 
@@ -349,10 +467,10 @@ def main():
     ctx.set_stream(stream.cuda_stream)
 
     t_gen = time.perf_counter()
-    descs, payload = gen_blocks(a.blocks, a.rows, seed=1234 + rank, kind=a.kind, ts_kind=a.ts)
+    descs, payload, gstats = gen_blocks(a.blocks, a.rows, seed=1234 + rank, kind=a.kind, ts_kind=a.ts, encoder=a.encoder)
     gen_s = time.perf_counter() - t_gen
     rows_total = int(a.blocks) * int(a.rows)
-    compressed = int(descs["val_size"].sum()) + (int(descs["ts_size"].sum()) if a.ts == "jitter" else int(descs["ts_size"][0]))
+    compressed = compressed_bytes(descs, a.ts)
 
     blocks = storage.Blocks(descs, payload, ctx)
     out_dev = torch.empty((a.blocks, points), dtype=torch.float64, device="cuda")
@@ -363,39 +481,66 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def time_steps(fn, warmup, steps):
+        """W untimed + K timed calls of fn bracketed by barrier + synchronize; CUDA events on the launching stream -> ms per step
+        (this rank), launches, wall-clock window"""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tb = time.time()
+        e0.record(stream)
+        r = None
+        for _ in range(steps):
+            r = fn()
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1) / steps, ctx.launch_count - l0, (tb, time.time()), r
+
+    def max_over_ranks(*xs):
+        t = torch.tensor([float(x) for x in xs], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
     func_args = np.full(points, 0.99) if a.func == "quantile_over_time" else None  # quantile_over_time(0.99, m[d])
 
     def dev_step():
         return promql.eval_rollup_func(a.func, blocks, start, end, step, a.window_ms, args=func_args, out_dev_ptr=out_dev.data_ptr())
 
-    if a.aggr:
-        # sum(rate(m[5m])) by (label): every rank folds its own series into [groups x points] partial states, one NCCL
-        # all-reduce of values and one of counts merges them, every rank finalizes
-        rc_aggr = promql.get_rollup_configs(a.func, start, end, step, a.window_ms)
-        group_ids = ((np.arange(a.blocks, dtype=np.int64) * world + rank) % a.groups).astype(np.uint32)
+    # aggr(rollup) by (label): every rank folds its own series into [groups x points] partial states; N > 1: merged by an
+    # NCCL all-reduce of values and counts (SURVEY.md 8e); every rank finalizes; the [groups x points] result goes to the host
+    rc_aggr = promql.get_rollup_configs(a.func, start, end, step, a.window_ms)
 
-        class Buf:
-            def __init__(self, nbytes):
-                self.t = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
-                self.ptr = self.t.data_ptr()
-        ia = promql.IncrementalAggr(a.aggr, a.groups, points, Buf)
+    class Buf:
+        def __init__(self, nbytes):
+            self.t = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+            self.ptr = self.t.data_ptr()
+
+    def make_aggr(aggr, groups):
+        group_ids = ((np.arange(a.blocks, dtype=np.int64) * world + rank) % groups).astype(np.uint32)
+        ia = promql.IncrementalAggr(aggr, groups, points, Buf)
         reduce_cb = (lambda v, c, op: promql.torch_all_reduce(v.t, c.t, op)) if world > 1 else None
-        h_aggr = _lib.lib().vmb_host_alloc(a.groups * points * 8)
-        assert h_aggr, "pinned host allocation failed"
-        aggr_host = np.ctypeslib.as_array(C.cast(h_aggr, C.POINTER(C.c_double)), shape=(a.groups, points))
+        h = _lib.lib().vmb_host_alloc(groups * points * 8)
+        assert h, "pinned host allocation failed"
+        res = np.ctypeslib.as_array(C.cast(h, C.POINTER(C.c_double)), shape=(groups, points))
 
-        def dev_step():  # noqa: F811
+        def aggr_step():
             scanned_ = ia.update_blocks(blocks, rc_aggr, group_ids)
-            ia.finalize(ctx, all_reduce=reduce_cb, out=aggr_host)  # D2H of the [groups x points] query result included
+            ia.finalize(ctx, all_reduce=reduce_cb, out=res)  # D2H of the [groups x points] query result included
             return None, scanned_
+        return aggr_step, ia, reduce_cb, group_ids, res
+
+    main_step = dev_step
+    if a.aggr:
+        main_step, ia, reduce_cb, group_ids, aggr_host = make_aggr(a.aggr, a.groups)
         base["metric"] = "rollup samples/sec (block decode + %s(%s) by label, raw samples decoded and scanned per second)" % (a.aggr, a.func)
         base["config"]["workload"] = workload.replace("configs[1]", "configs[4]-style") + "; %s by %d groups" % (a.aggr, a.groups)
         base["config"]["parallelism"] = ("series sharded by TSID across %d GPU(s); per-GPU partial [groups x points] states merged by "
                                          "NCCL all-reduce (values: %s, counts: sum)" % (a.gpus, promql.ALLREDUCE_OP[a.aggr]))
 
     # ---- kernel-only: compressed blocks resident in HBM
-    for _ in range(a.warmup):
-        dev_step()
     pci = None
     try:
         pr = torch.cuda.get_device_properties(local_rank)
@@ -421,25 +566,23 @@ def main():
         pass
     sampler = ClockSampler(local_rank, pci)
     sampler.start()
-    barrier()
-    l0 = ctx.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tb = time.time()
-    ev0.record(stream)
-    scanned = 0
-    for _ in range(a.steps):
-        _, scanned = dev_step()
-    ev1.record(stream)
-    barrier()
-    te = time.time()
-    launches = ctx.launch_count - l0
-    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms_step, launches, (tb, te), last = time_steps(main_step, a.warmup, a.steps)
+    scanned = last[1]
     clocks = sampler.window(tb, te)
     # per-stage device times of one extra step (CUDA events inside the library, same stream)
     ctx.enable_stage_timing(True)
-    dev_step()
+    main_step()
     stage_ms = ctx.stage_ms()
     ctx.enable_stage_timing(False)
+
+    # ---- full-size parity: sampled series of the timed batch against the oracle (rank 0)
+    parity = None
+    arm = None
+    if rank == 0 and a.parity_series > 0 and not a.aggr:
+        arm = CpuArm(descs, payload, a.func, start, end, step, a.window_ms)
+        dev_step()
+        parity = parity_check(arm, lambda idx: out_dev[torch.from_numpy(idx).cuda()].cpu().numpy(), a.parity_series)
+        assert parity["ok"], parity
 
     # ---- e2e: host buffers in, host result out
     e2e = None
@@ -465,37 +608,74 @@ def main():
                                                     a.window_ms, args=func_args, out=h_out, ctx=ctx)
             return promql.eval_rollup_func_host(a.func, h_descs, h_payload, start, end, step, a.window_ms, args=func_args,
                                                 out=h_out, nseries=a.blocks, ctx=ctx)
-        for _ in range(max(1, min(a.warmup, 2))):
-            host_step()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tw = time.perf_counter()
-        tb2 = time.time()
-        e0.record(stream)
-        for _ in range(a.steps):
-            host_step()
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - tw
-        e2e_clocks = sampler.window(tb2, time.time())
-        e2e_ms = max(e0.elapsed_time(e1), 0.0)
-        e2e = {"ms": e2e_ms, "wall_ms": wall * 1e3, "h2d": int(descs.nbytes + payload.size), "d2h": int(nbytes_out)}
+        e2e_ms_step, _, (tb2, te2), _ = time_steps(host_step, max(1, min(a.warmup, 2)), a.steps)
+        e2e_clocks = sampler.window(tb2, te2)
+        e2e = {"ms": e2e_ms_step, "h2d": int(descs.nbytes + payload.size), "d2h": int(nbytes_out)}
         if a.aggr:  # same query result as the device-resident arm (chunk-wise folding only reorders float additions)
             assert np.allclose(h_out, aggr_host, rtol=1e-9, atol=0, equal_nan=True)
         else:
             check = float(np.nansum(h_out[: min(a.blocks, 64)]))
             dcheck = float(torch.nansum(out_dev[: min(a.blocks, 64)]).item())
             assert abs(check - dcheck) <= 1e-9 * max(1.0, abs(dcheck)), (check, dcheck)
+        for p_ in (hp, ho, hd):
+            _lib.lib().vmb_host_free(p_)
+
+    # ---- sub-record: sum(rate(m[5m])) by (label), 8 and 1024 groups (configs[3] shape at this batch size)
+    aggr_rec = None
+    if not a.no_aggr and not a.aggr:
+        aggr_rec = {}
+        for groups in (8, 1024):
+            fn, _ia, _cb, _g, res = make_aggr("sum", groups)
+            ms_, launches_, _, _ = time_steps(fn, 2, max(3, min(a.steps, 5)))
+            ms_, = max_over_ranks(ms_)
+            aggr_rec["sum_by_%d_groups" % groups] = {
+                "value": world * rows_total / (ms_ / 1e3), "unit": "samples/s", "ms_per_step": ms_, "gpu_launches_per_step": launches_ / max(3, min(a.steps, 5)),
+                "result": "[%d x %d] f64 finalized on every rank, copied to pinned host memory inside the timed region" % (groups, points),
+                "collective": ("NCCL all-reduce of {values, counts}[%d x %d] f64 across %d ranks" % (groups, points, world)) if world > 1 else "none (one GPU)"}
+            del fn, _ia, res
 
     sampler.stop()
-    # ---- max over ranks
-    t = torch.tensor([dev_ms, e2e["ms"] if e2e else 0.0, e2e["wall_ms"] if e2e else 0.0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e_wall_ms = [float(x) for x in t.tolist()]
+    dev_ms_step, e2e_ms_step = max_over_ranks(dev_ms_step, e2e["ms"] if e2e else 0.0)
+
+    # ---- sub-record: the library-encoded input beside the default (same values, other zstd frames)
+    alt = None
+    if rank == 0 and world == 1 and not a.no_alt_encoder and not a.aggr:
+        other = "library" if a.encoder == "reference" else "reference"
+        try:
+            nalt = min(a.blocks, 20000)
+            d2, p2, _ = gen_blocks(nalt, a.rows, seed=1234 + rank, kind=a.kind, ts_kind=a.ts, encoder=other)
+            d1 = np.ascontiguousarray(descs[:nalt])
+            b1 = storage.Blocks(d1, payload, ctx)
+            b2 = storage.Blocks(d2, p2, ctx)
+            res = {}
+            for name, bl in ((a.encoder, b1), (other, b2)):
+                fn = lambda bl=bl: promql.eval_rollup_func(a.func, bl, start, end, step, a.window_ms, args=func_args, out_dev_ptr=out_dev.data_ptr())
+                ms_, _, _, _ = time_steps(fn, 2, 5)
+                ctx.enable_stage_timing(True)
+                fn()
+                st_ = ctx.stage_ms()
+                ctx.enable_stage_timing(False)
+                res[name] = {"ms_per_step": ms_, "value": nalt * a.rows / (ms_ / 1e3), "zstd_stage_ms": round(st_[0], 4)}
+            res["blocks"] = nalt
+            res["bytes_per_sample"] = {a.encoder: round(compressed_bytes(d1, a.ts) / (nalt * a.rows), 3),
+                                       other: round(compressed_bytes(d2, a.ts) / (nalt * a.rows), 3)}
+            alt = res
+            b1.close()
+            b2.close()
+        except Exception as e:
+            alt = {"failed": repr(e)}
+
+    # ---- sub-record: configs[2] / north-star size, 1 M series x 8192 on one GPU, chunked by 100 000 blocks
+    c2 = None
+    n2 = a.configs2_series
+    if n2 < 0:
+        n2 = 1_000_000 if (world == 1 and a.kind == "counter" and a.func == "rate" and a.blocks == 100_000 and a.ts == "regular") else 0
+    if rank == 0 and world == 1 and n2 > 0 and not a.aggr:
+        c2 = run_configs2(a, ctx, n2, out_dev, time_steps, start, end, step, points)
 
     if rank == 0:
-        ms_per_step = dev_ms / a.steps
+        ms_per_step = dev_ms_step
         value = world * rows_total / (ms_per_step / 1e3)
         peaks = {}
         try:
@@ -505,13 +685,13 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
         varint_bytes = int(2 * rows_total) * (2 if a.ts == "jitter" else 1)  # ~2 B/sample zig-zag varints per zstd column
-        drop_frac = (GEN_STATS["rows_from_first_drop"] / max(GEN_STATS["rows"], 1)) if a.func in RCR_FUNCS else 0.0
+        drop_frac = (gstats["rows_from_first_drop"] / max(gstats["rows"], 1)) if a.func in RCR_FUNCS else 0.0
         stage_names = ["zstd", "column_decode", "series_preamble", "rollup", "aggregate"]
         stage_bytes = [compressed + varint_bytes,                          # zstd: read frames, write varint bytes
                        varint_bytes + 64 * a.blocks + rows_total * 16,     # decode: read varints + descs, write ts+val
                        int(rows_total * 16 * drop_frac),                   # preamble: read+write values from the first value drop
                                                                            # of a series on (removeCounterResets); the rest is skipped
-                       rows_total * 16 + a.blocks * points * 8, 0]         # rollup: read ts+val, write result
+                       rows_total * 8 * (2 if a.ts == "jitter" else 1) + a.blocks * points * 8, 0]  # rollup: read val (+ts), write result
         stages = {}
         for n_, ms_, b_ in zip(stage_names, stage_ms, stage_bytes):
             if ms_ > 0:
@@ -520,38 +700,49 @@ def main():
 
         def traffic_of(stage):
             """dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernel from the committed `ncu --set full`
-            capture (profiles/r01/traffic.json: bytes per launch at 20 000 blocks, rate workload), scaled to this launch"""
-            try:
-                t = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))
-                if a.func != t["func"] or a.rows != t["rows"]:
-                    return None
-                return int(t["bytes_per_launch"][stage] * (a.blocks / t["blocks"]))
-            except Exception:
-                return None
+            capture (profiles/*/traffic.json: bytes per launch at 20 000 blocks, rate workload), scaled to this launch"""
+            for rnd in ("r02", "r01"):
+                try:
+                    t = json.load(open(os.path.join(ROOT, "profiles", rnd, "traffic.json")))
+                    if a.func != t["func"] or a.rows != t["rows"] or stage not in t["bytes_per_launch"]:
+                        continue
+                    return int(t["bytes_per_launch"][stage] * (a.blocks / t["blocks"])), "profiles/%s/traffic.json (ncu --set full capture of a %d-block run, scaled; not measured by this run)" % (rnd, t["blocks"])
+                except Exception:
+                    continue
+            return None, None
         fused_bytes = compressed + a.blocks * points * 8
         out = dict(base)
         out.update({"value": value, "ms_per_step": ms_per_step, "gpu_launches": int(launches), "clocks": clocks,
                     "samples_scanned_per_step": int(scanned)})
         if dom:
             ach = stages[dom]["GBps"]
+            tr, tr_src = traffic_of(dom)
             out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                               "traffic": traffic_of(dom), "peak_source": peak_src, "stages": stages,
+                               "traffic": tr, "traffic_source": tr_src, "peak_source": peak_src, "stages": stages,
                                "whole_step": {"fused_algorithmic_GB": round(fused_bytes / 1e9, 3),
                                               "GBps": round(fused_bytes / 1e9 / (ms_per_step / 1e3), 1),
                                               "frac": round(fused_bytes / 1e9 / (ms_per_step / 1e3) / peak, 4)}}
         out["decode_GBps_decoded_basis"] = round(rows_total * 16 / 1e9 / ((stage_ms[0] + stage_ms[1]) / 1e3), 1) if stage_ms[1] > 0 else None
         if e2e:
-            per = e2e_ms / a.steps
+            per = e2e_ms_step
             out["e2e"] = {"value": world * rows_total / (per / 1e3), "unit": "samples/s", "ms_per_step": per,
-                          "wall_ms_per_step": e2e_wall_ms / a.steps, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                          "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                           "api": (("vmb_eval_rollup_aggr_host_partial + NCCL all-reduce + vmb_aggr_finalize" if world > 1 else
                                    "vmb_eval_rollup_aggr_host") + " (pinned host descriptors+payload in, [groups x points] result out)"
                                   if a.aggr else "vmb_eval_rollup_host (pinned host descriptors+payload in, pinned host result out)"),
                           "clocks": e2e_clocks}
+        if parity:
+            out["parity_check"] = parity
+        if aggr_rec:
+            out["aggr"] = aggr_rec
+        if alt:
+            out["alt_encoder"] = alt
+        if c2:
+            out["configs2"] = c2
         out["config"]["compressed_bytes_per_gpu"] = compressed
         out["config"]["bytes_per_sample_compressed"] = round(compressed / rows_total, 3)
         out["config"]["input_generation_s"] = round(gen_s, 1)
-        out["config"]["series_with_a_counter_reset"] = round(GEN_STATS["series_with_drop"] / max(GEN_STATS["series"], 1), 3)
+        out["config"]["series_with_a_counter_reset"] = round(gstats["series_with_drop"] / max(gstats["series"], 1), 3)
         out["config"]["host_affinity"] = ("GPU-local NUMA node, %d CPUs" % numa_cpus) if numa_cpus else "unchanged"
         if affinity0:
             try:
@@ -560,8 +751,8 @@ def main():
                 pass
         if world == 1 and a.cpu_seconds > 0:
             try:
-                cb, _ = cpu_reference(descs, payload, a.func, start, end, step, a.window_ms, a.cpu_seconds)
-                out["cpu_baseline"] = cb
+                arm = arm or CpuArm(descs, payload, a.func, start, end, step, a.window_ms)
+                out["cpu_baseline"] = arm.measure(min_wall=a.cpu_seconds)
             except Exception as e:  # the oracle is optional for the product; report instead of failing the bench
                 out["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
         print(json.dumps(out))
@@ -569,6 +760,52 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def run_configs2(a, ctx, nseries, out_dev, time_steps, start, end, step, points):
+    """BASELINE.json configs[2] + the north-star size on ONE GPU: nseries x rows samples resident in HBM as compressed blocks
+    (chunks of a.blocks series, the [chunk x points] result buffer is reused: the result of 1 M series is 65 GB), rate() over
+    counters and avg/max/quantile_over_time(0.99) over gauges.  One step = one pass over all chunks."""
+    import torch
+    from victoriametrics_b200 import promql, storage
+    rec = {"series": nseries, "rows_per_series": a.rows, "chunk_series": a.blocks, "window_s": a.window_ms // 1000, "step_s": a.step_ms // 1000,
+           "note": "compressed blocks of all series resident in HBM; result written chunk by chunk into one reused [chunk x points] buffer"}
+    phis = np.full(points, 0.99)
+    for kind, funcs in (("counter", ["rate"]), ("gauge", ["avg_over_time", "max_over_time", "quantile_over_time"])):
+        t0 = time.perf_counter()
+        chunks, comp = [], 0
+        first = None
+        for c0 in range(0, nseries, a.blocks):
+            n = min(a.blocks, nseries - c0)
+            d, p, _ = gen_blocks(n, a.rows, seed=777 + c0, kind=kind, ts_kind="regular", encoder=a.encoder)
+            comp += compressed_bytes(d, "regular")
+            chunks.append(storage.Blocks(d, p, ctx))
+            if first is None:
+                first = (d, p)
+            del d, p
+        gen_s = time.perf_counter() - t0
+        for func in funcs:
+            args = phis if func == "quantile_over_time" else None
+
+            def fn():
+                r = None
+                for bl in chunks:
+                    r = promql.eval_rollup_func(func, bl, start, end, step, a.window_ms, args=args,
+                                                out_dev_ptr=out_dev.data_ptr())
+                return r
+            ms_, launches_, _, _ = time_steps(fn, 1, 2)
+            r = {"value": nseries * a.rows / (ms_ / 1e3), "unit": "samples/s", "ms_per_step": ms_, "gpu_launches_per_step": launches_ / 2,
+                 "values": kind, "compressed_GB": round(comp / 1e9, 2), "input_generation_and_upload_s": round(gen_s, 1)}
+            # parity of the first chunk (its result is recomputed last)
+            promql.eval_rollup_func(func, chunks[0], start, end, step, a.window_ms, args=args, out_dev_ptr=out_dev.data_ptr())
+            arm = CpuArm(first[0], first[1], func, start, end, step, a.window_ms)
+            r["parity_check"] = parity_check(arm, lambda idx: out_dev[torch.from_numpy(idx).cuda()].cpu().numpy(), 200)
+            assert r["parity_check"]["ok"], (func, r["parity_check"])
+            rec[func] = r
+        for bl in chunks:
+            bl.close()
+        del chunks, first
+    return rec
 
 
 if __name__ == "__main__":

@@ -319,15 +319,19 @@ def test_config4_mixed_codec_increase_1h_step60(oracle):
 
 
 @pytest.mark.gpu
-def test_full_block_size_properties_20k_blocks(oracle):
-    """size-independent properties at a bench-like size (20 000 blocks x 8192 rows through the product's own encoder):
+@pytest.mark.parametrize("encoder", ["reference", "library"])
+def test_full_block_size_properties_20k_blocks(oracle, encoder):
+    """size-independent properties at a bench-like size (20 000 blocks x 8192 rows; blocks marshaled by the reference encoder
+    -- oracle marshalInt64Array + the reference's libzstd 1.5.7 -- and by the library's own):
     (1) host pipeline == device path bit for bit; (2) rate >= 0 wherever defined (counter resets removed);
-    (3) 16 sampled series == oracle within 1e-12; (4) samplesScanned closed form"""
+    (3) 1000 sampled series == oracle (CPU pipeline of bench.py's reference arm) within 1e-12; (4) samplesScanned closed form"""
     import torch
     import victoriametrics_b200 as vm
     import bench
     nb, rows = 20_000, 8192
-    descs, payload = bench.gen_blocks(nb, rows, seed=77)
+    if encoder == "reference" and not oracle.lib().vmo_zstd_ref_available():
+        pytest.skip("oracle/_ref/libzstd_ref.so not built")
+    descs, payload, _ = bench.gen_blocks(nb, rows, seed=77, encoder=encoder)
     start, end, step = bench.query_range(rows, 300000, 15000)
     P = 1 + (end - start) // step
     B = vm.storage.Blocks(descs, payload)
@@ -339,15 +343,6 @@ def test_full_block_size_properties_20k_blocks(oracle):
     d = dev.cpu().numpy()
     assert np.array_equal(f64bits(d), f64bits(host))
     assert not np.isnan(d).any() and (d >= 0).all() and np.isfinite(d).all()
-    # sampled series against the oracle (decode with the oracle's own zstd decoder)
-    rc = vm.promql.get_rollup_configs("rate", start, end, step, 300000)
-    ts = bench.T0 + bench.SCRAPE_MS * np.arange(rows, dtype=np.int64)
-    for s in np.linspace(0, nb - 1, 16).astype(int):
-        dd = descs[s]
-        src = payload[int(dd["val_off"]):int(dd["val_off"]) + int(dd["val_size"])]
-        r, iv = oracle.unmarshal_int64_array(src, int(dd["val_mt"]), int(dd["first_value"]), rows)
-        assert r == 0
-        fv = oracle.decimal_to_float(iv, int(dd["scale"]))
-        oracle.lib().vmo_remove_counter_resets(fv.ctypes.data_as(oracle.f64p), ts.ctypes.data_as(oracle.i64p), rows, 0)
-        exp, _ = oracle.rollup_do(RF["rate"], fv, ts, start, end, step, 300000, may_adjust_window=True, samples_scanned_per_call=2)
-        assert np.allclose(d[s], exp, rtol=1e-12, atol=0), s
+    arm = bench.CpuArm(descs, payload, "rate", start, end, step, 300000)
+    res = bench.parity_check(arm, lambda idx: d[idx], 1000)
+    assert res["ok"] and res["series"] == 1000, res
