@@ -57,6 +57,12 @@ int vmb_ctx_set_stream(vmb_ctx* ctx, void* stream);
 /* storage.SetDedupInterval lib/storage/dedup.go:15 (-dedup.minScrapeInterval), in ms; 0 (default) = off.  Applied by every
  * block-decoding entry point after the series are assembled (netstorage.go:611 DeduplicateSamples). */
 int vmb_ctx_set_dedup_interval(vmb_ctx* ctx, int64_t interval_ms);
+/* The one-call device paths (vmb_eval_rollup_device, vmb_eval_rollup_aggr_device) run series that qualify -- one block,
+ * MarshalTypeDeltaConst timestamps at precisionBits 64 -- through one fused kernel per batch: decode into shared memory,
+ * removeCounterResets and rollupConfig.Do without materialising the decoded columns (the per-series shape of eval.go:1855-1866).
+ * Everything else takes the kernel-per-stage pipeline.  enable = 0 forces that pipeline for every series (default: 1; the
+ * environment variable VMB_NO_FUSED sets the default to 0).  Results are bit-identical either way. */
+int vmb_ctx_set_fused(vmb_ctx* ctx, int enable);
 int vmb_ctx_synchronize(vmb_ctx* ctx);
 const char* vmb_last_error(void);
 int vmb_version(void);
@@ -289,7 +295,8 @@ void* vmb_host_alloc(size_t bytes);
 void vmb_host_free(void* p);
 
 /* timing hooks: elapsed device time (ms) of the named stage during the last batched call on this ctx;
- * stage: 0 = zstd, 1 = column decode, 2 = series preamble, 3 = rollup, 4 = aggregate */
+ * stage: 0 = zstd, 1 = column decode, 2 = series preamble, 3 = rollup, 4 = aggregate, 5 = fused decode+rollup kernel
+ * (with the fused kernel on, stage 1 is the whole un-fused sub-batch of the series it did not take, stages 2-3 are 0) */
 float vmb_ctx_last_stage_ms(const vmb_ctx* ctx, int stage);
 int vmb_ctx_enable_stage_timing(vmb_ctx* ctx, int enable);
 

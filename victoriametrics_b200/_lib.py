@@ -65,6 +65,7 @@ def lib():
         "vmb_ctx_destroy": (None, [vp]),
         "vmb_ctx_set_stream": (C.c_int, [vp, vp]),
         "vmb_ctx_synchronize": (C.c_int, [vp]),
+        "vmb_ctx_set_fused": (C.c_int, [vp, C.c_int]),
         "vmb_last_error": (C.c_char_p, []),
         "vmb_version": (C.c_int, []),
         "vmb_ctx_launch_count": (C.c_uint64, [vp]),
@@ -167,11 +168,15 @@ class Context:
     def launch_count(self):
         return int(lib().vmb_ctx_launch_count(self.h))
 
+    def set_fused(self, on=True):
+        """vmb_ctx_set_fused: fused decode+rollup kernel for the series that qualify (default on)"""
+        check(lib().vmb_ctx_set_fused(self.h, int(on)))
+
     def enable_stage_timing(self, on=True):
         check(lib().vmb_ctx_enable_stage_timing(self.h, int(on)))
 
     def stage_ms(self):
-        return [float(lib().vmb_ctx_last_stage_ms(self.h, i)) for i in range(5)]
+        return [float(lib().vmb_ctx_last_stage_ms(self.h, i)) for i in range(6)]
 
     def close(self):
         if self.h:

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "decode.cu"
 #include "rollup.cu"
+#include "fused.cu"
 #include "zstd.cu"
 #include "marshal.inc"
 
@@ -67,11 +68,13 @@ struct vmb_ctx {
     cudaStream_t stream = 0;
     uint64_t launches = 0;
     bool timing = false;
-    float stage_ms[5] = {0, 0, 0, 0, 0};
+    float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[6] = {0, 0, 0, 0, 0, 0};
     // scratch (reused across calls)
     DevBuf zseq;  // decoded zstd sequences (8 B each) between k_zstd_seq_decode and k_zstd_seq_exec
     DevBuf zscratch, zlit, zstatus, zjobs, zws, args1, args2, rolled, counters, tmp_out, grp, mheap, mnext;
+    DevBuf bail, sub_arrays;  // fused path: series handed to the un-fused pipeline, and that sub-batch's arrays
+    bool fused = true;           // vmb_ctx_set_fused: series that qualify go through the fused decode+rollup kernel (fused.cu)
     int64_t dedup_interval = 0;  // storage.SetDedupInterval (lib/storage/dedup.go:15), ms; 0 = deduplication off
     struct vmb_series* col_cache = nullptr;  // decoded columns of the one-call device paths, sized for the largest batch seen
     void* h_pinned = nullptr;  // small pinned staging area for counters
@@ -98,6 +101,12 @@ struct vmb_blocks {
     uint32_t* d_bad_list = nullptr;
     uint32_t* d_ser_first = nullptr;
     uint32_t* d_ser_nblocks = nullptr;
+    // fused path (fused.cu): series the fused kernel may take (one block, delta-const timestamps at precisionBits 64, a known
+    // values MarshalType), the others, and host copies of what a sub-batch for the un-fused pipeline is built from
+    uint32_t* d_fused_list = nullptr;
+    std::vector<uint32_t> h_fused, h_unfused, h_ser_first, h_ser_nblocks;
+    std::vector<vmb_block_desc> h_descs;
+    std::vector<ColInfo> h_cols;
 };
 
 struct vmb_series {
@@ -116,6 +125,7 @@ struct vmb_series {
 };
 
 static inline void count_launch(vmb_ctx* c, int n = 1) { c->launches += (uint64_t)n; }
+static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // ------------------------------------------------------------------------------------------------ context
 extern "C" int vmb_ctx_create(int device, vmb_ctx** out) {
@@ -139,6 +149,7 @@ extern "C" int vmb_ctx_create(int device, vmb_ctx** out) {
     }
     vmb_ctx* c = new vmb_ctx();
     c->device = device;
+    c->fused = getenv("VMB_NO_FUSED") == nullptr;  // A/B switch for profiles
     for (int i = 0; i < 6; i++) CU(cudaEventCreate(&c->ev[i]));
     CU(cudaHostAlloc(&c->h_pinned, 4096, cudaHostAllocDefault));
     *out = c;
@@ -152,7 +163,7 @@ extern "C" void vmb_ctx_destroy(vmb_ctx* c) {
     if (c->col_cache) vmb_series_free(c->col_cache);
     c->col_cache = nullptr;
     DevBuf* bufs[] = {&c->zscratch, &c->zlit, &c->zstatus, &c->zjobs, &c->zws, &c->args1, &c->args2, &c->rolled,
-                      &c->counters, &c->tmp_out, &c->grp, &c->mheap, &c->mnext, &c->zseq};
+                      &c->counters, &c->tmp_out, &c->grp, &c->mheap, &c->mnext, &c->zseq, &c->bail, &c->sub_arrays};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 6; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -170,6 +181,11 @@ extern "C" int vmb_ctx_set_dedup_interval(vmb_ctx* c, int64_t interval_ms) {
     c->dedup_interval = interval_ms;
     return VMB_OK;
 }
+extern "C" int vmb_ctx_set_fused(vmb_ctx* c, int enable) {
+    if (!c) return VMB_ERR_INVALID_ARG;
+    c->fused = enable != 0;
+    return VMB_OK;
+}
 extern "C" int vmb_ctx_synchronize(vmb_ctx* c) {
     if (!c) return VMB_ERR_INVALID_ARG;
     CU(cudaSetDevice(c->device));
@@ -178,7 +194,7 @@ extern "C" int vmb_ctx_synchronize(vmb_ctx* c) {
 }
 extern "C" uint64_t vmb_ctx_launch_count(const vmb_ctx* c) { return c ? c->launches : 0; }
 extern "C" float vmb_ctx_last_stage_ms(const vmb_ctx* c, int stage) {
-    return (c && stage >= 0 && stage < 5) ? c->stage_ms[stage] : 0.f;
+    return (c && stage >= 0 && stage < 6) ? c->stage_ms[stage] : 0.f;
 }
 extern "C" int vmb_ctx_enable_stage_timing(vmb_ctx* c, int enable) {
     if (!c) return VMB_ERR_INVALID_ARG;
@@ -347,6 +363,7 @@ extern "C" void vmb_blocks_free(vmb_blocks* b) {
     cudaFree(b->d_bad_list);
     cudaFree(b->d_ser_first);
     cudaFree(b->d_ser_nblocks);
+    cudaFree(b->d_fused_list);
     delete b;
 }
 extern "C" size_t vmb_blocks_count(const vmb_blocks* b) { return b ? b->nblocks : 0; }
@@ -357,29 +374,67 @@ extern "C" uint64_t vmb_blocks_compressed_bytes(const vmb_blocks* b) { return b 
 struct BlocksPlan {
     std::vector<ColInfo> cols;
     std::vector<uint64_t> row_off;
-    std::vector<uint32_t> huf, gen, bad, ser_first, ser_nblocks;
+    std::vector<uint32_t> huf, gen, bad, ser_first, ser_nblocks, fused, unfused;
     std::vector<uint64_t> ser_merge_off;
     uint64_t rows = 0, compressed = 0, scratch_total = 0, merge_rows = 0, seq_total = 0;
     bool needs_lit = false;
 };
-static int plan_blocks(BlocksPlan& pl, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload, size_t payload_len) {
-    pl.cols.resize(2 * nblocks);
+// row layout of the decoded blocks, the series map and the merge area: needs the descriptors only
+static void plan_layout(BlocksPlan& pl, const vmb_block_desc* descs, size_t nblocks) {
     pl.row_off.resize(nblocks + 1);
-    uint64_t scratch = 0;
+    pl.rows = 0;
+    pl.ser_first.clear();
+    pl.ser_nblocks.clear();
     for (size_t b = 0; b < nblocks; b++) {
         const vmb_block_desc& d = descs[b];
         pl.row_off[b] = pl.rows;
         pl.rows += d.rows <= 16384 ? d.rows : 0;  // invalid blocks get status VMB_ERR_ROWS in the kernel and occupy no rows
-        pl.compressed += (uint64_t)d.ts_size + d.val_size;
-        if ((uint64_t)d.ts_off + d.ts_size > payload_len || (uint64_t)d.val_off + d.val_size > payload_len) {
-            vmb_set_error("block %zu: payload range outside the arena (len %zu)", b, payload_len);
-            return VMB_ERR_INVALID_ARG;
-        }
         if (b == 0 || d.series_idx != descs[b - 1].series_idx) {
             pl.ser_first.push_back((uint32_t)b);
             pl.ser_nblocks.push_back(1);
         } else {
             pl.ser_nblocks.back()++;
+        }
+    }
+    pl.row_off[nblocks] = pl.rows;
+    // Multi-block series (netstorage.go:566 mergeSortBlocks): lay the decoded blocks of a series out in min-timestamp order,
+    // whatever order they arrived in.  When consecutive blocks are strictly disjoint in time the series is then the plain
+    // concatenation of its blocks; otherwise (overlap, touching ranges, replicas) it is merged on the GPU into the merge
+    // area behind the decoded blocks.
+    pl.ser_merge_off.assign(pl.ser_first.size(), UINT64_MAX);
+    pl.merge_rows = 0;
+    std::vector<uint32_t> order;
+    for (size_t s = 0; s < pl.ser_first.size(); s++) {
+        const uint32_t fb = pl.ser_first[s], nb = pl.ser_nblocks[s];
+        if (nb < 2) continue;
+        order.resize(nb);
+        for (uint32_t k = 0; k < nb; k++) order[k] = fb + k;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return descs[a].min_ts < descs[b].min_ts; });
+        uint64_t r = pl.row_off[fb], total = 0;
+        bool overlap = false;
+        for (uint32_t k = 0; k < nb; k++) {
+            const vmb_block_desc& d = descs[order[k]];
+            const uint64_t rows = d.rows <= 16384 ? d.rows : 0;
+            pl.row_off[order[k]] = r + total;
+            total += rows;
+            if (k + 1 < nb && d.max_ts >= descs[order[k + 1]].min_ts) overlap = true;
+        }
+        if (overlap) {
+            pl.ser_merge_off[s] = pl.merge_rows;
+            pl.merge_rows += total;
+        }
+    }
+}
+
+static int plan_blocks(BlocksPlan& pl, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload, size_t payload_len) {
+    pl.cols.resize(2 * nblocks);
+    uint64_t scratch = 0;
+    for (size_t b = 0; b < nblocks; b++) {
+        const vmb_block_desc& d = descs[b];
+        pl.compressed += (uint64_t)d.ts_size + d.val_size;
+        if ((uint64_t)d.ts_off + d.ts_size > payload_len || (uint64_t)d.val_off + d.val_size > payload_len) {
+            vmb_set_error("block %zu: payload range outside the arena (len %zu)", b, payload_len);
+            return VMB_ERR_INVALID_ARG;
         }
         for (int which = 0; which < 2; which++) {
             ColInfo& ci = pl.cols[2 * b + which];
@@ -414,33 +469,16 @@ static int plan_blocks(BlocksPlan& pl, const vmb_block_desc* descs, size_t nbloc
             else pl.gen.push_back(col);
         }
     }
-    pl.row_off[nblocks] = pl.rows;
     pl.scratch_total = scratch;
-    // Multi-block series (netstorage.go:566 mergeSortBlocks): lay the decoded blocks of a series out in min-timestamp order,
-    // whatever order they arrived in.  When consecutive blocks are strictly disjoint in time the series is then the plain
-    // concatenation of its blocks; otherwise (overlap, touching ranges, replicas) it is merged on the GPU into the merge
-    // area behind the decoded blocks.
-    pl.ser_merge_off.assign(pl.ser_first.size(), UINT64_MAX);
-    std::vector<uint32_t> order;
+    plan_layout(pl, descs, nblocks);
+    // series the fused kernel (fused.cu) may take: one block, timestamps MarshalTypeDeltaConst at precisionBits 64, a values
+    // column it decodes; what it meets at run time beyond that (corrupt streams, staleness markers, ...) comes back on its bail list
     for (size_t s = 0; s < pl.ser_first.size(); s++) {
-        const uint32_t fb = pl.ser_first[s], nb = pl.ser_nblocks[s];
-        if (nb < 2) continue;
-        order.resize(nb);
-        for (uint32_t k = 0; k < nb; k++) order[k] = fb + k;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return descs[a].min_ts < descs[b].min_ts; });
-        uint64_t r = pl.row_off[fb], total = 0;
-        bool overlap = false;
-        for (uint32_t k = 0; k < nb; k++) {
-            const vmb_block_desc& d = descs[order[k]];
-            const uint64_t rows = d.rows <= 16384 ? d.rows : 0;
-            pl.row_off[order[k]] = r + total;
-            total += rows;
-            if (k + 1 < nb && d.max_ts >= descs[order[k + 1]].min_ts) overlap = true;
-        }
-        if (overlap) {
-            pl.ser_merge_off[s] = pl.merge_rows;
-            pl.merge_rows += total;
-        }
+        const uint32_t fb = pl.ser_first[s];
+        const vmb_block_desc& d = descs[fb];
+        const bool ok = pl.ser_nblocks[s] == 1 && d.ts_mt == 2 && d.precision_bits >= 64 && d.rows >= 2 && d.rows <= 16384 &&
+                        d.val_mt >= 1 && d.val_mt <= 6 && pl.cols[2 * fb + 1].kind != VMB_ZK_BAD;
+        (ok ? pl.fused : pl.unfused).push_back((uint32_t)s);
     }
     return 0;
 }
@@ -498,7 +536,14 @@ extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size
     TRY(upload_vec(&b->d_ser_first, pl.ser_first, st));
     TRY(upload_vec(&b->d_ser_nblocks, pl.ser_nblocks, st));
     TRY(upload_vec(&b->d_ser_merge_off, pl.ser_merge_off, st));
+    TRY(upload_vec(&b->d_fused_list, pl.fused, st));
 #undef TRY
+    b->h_descs.assign(descs, descs + nblocks);
+    b->h_cols = pl.cols;
+    b->h_ser_first = pl.ser_first;
+    b->h_ser_nblocks = pl.ser_nblocks;
+    b->h_fused = pl.fused;
+    b->h_unfused = pl.unfused;
     CU(cudaStreamSynchronize(st));  // the host vectors go out of scope
     *out = b;
     return VMB_OK;
@@ -582,16 +627,19 @@ static int run_zstd(vmb_ctx* ctx, const vmb_blocks* b, int32_t** d_zstatus_out) 
 }
 
 // runs zstd + column decode + series assembly into `s` (whose buffers are already allocated)
+// zstd_done: the zstd stage of the upload this (sub-)batch belongs to ran already, its status array is d_zstatus_in and block k of
+// `b` is block d_blk_map[k] of that upload
 static int run_decode(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, int64_t tr_min, int64_t tr_max, uint32_t flags,
-                      unsigned int* d_failed) {
+                      unsigned int* d_failed, bool zstd_done = false, int32_t* d_zstatus_in = nullptr,
+                      const uint32_t* d_blk_map = nullptr) {
     cudaStream_t st = ctx->stream;
-    if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
-    int32_t* d_zstatus = nullptr;
-    {
+    if (ctx->timing && !zstd_done) CU(cudaEventRecord(ctx->ev[0], st));
+    int32_t* d_zstatus = d_zstatus_in;
+    if (!zstd_done) {
         int rc = run_zstd(ctx, b, &d_zstatus);
         if (rc) return rc;
     }
-    if (ctx->timing) CU(cudaEventRecord(ctx->ev[1], st));
+    if (ctx->timing && !zstd_done) CU(cudaEventRecord(ctx->ev[1], st));
     DecodeParams D;
     memset(&D, 0, sizeof(D));
     D.descs = b->d_descs;
@@ -599,6 +647,7 @@ static int run_decode(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, int64_t 
     D.payload = b->d_payload;
     D.scratch = (const uint8_t*)ctx->zscratch.p;
     D.zstd_status = d_zstatus;
+    D.blk_map = d_blk_map;
     D.row_off = b->d_row_off;
     D.ts_out = s->d_ts;
     D.val_out = s->d_vals;
@@ -647,7 +696,7 @@ static int run_decode(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, int64_t 
         launch_series_dedup(R, st);
         count_launch(ctx);
     }
-    if (ctx->timing) CU(cudaEventRecord(ctx->ev[2], st));
+    if (ctx->timing && !zstd_done) CU(cudaEventRecord(ctx->ev[2], st));
     CU(cudaGetLastError());
     return 0;
 }
@@ -974,25 +1023,34 @@ static int check_cfg(const vmb_rollup_cfg* cfg, int64_t* points) {
 }
 
 // series preamble + rollup into d_out (device). d_scanned: device u64 accumulator (already zeroed) or nullptr
-static int run_rollup(vmb_ctx* ctx, vmb_series* s, const vmb_rollup_cfg* cfg, int64_t points, double* d_out,
-                      unsigned long long* d_scanned) {
+// the per-point arguments of a rollup config, uploaded into the ctx: dev = *cfg with DEVICE args / args2
+static int upload_cfg_args(vmb_ctx* ctx, const vmb_rollup_cfg* cfg, int64_t points, vmb_rollup_cfg* dev) {
     cudaStream_t st = ctx->stream;
-    RollupParams R;
-    memset(&R, 0, sizeof(R));
-    R.cfg = *cfg;
-    R.cfg.args = nullptr;
-    R.cfg.args2 = nullptr;
+    *dev = *cfg;
+    dev->args = nullptr;
+    dev->args2 = nullptr;
     int rc;
     if (cfg->args) {
         if ((rc = ctx->args1.reserve((size_t)points * 8))) return rc;
         CU(cudaMemcpyAsync(ctx->args1.p, cfg->args, (size_t)points * 8, cudaMemcpyHostToDevice, st));
-        R.cfg.args = (const double*)ctx->args1.p;
+        dev->args = (const double*)ctx->args1.p;
     }
     if (cfg->args2) {
         if ((rc = ctx->args2.reserve((size_t)points * 8))) return rc;
         CU(cudaMemcpyAsync(ctx->args2.p, cfg->args2, (size_t)points * 8, cudaMemcpyHostToDevice, st));
-        R.cfg.args2 = (const double*)ctx->args2.p;
+        dev->args2 = (const double*)ctx->args2.p;
     }
+    return 0;
+}
+
+static int run_rollup(vmb_ctx* ctx, vmb_series* s, const vmb_rollup_cfg* cfg, int64_t points, double* d_out,
+                      unsigned long long* d_scanned, const uint32_t* d_out_rows = nullptr, bool record_events = true) {
+    cudaStream_t st = ctx->stream;
+    RollupParams R;
+    memset(&R, 0, sizeof(R));
+    int rc;
+    if ((rc = upload_cfg_args(ctx, cfg, points, &R.cfg))) return rc;
+    R.out_rows = d_out_rows;
     R.meta = s->d_meta;
     R.ts = s->d_ts;
     R.vals = s->d_vals;
@@ -1022,11 +1080,11 @@ static int run_rollup(vmb_ctx* ctx, vmb_series* s, const vmb_rollup_cfg* cfg, in
     count_launch(ctx);
     if (flags & VMB_RC_DROP_STALE_NANS) s->stale_dropped = true;
     if (flags & VMB_RC_REMOVE_COUNTER_RESETS) s->resets_removed = true;
-    if (ctx->timing) CU(cudaEventRecord(ctx->ev[3], st));
+    if (ctx->timing && record_events) CU(cudaEventRecord(ctx->ev[3], st));
     R.cfg.flags = cfg->flags;
     launch_rollup(R, st);
     count_launch(ctx);
-    if (ctx->timing) CU(cudaEventRecord(ctx->ev[4], st));
+    if (ctx->timing && record_events) CU(cudaEventRecord(ctx->ev[4], st));
     CU(cudaGetLastError());
     return 0;
 }
@@ -1184,6 +1242,192 @@ static int ctx_column_cache(vmb_ctx* ctx, const vmb_blocks* b, vmb_series** out)
     return 0;
 }
 
+// ---- fused path (fused.cu): zstd stage, then ONE kernel per series batch that decodes into shared memory and rolls up; the series
+// it hands back (bail list) and the ones it never takes (multi-block series, other timestamp encodings) go through the un-fused
+// pipeline as a sub-batch that writes the same output rows.
+static void launch_fused(const FusedParams& P, cudaStream_t st) {
+    if (!P.nlist) return;
+    const size_t smem0 = (sizeof(FusedSmem) + 15) & ~(size_t)15;
+#define FUSED_LAUNCH(KERNEL, SMEM)                                                                                \
+    do {                                                                                                          \
+        static int blocks_per_sm = 0;                                                                             \
+        if (!blocks_per_sm) {                                                                                     \
+            cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));               \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, KERNEL, FU_THREADS, (SMEM)) != cudaSuccess || \
+                blocks_per_sm < 1)                                                                                \
+                blocks_per_sm = 1;                                                                                \
+        }                                                                                                         \
+        uint32_t grid = 148u * (uint32_t)blocks_per_sm;                                                           \
+        if (grid > P.nlist) grid = P.nlist;                                                                       \
+        KERNEL<<<grid, FU_THREADS, (SMEM), st>>>(P);                                                              \
+    } while (0)
+    switch (P.cfg.func_id) {  // the value-only functions of BASELINE.json's configs get their own instantiation
+#define FUSED_CASE(F) case F: FUSED_LAUNCH((k_fused_rollup<F>), smem0); break;
+        FUSED_CASE(VMB_RF_RATE)
+        FUSED_CASE(VMB_RF_DELTA)
+        FUSED_CASE(VMB_RF_AVG)
+        FUSED_CASE(VMB_RF_MIN)
+        FUSED_CASE(VMB_RF_MAX)
+        FUSED_CASE(VMB_RF_SUM)
+        FUSED_CASE(VMB_RF_COUNT)
+        FUSED_CASE(VMB_RF_QUANTILE)
+        FUSED_CASE(VMB_RF_DEFAULT_ROLLUP)
+#undef FUSED_CASE
+        default: FUSED_LAUNCH((k_fused_rollup<-1>), smem0); break;
+    }
+#undef FUSED_LAUNCH
+}
+
+static bool fused_enabled(const vmb_ctx* ctx, const vmb_blocks* b, const vmb_rollup_cfg* cfg) {
+    return ctx->fused && !b->h_fused.empty() && ctx->dedup_interval == 0 && !(cfg->flags & VMB_RC_PRE_MASK);
+}
+
+// the un-fused pipeline over the series `sub` (ascending) of an upload whose zstd stage already ran: a sub-batch is built from
+// the host copies of the descriptors, decoded into the ctx's column cache and rolled up into the rows sub[i] of d_out
+static int run_unfused_subset(vmb_ctx* ctx, const vmb_blocks* b, const std::vector<uint32_t>& sub, int32_t* d_zstatus,
+                              int64_t tr_min, int64_t tr_max, const vmb_rollup_cfg* cfg, int64_t points, double* d_out,
+                              unsigned int* d_failed, unsigned long long* d_scanned) {
+    cudaStream_t st = ctx->stream;
+    std::vector<vmb_block_desc> descs;
+    std::vector<ColInfo> cols;
+    std::vector<uint32_t> blk_map;
+    for (size_t i = 0; i < sub.size(); i++) {
+        const uint32_t fb = b->h_ser_first[sub[i]], nb = b->h_ser_nblocks[sub[i]];
+        for (uint32_t k = 0; k < nb; k++) {
+            vmb_block_desc d = b->h_descs[fb + k];
+            d.series_idx = (uint32_t)i;
+            descs.push_back(d);
+            cols.push_back(b->h_cols[2 * (size_t)(fb + k)]);
+            cols.push_back(b->h_cols[2 * (size_t)(fb + k) + 1]);
+            blk_map.push_back(fb + k);
+        }
+    }
+    const size_t cn = descs.size(), cs = sub.size();
+    BlocksPlan pl;
+    plan_layout(pl, descs.data(), cn);
+    // one staging vector -> one upload
+    size_t o_descs = 0;
+    size_t o_cols = al16(o_descs + cn * sizeof(vmb_block_desc));
+    size_t o_rowoff = al16(o_cols + 2 * cn * sizeof(ColInfo));
+    size_t o_sf = al16(o_rowoff + (cn + 1) * sizeof(uint64_t));
+    size_t o_sn = al16(o_sf + cs * 4);
+    size_t o_mo = al16(o_sn + cs * 4);
+    size_t o_map = al16(o_mo + cs * 8);
+    size_t o_rows = al16(o_map + cn * 4);
+    size_t total = al16(o_rows + cs * 4);
+    std::vector<uint8_t> hs(total);
+    memcpy(hs.data() + o_descs, descs.data(), cn * sizeof(vmb_block_desc));
+    memcpy(hs.data() + o_cols, cols.data(), 2 * cn * sizeof(ColInfo));
+    memcpy(hs.data() + o_rowoff, pl.row_off.data(), (cn + 1) * sizeof(uint64_t));
+    memcpy(hs.data() + o_sf, pl.ser_first.data(), cs * 4);
+    memcpy(hs.data() + o_sn, pl.ser_nblocks.data(), cs * 4);
+    memcpy(hs.data() + o_mo, pl.ser_merge_off.data(), cs * 8);
+    memcpy(hs.data() + o_map, blk_map.data(), cn * 4);
+    memcpy(hs.data() + o_rows, sub.data(), cs * 4);
+    int rc;
+    if ((rc = ctx->sub_arrays.reserve(total + 64))) return rc;
+    CU(cudaMemcpyAsync(ctx->sub_arrays.p, hs.data(), total, cudaMemcpyHostToDevice, st));
+    uint8_t* da = (uint8_t*)ctx->sub_arrays.p;
+    vmb_blocks bv;
+    bv.ctx = ctx;
+    bv.nblocks = cn;
+    bv.nseries = cs;
+    bv.rows = pl.rows;
+    bv.merge_rows = pl.merge_rows;
+    bv.d_descs = (vmb_block_desc*)(da + o_descs);
+    bv.d_payload = b->d_payload;
+    bv.d_cols = (ColInfo*)(da + o_cols);
+    bv.d_row_off = (uint64_t*)(da + o_rowoff);
+    bv.d_ser_first = (uint32_t*)(da + o_sf);
+    bv.d_ser_nblocks = (uint32_t*)(da + o_sn);
+    bv.d_ser_merge_off = (uint64_t*)(da + o_mo);
+    vmb_series* cache = nullptr;
+    if ((rc = ctx_column_cache(ctx, &bv, &cache))) return rc;
+    vmb_series view = *cache;
+    view.nseries = cs;
+    view.nblocks = cn;
+    view.rows = pl.rows + pl.merge_rows;
+    view.stale_dropped = view.resets_removed = false;
+    view.pre_applied = 0;
+    rc = run_decode(ctx, &bv, &view, tr_min, tr_max, 0, d_failed, true, d_zstatus, (const uint32_t*)(da + o_map));
+    if (!rc) rc = run_rollup(ctx, &view, cfg, points, d_out, d_scanned, (const uint32_t*)(da + o_rows), false);
+    cudaError_t e = cudaStreamSynchronize(st);  // `hs` goes out of scope
+    if (!rc && e != cudaSuccess) {
+        vmb_set_error("un-fused sub-batch: %s", cudaGetErrorString(e));
+        rc = VMB_ERR_CUDA;
+    }
+    return rc;
+}
+
+// decode + preamble + rollup of an uploaded block set into d_out through the fused kernel.  Synchronises the stream once (the
+// bail count has to reach the host); counters (failed series, samplesScanned) are left in the device accumulators.
+static int eval_fused(vmb_ctx* ctx, const vmb_blocks* b, int64_t tr_min, int64_t tr_max, const vmb_rollup_cfg* cfg, int64_t points,
+                      double* d_out, unsigned int* d_failed, unsigned long long* d_scanned) {
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
+    int32_t* d_zstatus = nullptr;
+    if ((rc = run_zstd(ctx, b, &d_zstatus))) return rc;
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[1], st));
+    const size_t nf = b->h_fused.size();
+    if ((rc = ctx->bail.reserve((nf + 2) * sizeof(uint32_t)))) return rc;
+    unsigned int* d_bail_count = (unsigned int*)ctx->bail.p;
+    uint32_t* d_bail_list = (uint32_t*)ctx->bail.p + 2;
+    CU(cudaMemsetAsync(d_bail_count, 0, 8, st));
+    FusedParams F;
+    memset(&F, 0, sizeof(F));
+    if ((rc = upload_cfg_args(ctx, cfg, points, &F.cfg))) return rc;
+    F.descs = b->d_descs;
+    F.cols = b->d_cols;
+    F.payload = b->d_payload;
+    F.scratch = (const uint8_t*)ctx->zscratch.p;
+    F.zstd_status = d_zstatus;
+    F.ser_list = b->d_fused_list;
+    F.ser_first_block = b->d_ser_first;
+    F.out = d_out;
+    F.scanned = d_scanned;
+    F.bail_list = d_bail_list;
+    F.bail_count = d_bail_count;
+    F.nlist = (uint32_t)nf;
+    F.npoints = (uint32_t)points;
+    F.tr_min = tr_min;
+    F.tr_max = tr_max;
+    launch_fused(F, st);
+    count_launch(ctx);
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[2], st));
+    CU(cudaGetLastError());
+    unsigned int* h_bail = (unsigned int*)((char*)ctx->h_pinned + 64);
+    CU(cudaMemcpyAsync(h_bail, d_bail_count, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::vector<uint32_t> sub(b->h_unfused);
+    if (*h_bail) {
+        const size_t n0 = sub.size();
+        sub.resize(n0 + *h_bail);
+        CU(cudaMemcpy(sub.data() + n0, d_bail_list, (size_t)*h_bail * 4, cudaMemcpyDeviceToHost));
+        std::sort(sub.begin(), sub.end());
+    }
+    if (ctx->timing) {
+        for (int i = 0; i < 6; i++) ctx->stage_ms[i] = 0.f;
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        ctx->stage_ms[0] = ms;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+        ctx->stage_ms[5] = ms;
+    }
+    if (!sub.empty()) {
+        if (ctx->timing) CU(cudaEventRecord(ctx->ev[3], st));
+        if ((rc = run_unfused_subset(ctx, b, sub, d_zstatus, tr_min, tr_max, cfg, points, d_out, d_failed, d_scanned))) return rc;
+        if (ctx->timing) {
+            CU(cudaEventRecord(ctx->ev[4], st));
+            CU(cudaStreamSynchronize(st));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+            ctx->stage_ms[1] = ms;  // the un-fused sub-batch as a whole (decode + preamble + rollup)
+        }
+    }
+    return 0;
+}
+
 extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t tr_min, int64_t tr_max,
                                       const vmb_rollup_cfg* cfg, double* d_out, uint64_t* samples_scanned) {
     if (!ctx || !b || !d_out) return VMB_ERR_INVALID_ARG;
@@ -1191,22 +1435,27 @@ extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t
     int rc = check_cfg(cfg, &points);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
-    vmb_series* cache = nullptr;
-    if ((rc = ctx_column_cache(ctx, b, &cache))) return rc;
-    vmb_series view = *cache;  // shallow view with this batch's logical sizes
-    view.nseries = b->nseries;
-    view.nblocks = b->nblocks;
-    view.rows = b->rows + b->merge_rows;
     if ((rc = ctx->counters.reserve(64))) return rc;
     unsigned int* d_failed = (unsigned int*)ctx->counters.p;
     unsigned long long* d_scanned = (unsigned long long*)((char*)ctx->counters.p + 8);
     CU(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
-    rc = eval_device_async(ctx, b, &view, tr_min, tr_max, cfg, points, d_out, d_failed, d_scanned);
-    if (rc) return rc;
+    if (fused_enabled(ctx, b, cfg)) {
+        if ((rc = eval_fused(ctx, b, tr_min, tr_max, cfg, points, d_out, d_failed, d_scanned))) return rc;
+    } else {
+        vmb_series* cache = nullptr;
+        if ((rc = ctx_column_cache(ctx, b, &cache))) return rc;
+        vmb_series view = *cache;  // shallow view with this batch's logical sizes
+        view.nseries = b->nseries;
+        view.nblocks = b->nblocks;
+        view.rows = b->rows + b->merge_rows;
+        rc = eval_device_async(ctx, b, &view, tr_min, tr_max, cfg, points, d_out, d_failed, d_scanned);
+        if (rc) return rc;
+    }
     CU(cudaMemcpyAsync(ctx->h_pinned, ctx->counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    if (ctx->timing) {
+    if (ctx->timing && !fused_enabled(ctx, b, cfg)) {
         collect_stage_times(ctx, 0, 4, 0);
+        ctx->stage_ms[5] = 0.f;
     }
     if (samples_scanned) *samples_scanned = *(unsigned long long*)((char*)ctx->h_pinned + 8);
     unsigned int failed = *(unsigned int*)ctx->h_pinned;

@@ -199,6 +199,7 @@ struct DecodeParams {
     const uint8_t* payload;
     const uint8_t* scratch;       // zstd output arena
     const int32_t* zstd_status;   // per column (2*nblocks) or nullptr
+    const uint32_t* blk_map;      // sub-batch of a larger upload: block b is block blk_map[b] of the batch zstd_status belongs to
     const uint64_t* row_off;      // per block: first row in the dense columns
     int64_t* ts_out;
     void* val_out;
@@ -222,7 +223,8 @@ __global__ void __launch_bounds__(128) k_decode_columns(DecodeParams P) {
         uint32_t lo = 0, hi = 0;
         if (d.rows == 0 || d.rows > 16384u) rc = VMB_ERR_ROWS;  // block.go:262, block_header.go:233
         if (!rc && P.zstd_status) {
-            int z0 = P.zstd_status[2 * b], z1 = P.zstd_status[2 * b + 1];
+            const uint32_t zb = P.blk_map ? P.blk_map[b] : b;
+            int z0 = P.zstd_status[2 * zb], z1 = P.zstd_status[2 * zb + 1];
             if (z0) rc = z0;
             else if (z1) rc = z1;
         }

@@ -1,0 +1,752 @@
+// Fused series kernel: varint / nearest-delta(2) decode -> decimal->float -> removeCounterResets -> rollupConfig.Do in ONE CTA per
+// series, the decoded column living only in shared memory.
+//
+// Reference shape (one goroutine per series, nothing materialised per batch):
+//   app/vmselect/promql/eval.go:1855-1866   the per-series closure of evalRollupNoIncrementalAggregate
+//   app/vmselect/netstorage/netstorage.go:425  packedTimeseries.Unpack
+//   lib/storage/block.go:250-296            Block.UnmarshalData  (lib/encoding/encoding.go:173 unmarshalInt64Array,
+//                                           nearest_delta2.go:57, nearest_delta.go:53, int.go:182-284)
+//   lib/decimal/decimal.go:100              AppendDecimalToFloat
+//   app/vmselect/promql/rollup.go:921       removeCounterResets
+//   app/vmselect/promql/rollup.go:701-823   rollupConfig.doInternal + the rollup functions
+//
+// What the un-fused pipeline (k_decode_columns -> k_series_assemble -> k_series_prepare -> k_rollup) writes to and re-reads
+// from HBM -- 16 bytes per sample of decoded columns -- never leaves the SM here: per series the kernel reads the varint bytes
+// once (TMA bulk copies into a double-buffered shared-memory stage, completion on an mbarrier) and writes the result row once.
+//
+// Scope: series made of ONE block whose timestamps column is MarshalTypeDeltaConst at precisionBits = 64 (rows sit at
+// t0 + row * dt: no timestamp is ever materialised), inside the query's time range, without staleness markers when they
+// would have to be dropped.  Everything else -- multi-block series, jittered timestamp columns, corrupt input, windows that
+// do not fit the resident rows -- is handed to the un-fused pipeline through a device-side bail list; the host runs it for
+// exactly those series afterwards (same output rows), so every error code and corner case keeps its one implementation.
+//
+// Decode inside the CTA (8 warps, one 512-byte tile each per fill):
+//   1. every lane takes 16 bytes of its warp's tile, finds the varint terminators (bytes < 0x80); counts are scanned over
+//      the warp and over the CTA, which gives every lane the row of its first value;
+//   2. a lane decodes the varints whose terminator lies in its 16 bytes (7-bit groups compacted once per lane, then one
+//      shift-and-mask per value; the bytes of a varint that starts in the previous 16 bytes are carried in), zig-zag decodes
+//      them, stores them raw at their rows and keeps (count, sum, sum of prefix sums);
+//   3. one warp scan + one 8-entry scan over the warps of those triples -- associative under wrapping int64 arithmetic, so
+//      the prefix sums are bit-identical to the sequential Go loop;
+//   4. every lane replays its values with the scanned prefix, converts mantissa -> float64 (decimal.go:100) and overwrites
+//      the raw value in place.
+#pragma once
+
+#define FU_THREADS 256
+#define FU_WARPS 8
+#define FU_CAP 4096                       /* rows of one series resident in shared memory */
+#define FU_TILE 512
+#define FU_FILL (FU_WARPS * FU_TILE)      /* bytes staged per fill */
+#define FU_STAGE (16 + FU_FILL + 16)      /* 16 bytes of the previous tile in front, 16 bytes of padding behind */
+#define FU_MAX_EVENTS 32                  /* counter resets inside one fill handled by the parallel path */
+
+struct FusedParams {
+    const vmb_block_desc* descs;
+    const ColInfo* cols;
+    const uint8_t* payload;
+    const uint8_t* scratch;          // zstd output arena
+    const int32_t* zstd_status;      // per column (2*nblocks) or nullptr
+    const uint32_t* ser_list;        // series handled by this launch
+    const uint32_t* ser_first_block; // per series
+    vmb_rollup_cfg cfg;              // args / args2: DEVICE pointers
+    double* out;                     // [nseries x P]
+    unsigned long long* scanned;
+    uint32_t* bail_list;             // series this kernel could not finish (-> un-fused pipeline)
+    unsigned int* bail_count;
+    uint32_t nlist;
+    uint32_t npoints;
+    int64_t tr_min, tr_max;
+};
+
+namespace {
+
+struct FusedSmem {
+    double val[FU_CAP];
+    alignas(16) uint8_t stage[2][FU_STAGE];
+    unsigned long long mbar[2];
+    unsigned long long w_s1[FU_WARPS], w_s2[FU_WARPS];
+    uint32_t w_cnt[FU_WARPS];
+    double ev_amt[FU_MAX_EVENTS], ev_cum[FU_MAX_EVENTS];
+    uint32_t ev_row[FU_MAX_EVENTS];
+    uint32_t nev;
+    uint32_t flags;  // bit 0: bail, bit 1: slow removeCounterResets pass needed
+    unsigned long long s_part[FU_WARPS];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// waits for the phase with the given parity; a copy that never lands (a driver / addressing fault) traps instead of hanging
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            if ((threadIdx.x & 31) == 0) printf("fused: TMA copy did not land (block %u warp %u parity %u)\n", blockIdx.x, threadIdx.x >> 5, parity);
+            __trap();
+        }
+    }
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion is signalled on the mbarrier (complete_tx)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Resident rows: absolute row r of the series lives at val[fu_swz(r)] -- a ring over FU_CAP rows (sliding the window moves
+// no data) whose low index bits are XOR-swizzled with bits 3..6: the lanes of a warp write / replay runs of ~8 consecutive
+// rows each (stride 64 bytes: two banks without the swizzle, a 16-way conflict), and the points read consecutive rows; both
+// patterns spread over all banks this way.
+#define FU_MASK (FU_CAP - 1)
+__device__ __forceinline__ uint32_t fu_swz(uint32_t row) {
+    row &= FU_MASK;
+    return row ^ ((row >> 3) & 15u);
+}
+struct FuVals {  // read view for the rollup functions: element i is row r + i
+    const double* s;
+    uint32_t r;
+    __device__ __forceinline__ double operator[](uint32_t i) const { return s[fu_swz(r + i)]; }
+    __device__ __forceinline__ FuVals operator+(uint32_t k) const { return FuVals{s, r + k}; }
+    __device__ __forceinline__ FuVals& operator++() { r++; return *this; }
+    __device__ __forceinline__ FuVals operator++(int) { FuVals o = *this; r++; return o; }
+};
+struct FuValsRW {  // read/write by absolute row
+    double* s;
+    __device__ __forceinline__ double& operator[](uint32_t row) const { return s[fu_swz(row)]; }
+};
+struct FuTs {  // timestamps of a MarshalTypeDeltaConst column are never stored: element i is t + i * dt
+    int64_t t, dt;
+    __device__ __forceinline__ int64_t operator[](uint32_t i) const { return t + (int64_t)i * dt; }
+    __device__ __forceinline__ FuTs operator+(uint32_t k) const { return FuTs{t + (int64_t)k * dt, dt}; }
+    __device__ __forceinline__ FuTs& operator++() { t += dt; return *this; }
+    __device__ __forceinline__ FuTs operator++(int) { FuTs o = *this; t += dt; return o; }
+};
+
+__device__ __forceinline__ uint32_t fu_term_mask16(const uint4& c) {
+    return term_mask4(c.x) | (term_mask4(c.y) << 4) | (term_mask4(c.z) << 8) | (term_mask4(c.w) << 12);
+}
+// bits k of a 16-byte group at stream position g0 that lie inside [lo, hi)
+__device__ __forceinline__ uint32_t fu_valid16(int64_t g0, int64_t lo, int64_t hi) {
+    int64_t a = lo - g0, b = hi - g0;
+    a = a < 0 ? 0 : (a > 16 ? 16 : a);
+    b = b < 0 ? 0 : (b > 16 ? 16 : b);
+    if (b <= a) return 0u;
+    return ((1u << b) - 1u) & ~((1u << a) - 1u);
+}
+__device__ __forceinline__ uint32_t compact7(uint32_t w) {
+    return (w & 0x7fu) | ((w & 0x7f00u) >> 1) | ((w & 0x7f0000u) >> 2) | ((w & 0x7f000000u) >> 3);
+}
+
+// getScrapeInterval (rollup.go:871) + getMaxPrevInterval (:899) + the window rules (:719-756) for a series whose rows sit at
+// t0 + row * dt: same float operations as k_series_prepare on twenty equal intervals
+__device__ void fu_prev_interval_window(const vmb_rollup_cfg& rc, uint32_t n, int64_t dt, int64_t* max_prev_out, int64_t* window_out) {
+    int64_t maxPrev = rc.step;
+    if (rc.start < rc.end) {
+        int64_t si = rc.step;
+        if (n >= 2) {
+            uint32_t k = n - 1 > 20 ? 20 : n - 1;
+            double iv = (double)dt;
+            double nn = (double)k;
+            double rank = 0.6 * (nn - 1);
+            double weight = rank - floor(rank);
+            double q = __dadd_rn(__dmul_rn(iv, 1 - weight), __dmul_rn(iv, weight));
+            int64_t sq = (int64_t)q;
+            if (sq > 0) si = sq;
+        }
+        if (si <= 2 * 1000) maxPrev = si + 4 * si;
+        else if (si <= 4 * 1000) maxPrev = si + 2 * si;
+        else if (si <= 8 * 1000) maxPrev = si + si;
+        else if (si <= 16 * 1000) maxPrev = si + si / 2;
+        else if (si <= 32 * 1000) maxPrev = si + si / 4;
+        else maxPrev = si + si / 8;
+    }
+    if (rc.lookback_delta > 0 && maxPrev > rc.lookback_delta) maxPrev = rc.lookback_delta;
+    if (rc.min_staleness_ms > 0 && maxPrev < rc.min_staleness_ms) maxPrev = rc.min_staleness_ms;
+    int64_t window = rc.window;
+    if (window <= 0) {
+        window = rc.step;
+        if ((rc.flags & VMB_RC_MAY_ADJUST_WINDOW) && window < maxPrev) window = maxPrev;
+        if ((rc.flags & VMB_RC_IS_DEFAULT_ROLLUP) && rc.lookback_delta > 0 && window > rc.lookback_delta) window = rc.lookback_delta;
+    }
+    *max_prev_out = maxPrev;
+    *window_out = window;
+}
+
+// one output point from the window edges i, j (absolute rows) of a series whose rows sit at t_org + row * dt (rollup.go:769-819);
+// rows [i-1, j] are resident
+template <int F>
+__device__ __forceinline__ double fu_point(const vmb_rollup_cfg& rc, int64_t window, int64_t max_prev, const double* sval, uint32_t n,
+                                           uint32_t i, uint32_t j, uint32_t p, int64_t t_org, int64_t dt, unsigned long long& scanned) {
+    const int64_t tEnd = rc.start + (int64_t)p * rc.step;
+    const int64_t tStart = tEnd - window;
+    if (j < i) j = i;
+    WinT<FuVals, FuTs> r;
+    r.prevValue = D_NAN;
+    r.prevTimestamp = tStart - max_prev;
+    const int64_t t_im1 = t_org + ((int64_t)i - 1) * dt;
+    if (i < n && i > 0 && t_im1 > r.prevTimestamp) {
+        r.prevValue = sval[fu_swz(i - 1)];
+        r.prevTimestamp = t_im1;
+    }
+    r.values = FuVals{sval, i};
+    r.timestamps = FuTs{t_im1 + dt, dt};
+    r.n = j - i;
+    r.realPrevValue = D_NAN;
+    if (i > 0) {
+        const int64_t curr = r.n > 0 ? t_im1 + dt : tStart;
+        if (rc.lookback_delta == 0 || (curr - t_im1) < rc.lookback_delta) r.realPrevValue = sval[fu_swz(i - 1)];
+    }
+    r.realNextValue = j < n ? sval[fu_swz(j)] : D_NAN;
+    r.currTimestamp = tEnd;
+    r.idx = p;
+    r.window = window;
+    r.args = rc.args;
+    r.args2 = rc.args2;
+    scanned += rc.samples_scanned_per_call > 0 ? (unsigned long long)rc.samples_scanned_per_call : (unsigned long long)r.n;
+    return call_func(F >= 0 ? F : rc.func_id, r);
+}
+
+}  // namespace
+
+template <int F>
+__global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
+    extern __shared__ __align__(16) unsigned char fu_raw[];
+    FusedSmem& S = *reinterpret_cast<FusedSmem*>(fu_raw);
+    const FuValsRW RV{S.val};  // RV[absolute row]
+    const vmb_rollup_cfg& rc = P.cfg;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    unsigned long long scanned_cta = 0;  // this thread's share of samplesScanned over the series the CTA finished
+    uint32_t par0 = 0, par1 = 0;  // mbarrier phase parities of the two stage buffers
+    if (tid == 0) {
+        mbar_init(&S.mbar[0], 1);
+        mbar_init(&S.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    for (uint32_t li = blockIdx.x; li < P.nlist; li += gridDim.x) {
+        __syncthreads();  // the previous series is done with the shared memory
+        const uint32_t s = P.ser_list[li];
+        unsigned long long scanned = 0;  // this series (dropped when the series is handed to the un-fused path)
+        const uint32_t b = P.ser_first_block[s];
+        const vmb_block_desc d = P.descs[b];
+        const uint32_t n = d.rows;
+        bool bail = n < 2u || n > 16384u || d.ts_mt != 2 || d.precision_bits < 64;
+        if (!bail && P.zstd_status) bail = P.zstd_status[2 * b] != 0 || P.zstd_status[2 * b + 1] != 0;
+        // ---- timestamps: MarshalTypeDeltaConst (encoding.go:231) = first + i * dt
+        int64_t dts = 0;
+        if (!bail) {
+            uint32_t used = 0;
+            bail = read_single_varint(P.payload + d.ts_off, d.ts_size, &dts, &used) != 0 || used < d.ts_size;
+        }
+        const int64_t LIM = (int64_t)1 << 30;
+        bail = bail || dts <= 0 || dts >= LIM || (int64_t)(n - 1) * dts >= LIM;
+        const int64_t t_org = d.min_ts;
+        bail = bail || t_org < P.tr_min || t_org + (int64_t)(n - 1) * dts > P.tr_max;  // rows trimmed by the time range: un-fused path
+        int64_t max_prev = 0, window = 0;
+        if (!bail) {
+            fu_prev_interval_window(rc, n, dts, &max_prev, &window);
+            const int64_t a0 = rc.start - window - max_prev - t_org, a1 = rc.end - t_org;
+            bail = !(a0 > -LIM && a0 < LIM && a1 > -LIM && a1 < LIM && window < LIM && max_prev < LIM && rc.step < LIM);
+        }
+        // ---- values column
+        const uint8_t* A = nullptr;  // 16-byte aligned base of the stream; stream byte i sits at A[shift + i]
+        uint32_t shift = 0, len = 0;
+        const int mt = d.val_mt;
+        const bool is_stream = mt == 1 || mt == 4 || mt == 5 || mt == 6;
+        const bool delta2 = mt == 1 || mt == 5;
+        int64_t dconst = 0;  // MarshalTypeDeltaConst values
+        if (!bail) {
+            if (is_stream) {
+                const ColInfo ci = P.cols[2 * b + 1];
+                const uint8_t* src = ci.kind == VMB_ZK_NONE ? P.payload + d.val_off : P.scratch + ci.scratch_off;
+                len = ci.kind == VMB_ZK_NONE ? d.val_size : ci.content_size;
+                shift = (uint32_t)((uintptr_t)src & 15u);
+                A = src - shift;
+                bail = len < n - 1;  // int.go:183
+            } else if (mt == 3) {
+                bail = d.val_size != 0;
+            } else if (mt == 2) {
+                uint32_t used = 0;
+                bail = read_single_varint(P.payload + d.val_off, d.val_size, &dconst, &used) != 0 || used < d.val_size;
+                // a wrapping / decreasing progression is a removeCounterResets matter: leave it to the un-fused path
+                bail = bail || dconst < 0 || (uint64_t)dconst > (uint64_t)0x7fffffffffffffffLL / (n - 1) ||
+                       (int64_t)((uint64_t)d.first_value + (uint64_t)(n - 1) * (uint64_t)dconst) < d.first_value;
+            } else {
+                bail = true;
+            }
+        }
+        const bool want_rcr = (rc.flags & VMB_RC_REMOVE_COUNTER_RESETS) != 0;
+        const bool stale_matters = (rc.flags & VMB_RC_DROP_STALE_NANS) != 0 || want_rcr || (rc.flags & VMB_RC_PRE_MASK) != 0;
+        bail = bail || (rc.flags & VMB_RC_PRE_MASK) != 0;  // value preFuncs of the multi-output rollups: un-fused path
+        // removeCounterResets with a staleness interval below the scrape interval leaves every row raw (rollup.go:937): nothing to do
+        const int64_t max_stale = rc.lookback_delta != 0 ? rc.lookback_delta + rc.window : 0;
+        const bool do_rcr = want_rcr && !(max_stale > 0 && dts > max_stale);
+        Dec dec;
+        dec.init(d.scale);
+        if (tid == 0) {
+            S.flags = 0;
+            S.nev = 0;
+        }
+        const int32_t dt_row = (int32_t)dts;
+        const float inv_row = 1.0f / (float)dt_row;
+        const int32_t start_r = (int32_t)(rc.start - t_org), step32 = (int32_t)rc.step, win32 = (int32_t)window, mpi32 = (int32_t)max_prev;
+        const uint32_t nvar = n - 1;
+        const int64_t vlo = (int64_t)shift, vhi = (int64_t)shift + len;  // valid stream positions in aligned coordinates
+        const uint32_t end_al = (uint32_t)((vhi + 15) & ~(int64_t)15);
+
+        // stage buffer `bf` <- aligned bytes [fs - 16, fs + FU_FILL) of the stream (clamped to its 16-byte aligned end)
+        auto issue_copy = [&](uint32_t fs, uint32_t bf) {
+            if (tid == 0 && fs < end_al) {
+                const uint32_t lo = fs ? fs - 16u : 0u;
+                const uint32_t hi = fs + FU_FILL < end_al ? fs + FU_FILL : end_al;
+                mbar_expect_tx(&S.mbar[bf], hi - lo);
+                bulk_g2s(&S.stage[bf][fs ? 0 : 16], A + lo, hi - lo, &S.mbar[bf]);
+            }
+        };
+        uint32_t fs = 0, buf = 0;          // next unconsumed tile (aligned stream offset), stage buffer holding it
+        bool copy_pending = false;
+        if (!bail && is_stream) {
+            issue_copy(0, 0);
+            copy_pending = true;
+        }
+        // first row (nearest_delta2.go:75 / nearest_delta.go:64: as[0] = firstValue)
+        uint32_t N = 0;                    // varints decoded so far
+        uint64_t V = (uint64_t)d.first_value, D1 = 0;
+        uint32_t base = 0, cnt = 0, p = 0;
+        uint32_t gen_rows = 0;             // rows produced so far (const / delta-const columns)
+        double corr = 0.0, prev_raw = 0.0;
+        bool stream_done = !is_stream;
+        if (!bail) {
+            if (tid == 0) {
+                S.val[0] = dec.conv(d.first_value);  // (fu_swz(0) == 0)
+            }
+            cnt = 1;
+            gen_rows = 1;
+            if (stale_matters && d.first_value == VMB_V_STALE_NAN) bail = true;
+        }
+        if (tid == 0) scanned += n;  // samplesScanned starts at len(values) rollup.go:766
+        __syncthreads();
+        if (!bail) prev_raw = S.val[0];
+
+        uint32_t guard = 0;
+        while (!bail && (p < P.npoints || !stream_done)) {
+            if (++guard > 200000u) {  // every iteration consumes a tile or emits a point: this cannot be reached
+                if (tid == 0) {
+                    printf("fused guard: series %u p %u/%u cnt %u base %u fs %u end_al %u N %u nvar %u stream_done %d is_stream %d gen_rows %u n %u\n", s, p,
+                           P.npoints, cnt, base, fs, end_al, N, nvar, (int)stream_done, (int)is_stream, gen_rows, n);
+                }
+                bail = true;
+                break;
+            }
+            // ================= fill: decode the next tiles of the stream into rows [cnt, ...)
+            uint32_t cnt_old = cnt;
+            bool progressed = false;
+            if (is_stream && !stream_done) {
+                if (copy_pending) {
+                    mbar_wait(&S.mbar[buf], buf ? par1 : par0);
+                    if (buf) par1 ^= 1u; else par0 ^= 1u;
+                    copy_pending = false;
+                }
+                const uint8_t* st = &S.stage[buf][16];  // aligned stream byte `fs` sits at st[0]
+                const uint32_t off = w * FU_TILE + lane * 16u;
+                const int64_t g0 = (int64_t)fs + off;
+                const uint4 own = *reinterpret_cast<const uint4*>(st + off);
+                const uint4 prv = *reinterpret_cast<const uint4*>(st + off - 16);
+                const uint32_t vm = fu_valid16(g0, vlo, vhi);
+                const uint32_t tm = fu_term_mask16(own) & vm;
+                // boundaries of the previous 16 bytes: terminators, and everything in front of the stream start
+                const uint32_t pvm = fu_valid16(g0 - 16, vlo, vhi);
+                const uint32_t pbm = ((fu_term_mask16(prv) & pvm) | (g0 - 16 < vlo ? ~pvm : 0u)) & 0xffffu;
+                const uint32_t cl = (uint32_t)__popc(tm);
+                uint32_t incl = cl;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_up_sync(VMB_FULL, incl, o);
+                    if (lane >= (uint32_t)o) incl += t;
+                }
+                if (lane == 31) S.w_cnt[w] = incl;
+                if (tid == 0) S.nev = 0;  // (everybody read the previous fill's events before the barrier that ended it)
+                __syncthreads();
+                // whole tiles that fit the resident rows (pass-through once the points are done: rows are only validated)
+                const bool discard = p >= P.npoints;
+                if (discard) { cnt = 1; cnt_old = 1; }  // rows are not needed any more: decode over the same ring slots
+                uint32_t K = 0, tot = 0, rb = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < FU_WARPS; k++) {
+                    const uint32_t t = S.w_cnt[k];
+                    if (K == k && cnt + tot + t <= FU_CAP) {
+                        if (k < w) rb += t;
+                        tot += t;
+                        K++;
+                    }
+                }
+                if (N + tot > nvar) bail = true;  // more varints than rows: nearest_delta.go:65 "unexpected tail" -> un-fused path
+                const uint32_t fs_next = fs + K * FU_TILE;
+                const bool done_after = fs_next >= end_al;
+                if (!bail && K) {
+                    if (!done_after) {
+                        issue_copy(fs_next, buf ^ 1u);
+                        copy_pending = true;
+                    }
+                    // ---- parse: the varints whose terminator lies in this lane's 16 bytes
+                    uint64_t s1 = 0, s2 = 0;
+                    const uint32_t row0 = base + cnt + rb + incl - cl;  // absolute row of the lane's first value
+                    bool bad = false;
+                    if (w < K && cl) {
+                        // carried-in bytes: behind the last boundary of the previous 16 bytes
+                        const uint32_t carry = pbm ? (uint32_t)__clz((int)pbm) - 16u : 16u;  // 15 - msb(pbm)
+                        uint32_t m = tm;
+                        // 7-bit groups of the own 16 bytes as a 112-bit number q3:q2:q1:q0
+                        const uint32_t c0 = compact7(own.x), c1 = compact7(own.y), c2 = compact7(own.z), c3 = compact7(own.w);
+                        uint32_t q0 = c0 | (c1 << 28), q1 = (c1 >> 4) | (c2 << 24), q2 = (c2 >> 8) | (c3 << 20), q3 = c3 >> 12;
+                        uint32_t cval = 0, cbits = 0;  // value and width of the carried-in bytes
+                        bool first_slow = false;
+                        if (carry) {
+                            if (carry <= 3) {
+                                cval = compact7(prv.w) >> (7u * (4u - carry));
+                                cbits = 7u * carry;
+                            } else {
+                                first_slow = true;
+                            }
+                        }
+                        auto drop_groups = [&](uint32_t sh) {  // q >>= sh (sh = 7 * bytes <= 112)
+                            while (sh >= 32u) {
+                                q0 = q1; q1 = q2; q2 = q3; q3 = 0;
+                                sh -= 32u;
+                            }
+                            q0 = __funnelshift_r(q0, q1, sh);
+                            q1 = __funnelshift_r(q1, q2, sh);
+                            q2 = __funnelshift_r(q2, q3, sh);
+                            q3 >>= sh;
+                        };
+                        uint32_t k = 0, pos = 0;  // value index inside the lane, byte position of the current varint's first own byte
+                        if (!(vm & 1u)) {  // the stream starts inside this group: skip the bytes in front of it
+                            pos = (uint32_t)__ffs((int)vm) - 1u;
+                            m >>= pos;
+                            drop_groups(7u * pos);
+                        }
+                        while (m) {
+                            const uint32_t L = (uint32_t)__ffs((int)m);  // own bytes of this varint
+                            long long v;
+                            if (!first_slow && L * 7u + cbits <= 28u) {
+                                const uint32_t u = ((q0 & ((1u << (7u * L)) - 1u)) << cbits) | cval;
+                                v = (long long)(int)((u >> 1) ^ (0u - (u & 1u)));
+                            } else {
+                                // long varint (> 4 bytes): byte loop over the staged bytes, int.go:196-284
+                                const int sb = (int)(off + pos) - (int)(k == 0 ? carry : 0u);  // first byte, relative to st
+                                const uint32_t vl = L + (k == 0 ? carry : 0u);
+                                uint64_t u = 0;
+                                if (vl > 10) {
+                                    bad = true;
+                                } else {
+                                    for (uint32_t bb = 0; bb < vl; bb++) {
+                                        const uint32_t byte = st[sb + (int)bb];
+                                        if (bb == 9) {
+                                            if (byte > 1u) bad = true;
+                                            u |= (uint64_t)1 << 63;
+                                        } else {
+                                            u |= (uint64_t)(byte & 0x7fu) << (7 * bb);
+                                        }
+                                    }
+                                }
+                                v = (long long)(u >> 1) ^ -(long long)(u & 1);
+                            }
+                            first_slow = false;
+                            cval = 0;
+                            cbits = 0;
+                            RV[row0 + k] = __longlong_as_double(v);  // raw zig-zag decoded delta, replaced by the value in step 4
+                            s1 += (uint64_t)v;
+                            s2 += s1;
+                            k++;
+                            pos += L;
+                            m >>= L;
+                            drop_groups(7u * L);
+                        }
+                    }
+                    // a run of continuation bytes over a whole 16-byte group inside the stream: a varint of > 16 bytes
+                    if (w < K && vm == 0xffffu && tm == 0 && pbm == 0) bad = true;
+                    // ---- scan (count, s1, s2) over the warp; combine(A then B): s2 = s2A + s2B + cntB * s1A
+                    uint32_t icnt = w < K ? cl : 0u;
+                    uint64_t is1 = s1, is2 = s2;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        uint32_t acnt = __shfl_up_sync(VMB_FULL, icnt, o);
+                        uint64_t as1 = shfl_up_u64(is1, o);
+                        uint64_t as2 = shfl_up_u64(is2, o);
+                        if (lane >= (uint32_t)o) {
+                            if (delta2) is2 = as2 + is2 + (uint64_t)icnt * as1;
+                            is1 += as1;
+                            icnt += acnt;
+                        }
+                    }
+                    if (lane == 31) {
+                        S.w_s1[w] = is1;
+                        S.w_s2[w] = is2;
+                    }
+                    if (bad) S.flags = 1u;
+                    __syncthreads();
+                    if (S.flags & 1u) bail = true;
+                    // exclusive prefix over the warps in front, and the totals of the fill
+                    uint32_t pc = 0, tc = 0;
+                    uint64_t ps1 = 0, ps2 = 0, ts1 = 0, ts2 = 0;
+#pragma unroll
+                    for (uint32_t k = 0; k < FU_WARPS; k++) {
+                        if (k < K) {
+                            const uint32_t c_ = S.w_cnt[k];
+                            const uint64_t a1 = S.w_s1[k], a2 = S.w_s2[k];
+                            if (k < w) {
+                                if (delta2) ps2 = ps2 + a2 + (uint64_t)c_ * ps1;
+                                ps1 += a1;
+                                pc += c_;
+                            }
+                            if (delta2) ts2 = ts2 + a2 + (uint64_t)c_ * ts1;
+                            ts1 += a1;
+                            tc += c_;
+                        }
+                    }
+                    // ---- emit: replay the lane's values with the scanned prefix, mantissa -> float64 in place
+                    uint32_t ecnt = __shfl_up_sync(VMB_FULL, icnt, 1);  // (all lanes take part in the shuffles)
+                    uint64_t es1 = shfl_up_u64(is1, 1), es2 = shfl_up_u64(is2, 1);
+                    if (lane == 0) { ecnt = 0; es1 = 0; es2 = 0; }
+                    if (!bail && w < K && cl) {
+                        // prefix in front of the lane = (warps in front) then (lanes in front)
+                        const uint32_t fcnt = pc + ecnt;
+                        const uint64_t fs1 = ps1 + es1;
+                        const uint64_t fs2 = ps2 + es2 + (uint64_t)ecnt * ps1;
+                        uint64_t d1 = D1 + fs1;
+                        uint64_t v = delta2 ? (V + fs2 + (uint64_t)fcnt * D1) : (V + fs1);
+                        bool saw_stale = false;
+                        for (uint32_t k = 0; k < cl; k++) {
+                            const uint64_t pv = v;
+                            const uint64_t x = (uint64_t)__double_as_longlong(RV[row0 + k]);
+                            if (delta2) {
+                                d1 += x;
+                                v += d1;
+                            } else {
+                                v += x;
+                            }
+                            const double f = dec.conv((int64_t)v);
+                            if ((uint64_t)v - 0x7FFFFFFFFFFFFFFEull < 3ull) saw_stale |= ((int64_t)v == VMB_V_STALE_NAN);
+                            if (do_rcr && (int64_t)v < (int64_t)pv) {
+                                // candidate counter reset (the conversion is monotone): the exact test is on the floats, rollup.go:928
+                                const double pf = dec.conv((int64_t)pv);
+                                const double dd = f - pf;
+                                if (dd < 0) {
+                                    const double amt = ((-dd * 8) < pf) ? (pf - f) : pf;
+                                    const uint32_t e = atomicAdd(&S.nev, 1u);
+                                    if (e < FU_MAX_EVENTS) {
+                                        S.ev_row[e] = row0 + k;
+                                        S.ev_amt[e] = amt;
+                                    }
+                                }
+                            }
+                            RV[row0 + k] = f;
+                        }
+                        if (saw_stale && stale_matters) S.flags = 1u;
+                    }
+                    // ---- carries
+                    if (delta2) {
+                        V += ts2 + (uint64_t)tc * D1;
+                        D1 += ts1;
+                    } else {
+                        V += ts1;
+                    }
+                    N += tc;
+                    cnt += tot;
+                    fs = fs_next;
+                    buf ^= 1u;
+                    progressed = true;
+                    if (done_after) {
+                        stream_done = true;
+                        // nearest_delta.go:59-71: exactly n - 1 varints, the stream ends on a terminator
+                        if (N != nvar) bail = true;
+                    }
+                    __syncthreads();
+                    if (S.flags & 1u) bail = true;
+                    if (stream_done && !bail) {
+                        const uint32_t last_al = (uint32_t)(vhi - 1);  // aligned position of the last stream byte
+                        if (A[last_al] >= 0x80) bail = true;
+                    }
+                }
+            } else if (!is_stream && gen_rows < n) {
+                // MarshalTypeConst (encoding.go:215) / MarshalTypeDeltaConst (:231) values: rows generated in place
+                const uint32_t take = min(n - gen_rows, (uint32_t)FU_CAP - cnt);
+                for (uint32_t k = tid; k < take; k += FU_THREADS) {
+                    const uint32_t r = gen_rows + k;
+                    const int64_t v = (int64_t)((uint64_t)d.first_value + (uint64_t)r * (uint64_t)dconst);
+                    RV[base + cnt + k] = dec.conv(v);
+                    if (stale_matters && v == VMB_V_STALE_NAN) S.flags = 1u;
+                }
+                progressed = take > 0;
+                gen_rows += take;
+                cnt += take;
+                N = gen_rows - 1;
+                __syncthreads();
+                if (S.flags & 1u) bail = true;
+            }
+            if (bail) break;
+            const bool all_rows = is_stream ? stream_done : gen_rows == n;
+            if (p >= P.npoints) continue;  // only validating the rest of the stream
+
+            // ================= removeCounterResets over the new rows [cnt_old, cnt)  (rollup.go:921)
+            if (do_rcr && cnt > cnt_old) {
+                const uint32_t nev = S.nev;
+                const double raw_last = RV[base + cnt - 1];
+                if (nev > FU_MAX_EVENTS) {
+                    bail = true;  // a fill full of resets: un-fused path
+                } else if (nev || corr != 0.0) {
+                    if (tid == 0) {
+                        // events in row order, corrections accumulated sequentially like the Go loop
+                        for (uint32_t a = 1; a < nev; a++) {
+                            const uint32_t rr = S.ev_row[a];
+                            const double aa = S.ev_amt[a];
+                            int bq = (int)a - 1;
+                            while (bq >= 0 && S.ev_row[bq] > rr) {
+                                S.ev_row[bq + 1] = S.ev_row[bq];
+                                S.ev_amt[bq + 1] = S.ev_amt[bq];
+                                bq--;
+                            }
+                            S.ev_row[bq + 1] = rr;
+                            S.ev_amt[bq + 1] = aa;
+                        }
+                        double c = corr;
+                        for (uint32_t a = 0; a < nev; a++) {
+                            c = c + S.ev_amt[a];
+                            S.ev_cum[a] = c;
+                        }
+                    }
+                    __syncthreads();
+                    // corrected values are non-decreasing unless float rounding interferes: check that first, without writing
+                    const double prev_out = RV[base + cnt_old - 1];
+                    bool viol = false;
+                    for (uint32_t k = cnt_old + tid; k < cnt; k += FU_THREADS) {
+                        const uint32_t ar = base + k;
+                        double ck = corr, cp = corr;
+                        for (uint32_t a = 0; a < nev; a++) {
+                            if (S.ev_row[a] <= ar) ck = S.ev_cum[a];
+                            if (S.ev_row[a] + 1u <= ar) cp = S.ev_cum[a];
+                        }
+                        const double mk = RV[ar] + ck;
+                        const double mp = k == cnt_old ? prev_out : RV[ar - 1] + cp;
+                        viol |= !(mk >= mp);  // a clamp would fire, or a NaN is involved
+                    }
+                    const int any_viol = __syncthreads_or((int)viol);
+                    if (!any_viol) {
+                        for (uint32_t k = cnt_old + tid; k < cnt; k += FU_THREADS) {
+                            const uint32_t ar = base + k;
+                            double ck = corr;
+                            for (uint32_t a = 0; a < nev; a++)
+                                if (S.ev_row[a] <= ar) ck = S.ev_cum[a];
+                            RV[ar] = RV[ar] + ck;
+                        }
+                    } else if (w == 0) {
+                        // the exact sequential pass (rare): one warp, 32 rows at a time, state carried like k_series_prepare
+                        RcrState stt;
+                        stt.corr = corr;
+                        stt.prev_raw = prev_raw;
+                        stt.prev_out = prev_out;
+                        stt.prev_ts = 0;
+                        for (uint32_t cb = base + cnt_old; cb < base + cnt; cb += 32) {
+                            const uint32_t i_ = cb + lane;
+                            const double x = i_ < base + cnt ? RV[i_] : 0.0;
+                            rcr_chunk(stt, RV, cb, base + cnt, x, 0, 0, (int)lane);
+                        }
+                    }
+                    if (nev) corr = S.ev_cum[nev - 1];
+                    __syncthreads();
+                }
+                prev_raw = raw_last;
+            }
+
+            // ================= points whose window lies inside the resident rows
+            uint32_t p_end;
+            if (all_rows) p_end = P.npoints;
+            else {
+                const int64_t tl = (int64_t)(base + cnt - 1) * dt_row - 1 - start_r;  // tEnd < timestamp of the last resident row
+                p_end = tl < 0 ? 0u : min(P.npoints, (uint32_t)tl / (uint32_t)step32 + 1u);
+            }
+            if (p_end <= p) {
+                if (!progressed) bail = true;  // the window of point p does not fit FU_CAP rows: un-fused path
+                __syncthreads();
+                continue;
+            }
+            {
+                const uint32_t spc = (uint32_t)rc.samples_scanned_per_call;
+                uint32_t sc32 = 0;
+#pragma unroll 2
+                for (uint32_t q = p + tid; q < p_end; q += FU_THREADS) {
+                    const int32_t xj = start_r + (int32_t)q * step32;
+                    uint32_t i = seek_ap(xj - win32, dt_row, inv_row, n);
+                    uint32_t j = seek_ap(xj, dt_row, inv_row, n);
+                    i = i < base ? base : (i > base + cnt ? base + cnt : i);
+                    j = j < base ? base : (j > base + cnt ? base + cnt : j);
+                    if (j < i) j = i;
+                    if (F == VMB_RF_RATE) {
+                        sc32 += spc ? spc : j - i;
+                        P.out[(size_t)s * P.npoints + q] = rate_point_ap(i, j, base, n, cnt, xj - win32 - mpi32, dt_row, FuVals{S.val, base});
+                    } else {
+                        P.out[(size_t)s * P.npoints + q] = fu_point<F>(rc, window, max_prev, S.val, n, i, j, q, t_org, dts, scanned);
+                    }
+                }
+                scanned += sc32;
+            }
+            p = p_end;
+            __syncthreads();
+            if (p >= P.npoints) continue;
+            // ================= slide: keep rows from (first row after tStart(p)) - 1
+            {
+                uint32_t lo = seek_ap(start_r + (int32_t)p * step32 - win32, dt_row, inv_row, n);
+                lo = lo < base ? base : (lo > base + cnt ? base + cnt : lo);
+                uint32_t nb = lo > base ? lo - 1 : base;
+                if (nb > base + cnt - 1) nb = base + cnt - 1;
+                cnt -= nb - base;  // a ring: sliding the window moves no data
+                base = nb;
+            }
+        }
+        // a copy still in flight must land before the buffer is reused by the next series
+        if (copy_pending) {
+            mbar_wait(&S.mbar[buf], buf ? par1 : par0);
+            if (buf) par1 ^= 1u; else par0 ^= 1u;
+        }
+        if (bail) {
+            if (tid == 0) {
+                const unsigned int e = atomicAdd(P.bail_count, 1u);
+                P.bail_list[e] = s;
+            }
+        } else {
+            scanned_cta += scanned;
+        }
+    }
+    unsigned long long scanned = scanned_cta;
+    // block reduce -> one atomic per CTA
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) scanned += shfl_u64(scanned, (lane_id() ^ o));
+    if (lane == 0) S.s_part[w] = scanned;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long tot = 0;
+        for (int k = 0; k < FU_WARPS; k++) tot += S.s_part[k];
+        if (tot) atomicAdd(P.scanned, tot);
+    }
+}

@@ -18,8 +18,8 @@ namespace {
 __device__ __forceinline__ bool is_stale_nan(double f) { return (uint64_t)__double_as_longlong(f) == VMB_STALE_NAN_BITS; }
 
 // ---- order statistics without storage: the k-th smallest (0-based) non-NaN value of T(v[0..n)).
-template <class T>
-__device__ double kth_smallest(const double* v, uint32_t n, uint32_t k, T tf) {
+template <class VP, class T>
+__device__ double kth_smallest(VP v, uint32_t n, uint32_t k, T tf) {
     for (uint32_t a = 0; a < n; a++) {
         double x = tf(v[a]);
         if (isnan(x)) continue;
@@ -43,8 +43,8 @@ struct AbsDev {
 };
 
 // quantile aggr.go:870 = drop NaNs, sort, quantileSorted aggr.go:922
-template <class T>
-__device__ double quantile_tf(double phi, const double* v, uint32_t n, T tf) {
+template <class VP, class T>
+__device__ double quantile_tf(double phi, VP v, uint32_t n, T tf) {
     uint32_t m = 0;
     for (uint32_t a = 0; a < n; a++) m += !isnan(tf(v[a]));
     if (m == 0 || isnan(phi)) return D_NAN;
@@ -106,13 +106,18 @@ __device__ double quantile_tf(double phi, const double* v, uint32_t n, T tf) {
     }
     return vlo * (1 - weight) + vhi * weight;
 }
-__device__ double quantile(double phi, const double* v, uint32_t n) { return quantile_tf(phi, v, n, Ident()); }
+template <class VP>
+__device__ double quantile(double phi, VP v, uint32_t n) { return quantile_tf(phi, v, n, Ident()); }
 
-struct Win {  // rollupFuncArg rollup.go:523
+// rollupFuncArg rollup.go:523.  VP / TP: how the window's values / timestamps are reached -- plain pointers for columns in global
+// or shared memory, small view types (operator[], +, ++) for the fused kernel's swizzled ring of values and its computed
+// timestamps (fused.cu)
+template <class VP, class TP>
+struct WinT {
     double prevValue;
     int64_t prevTimestamp;
-    const double* values;
-    const int64_t* timestamps;
+    VP values;
+    TP timestamps;
     uint32_t n;
     double realPrevValue, realNextValue;
     int64_t currTimestamp;
@@ -121,8 +126,10 @@ struct Win {  // rollupFuncArg rollup.go:523
     const double* args;
     const double* args2;
 };
+typedef WinT<const double*, const int64_t*> Win;
 
-__device__ double stdvar(const double* v, uint32_t n) {  // rollup.go:1808
+template <class VP>
+__device__ double stdvar(VP v, uint32_t n) {  // rollup.go:1808
     if (n == 0) return D_NAN;
     if (n == 1) return 0;
     double avg = 0, count = 0, q = 0;
@@ -137,36 +144,43 @@ __device__ double stdvar(const double* v, uint32_t n) {  // rollup.go:1808
     if (count == 0) return D_NAN;
     return q / count;
 }
-__device__ double r_sum(const Win& r) {
+template <class W>
+__device__ double r_sum(const W& r) {
     if (r.n == 0) return D_NAN;
     double s = 0;
     for (uint32_t i = 0; i < r.n; i++) s += r.values[i];
     return s;
 }
-__device__ double r_avg(const Win& r) { return r.n == 0 ? D_NAN : r_sum(r) / (double)r.n; }
-__device__ double r_min(const Win& r) {
+template <class W>
+__device__ double r_avg(const W& r) { return r.n == 0 ? D_NAN : r_sum(r) / (double)r.n; }
+template <class W>
+__device__ double r_min(const W& r) {
     if (r.n == 0) return D_NAN;
     double m = r.values[0];
     for (uint32_t i = 0; i < r.n; i++)
         if (r.values[i] < m) m = r.values[i];
     return m;
 }
-__device__ double r_max(const Win& r) {
+template <class W>
+__device__ double r_max(const W& r) {
     if (r.n == 0) return D_NAN;
     double m = r.values[0];
     for (uint32_t i = 0; i < r.n; i++)
         if (r.values[i] > m) m = r.values[i];
     return m;
 }
-__device__ double r_last(const Win& r) { return r.n == 0 ? D_NAN : r.values[r.n - 1]; }
-__device__ double r_lag(const Win& r) {  // rollup.go:2055
+template <class W>
+__device__ double r_last(const W& r) { return r.n == 0 ? D_NAN : r.values[r.n - 1]; }
+template <class W>
+__device__ double r_lag(const W& r) {  // rollup.go:2055
     if (r.n == 0) {
         if (isnan(r.prevValue)) return D_NAN;
         return (double)(r.currTimestamp - r.prevTimestamp) / 1e3;
     }
     return (double)(r.currTimestamp - r.timestamps[r.n - 1]) / 1e3;
 }
-__device__ double r_scrape_interval(const Win& r) {  // rollup.go:2067
+template <class W>
+__device__ double r_scrape_interval(const W& r) {  // rollup.go:2067
     if (isnan(r.prevValue)) {
         if (r.n < 2) return D_NAN;
         return ((double)(r.timestamps[r.n - 1] - r.timestamps[0]) / 1e3) / (double)(r.n - 1);
@@ -175,8 +189,9 @@ __device__ double r_scrape_interval(const Win& r) {  // rollup.go:2067
     return ((double)(r.timestamps[r.n - 1] - r.prevTimestamp) / 1e3) / (double)r.n;
 }
 
-__device__ void linear_regression(const Win& r, double* vout, double* kout) {  // rollup.go:1099
-    const double* values = r.values;
+template <class W>
+__device__ void linear_regression(const W& r, double* vout, double* kout) {  // rollup.go:1099
+    auto values = r.values;
     uint32_t n = r.n;
     if (n == 0) {
         *vout = D_NAN;
@@ -218,8 +233,9 @@ __device__ void linear_regression(const Win& r, double* vout, double* kout) {  /
     *kout = k;
 }
 
-__device__ double r_delta(const Win& r) {  // rollupDelta rollup.go:1859
-    const double* values = r.values;
+template <class W>
+__device__ double r_delta(const W& r) {  // rollupDelta rollup.go:1859
+    auto values = r.values;
     uint32_t n = r.n;
     double prevValue = r.prevValue;
     if (isnan(prevValue)) {
@@ -238,7 +254,8 @@ __device__ double r_delta(const Win& r) {  // rollupDelta rollup.go:1859
     if (n == 0) return 0;
     return values[n - 1] - prevValue;
 }
-__device__ double r_deriv_fast(const Win& r) {  // rollupDerivFast rollup.go:1954
+template <class W>
+__device__ double r_deriv_fast(const W& r) {  // rollupDerivFast rollup.go:1954
     double prevValue = r.prevValue;
     int64_t prevTimestamp = r.prevTimestamp;
     if (isnan(prevValue)) {
@@ -252,9 +269,10 @@ __device__ double r_deriv_fast(const Win& r) {  // rollupDerivFast rollup.go:195
     double dt = (double)(r.timestamps[r.n - 1] - prevTimestamp) / 1e3;
     return dv / dt;
 }
-__device__ double r_ideriv(const Win& r) {  // rollupIderiv rollup.go:1991
-    const double* values = r.values;
-    const int64_t* ts = r.timestamps;
+template <class W>
+__device__ double r_ideriv(const W& r) {  // rollupIderiv rollup.go:1991
+    auto values = r.values;
+    auto ts = r.timestamps;
     uint32_t n = r.n;
     if (n < 2) {
         if (n == 0) return D_NAN;
@@ -277,13 +295,15 @@ __device__ double r_ideriv(const Win& r) {  // rollupIderiv rollup.go:1991
     }
     return (vEnd - vStart) / ((double)(tEnd - tStart) / 1e3);
 }
-__device__ double r_idelta(const Win& r) {  // rollup.go:1915
+template <class W>
+__device__ double r_idelta(const W& r) {  // rollup.go:1915
     if (r.n == 0) return isnan(r.prevValue) ? D_NAN : 0.0;
     double last = r.values[r.n - 1];
     if (r.n == 1) return isnan(r.prevValue) ? last : last - r.prevValue;
     return last - r.values[r.n - 2];
 }
-__device__ double r_increase_pure(const Win& r) {  // rollup.go:1835
+template <class W>
+__device__ double r_increase_pure(const W& r) {  // rollup.go:1835
     double prevValue = r.prevValue;
     if (isnan(prevValue)) {
         if (r.n == 0) return D_NAN;
@@ -293,8 +313,9 @@ __device__ double r_increase_pure(const Win& r) {  // rollup.go:1835
     if (r.n == 0) return 0;
     return r.values[r.n - 1] - prevValue;
 }
-__device__ double r_changes(const Win& r, bool prometheus) {  // rollup.go:2106 / :2080
-    const double* values = r.values;
+template <class W>
+__device__ double r_changes(const W& r, bool prometheus) {  // rollup.go:2106 / :2080
+    auto values = r.values;
     uint32_t n = r.n;
     double prev;
     int cnt = 0;
@@ -326,8 +347,9 @@ __device__ double r_changes(const Win& r, bool prometheus) {  // rollup.go:2106 
     }
     return (double)cnt;
 }
-__device__ double r_incr_or_resets(const Win& r, bool increases) {  // rollup.go:2139 / :2174
-    const double* values = r.values;
+template <class W>
+__device__ double r_incr_or_resets(const W& r, bool increases) {  // rollup.go:2139 / :2174
+    auto values = r.values;
     uint32_t n = r.n;
     if (n == 0) return isnan(r.prevValue) ? D_NAN : 0.0;
     double prev = r.prevValue;
@@ -349,9 +371,10 @@ __device__ double r_incr_or_resets(const Win& r, bool increases) {  // rollup.go
     }
     return (double)cnt;
 }
-__device__ double r_integrate(const Win& r) {  // rollup.go:2417
-    const double* values = r.values;
-    const int64_t* ts = r.timestamps;
+template <class W>
+__device__ double r_integrate(const W& r) {  // rollup.go:2417
+    auto values = r.values;
+    auto ts = r.timestamps;
     uint32_t n = r.n;
     double prevValue = r.prevValue;
     int64_t prevTimestamp = r.currTimestamp - r.window;
@@ -373,7 +396,8 @@ __device__ double r_integrate(const Win& r) {  // rollup.go:2417
     double dt = (double)(r.currTimestamp - prevTimestamp) / 1e3;
     return __dadd_rn(sum, __dmul_rn(prevValue, dt));
 }
-__device__ double r_lifetime(const Win& r) {  // rollup.go:2040
+template <class W>
+__device__ double r_lifetime(const W& r) {  // rollup.go:2040
     if (isnan(r.prevValue)) {
         if (r.n < 2) return D_NAN;
         return (double)(r.timestamps[r.n - 1] - r.timestamps[0]) / 1e3;
@@ -381,7 +405,8 @@ __device__ double r_lifetime(const Win& r) {  // rollup.go:2040
     if (r.n == 0) return D_NAN;
     return (double)(r.timestamps[r.n - 1] - r.prevTimestamp) / 1e3;
 }
-__device__ double r_tminmax(const Win& r, bool is_min) {  // rollup.go:1603 / :1623
+template <class W>
+__device__ double r_tminmax(const W& r, bool is_min) {  // rollup.go:1603 / :1623
     if (r.n == 0) return D_NAN;
     double m = r.values[0];
     int64_t t = r.timestamps[0];
@@ -394,7 +419,8 @@ __device__ double r_tminmax(const Win& r, bool is_min) {  // rollup.go:1603 / :1
     }
     return (double)t / 1e3;
 }
-__device__ double r_tlast_change(const Win& r) {  // rollup.go:1669
+template <class W>
+__device__ double r_tlast_change(const W& r) {  // rollup.go:1669
     if (r.n == 0) return D_NAN;
     double last = r.values[r.n - 1];
     for (int i = (int)r.n - 2; i >= 0; i--)
@@ -403,11 +429,12 @@ __device__ double r_tlast_change(const Win& r) {  // rollup.go:1669
     return D_NAN;
 }
 // modeNoNaNs aggr.go:541 driven by runs of equal values in ascending order (no sort buffer)
-__device__ double r_mode(const Win& r) {
+template <class W>
+__device__ double r_mode(const W& r) {
     double prevValue = r.prevValue;
     uint32_t n = r.n;
     if (n == 0) return prevValue;
-    const double* v = r.values;
+    auto v = r.values;
     long long j = -1, dMax = 0;
     double mode = prevValue;
     // the Go code sorts with sort.Float64s, which orders NaNs first; windows never hold NaNs here (eval.go:1985)
@@ -446,7 +473,8 @@ __device__ double r_mode(const Win& r) {
     if (d > dMax || isnan(mode)) mode = prevValue;
     return mode;
 }
-__device__ double r_outlier_iqr(const Win& r) {  // rollup.go:1427
+template <class W>
+__device__ double r_outlier_iqr(const W& r) {  // rollup.go:1427
     if (r.n < 2) return D_NAN;
     double q25 = quantile(0.25, r.values, r.n), q75 = quantile(0.75, r.values, r.n);
     double iqr = 1.5 * (q75 - q25);
@@ -454,15 +482,17 @@ __device__ double r_outlier_iqr(const Win& r) {  // rollup.go:1427
     if (v > q75 + iqr || v < q25 - iqr) return v;
     return D_NAN;
 }
-__device__ double r_zscore(const Win& r) {  // rollup.go:2361
+template <class W>
+__device__ double r_zscore(const W& r) {  // rollup.go:2361
     double si = r_scrape_interval(r), lag = r_lag(r);
     if (isnan(si) || isnan(lag) || lag > si) return D_NAN;
     double d = r_last(r) - r_avg(r);
     if (d == 0) return 0;
     return d / sqrt(stdvar(r.values, r.n));
 }
-__device__ double r_ascent_descent(const Win& r, bool ascent) {  // rollup.go:2315 / :2338
-    const double* values = r.values;
+template <class W>
+__device__ double r_ascent_descent(const W& r, bool ascent) {  // rollup.go:2315 / :2338
+    auto values = r.values;
     uint32_t n = r.n;
     double prev = r.prevValue;
     if (isnan(prev)) {
@@ -480,7 +510,8 @@ __device__ double r_ascent_descent(const Win& r, bool ascent) {  // rollup.go:23
     }
     return s;
 }
-__device__ double r_distinct(const Win& r) {  // rollup.go:2403 (Go map[float64]: NaN keys never collide)
+template <class W>
+__device__ double r_distinct(const W& r) {  // rollup.go:2403 (Go map[float64]: NaN keys never collide)
     if (r.n == 0) return D_NAN;
     uint32_t d = 0;
     for (uint32_t a = 0; a < r.n; a++) {
@@ -495,8 +526,9 @@ __device__ double r_distinct(const Win& r) {  // rollup.go:2403 (Go map[float64]
     }
     return (double)d;
 }
-__device__ double r_holt_winters(const Win& r) {  // rollup.go:1030
-    const double* values = r.values;
+template <class W>
+__device__ double r_holt_winters(const W& r) {  // rollup.go:1030
+    auto values = r.values;
     uint32_t n = r.n;
     if (n == 0) return D_NAN;
     double sf = r.args[r.idx];
@@ -520,7 +552,8 @@ __device__ double r_holt_winters(const Win& r) {  // rollup.go:1030
     }
     return s0;
 }
-__device__ void hoeffding(const Win& r, double* bound, double* avg) {  // rollup.go:1353
+template <class W>
+__device__ void hoeffding(const W& r, double* bound, double* avg) {  // rollup.go:1353
     if (r.n == 0) {
         *bound = D_NAN;
         *avg = D_NAN;
@@ -548,7 +581,8 @@ __device__ void hoeffding(const Win& r, double* bound, double* avg) {  // rollup
     }
     *bound = vRange * sqrt(log(1 / (1 - phi)) / (2 * (double)r.n));
 }
-__device__ double r_duration(const Win& r) {  // rollup.go:1151
+template <class W>
+__device__ double r_duration(const W& r) {  // rollup.go:1151
     if (r.n == 0) return D_NAN;
     int64_t tPrev = r.timestamps[0], dSum = 0;
     int64_t dMax = (int64_t)(r.args[r.idx] * 1000);
@@ -560,7 +594,8 @@ __device__ double r_duration(const Win& r) {  // rollup.go:1151
     return (double)dSum / 1000;
 }
 enum { F_LE, F_GT, F_EQ, F_NE };
-__device__ double r_filter(const Win& r, int cmp, bool sum, bool share) {  // rollup.go:1321, :1275
+template <class W>
+__device__ double r_filter(const W& r, int cmp, bool sum, bool share) {  // rollup.go:1321, :1275
     if (r.n == 0) return D_NAN;
     double lim = r.args[r.idx], acc = 0;
     int cnt = 0;
@@ -576,16 +611,19 @@ __device__ double r_filter(const Win& r, int cmp, bool sum, bool share) {  // ro
     if (share) return (double)cnt / (double)r.n;
     return (double)cnt;
 }
-__device__ uint32_t candlestick_len(const Win& r) {  // rollup.go:2228
+template <class W>
+__device__ uint32_t candlestick_len(const W& r) {  // rollup.go:2228
     uint32_t n = r.n;
     while (n > 0 && r.timestamps[n - 1] >= r.currTimestamp) n--;
     return n;
 }
-__device__ double candlestick_first(const Win& r) {
+template <class W>
+__device__ double candlestick_first(const W& r) {
     return (r.prevTimestamp + r.window >= r.currTimestamp) ? r.prevValue : D_NAN;
 }
 
-__device__ double call_func(int f, const Win& r) {
+template <class W>
+__device__ double call_func(int f, const W& r) {
     switch (f) {
         case VMB_RF_DEFAULT_ROLLUP:
         case VMB_RF_LAST: return r_last(r);
@@ -706,7 +744,7 @@ __device__ double call_func(int f, const Win& r) {
         case VMB_RF_HIGH:
         case VMB_RF_LOW: {
             uint32_t n = candlestick_len(r);
-            const double* values = r.values;
+            auto values = r.values;
             double m = candlestick_first(r);
             if (isnan(m)) {
                 if (n == 0) return D_NAN;
@@ -741,6 +779,7 @@ struct RollupParams {
     int64_t* ts;
     double* vals;
     double* out;             // [nseries x P]
+    const uint32_t* out_rows;  // series s writes row out_rows[s] of `out` (nullptr: row s)
     unsigned long long* scanned;  // device accumulator
     uint32_t nseries;
     uint32_t npoints;
@@ -1077,7 +1116,8 @@ struct RcrState {
 // the final clamp `values[i] = max(values[i], values[i-1])` is a segmented prefix max (order-independent).  A chunk without
 // events (the common case) needs no scan at all: raw values are non-decreasing there, so the clamp is an elementwise max
 // with the last output of the previous chunk.
-__device__ __forceinline__ void rcr_chunk(RcrState& st, double* v, uint32_t cb, uint32_t n, double x, int64_t tt,
+template <class VP>
+__device__ __forceinline__ void rcr_chunk(RcrState& st, VP v, uint32_t cb, uint32_t n, double x, int64_t tt,
                                           int64_t max_stale, int lane) {
     const uint32_t i = cb + lane;
     const bool valid = i < n;
@@ -1449,8 +1489,9 @@ __device__ __forceinline__ double rollup_point(const vmb_rollup_cfg& rc, const S
 // memory directly.  F >= 0 instantiates the kernel for one rollup function (the switch in call_func folds away).
 // rate() for one point of a series whose timestamps are t_org + row * dt (rows absolute): same selects as rate_point32 below
 // with the timestamps derived from the row indices
+template <class VP>
 __device__ __forceinline__ double rate_point_ap(uint32_t i, uint32_t j, uint32_t base, uint32_t n, uint32_t cnt, int32_t tsp,
-                                                int32_t dt_row, const double* __restrict__ val) {
+                                                int32_t dt_row, VP val) {
     const uint32_t ri = i - base, rj = j - base, nw = j - i;
     const bool have_prev = i > 0 && i < n;
     const uint32_t ip = have_prev ? ri - 1 : 0u;
@@ -1530,7 +1571,7 @@ __global__ void __launch_bounds__(ROLLUP_THREADS, 4) k_rollup(RollupParams P) {
         const double* vg = P.vals + m.start;
         const int64_t* tg = P.ts + m.start;
         const uint32_t n = m.n;
-        double* out = P.out + (size_t)s * P.npoints;
+        double* out = P.out + (size_t)(P.out_rows ? P.out_rows[s] : s) * P.npoints;
         if (tid == 0) scanned += n;  // samplesScanned starts at len(values) rollup.go:766
         // window / step and window % step: 32-bit arithmetic when both fit (a 64-bit division is ~100 instructions and every
         // thread of the CTA computes this)
