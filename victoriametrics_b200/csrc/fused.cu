@@ -60,6 +60,20 @@ struct FusedParams {
 
 namespace {
 
+// what one thread derives from the block header and the query for a series (everybody else reads it from shared memory)
+struct FuSeries {
+    const uint8_t* A;        // 16-byte aligned base of the values stream; stream byte i sits at A[shift + i]
+    int64_t t_org, dts, window, max_prev, dconst, first_value;
+    uint32_t shift, len, n, end_al;
+    int32_t start_r, step32, win32, mpi32;  // the query grid relative to the first row, all below 2^30 in magnitude
+    int32_t lin_k, iq0, jq0;                // step % dt == 0: the window edges of point q are iq0 + q * lin_k, jq0 + q * lin_k
+    double dec_e10, dec_rcp;                // Dec (decimal.go:100) of the block's scale
+    double rate_D, rate_R;                  // rate(): divisor of a full window and its reciprocal (rate_dt = the span in ms, -1: none)
+    int32_t rate_dt, rate_rows, dec_mode;
+    int16_t scale;
+    uint8_t bail, is_stream, delta2, do_rcr, stale_matters, lin;
+};
+
 struct FusedSmem {
     double val[FU_CAP];
     alignas(16) uint8_t stage[2][FU_STAGE];
@@ -71,6 +85,7 @@ struct FusedSmem {
     uint32_t nev;
     uint32_t flags;  // bit 0: bail, bit 1: slow removeCounterResets pass needed
     unsigned long long s_part[FU_WARPS];
+    FuSeries ser;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,17 +136,28 @@ __device__ __forceinline__ uint32_t fu_swz(uint32_t row) {
     row &= FU_MASK;
     return row ^ ((row >> 3) & 15u);
 }
+// the same on byte offsets (row * 8): three instructions per access
+__device__ __forceinline__ uint32_t fu_swz_b(uint32_t row) {
+    const uint32_t o = row << 3;
+    return (o ^ ((o >> 3) & 0x78u)) & (uint32_t)(FU_CAP * 8 - 1);
+}
+__device__ __forceinline__ double fu_ld(const double* s, uint32_t row) {
+    return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s) + fu_swz_b(row));
+}
+__device__ __forceinline__ double& fu_ref(double* s, uint32_t row) {
+    return *reinterpret_cast<double*>(reinterpret_cast<char*>(s) + fu_swz_b(row));
+}
 struct FuVals {  // read view for the rollup functions: element i is row r + i
     const double* s;
     uint32_t r;
-    __device__ __forceinline__ double operator[](uint32_t i) const { return s[fu_swz(r + i)]; }
+    __device__ __forceinline__ double operator[](uint32_t i) const { return fu_ld(s, r + i); }
     __device__ __forceinline__ FuVals operator+(uint32_t k) const { return FuVals{s, r + k}; }
     __device__ __forceinline__ FuVals& operator++() { r++; return *this; }
     __device__ __forceinline__ FuVals operator++(int) { FuVals o = *this; r++; return o; }
 };
 struct FuValsRW {  // read/write by absolute row
     double* s;
-    __device__ __forceinline__ double& operator[](uint32_t row) const { return s[fu_swz(row)]; }
+    __device__ __forceinline__ double& operator[](uint32_t row) const { return fu_ref(s, row); }
 };
 struct FuTs {  // timestamps of a MarshalTypeDeltaConst column are never stored: element i is t + i * dt
     int64_t t, dt;
@@ -204,7 +230,7 @@ __device__ __forceinline__ double fu_point(const vmb_rollup_cfg& rc, int64_t win
     r.prevTimestamp = tStart - max_prev;
     const int64_t t_im1 = t_org + ((int64_t)i - 1) * dt;
     if (i < n && i > 0 && t_im1 > r.prevTimestamp) {
-        r.prevValue = sval[fu_swz(i - 1)];
+        r.prevValue = fu_ld(sval, i - 1);
         r.prevTimestamp = t_im1;
     }
     r.values = FuVals{sval, i};
@@ -213,9 +239,9 @@ __device__ __forceinline__ double fu_point(const vmb_rollup_cfg& rc, int64_t win
     r.realPrevValue = D_NAN;
     if (i > 0) {
         const int64_t curr = r.n > 0 ? t_im1 + dt : tStart;
-        if (rc.lookback_delta == 0 || (curr - t_im1) < rc.lookback_delta) r.realPrevValue = sval[fu_swz(i - 1)];
+        if (rc.lookback_delta == 0 || (curr - t_im1) < rc.lookback_delta) r.realPrevValue = fu_ld(sval, i - 1);
     }
-    r.realNextValue = j < n ? sval[fu_swz(j)] : D_NAN;
+    r.realNextValue = j < n ? fu_ld(sval, j) : D_NAN;
     r.currTimestamp = tEnd;
     r.idx = p;
     r.window = window;
@@ -223,6 +249,116 @@ __device__ __forceinline__ double fu_point(const vmb_rollup_cfg& rc, int64_t win
     r.args2 = rc.args2;
     scanned += rc.samples_scanned_per_call > 0 ? (unsigned long long)rc.samples_scanned_per_call : (unsigned long long)r.n;
     return call_func(F >= 0 ? F : rc.func_id, r);
+}
+
+__device__ __forceinline__ int32_t fu_floor_div(int32_t a, int32_t b) {  // b > 0
+    int32_t q = a / b;
+    return q - ((a % b) < 0 ? 1 : 0);
+}
+
+// per-series setup, executed by ONE thread: block header -> what the fill / points loops need; bail = the series goes to the
+// un-fused pipeline (anything this kernel does not take, see the head of the file)
+__device__ void fu_series_setup(const FusedParams& P, uint32_t s, FuSeries* out) {
+    const vmb_rollup_cfg& rc = P.cfg;
+    FuSeries o;
+    memset(&o, 0, sizeof(o));
+    const uint32_t b = P.ser_first_block[s];
+    const vmb_block_desc d = P.descs[b];
+    const uint32_t n = d.rows;
+    bool bail = n < 2u || n > 16384u || d.ts_mt != 2 || d.precision_bits < 64;
+    if (!bail && P.zstd_status) bail = P.zstd_status[2 * b] != 0 || P.zstd_status[2 * b + 1] != 0;
+    // ---- timestamps: MarshalTypeDeltaConst (encoding.go:231) = first + i * dt
+    int64_t dts = 0;
+    if (!bail) {
+        uint32_t used = 0;
+        bail = read_single_varint(P.payload + d.ts_off, d.ts_size, &dts, &used) != 0 || used < d.ts_size;
+    }
+    const int64_t LIM = (int64_t)1 << 30;
+    bail = bail || dts <= 0 || dts >= LIM || (int64_t)(n - 1) * dts >= LIM;
+    const int64_t t_org = d.min_ts;
+    bail = bail || t_org < P.tr_min || t_org + (int64_t)(n - 1) * dts > P.tr_max;  // rows trimmed by the time range: un-fused path
+    int64_t max_prev = 0, window = 0;
+    if (!bail) {
+        fu_prev_interval_window(rc, n, dts, &max_prev, &window);
+        const int64_t a0 = rc.start - window - max_prev - t_org, a1 = rc.end - t_org;
+        bail = !(a0 > -LIM && a0 < LIM && a1 > -LIM && a1 < LIM && window < LIM && max_prev < LIM && rc.step < LIM);
+    }
+    // ---- values column
+    const int mt = d.val_mt;
+    o.is_stream = mt == 1 || mt == 4 || mt == 5 || mt == 6;
+    o.delta2 = mt == 1 || mt == 5;
+    if (!bail) {
+        if (o.is_stream) {
+            const ColInfo ci = P.cols[2 * b + 1];
+            const uint8_t* src = ci.kind == VMB_ZK_NONE ? P.payload + d.val_off : P.scratch + ci.scratch_off;
+            o.len = ci.kind == VMB_ZK_NONE ? d.val_size : ci.content_size;
+            o.shift = (uint32_t)((uintptr_t)src & 15u);
+            o.A = src - o.shift;
+            bail = o.len < n - 1;  // int.go:183
+        } else if (mt == 3) {
+            bail = d.val_size != 0;
+        } else if (mt == 2) {
+            uint32_t used = 0;
+            bail = read_single_varint(P.payload + d.val_off, d.val_size, &o.dconst, &used) != 0 || used < d.val_size;
+            // a wrapping / decreasing progression is a removeCounterResets matter: leave it to the un-fused path
+            bail = bail || o.dconst < 0 || (uint64_t)o.dconst > (uint64_t)0x7fffffffffffffffLL / (n - 1) ||
+                   (int64_t)((uint64_t)d.first_value + (uint64_t)(n - 1) * (uint64_t)o.dconst) < d.first_value;
+        } else {
+            bail = true;
+        }
+    }
+    const bool want_rcr = (rc.flags & VMB_RC_REMOVE_COUNTER_RESETS) != 0;
+    o.stale_matters = (rc.flags & VMB_RC_DROP_STALE_NANS) != 0 || want_rcr || (rc.flags & VMB_RC_PRE_MASK) != 0;
+    bail = bail || (rc.flags & VMB_RC_PRE_MASK) != 0;  // value preFuncs of the multi-output rollups: un-fused path
+    // removeCounterResets with a staleness interval below the scrape interval leaves every row raw (rollup.go:937): nothing to do
+    const int64_t max_stale = rc.lookback_delta != 0 ? rc.lookback_delta + rc.window : 0;
+    o.do_rcr = want_rcr && !(max_stale > 0 && dts > max_stale);
+    if (!bail && o.stale_matters && d.first_value == VMB_V_STALE_NAN) bail = true;
+    o.t_org = t_org;
+    o.dts = dts;
+    o.window = window;
+    o.max_prev = max_prev;
+    o.first_value = d.first_value;
+    o.n = n;
+    o.end_al = (uint32_t)(((uint64_t)o.shift + o.len + 15u) & ~(uint64_t)15);
+    o.scale = d.scale;
+    if (!bail) {
+        o.start_r = (int32_t)(rc.start - t_org);
+        o.step32 = (int32_t)rc.step;
+        o.win32 = (int32_t)window;
+        o.mpi32 = (int32_t)max_prev;
+        const int32_t dt_row = (int32_t)dts;
+        if (o.step32 % dt_row == 0) {
+            // rows with timestamp <= t_org + x: clamp(floor(x / dt) + 1, 0, n); x advances by a whole number of rows per point
+            o.lin = 1;
+            o.lin_k = o.step32 / dt_row;
+            o.jq0 = fu_floor_div(o.start_r, dt_row) + 1;
+            o.iq0 = fu_floor_div(o.start_r - o.win32, dt_row) + 1;
+        }
+    }
+    {
+        Dec dec;
+        dec.init(d.scale);
+        o.dec_e10 = dec.e10;
+        o.dec_rcp = dec.rcp;
+        o.dec_mode = dec.mode;
+    }
+    o.rate_dt = -1;
+    o.rate_D = o.rate_R = 1.0;
+    if (!bail && rc.func_id == VMB_RF_RATE) {
+        const int32_t dt_row = (int32_t)dts;
+        const int32_t rows_w = o.lin ? o.jq0 - o.iq0 : o.win32 / dt_row;
+        if (rows_w >= 1 && (int64_t)rows_w * dt_row < ((int64_t)1 << 30)) {
+            o.rate_rows = rows_w;
+            o.rate_dt = rows_w * dt_row;
+            o.rate_D = ms_to_s((int64_t)o.rate_dt);
+            o.rate_R = 1.0 / o.rate_D;
+            // (Markstein's correction needs a significand of D that is not all ones)
+            if (((unsigned long long)__double_as_longlong(o.rate_D) & 0xfffffffffffffull) == 0xfffffffffffffull) o.rate_dt = -1;
+        }
+    }
+    o.bail = bail;
+    *out = o;
 }
 
 }  // namespace
@@ -247,72 +383,36 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
         __syncthreads();  // the previous series is done with the shared memory
         const uint32_t s = P.ser_list[li];
         unsigned long long scanned = 0;  // this series (dropped when the series is handed to the un-fused path)
-        const uint32_t b = P.ser_first_block[s];
-        const vmb_block_desc d = P.descs[b];
-        const uint32_t n = d.rows;
-        bool bail = n < 2u || n > 16384u || d.ts_mt != 2 || d.precision_bits < 64;
-        if (!bail && P.zstd_status) bail = P.zstd_status[2 * b] != 0 || P.zstd_status[2 * b + 1] != 0;
-        // ---- timestamps: MarshalTypeDeltaConst (encoding.go:231) = first + i * dt
-        int64_t dts = 0;
-        if (!bail) {
-            uint32_t used = 0;
-            bail = read_single_varint(P.payload + d.ts_off, d.ts_size, &dts, &used) != 0 || used < d.ts_size;
-        }
-        const int64_t LIM = (int64_t)1 << 30;
-        bail = bail || dts <= 0 || dts >= LIM || (int64_t)(n - 1) * dts >= LIM;
-        const int64_t t_org = d.min_ts;
-        bail = bail || t_org < P.tr_min || t_org + (int64_t)(n - 1) * dts > P.tr_max;  // rows trimmed by the time range: un-fused path
-        int64_t max_prev = 0, window = 0;
-        if (!bail) {
-            fu_prev_interval_window(rc, n, dts, &max_prev, &window);
-            const int64_t a0 = rc.start - window - max_prev - t_org, a1 = rc.end - t_org;
-            bail = !(a0 > -LIM && a0 < LIM && a1 > -LIM && a1 < LIM && window < LIM && max_prev < LIM && rc.step < LIM);
-        }
-        // ---- values column
-        const uint8_t* A = nullptr;  // 16-byte aligned base of the stream; stream byte i sits at A[shift + i]
-        uint32_t shift = 0, len = 0;
-        const int mt = d.val_mt;
-        const bool is_stream = mt == 1 || mt == 4 || mt == 5 || mt == 6;
-        const bool delta2 = mt == 1 || mt == 5;
-        int64_t dconst = 0;  // MarshalTypeDeltaConst values
-        if (!bail) {
-            if (is_stream) {
-                const ColInfo ci = P.cols[2 * b + 1];
-                const uint8_t* src = ci.kind == VMB_ZK_NONE ? P.payload + d.val_off : P.scratch + ci.scratch_off;
-                len = ci.kind == VMB_ZK_NONE ? d.val_size : ci.content_size;
-                shift = (uint32_t)((uintptr_t)src & 15u);
-                A = src - shift;
-                bail = len < n - 1;  // int.go:183
-            } else if (mt == 3) {
-                bail = d.val_size != 0;
-            } else if (mt == 2) {
-                uint32_t used = 0;
-                bail = read_single_varint(P.payload + d.val_off, d.val_size, &dconst, &used) != 0 || used < d.val_size;
-                // a wrapping / decreasing progression is a removeCounterResets matter: leave it to the un-fused path
-                bail = bail || dconst < 0 || (uint64_t)dconst > (uint64_t)0x7fffffffffffffffLL / (n - 1) ||
-                       (int64_t)((uint64_t)d.first_value + (uint64_t)(n - 1) * (uint64_t)dconst) < d.first_value;
-            } else {
-                bail = true;
-            }
-        }
-        const bool want_rcr = (rc.flags & VMB_RC_REMOVE_COUNTER_RESETS) != 0;
-        const bool stale_matters = (rc.flags & VMB_RC_DROP_STALE_NANS) != 0 || want_rcr || (rc.flags & VMB_RC_PRE_MASK) != 0;
-        bail = bail || (rc.flags & VMB_RC_PRE_MASK) != 0;  // value preFuncs of the multi-output rollups: un-fused path
-        // removeCounterResets with a staleness interval below the scrape interval leaves every row raw (rollup.go:937): nothing to do
-        const int64_t max_stale = rc.lookback_delta != 0 ? rc.lookback_delta + rc.window : 0;
-        const bool do_rcr = want_rcr && !(max_stale > 0 && dts > max_stale);
-        Dec dec;
-        dec.init(d.scale);
         if (tid == 0) {
+            fu_series_setup(P, s, &S.ser);
             S.flags = 0;
             S.nev = 0;
         }
+        __syncthreads();
+        bool bail = S.ser.bail != 0;
+        const uint32_t n = S.ser.n;
+        const int64_t dts = S.ser.dts, t_org = S.ser.t_org, window = S.ser.window, max_prev = S.ser.max_prev;
+        const uint8_t* const A = S.ser.A;
+        const uint32_t shift = S.ser.shift, len = S.ser.len, end_al = S.ser.end_al;
+        const bool is_stream = S.ser.is_stream != 0, delta2 = S.ser.delta2 != 0, do_rcr = S.ser.do_rcr != 0;
+        const bool stale_matters = S.ser.stale_matters != 0;
+        const int64_t dconst = S.ser.dconst, first_value = S.ser.first_value;
+        Dec dec;
+        dec.e10 = S.ser.dec_e10;
+        dec.rcp = S.ser.dec_rcp;
+        dec.mode = S.ser.dec_mode;
         const int32_t dt_row = (int32_t)dts;
         const float inv_row = 1.0f / (float)dt_row;
-        const int32_t start_r = (int32_t)(rc.start - t_org), step32 = (int32_t)rc.step, win32 = (int32_t)window, mpi32 = (int32_t)max_prev;
+        const int32_t start_r = S.ser.start_r, step32 = S.ser.step32, win32 = S.ser.win32, mpi32 = S.ser.mpi32;
+        const bool lin = S.ser.lin != 0;
+        const int32_t lin_k = S.ser.lin_k, iq0 = S.ser.iq0, jq0 = S.ser.jq0;
         const uint32_t nvar = n - 1;
         const int64_t vlo = (int64_t)shift, vhi = (int64_t)shift + len;  // valid stream positions in aligned coordinates
-        const uint32_t end_al = (uint32_t)((vhi + 15) & ~(int64_t)15);
+        // rate(): the divisor of a full window, its reciprocal (used only when a point's divisor is exactly this one)
+        const int32_t rate_dt = S.ser.rate_dt, rate_rows = S.ser.rate_rows;
+        const double rate_D = S.ser.rate_D, rate_R = S.ser.rate_R;
+        // a previous sample right in front of the window always passes `ts > tStart - maxPrevInterval` when maxPrevInterval >= dt
+        const bool prev_always = mpi32 >= dt_row;
 
         // stage buffer `bf` <- aligned bytes [fs - 16, fs + FU_FILL) of the stream (clamped to its 16-byte aligned end)
         auto issue_copy = [&](uint32_t fs, uint32_t bf) {
@@ -331,18 +431,17 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
         }
         // first row (nearest_delta2.go:75 / nearest_delta.go:64: as[0] = firstValue)
         uint32_t N = 0;                    // varints decoded so far
-        uint64_t V = (uint64_t)d.first_value, D1 = 0;
+        uint64_t V = (uint64_t)first_value, D1 = 0;
         uint32_t base = 0, cnt = 0, p = 0;
         uint32_t gen_rows = 0;             // rows produced so far (const / delta-const columns)
         double corr = 0.0, prev_raw = 0.0;
         bool stream_done = !is_stream;
         if (!bail) {
             if (tid == 0) {
-                S.val[0] = dec.conv(d.first_value);  // (fu_swz(0) == 0)
+                S.val[0] = dec.conv(first_value);  // (fu_swz(0) == 0)
             }
             cnt = 1;
             gen_rows = 1;
-            if (stale_matters && d.first_value == VMB_V_STALE_NAN) bail = true;
         }
         if (tid == 0) scanned += n;  // samplesScanned starts at len(values) rollup.go:766
         __syncthreads();
@@ -390,15 +489,22 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                 // whole tiles that fit the resident rows (pass-through once the points are done: rows are only validated)
                 const bool discard = p >= P.npoints;
                 if (discard) { cnt = 1; cnt_old = 1; }  // rows are not needed any more: decode over the same ring slots
-                uint32_t K = 0, tot = 0, rb = 0;
+                // lane k < 8 holds the count of warp k; inclusive scan over those lanes; a tile fits when the rows before it and its own
+                // fit the ring; K = the leading tiles that fit
+                uint32_t K, tot, rb;
+                {
+                    const uint32_t t = lane < FU_WARPS ? S.w_cnt[lane] : 0u;
+                    uint32_t ic = t;
 #pragma unroll
-                for (uint32_t k = 0; k < FU_WARPS; k++) {
-                    const uint32_t t = S.w_cnt[k];
-                    if (K == k && cnt + tot + t <= FU_CAP) {
-                        if (k < w) rb += t;
-                        tot += t;
-                        K++;
+                    for (int o = 1; o < FU_WARPS; o <<= 1) {
+                        const uint32_t u = __shfl_up_sync(VMB_FULL, ic, o);
+                        if (lane >= (uint32_t)o) ic += u;
                     }
+                    const uint32_t fits = __ballot_sync(VMB_FULL, lane < FU_WARPS && cnt + ic <= FU_CAP) & 0xffu;
+                    K = (uint32_t)__ffs((int)(~fits & 0x1ffu)) - 1u;  // number of leading ones
+                    tot = K ? __shfl_sync(VMB_FULL, ic, (int)K - 1) : 0u;
+                    const uint32_t ex = __shfl_sync(VMB_FULL, ic - t, (int)(w < FU_WARPS ? w : 0));
+                    rb = w < K ? ex : 0u;
                 }
                 if (N + tot > nvar) bail = true;  // more varints than rows: nearest_delta.go:65 "unexpected tail" -> un-fused path
                 const uint32_t fs_next = fs + K * FU_TILE;
@@ -506,23 +612,32 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                     if (bad) S.flags = 1u;
                     __syncthreads();
                     if (S.flags & 1u) bail = true;
-                    // exclusive prefix over the warps in front, and the totals of the fill
-                    uint32_t pc = 0, tc = 0;
-                    uint64_t ps1 = 0, ps2 = 0, ts1 = 0, ts2 = 0;
+                    // exclusive prefix over the warps in front, and the totals of the fill: lane k < K holds warp k's triple, one
+                    // 8-lane scan, warp w picks lane w - 1 (prefix) and everybody lane K - 1 (totals)
+                    uint32_t pc, tc;
+                    uint64_t ps1, ps2, ts1, ts2;
+                    {
+                        const bool act = lane < K;
+                        uint32_t c_ = act ? S.w_cnt[lane] : 0u;
+                        uint64_t a1 = act ? S.w_s1[lane] : 0ull, a2 = act ? S.w_s2[lane] : 0ull;
 #pragma unroll
-                    for (uint32_t k = 0; k < FU_WARPS; k++) {
-                        if (k < K) {
-                            const uint32_t c_ = S.w_cnt[k];
-                            const uint64_t a1 = S.w_s1[k], a2 = S.w_s2[k];
-                            if (k < w) {
-                                if (delta2) ps2 = ps2 + a2 + (uint64_t)c_ * ps1;
-                                ps1 += a1;
-                                pc += c_;
+                        for (int o = 1; o < FU_WARPS; o <<= 1) {
+                            const uint32_t bc = __shfl_up_sync(VMB_FULL, c_, o);
+                            const uint64_t b1 = shfl_up_u64(a1, o), b2 = shfl_up_u64(a2, o);
+                            if (lane >= (uint32_t)o) {
+                                if (delta2) a2 = b2 + a2 + (uint64_t)c_ * b1;
+                                a1 += b1;
+                                c_ += bc;
                             }
-                            if (delta2) ts2 = ts2 + a2 + (uint64_t)c_ * ts1;
-                            ts1 += a1;
-                            tc += c_;
                         }
+                        const int src_p = w ? (int)w - 1 : 0, src_t = (int)K - 1;
+                        pc = __shfl_sync(VMB_FULL, c_, src_p);
+                        ps1 = shfl_u64(a1, src_p);
+                        ps2 = shfl_u64(a2, src_p);
+                        if (w == 0) { pc = 0; ps1 = 0; ps2 = 0; }
+                        tc = __shfl_sync(VMB_FULL, c_, src_t);
+                        ts1 = shfl_u64(a1, src_t);
+                        ts2 = shfl_u64(a2, src_t);
                     }
                     // ---- emit: replay the lane's values with the scanned prefix, mantissa -> float64 in place
                     uint32_t ecnt = __shfl_up_sync(VMB_FULL, icnt, 1);  // (all lanes take part in the shuffles)
@@ -593,7 +708,7 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                 const uint32_t take = min(n - gen_rows, (uint32_t)FU_CAP - cnt);
                 for (uint32_t k = tid; k < take; k += FU_THREADS) {
                     const uint32_t r = gen_rows + k;
-                    const int64_t v = (int64_t)((uint64_t)d.first_value + (uint64_t)r * (uint64_t)dconst);
+                    const int64_t v = (int64_t)((uint64_t)first_value + (uint64_t)r * (uint64_t)dconst);
                     RV[base + cnt + k] = dec.conv(v);
                     if (stale_matters && v == VMB_V_STALE_NAN) S.flags = 1u;
                 }
@@ -614,6 +729,14 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                 const double raw_last = RV[base + cnt - 1];
                 if (nev > FU_MAX_EVENTS) {
                     bail = true;  // a fill full of resets: un-fused path
+                } else if (nev == 0 && corr != 0.0 && isfinite(corr) && fu_ld(S.val, base + cnt_old) + corr >= fu_ld(S.val, base + cnt_old - 1)) {
+                    // no value drop inside the fill (nor at its front) and its first corrected row is not below the last output: raw
+                    // rows are non-decreasing, x -> RN(x + corr) keeps the order, so the clamp of rollup.go:954 cannot fire: one pass
+                    for (uint32_t k = cnt_old + tid; k < cnt; k += FU_THREADS) {
+                        double& rv = fu_ref(S.val, base + k);
+                        rv = rv + corr;
+                    }
+                    __syncthreads();
                 } else if (nev || corr != 0.0) {
                     if (tid == 0) {
                         // events in row order, corrections accumulated sequentially like the Go loop
@@ -693,17 +816,66 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
             {
                 const uint32_t spc = (uint32_t)rc.samples_scanned_per_call;
                 uint32_t sc32 = 0;
+                const FuVals WV{S.val, base};  // WV[k] = resident row base + k
 #pragma unroll 2
                 for (uint32_t q = p + tid; q < p_end; q += FU_THREADS) {
+                    if (F == VMB_RF_RATE && lin && rate_dt > 0 && prev_always) {
+                        // interior point: the window [i, j) holds rate_rows rows and row i - 1 exists: (v[j-1] - v[i-1]) / D
+                        const int32_t is_ = iq0 + (int32_t)q * lin_k;
+                        if (is_ >= 1 && is_ + rate_rows <= (int32_t)n) {
+                            const double vp = fu_ld(S.val, (uint32_t)is_ - 1u), vl = fu_ld(S.val, (uint32_t)(is_ + rate_rows) - 1u);
+                            const double x = vl - vp;
+                            const uint32_t ex = ((uint32_t)__double2hiint(x) >> 20) & 0x7ffu;
+                            if (!isnan(vp) && (x == 0.0 || ex - 123u < 1800u)) {
+                                const double q0 = __dmul_rn(x, rate_R);
+                                const double rem = __fma_rn(-q0, rate_D, x);
+                                sc32 += spc ? spc : (uint32_t)rate_rows;
+                                P.out[(size_t)s * P.npoints + q] = x == 0.0 ? x : __fma_rn(rem, rate_R, q0);
+                                continue;
+                            }
+                        }
+                    }
                     const int32_t xj = start_r + (int32_t)q * step32;
-                    uint32_t i = seek_ap(xj - win32, dt_row, inv_row, n);
-                    uint32_t j = seek_ap(xj, dt_row, inv_row, n);
+                    uint32_t i, j;
+                    if (lin) {  // edges advance by a whole number of rows per point: no division
+                        const int32_t is_ = iq0 + (int32_t)q * lin_k, js_ = jq0 + (int32_t)q * lin_k;
+                        i = (uint32_t)min(max(is_, 0), (int32_t)n);
+                        j = (uint32_t)min(max(js_, 0), (int32_t)n);
+                    } else {
+                        i = seek_ap(xj - win32, dt_row, inv_row, n);
+                        j = seek_ap(xj, dt_row, inv_row, n);
+                    }
                     i = i < base ? base : (i > base + cnt ? base + cnt : i);
                     j = j < base ? base : (j > base + cnt ? base + cnt : j);
                     if (j < i) j = i;
                     if (F == VMB_RF_RATE) {
+                        // rollupDerivFast (rollup.go:1954), the selects of rate_point_ap with the division through the cached reciprocal
                         sc32 += spc ? spc : j - i;
-                        P.out[(size_t)s * P.npoints + q] = rate_point_ap(i, j, base, n, cnt, xj - win32 - mpi32, dt_row, FuVals{S.val, base});
+                        const uint32_t ri = i - base, rj = j - base, nw = j - i;
+                        const bool have_prev = i > 0 && i < n;
+                        const uint32_t ip = have_prev ? ri - 1 : 0u;
+                        const uint32_t i0 = ri < cnt ? ri : cnt - 1;
+                        const uint32_t il = rj ? rj - 1 : 0u;
+                        const double vp = WV[ip], v0 = WV[i0], vl = WV[il];
+                        const int32_t tp = (int32_t)(base + ip) * dt_row;
+                        const bool prev_ok = have_prev && tp > xj - win32 - mpi32 && !isnan(vp);
+                        const bool fixed = prev_ok ? nw == 0 : nw < 2;
+                        const double a = prev_ok ? vp : v0;
+                        int32_t dtm = (int32_t)(il - (prev_ok ? ip : i0)) * dt_row;
+                        dtm = fixed ? 1000 : dtm;
+                        const double x = vl - a;
+                        double qv;
+                        const uint32_t ex = ((uint32_t)__double2hiint(x) >> 20) & 0x7ffu;
+                        if (dtm == rate_dt && (x == 0.0 || ex - 123u < 1800u)) {
+                            // x / D with D = RN(dtm / 1e3), R = RN(1 / D): q = RN(x R), rem = x - q D (exact), RN(q + rem R) is the correctly
+                            // rounded quotient (Markstein's step; |x| in [2^-900, 2^900], D in [1e-3, 2^30/1e3]: no under/overflow anywhere)
+                            const double q0 = __dmul_rn(x, rate_R);
+                            const double rem = __fma_rn(-q0, rate_D, x);
+                            qv = x == 0.0 ? x : __fma_rn(rem, rate_R, q0);
+                        } else {
+                            qv = x / ms_to_s((int64_t)dtm);
+                        }
+                        P.out[(size_t)s * P.npoints + q] = fixed ? (prev_ok ? 0.0 : D_NAN) : qv;
                     } else {
                         P.out[(size_t)s * P.npoints + q] = fu_point<F>(rc, window, max_prev, S.val, n, i, j, q, t_org, dts, scanned);
                     }
@@ -715,7 +887,8 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
             if (p >= P.npoints) continue;
             // ================= slide: keep rows from (first row after tStart(p)) - 1
             {
-                uint32_t lo = seek_ap(start_r + (int32_t)p * step32 - win32, dt_row, inv_row, n);
+                uint32_t lo = lin ? (uint32_t)min(max(iq0 + (int32_t)p * lin_k, 0), (int32_t)n)
+                                  : seek_ap(start_r + (int32_t)p * step32 - win32, dt_row, inv_row, n);
                 lo = lo < base ? base : (lo > base + cnt ? base + cnt : lo);
                 uint32_t nb = lo > base ? lo - 1 : base;
                 if (nb > base + cnt - 1) nb = base + cnt - 1;
