@@ -518,19 +518,32 @@ def main():
             self.t = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
             self.ptr = self.t.data_ptr()
 
+    # N > 1: the library's own NCCL communicator (csrc/comm.inc); torch.distributed only carries the 128-byte unique id
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(vm.Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank)
+
     def make_aggr(aggr, groups):
         group_ids = ((np.arange(a.blocks, dtype=np.int64) * world + rank) % groups).astype(np.uint32)
-        ia = promql.IncrementalAggr(aggr, groups, points, Buf)
-        reduce_cb = (lambda v, c, op: promql.torch_all_reduce(v.t, c.t, op)) if world > 1 else None
         h = _lib.lib().vmb_host_alloc(groups * points * 8)
         assert h, "pinned host allocation failed"
         res = np.ctypeslib.as_array(C.cast(h, C.POINTER(C.c_double)), shape=(groups, points))
 
         def aggr_step():
-            scanned_ = ia.update_blocks(blocks, rc_aggr, group_ids)
-            ia.finalize(ctx, all_reduce=reduce_cb, out=res)  # D2H of the [groups x points] query result included
+            # one library call: fold this rank's series on the GPU, all-reduce {values, counts} over NCCL, finalize, D2H of the result
+            _, scanned_ = promql.eval_rollup_aggr_dist(aggr, a.func, blocks, group_ids, groups, start, end, step, a.window_ms,
+                                                       args=func_args, out=res)
             return None, scanned_
+        ia = promql.IncrementalAggr(aggr, groups, points, Buf) if not a.no_e2e and a.aggr else None
+        reduce_cb = (lambda v, c, op: check_rc(_lib.lib().vmb_aggr_allreduce(ctx.h, promql.AGGR_FUNCS[aggr], C.c_void_p(v.ptr), C.c_void_p(c.ptr),
+                                                                            groups * points))) if world > 1 else None
         return aggr_step, ia, reduce_cb, group_ids, res
+
+    def check_rc(rc_):
+        _lib.check(rc_)
 
     main_step = dev_step
     if a.aggr:
@@ -632,7 +645,8 @@ def main():
             aggr_rec["sum_by_%d_groups" % groups] = {
                 "value": world * rows_total / (ms_ / 1e3), "unit": "samples/s", "ms_per_step": ms_, "gpu_launches_per_step": launches_ / max(3, min(a.steps, 5)),
                 "result": "[%d x %d] f64 finalized on every rank, copied to pinned host memory inside the timed region" % (groups, points),
-                "collective": ("NCCL all-reduce of {values, counts}[%d x %d] f64 across %d ranks" % (groups, points, world)) if world > 1 else "none (one GPU)"}
+                "api": "vmb_eval_rollup_aggr_dist (fold inside the fused kernel; NCCL inside the library)",
+                "collective": ("ncclAllReduce of {values, counts}[%d x %d] f64 across %d ranks, issued by libvmb200 on its stream" % (groups, points, world)) if world > 1 else "none (one GPU)"}
             del fn, _ia, res
 
     sampler.stop()

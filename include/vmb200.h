@@ -44,6 +44,7 @@ extern "C" {
 #define VMB_ERR_NOMEM (-52)
 #define VMB_ERR_BLOCK_FAILED (-53)    /* at least one block failed to decode; see the per-block status array */
 #define VMB_ERR_CAP (-54)
+#define VMB_ERR_COMM (-55)            /* NCCL could not be loaded, or a collective failed (vmb_last_error has the NCCL text) */
 
 typedef struct vmb_ctx vmb_ctx;
 typedef struct vmb_blocks vmb_blocks;  /* compressed blocks resident in HBM (descriptors + payload arena) */
@@ -289,6 +290,30 @@ int vmb_eval_rollup_aggr_host_partial(vmb_ctx* ctx, const vmb_block_desc* descs,
 int vmb_eval_rollup_aggr_device(vmb_ctx* ctx, const vmb_blocks* blocks, int64_t tr_min, int64_t tr_max,
                                 const vmb_rollup_cfg* cfg, int aggr_id, const uint32_t* group_ids, uint32_t ngroups,
                                 double* d_values, double* d_counts, uint64_t* samples_scanned);
+
+/* ---- multi-GPU: one process per GPU, the ONE exchange step of the path inside the library ------------------
+ * aggr(rollup(m[d])) by (...): every rank folds its shard of the series into {values, counts}[G x P] (the per-worker
+ * incrementalAggrContext, aggr_incremental.go:184), the partial states are merged by one ncclAllReduce per array -- the GPU
+ * counterpart of the merge loop in finalizeTimeseries (aggr_incremental.go:141-168) -- and finalized on every rank.
+ * NCCL is dlopen()ed ("libnccl.so.2", or $VMB_NCCL_LIB): no link-time dependency; in a process that already holds an NCCL it is
+ * the same library instance.  Bootstrap: rank 0 calls vmb_comm_get_unique_id and hands the 128 bytes to the other ranks by any
+ * means (the Go host: over vmselect's own RPC), then every rank calls vmb_ctx_comm_init; or vmb_ctx_comm_attach with an
+ * ncclComm_t the host created itself.  Group ids must be assigned identically on all ranks. */
+int vmb_comm_get_unique_id(uint8_t id[128]);                                  /* ncclGetUniqueId */
+int vmb_ctx_comm_init(vmb_ctx* ctx, const uint8_t id[128], int nranks, int rank); /* ncclCommInitRank on the ctx's device */
+int vmb_ctx_comm_attach(vmb_ctx* ctx, void* nccl_comm, int nranks, int rank);  /* the host's own ncclComm_t (not destroyed by the ctx) */
+int vmb_ctx_comm_destroy(vmb_ctx* ctx);
+int vmb_ctx_comm_size(const vmb_ctx* ctx);                                     /* 1 without a communicator */
+int vmb_ctx_comm_rank(const vmb_ctx* ctx);
+/* exchange step on DEVICE partial states, in place, on the ctx stream: identity into empty cells, all-reduce of the values with
+ * the aggregate's operator (sum / min / max / prod) and of the counts with sum.  No-op without a communicator. */
+int vmb_aggr_allreduce(vmb_ctx* ctx, int aggr_id, double* d_values, double* d_counts, size_t n);
+/* topk(): candidate lists of all ranks side by side, d_parts[nranks x count] (input of vmb_topk_merge) -- ncclAllGather */
+int vmb_topk_allgather(vmb_ctx* ctx, const double* d_cand, size_t count, double* d_parts);
+/* the whole query step on every rank in one call: fold this rank's device-resident blocks, all-reduce, finalize;
+ * out_host [ngroups x P] (may be NULL) receives the (identical on all ranks) result */
+int vmb_eval_rollup_aggr_dist(vmb_ctx* ctx, const vmb_blocks* blocks, int64_t tr_min, int64_t tr_max, const vmb_rollup_cfg* cfg,
+                              int aggr_id, const uint32_t* group_ids, uint32_t ngroups, double* out_host, uint64_t* samples_scanned);
 
 /* pinned host memory helpers (cudaHostAlloc) for callers that want full PCIe speed */
 void* vmb_host_alloc(size_t bytes);

@@ -136,11 +136,23 @@ def test_config3_sum_rate_by_label_single_rank(oracle):
         oracle.lib().vmo_aggr_finalize(AGGR["sum"], exp_v[g].ctypes.data_as(oracle.f64p), exp_c[g].ctypes.data_as(oracle.f64p), rc.points)
     assert np.allclose(got, exp_v, rtol=1e-12, atol=0, equal_nan=True)
     # the one-call variant on compressed device blocks (vmb_eval_rollup_aggr_device) yields the same bits
-    ia2 = vm.promql.IncrementalAggr("sum", G, rc.points, Buf)
-    scanned = ia2.update_blocks(B, rc, groups)
-    got2 = ia2.finalize(vm.default_context())
+    ctx = vm.default_context()
+    ctx.set_fused(False)
+    try:
+        ia2 = vm.promql.IncrementalAggr("sum", G, rc.points, Buf)
+        scanned = ia2.update_blocks(B, rc, groups)
+        got2 = ia2.finalize(ctx)
+    finally:
+        ctx.set_fused(True)
     assert np.array_equal(got, got2, equal_nan=True)
     assert scanned > 0
+    # ... and through the fused kernel, which folds every finished series into the group cells with atomic adds: the order of the
+    # additions is not fixed (as in the reference, whose workers race for the series), the bits may differ in the last place
+    ia4 = vm.promql.IncrementalAggr("sum", G, rc.points, Buf)
+    scanned4 = ia4.update_blocks(B, rc, groups)
+    got4 = ia4.finalize(ctx)
+    assert scanned4 == scanned
+    assert np.allclose(got4, got, rtol=1e-13, atol=0, equal_nan=True)
     # and the host path (chunked pipeline folding every chunk on the GPU): several chunks, every aggregate
     import os
     os.environ["VMB_PIPE_CHUNK_BLOCKS"] = "10"

@@ -204,3 +204,62 @@ def test_fused_unaligned_plain_streams_and_all_varint_widths(oracle):
         assert np.array_equal(f64bits(a), f64bits(b)), func
         exp = _oracle_rollup_matrix(oracle, blocks, func, start, end, step, window)
         assert np.allclose(a, exp, rtol=1e-12, atol=0, equal_nan=True), func
+
+
+@pytest.mark.parametrize("aggr", ["sum", "avg", "count", "min", "max", "sum2", "group", "geomean", "any"])
+def test_fused_incremental_aggregate(oracle, aggr):
+    """aggr(rollup(m[d])) by (g) with the fold inside the fused kernel (vmb_eval_rollup_aggr_device): every finished series is folded
+    into {values, counts}[G x P] from the kernel; series the kernel hands back (jittered timestamps, staleness markers, several
+    blocks) are folded by the pipeline into the same state.  geomean / any have no atomic fold: they take the pipeline."""
+    import torch
+    import victoriametrics_b200 as vm
+    from rollup_names import AGGR
+    rng = np.random.default_rng(SEED0 + 2024)
+    blocks, s = [], 0
+    for k in range(60):
+        kind = ["counter", "gauge", "counter_resets", "gauge_small"][k % 4]
+        tk = "jitter" if k % 6 == 1 else "regular"
+        v = blockgen.gen_values(rng, kind, 3000)
+        if k % 10 == 7:
+            v = v.copy()
+            v[rng.integers(1, 3000, 2)] = (1 << 63) - 2
+        blocks.append(blockgen.OBlock(blockgen.gen_timestamps(rng, tk, 3000, T0), v, -2, 64, s))
+        s += 1
+    S, G = s, 7
+    groups = (np.arange(S) * 5 % G).astype(np.uint32)
+    start, end, step, window = T0 + 300000, T0 + 15000 * 2990, 15000, 300000
+    func = "rate" if aggr not in ("min", "max") else "avg_over_time"
+    rc = vm.promql.get_rollup_configs(func, start, end, step, window)
+    descs, payload = blockgen.to_blockset(blocks)
+    ctx = vm.default_context()
+    B = vm.storage.Blocks(descs, payload, ctx)
+
+    class Buf:
+        def __init__(self, nbytes):
+            self.t = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+            self.ptr = self.t.data_ptr()
+    res = {}
+    for fused in (True, False):
+        ctx.set_fused(fused)
+        try:
+            ia = vm.promql.IncrementalAggr(aggr, G, rc.points, Buf)
+            sc = ia.update_blocks(B, rc, groups)
+            res[fused] = (ia.finalize(ctx), sc)
+        finally:
+            ctx.set_fused(True)
+    assert res[True][1] == res[False][1]
+    rolled = _oracle_rollup_matrix(oracle, blocks, func, start, end, step, window)
+    e_v, e_c = np.zeros((G, rc.points)), np.zeros((G, rc.points))
+    for s_ in range(S):
+        row = np.ascontiguousarray(rolled[s_])
+        g = int(groups[s_])
+        oracle.lib().vmo_aggr_update(AGGR[aggr], e_v[g].ctypes.data_as(oracle.f64p), e_c[g].ctypes.data_as(oracle.f64p),
+                                     row.ctypes.data_as(oracle.f64p), rc.points)
+    for g in range(G):
+        oracle.lib().vmo_aggr_finalize(AGGR[aggr], e_v[g].ctypes.data_as(oracle.f64p), e_c[g].ctypes.data_as(oracle.f64p), rc.points)
+    for fused in (True, False):
+        got = res[fused][0]
+        assert np.array_equal(np.isnan(got), np.isnan(e_v)), (aggr, fused)
+        assert np.allclose(got, e_v, rtol=1e-12, atol=0, equal_nan=True), (aggr, fused)
+    if aggr in ("min", "max", "count", "group"):  # order independent
+        assert np.array_equal(f64bits(res[True][0]), f64bits(res[False][0]))

@@ -66,6 +66,15 @@ def lib():
         "vmb_ctx_set_stream": (C.c_int, [vp, vp]),
         "vmb_ctx_synchronize": (C.c_int, [vp]),
         "vmb_ctx_set_fused": (C.c_int, [vp, C.c_int]),
+        "vmb_comm_get_unique_id": (C.c_int, [u8p]),
+        "vmb_ctx_comm_init": (C.c_int, [vp, u8p, C.c_int, C.c_int]),
+        "vmb_ctx_comm_attach": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "vmb_ctx_comm_destroy": (C.c_int, [vp]),
+        "vmb_ctx_comm_size": (C.c_int, [vp]),
+        "vmb_ctx_comm_rank": (C.c_int, [vp]),
+        "vmb_aggr_allreduce": (C.c_int, [vp, C.c_int, vp, vp, sz]),
+        "vmb_topk_allgather": (C.c_int, [vp, vp, sz, vp]),
+        "vmb_eval_rollup_aggr_dist": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.POINTER(RollupCfg), C.c_int, u32p, C.c_uint32, f64p, u64p]),
         "vmb_last_error": (C.c_char_p, []),
         "vmb_version": (C.c_int, []),
         "vmb_ctx_launch_count": (C.c_uint64, [vp]),
@@ -171,6 +180,25 @@ class Context:
     def set_fused(self, on=True):
         """vmb_ctx_set_fused: fused decode+rollup kernel for the series that qualify (default on)"""
         check(lib().vmb_ctx_set_fused(self.h, int(on)))
+
+    # ---- multi-GPU (csrc/comm.inc): one process per GPU, NCCL inside the library
+    @staticmethod
+    def comm_unique_id():
+        """vmb_comm_get_unique_id (rank 0) -> 128 bytes to hand to every rank"""
+        buf = (C.c_uint8 * 128)()
+        check(lib().vmb_comm_get_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id, nranks, rank):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        check(lib().vmb_ctx_comm_init(self.h, buf, int(nranks), int(rank)))
+
+    def comm_destroy(self):
+        check(lib().vmb_ctx_comm_destroy(self.h))
+
+    @property
+    def comm_size(self):
+        return int(lib().vmb_ctx_comm_size(self.h))
 
     def enable_stage_timing(self, on=True):
         check(lib().vmb_ctx_enable_stage_timing(self.h, int(on)))

@@ -74,6 +74,10 @@ struct vmb_ctx {
     DevBuf zseq;  // decoded zstd sequences (8 B each) between k_zstd_seq_decode and k_zstd_seq_exec
     DevBuf zscratch, zlit, zstatus, zjobs, zws, args1, args2, rolled, counters, tmp_out, grp, mheap, mnext;
     DevBuf bail, sub_arrays;  // fused path: series handed to the un-fused pipeline, and that sub-batch's arrays
+    DevBuf aggr_state, grp_ids;  // vmb_eval_rollup_aggr_dist: {values, counts}[G x P]; device copy of the per-series group ids
+    void* comm = nullptr;     // ncclComm_t (comm.inc); nullptr = single GPU
+    bool comm_owned = false;
+    int comm_ranks = 1, comm_rank = 0;
     bool fused = true;           // vmb_ctx_set_fused: series that qualify go through the fused decode+rollup kernel (fused.cu)
     int64_t dedup_interval = 0;  // storage.SetDedupInterval (lib/storage/dedup.go:15), ms; 0 = deduplication off
     struct vmb_series* col_cache = nullptr;  // decoded columns of the one-call device paths, sized for the largest batch seen
@@ -156,14 +160,16 @@ extern "C" int vmb_ctx_create(int device, vmb_ctx** out) {
     return VMB_OK;
 }
 extern "C" void vmb_series_free(vmb_series* s);
+extern "C" int vmb_ctx_comm_destroy(vmb_ctx* ctx);
 extern "C" void vmb_ctx_destroy(vmb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    vmb_ctx_comm_destroy(c);
     if (c->col_cache) vmb_series_free(c->col_cache);
     c->col_cache = nullptr;
     DevBuf* bufs[] = {&c->zscratch, &c->zlit, &c->zstatus, &c->zjobs, &c->zws, &c->args1, &c->args2, &c->rolled,
-                      &c->counters, &c->tmp_out, &c->grp, &c->mheap, &c->mnext, &c->zseq, &c->bail, &c->sub_arrays};
+                      &c->counters, &c->tmp_out, &c->grp, &c->mheap, &c->mnext, &c->zseq, &c->bail, &c->sub_arrays, &c->aggr_state, &c->grp_ids};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 6; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -1284,9 +1290,10 @@ static bool fused_enabled(const vmb_ctx* ctx, const vmb_blocks* b, const vmb_rol
 
 // the un-fused pipeline over the series `sub` (ascending) of an upload whose zstd stage already ran: a sub-batch is built from
 // the host copies of the descriptors, decoded into the ctx's column cache and rolled up into the rows sub[i] of d_out
+// (dense_rows: series sub[i] writes row i of d_out instead of row sub[i])
 static int run_unfused_subset(vmb_ctx* ctx, const vmb_blocks* b, const std::vector<uint32_t>& sub, int32_t* d_zstatus,
                               int64_t tr_min, int64_t tr_max, const vmb_rollup_cfg* cfg, int64_t points, double* d_out,
-                              unsigned int* d_failed, unsigned long long* d_scanned) {
+                              unsigned int* d_failed, unsigned long long* d_scanned, bool dense_rows = false) {
     cudaStream_t st = ctx->stream;
     std::vector<vmb_block_desc> descs;
     std::vector<ColInfo> cols;
@@ -1350,7 +1357,7 @@ static int run_unfused_subset(vmb_ctx* ctx, const vmb_blocks* b, const std::vect
     view.stale_dropped = view.resets_removed = false;
     view.pre_applied = 0;
     rc = run_decode(ctx, &bv, &view, tr_min, tr_max, 0, d_failed, true, d_zstatus, (const uint32_t*)(da + o_map));
-    if (!rc) rc = run_rollup(ctx, &view, cfg, points, d_out, d_scanned, (const uint32_t*)(da + o_rows), false);
+    if (!rc) rc = run_rollup(ctx, &view, cfg, points, d_out, d_scanned, dense_rows ? nullptr : (const uint32_t*)(da + o_rows), false);
     cudaError_t e = cudaStreamSynchronize(st);  // `hs` goes out of scope
     if (!rc && e != cudaSuccess) {
         vmb_set_error("un-fused sub-batch: %s", cudaGetErrorString(e));
@@ -1361,8 +1368,30 @@ static int run_unfused_subset(vmb_ctx* ctx, const vmb_blocks* b, const std::vect
 
 // decode + preamble + rollup of an uploaded block set into d_out through the fused kernel.  Synchronises the stream once (the
 // bail count has to reach the host); counters (failed series, samplesScanned) are left in the device accumulators.
+// incremental-aggregate sink of the fused path: every series is folded into {values, counts}[G x P] (caller-initialised DEVICE
+// state) instead of being written to a [series x P] matrix
+struct FusedAggr {
+    int aggr_id;
+    const uint32_t* h_group_ids;  // per series of the batch (host)
+    const uint32_t* d_group_ids;  // the same on the device
+    uint32_t ngroups;
+    double* d_values;
+    double* d_counts;
+};
+static bool aggr_fusable(int aggr_id) {
+    return aggr_id == VMB_AGGR_SUM || aggr_id == VMB_AGGR_AVG || aggr_id == VMB_AGGR_COUNT || aggr_id == VMB_AGGR_GROUP ||
+           aggr_id == VMB_AGGR_SUM2 || aggr_id == VMB_AGGR_MIN || aggr_id == VMB_AGGR_MAX;
+}
+// identity of the fold: 0 for sum-like states, +-Inf for min / max; counts 0
+__global__ void k_aggr_init(int aggr, double* dv, double* dc, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dv[i] = aggr == VMB_AGGR_MIN ? D_INF : (aggr == VMB_AGGR_MAX ? -D_INF : 0.0);
+    dc[i] = 0.0;
+}
+
 static int eval_fused(vmb_ctx* ctx, const vmb_blocks* b, int64_t tr_min, int64_t tr_max, const vmb_rollup_cfg* cfg, int64_t points,
-                      double* d_out, unsigned int* d_failed, unsigned long long* d_scanned) {
+                      double* d_out, unsigned int* d_failed, unsigned long long* d_scanned, const FusedAggr* af = nullptr) {
     cudaStream_t st = ctx->stream;
     int rc;
     if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
@@ -1385,6 +1414,14 @@ static int eval_fused(vmb_ctx* ctx, const vmb_blocks* b, int64_t tr_min, int64_t
     F.ser_list = b->d_fused_list;
     F.ser_first_block = b->d_ser_first;
     F.out = d_out;
+    if (af) {  // one scratch row per CTA (the grid never exceeds 148 * 8 CTAs)
+        if ((rc = ctx->tmp_out.reserve((size_t)148 * 8 * (size_t)points * 8))) return rc;
+        F.out = (double*)ctx->tmp_out.p;
+        F.aggr_values = af->d_values;
+        F.aggr_counts = af->d_counts;
+        F.group_ids = af->d_group_ids;
+        F.aggr_id = af->aggr_id;
+    }
     F.scanned = d_scanned;
     F.bail_list = d_bail_list;
     F.bail_count = d_bail_count;
@@ -1416,7 +1453,42 @@ static int eval_fused(vmb_ctx* ctx, const vmb_blocks* b, int64_t tr_min, int64_t
     }
     if (!sub.empty()) {
         if (ctx->timing) CU(cudaEventRecord(ctx->ev[3], st));
-        if ((rc = run_unfused_subset(ctx, b, sub, d_zstatus, tr_min, tr_max, cfg, points, d_out, d_failed, d_scanned))) return rc;
+        if (!af) {
+            if ((rc = run_unfused_subset(ctx, b, sub, d_zstatus, tr_min, tr_max, cfg, points, d_out, d_failed, d_scanned))) return rc;
+        } else {
+            // the sub-batch's rows go to a dense scratch matrix, are folded per group (ascending series order) and merged in
+            const size_t cs = sub.size(), cells = (size_t)af->ngroups * (size_t)points;
+            if ((rc = ctx->rolled.reserve((cs * (size_t)points + 2 * cells) * 8 + 64))) return rc;
+            double* d_rows = (double*)ctx->rolled.p;
+            double* d_pv = d_rows + cs * (size_t)points;
+            double* d_pc = d_pv + cells;
+            if ((rc = run_unfused_subset(ctx, b, sub, d_zstatus, tr_min, tr_max, cfg, points, d_rows, d_failed, d_scanned, true))) return rc;
+            std::vector<uint32_t> start(af->ngroups + 1, 0), order(cs);
+            for (size_t i = 0; i < cs; i++) start[af->h_group_ids[sub[i]] + 1]++;
+            for (uint32_t g = 0; g < af->ngroups; g++) start[g + 1] += start[g];
+            {
+                std::vector<uint32_t> cur(start.begin(), start.end() - 1);
+                for (size_t i = 0; i < cs; i++) order[cur[af->h_group_ids[sub[i]]]++] = (uint32_t)i;
+            }
+            if ((rc = ctx->grp.reserve((af->ngroups + 1 + cs) * sizeof(uint32_t)))) return rc;
+            uint32_t* d_start = (uint32_t*)ctx->grp.p;
+            uint32_t* d_order = d_start + af->ngroups + 1;
+            CU(cudaMemcpyAsync(d_start, start.data(), (af->ngroups + 1) * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(d_order, order.data(), cs * 4, cudaMemcpyHostToDevice, st));
+            AggrParams A;
+            A.rolled = d_rows;
+            A.grp_start = d_start;
+            A.grp_series = d_order;
+            A.values = d_pv;
+            A.counts = d_pc;
+            A.ngroups = af->ngroups;
+            A.npoints = (uint32_t)points;
+            A.aggr = af->aggr_id;
+            k_aggr_fold<<<(unsigned)((cells + 127) / 128), 128, 0, st>>>(A);
+            k_aggr_merge<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(af->aggr_id, af->d_values, af->d_counts, d_pv, d_pc, cells);
+            count_launch(ctx, 2);
+            CU(cudaStreamSynchronize(st));  // `start` / `order` go out of scope
+        }
         if (ctx->timing) {
             CU(cudaEventRecord(ctx->ev[4], st));
             CU(cudaStreamSynchronize(st));
@@ -1469,6 +1541,7 @@ extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t
 #include "pipeline.inc"
 #include "aggr_eval.inc"
 #include "topk.inc"
+#include "comm.inc"
 
 // ------------------------------------------------------------------------------------------------ batched host encoder
 #include <atomic>

@@ -56,6 +56,13 @@ struct FusedParams {
     uint32_t nlist;
     uint32_t npoints;
     int64_t tr_min, tr_max;
+    // incremental aggregate sink (aggr_incremental.go:98 updateTimeseries): with aggr_values set, `out` is a scratch of one row
+    // per CTA ([gridDim.x x P], L2 resident); a series that made it to its end is folded from there into {values, counts}
+    // [group x P] of its group (red.global: the cells of a query live in L2) -- a series handed to the un-fused path folds nothing
+    double* aggr_values;
+    double* aggr_counts;
+    const uint32_t* group_ids;       // per series (device)
+    int aggr_id;
 };
 
 namespace {
@@ -180,6 +187,46 @@ __device__ __forceinline__ uint32_t fu_valid16(int64_t g0, int64_t lo, int64_t h
 }
 __device__ __forceinline__ uint32_t compact7(uint32_t w) {
     return (w & 0x7fu) | ((w & 0x7f00u) >> 1) | ((w & 0x7f0000u) >> 2) | ((w & 0x7f000000u) >> 3);
+}
+
+// max / min on a double cell by integer atomics (no NaN operands; -0.0 counts as +0.0).  Non-negative doubles order like signed
+// integers and sit above every negative one; negative doubles order in reverse as unsigned integers and sit above every
+// non-negative one there:   max: v >= 0 -> signed max, v < 0 -> unsigned min;   min: v >= 0 -> signed min, v < 0 -> unsigned max
+__device__ __forceinline__ void fu_atomic_max(double* a, double v) {
+    if (v >= 0) atomicMax((long long*)a, __double_as_longlong(v == 0 ? 0.0 : v));
+    else atomicMin((unsigned long long*)a, (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ void fu_atomic_min(double* a, double v) {
+    if (v >= 0) atomicMin((long long*)a, __double_as_longlong(v == 0 ? 0.0 : v));
+    else atomicMax((unsigned long long*)a, (unsigned long long)__double_as_longlong(v));
+}
+// updateAggrSum / Min / Max / Avg / Count / Sum2 (aggr_incremental.go:200-458) for one point of one series: NaN is skipped;
+// the order in which series reach a cell is scheduling dependent, as in the reference (one incrementalAggrContext per worker)
+__device__ __forceinline__ void fu_fold(int aggr, double* values, double* counts, size_t cell, double v) {
+    if (isnan(v)) return;
+    switch (aggr) {
+        case VMB_AGGR_SUM:
+        case VMB_AGGR_AVG:
+            atomicAdd(values + cell, v);
+            atomicAdd(counts + cell, 1.0);
+            break;
+        case VMB_AGGR_COUNT:
+        case VMB_AGGR_GROUP:
+            atomicAdd(values + cell, 1.0);
+            break;
+        case VMB_AGGR_SUM2:
+            atomicAdd(values + cell, __dmul_rn(v, v));
+            atomicAdd(counts + cell, 1.0);
+            break;
+        case VMB_AGGR_MIN:
+            fu_atomic_min(values + cell, v);
+            atomicAdd(counts + cell, 1.0);
+            break;
+        case VMB_AGGR_MAX:
+            fu_atomic_max(values + cell, v);
+            atomicAdd(counts + cell, 1.0);
+            break;
+    }
 }
 
 // getScrapeInterval (rollup.go:871) + getMaxPrevInterval (:899) + the window rules (:719-756) for a series whose rows sit at
@@ -586,7 +633,15 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                             k++;
                             pos += L;
                             m >>= L;
-                            drop_groups(7u * L);
+                            if (L <= 4u) {  // (the usual case: one funnel shift per word)
+                                const uint32_t sh = 7u * L;
+                                q0 = __funnelshift_r(q0, q1, sh);
+                                q1 = __funnelshift_r(q1, q2, sh);
+                                q2 = __funnelshift_r(q2, q3, sh);
+                                q3 >>= sh;
+                            } else {
+                                drop_groups(7u * L);
+                            }
                         }
                     }
                     // a run of continuation bytes over a whole 16-byte group inside the stream: a varint of > 16 bytes
@@ -817,6 +872,9 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                 const uint32_t spc = (uint32_t)rc.samples_scanned_per_call;
                 uint32_t sc32 = 0;
                 const FuVals WV{S.val, base};  // WV[k] = resident row base + k
+                const bool to_aggr = P.aggr_values != nullptr;
+                const size_t out_base = (to_aggr ? (size_t)blockIdx.x : (size_t)s) * P.npoints;
+                auto put = [&](uint32_t q, double v) { P.out[out_base + q] = v; };
 #pragma unroll 2
                 for (uint32_t q = p + tid; q < p_end; q += FU_THREADS) {
                     if (F == VMB_RF_RATE && lin && rate_dt > 0 && prev_always) {
@@ -830,7 +888,7 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                                 const double q0 = __dmul_rn(x, rate_R);
                                 const double rem = __fma_rn(-q0, rate_D, x);
                                 sc32 += spc ? spc : (uint32_t)rate_rows;
-                                P.out[(size_t)s * P.npoints + q] = x == 0.0 ? x : __fma_rn(rem, rate_R, q0);
+                                put(q, x == 0.0 ? x : __fma_rn(rem, rate_R, q0));
                                 continue;
                             }
                         }
@@ -875,9 +933,9 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                         } else {
                             qv = x / ms_to_s((int64_t)dtm);
                         }
-                        P.out[(size_t)s * P.npoints + q] = fixed ? (prev_ok ? 0.0 : D_NAN) : qv;
+                        put(q, fixed ? (prev_ok ? 0.0 : D_NAN) : qv);
                     } else {
-                        P.out[(size_t)s * P.npoints + q] = fu_point<F>(rc, window, max_prev, S.val, n, i, j, q, t_org, dts, scanned);
+                        put(q, fu_point<F>(rc, window, max_prev, S.val, n, i, j, q, t_org, dts, scanned));
                     }
                 }
                 scanned += sc32;
@@ -908,6 +966,12 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
             }
         } else {
             scanned_cta += scanned;
+            if (P.aggr_values) {  // the finished row -> the group's partial state
+                __syncthreads();
+                const double* row = P.out + (size_t)blockIdx.x * P.npoints;
+                const size_t cell0 = (size_t)P.group_ids[s] * P.npoints;
+                for (uint32_t q = tid; q < P.npoints; q += FU_THREADS) fu_fold(P.aggr_id, P.aggr_values, P.aggr_counts, cell0 + q, row[q]);
+            }
         }
     }
     unsigned long long scanned = scanned_cta;

@@ -209,6 +209,22 @@ def eval_rollup_aggr_host(aggr_name, func_name, descs, payload, group_ids, ngrou
     return out, scanned.value
 
 
+def eval_rollup_aggr_dist(aggr_name, func_name, blocks, group_ids, ngroups, start, end, step, window=0, lookback_delta=0, args=None,
+                          args2=None, tr_min=storage.INT64_MIN, tr_max=storage.INT64_MAX, out=None, rc=None):
+    """aggr(rollup(m[d])) by (...) over every rank of the ctx's communicator in ONE library call (vmb_eval_rollup_aggr_dist): this
+    rank's device-resident blocks are folded on the GPU, the partial states are merged by the library's NCCL all-reduce, every rank
+    finalizes -> (np.float64[ngroups, points], this rank's samplesScanned).  Without a communicator: the single-GPU result."""
+    rc = rc or get_rollup_configs(func_name, start, end, step, window, lookback_delta, args, args2)
+    cfg = rc._cfg()
+    if out is None:
+        out = np.empty((int(ngroups), rc.points), dtype=np.float64)
+    g = np.ascontiguousarray(group_ids, dtype=np.uint32)
+    scanned = C.c_uint64(0)
+    check(lib().vmb_eval_rollup_aggr_dist(blocks.ctx.h, blocks.h, tr_min, tr_max, C.byref(cfg), AGGR_FUNCS[aggr_name.lower()],
+                                          g.ctypes.data_as(_lib.u32p), int(ngroups), out.ctypes.data_as(_lib.f64p), C.byref(scanned)))
+    return out, scanned.value
+
+
 class IncrementalAggr:
     """incrementalAggrFuncContext aggr_incremental.go:73: aggr(rollup(m[d])) by (...) without keeping [series x points]
     on the host.  update() == updateTimeseries for every series of a device batch (per-GPU partial state);
