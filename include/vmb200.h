@@ -113,7 +113,7 @@ int vmb_metaindex_rows_unmarshal(vmb_metaindex_row* out, size_t cap, size_t* n, 
 int vmb_metaindex_row_marshal(uint8_t out[56], const vmb_metaindex_row* row); /* metaindexRow.Marshal :61 */
 /* encoding.DecompressZSTD (lib/encoding/compress.go:27) for n frames at once on the GPU -- index blocks (part_search.go:238)
  * and metaindex.bin (metaindex_row.go:134) go through the same kernels as the block payloads.  frames + offs[n+1] = the
- * compressed frames back to back; every frame must declare its content size (libzstd/gozstd always do) of <= 163840 bytes.
+ * compressed frames back to back; every frame must declare its content size (libzstd/gozstd always do; sanity cap 128 MiB).
  * Frame i is written to dst + dst_offs[i] (16-byte aligned), dst_lens[i] bytes; vmb_zstd_decompress_bound gives the dst size.
  * statuses ([n], may be NULL): 0 or VMB_ERR_ZSTD per frame; returns VMB_ERR_ZSTD if any frame failed. */
 int vmb_zstd_decompress_bound(const uint8_t* frames, const uint64_t* offs, size_t n, uint64_t* out_bytes);
@@ -246,18 +246,21 @@ int vmb_aggr_finalize(vmb_ctx* ctx, int aggr_id, double* d_values, const double*
 /* ---- topk(k, q) / bottomk(k, q)  ==  newAggrFuncTopK aggr.go:646 on a DEVICE matrix d_vals[nseries x P] (e.g. the output
  * of vmb_rollup / vmb_eval_rollup_device): per group and point only the k best values survive, the others become NaN
  * (fillNaNsAtIdx aggr.go:786); rows left without a value are reported so that the host drops them (removeEmptySeries).
- * Values equal to the k-th best are all kept (the reference's unstable sort keeps an arbitrary subset of them).
- *   1. vmb_topk_candidates: d_cand[ngroups x P x kmax] <- the kmax best non-NaN values of this process per (group, point), best
- *      first, NaN padded; kmax = the largest k of the query, <= 64.  reverse != 0: bottomk.
- *   2. several processes: all-gather the candidate arrays, then vmb_topk_merge([nparts x cells x kmax], cells = ngroups*P).
+ * Exactly k values survive per (group, point); equal values rank by ascending GLOBAL series id (series_id_base + row), one of
+ * the outcomes of the reference's unstable sort.Slice, identical on every run and rank.
+ *   1. vmb_topk_candidates: d_cand[ngroups x P x kmax] entries of 16 bytes {f64 value, f64 global series id} <- the kmax best
+ *      non-NaN values of this process per (group, point), best first, NaN padded; kmax = the largest k of the query, <= 64.
+ *      reverse != 0: bottomk.  series_id_base: global id of this process's row 0 (0 on a single GPU).
+ *   2. several processes: all-gather the candidate arrays (vmb_topk_allgather: count = cells * kmax * 2 doubles), then
+ *      vmb_topk_merge([nparts x cells x kmax] entries, cells = ngroups*P).
  *   3. vmb_topk_apply: ks = one k per point (HOST, getIntK aggr.go:793: NaN / negative -> 0, capped by the group size);
  *      group_sizes = series per group over ALL processes (HOST); row_nonempty = HOST array, 1 byte per series. */
 int vmb_topk_candidates(vmb_ctx* ctx, const double* d_vals, size_t nseries, size_t points, const uint32_t* group_ids,
-                        uint32_t ngroups, uint32_t kmax, int reverse, double* d_cand);
+                        uint32_t ngroups, uint32_t kmax, int reverse, uint64_t series_id_base, double* d_cand);
 int vmb_topk_merge(vmb_ctx* ctx, const double* d_parts, uint32_t nparts, size_t cells, uint32_t kmax, int reverse, double* d_cand);
 int vmb_topk_apply(vmb_ctx* ctx, double* d_vals, size_t nseries, size_t points, const uint32_t* group_ids, uint32_t ngroups,
                    const uint32_t* group_sizes, const double* d_cand, uint32_t kmax, const double* ks, int reverse,
-                   unsigned char* row_nonempty);
+                   uint64_t series_id_base, unsigned char* row_nonempty);
 
 /* ---- whole path in one call with HOST buffers (what a patched evalRollupNoIncrementalAggregate, eval.go:1845,
  * would call): H2D of descriptors+payload, decode, preamble, rollup, D2H of the [nseries x P] result; processed in

@@ -16,8 +16,11 @@ import "C"
 
 import (
 	"fmt"
+	"log"
 	"runtime"
 	"sync"
+	"sync/atomic"
+	"time"
 	"unsafe"
 )
 
@@ -88,11 +91,11 @@ func Enabled(n int) bool {
 
 var inUseN int32
 
-func inUse() int { return int(inUseN) }
+func inUse() int { return int(atomic.LoadInt32(&inUseN)) }
 
 // Get / Put hand out pooled contexts.
-func Get() *Ctx  { c := <-pool; inUseN++; return c }
-func Put(c *Ctx) { inUseN--; pool <- c }
+func Get() *Ctx  { c := <-pool; atomic.AddInt32(&inUseN, 1); return c }
+func Put(c *Ctx) { atomic.AddInt32(&inUseN, -1); pool <- c }
 
 func descPtr(d []BlockDesc) *C.vmb_block_desc { return (*C.vmb_block_desc)(unsafe.Pointer(&d[0])) }
 func bytePtr(b []byte) *C.uint8_t {
@@ -133,6 +136,39 @@ func (c *Ctx) EvalRollupAggr(descs []BlockDesc, payload []byte, trMin, trMax int
 	}
 	return uint64(scanned), nil
 }
+
+// ---- multi-GPU: one vmselect process per GPU; the partial states of aggr(rollup) by (...) are merged by the library's NCCL
+// all-reduce (include/vmb200.h "multi-GPU").  The 128-byte unique id travels over vmselect's own RPC.
+
+// CommUniqueID == ncclGetUniqueId on the process that owns rank 0.
+func CommUniqueID() ([128]byte, error) {
+	var id [128]byte
+	if rc := C.vmb_comm_get_unique_id((*C.uint8_t)(unsafe.Pointer(&id[0]))); rc != 0 {
+		return id, lastError(rc, "vmb_comm_get_unique_id")
+	}
+	return id, nil
+}
+
+// CommInit joins the communicator of nranks processes as `rank`.
+func (c *Ctx) CommInit(id [128]byte, nranks, rank int) error {
+	if rc := C.vmb_ctx_comm_init(c.p, (*C.uint8_t)(unsafe.Pointer(&id[0])), C.int(nranks), C.int(rank)); rc != 0 {
+		return lastError(rc, "vmb_ctx_comm_init")
+	}
+	return nil
+}
+
+// Available reports whether a usable B200 was found (Enabled created at least one context for the pool behind Get / Put).
+func Available() bool { return Enabled(runtime.GOMAXPROCS(0)) }
+
+// LogErrorRateLimited logs a library error at most once per minute (the query falls back to the stock Go path).
+func LogErrorRateLimited(err error) {
+	now := time.Now().Unix()
+	if last := atomic.LoadInt64(&lastErrLog); now-last >= 60 && atomic.CompareAndSwapInt64(&lastErrLog, last, now) {
+		log.Printf("vmb200: falling back to the CPU path: %s", err)
+	}
+}
+
+var lastErrLog int64
 
 // DescFromHeader == blockHeader.Unmarshal + validate (block_header.go:122, :230) on the 81-byte wire form.
 func DescFromHeader(d *BlockDesc, header []byte) error {

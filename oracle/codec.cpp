@@ -329,6 +329,7 @@ typedef size_t (*ref_decompress_fn)(void*, size_t, const void*, size_t);
 typedef unsigned (*ref_iserr_fn)(size_t);
 static ref_compress_fn g_ref_compress;
 static ref_decompress_fn g_ref_decompress;
+static ref_compress_fn g_ref_compress_ck;
 static ref_iserr_fn g_ref_iserr;
 static int g_ref_state;  // 0 = not tried, 1 = ok, -1 = unavailable
 
@@ -347,6 +348,7 @@ static void load_ref() {
     if (!h) return;
     g_ref_compress = (ref_compress_fn)dlsym(h, "ref_zstd_compress");
     g_ref_decompress = (ref_decompress_fn)dlsym(h, "ref_zstd_decompress");
+    g_ref_compress_ck = (ref_compress_fn)dlsym(h, "ref_zstd_compress_checksum");
     g_ref_iserr = (ref_iserr_fn)dlsym(h, "ref_zstd_is_error");
     if (g_ref_compress && g_ref_decompress && g_ref_iserr) g_ref_state = 1;
 }
@@ -358,6 +360,12 @@ int64_t vmo_zstd_ref_compress(uint8_t* dst, size_t cap, const uint8_t* src, size
     load_ref();
     if (g_ref_state != 1) return VMO_ERR_NO_ZSTD_REF;
     size_t r = g_ref_compress(dst, cap, src, n, level);
+    if (g_ref_iserr(r)) return VMO_ERR_ZSTD;
+    return (int64_t)r;
+}
+int64_t vmo_zstd_ref_compress_checksum(uint8_t* dst, size_t cap, const uint8_t* src, size_t n, int level) {
+    if (!vmo_zstd_ref_available() || !g_ref_compress_ck) return VMO_ERR_NO_ZSTD_REF;
+    size_t r = g_ref_compress_ck(dst, cap, src, n, level);
     if (g_ref_iserr(r)) return VMO_ERR_ZSTD;
     return (int64_t)r;
 }

@@ -73,6 +73,7 @@ int64_t vmo_zstd_content_size(const uint8_t* src, size_t src_len);
 int vmo_zstd_ref_available(void);
 int64_t vmo_zstd_ref_compress(uint8_t* dst, size_t cap, const uint8_t* src, size_t n, int level);
 int64_t vmo_zstd_ref_decompress(uint8_t* dst, size_t cap, const uint8_t* src, size_t n);
+int64_t vmo_zstd_ref_compress_checksum(uint8_t* dst, size_t cap, const uint8_t* src, size_t n, int level); /* with Content_Checksum */
 
 /* ---- lib/decimal/decimal.go ---- */
 double vmo_pow10(int n); /* Go math.Pow10 */

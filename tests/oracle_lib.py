@@ -70,6 +70,7 @@ def lib():
         "vmo_zstd_ref_available": (C.c_int, []),
         "vmo_zstd_ref_compress": (C.c_int64, [u8p, sz, u8p, sz, C.c_int]),
         "vmo_zstd_ref_decompress": (C.c_int64, [u8p, sz, u8p, sz]),
+        "vmo_zstd_ref_compress_checksum": (C.c_int64, [u8p, sz, u8p, sz, C.c_int]),
         "vmo_pow10": (C.c_double, [C.c_int]),
         "vmo_decimal_to_float": (None, [f64p, i64p, sz, C.c_int16]),
         "vmo_float_to_decimal": (C.c_int16, [i64p, f64p, sz]),
@@ -206,6 +207,16 @@ def zstd_ref_compress(src, level):
     n = lib().vmo_zstd_ref_compress(_u8(dst), dst.size, _u8(src), len(src), level)
     if n < 0:
         raise RuntimeError("zstd ref compress rc=%d" % n)
+    return dst[:n].copy()
+
+
+def zstd_ref_compress_checksum(src, level):
+    """a frame with a Content_Checksum (RFC 8878 3.1.1)"""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    dst = np.empty(len(src) + (len(src) >> 7) + 1024, dtype=np.uint8)
+    n = lib().vmo_zstd_ref_compress_checksum(_u8(dst), dst.size, _u8(src), len(src), level)
+    if n < 0:
+        raise RuntimeError("zstd ref compress (checksum) rc=%d" % n)
     return dst[:n].copy()
 
 

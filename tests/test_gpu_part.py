@@ -65,7 +65,10 @@ def test_zstd_decompress_batch_reports_bad_frames(oracle):
     frames = [oracle.zstd_ref_compress(r, 3) for r in raws]
     frames[1] = frames[1][: len(frames[1]) // 2].copy()        # truncated
     frames[3] = np.frombuffer(b"not a zstd frame at all....", dtype=np.uint8)
-    frames[4] = oracle.zstd_ref_compress(np.zeros(163841, dtype=np.uint8), 1)  # declares more than the 163840-byte bound
+    big = oracle.zstd_ref_compress(np.zeros(163841, dtype=np.uint8), 1).copy()
+    assert (big[4] >> 6) == 2                                    # Frame_Header_Descriptor: 4-byte Frame_Content_Size
+    big[5:9] = np.frombuffer((1 << 28).to_bytes(4, "little"), dtype=np.uint8)  # declares 256 MiB: over the 128 MiB sanity cap
+    frames[4] = big
     ctx = vm.default_context()
     offs = np.zeros(7, dtype=np.uint64)
     offs[1:] = np.cumsum([f.size for f in frames])
@@ -81,6 +84,35 @@ def test_zstd_decompress_batch_reports_bad_frames(oracle):
         assert np.array_equal(dst[int(doffs[k]):int(doffs[k]) + int(dlens[k])], raws[k])
     with pytest.raises(_lib.VmbError):
         vm.encoding.decompress_zstd_batch(frames)
+
+
+def test_zstd_decompress_batch_large_frames_and_content_checksums(oracle):
+    """metaindex.bin has no size limit in the reference (metaindex_row.go:134): frames far above one block decompress (multi-block
+    frames take the serial decoder); a frame that carries a Content_Checksum is verified (XXH64), a flipped content byte fails"""
+    import victoriametrics_b200 as vm
+    if not oracle.lib().vmo_zstd_ref_available():
+        pytest.skip("oracle/_ref (the reference's libzstd) was not built")
+    rng = np.random.default_rng(SEED0 + 22)
+    rows = rng.integers(0, 50, (20000, 56)).astype(np.uint8).reshape(-1)       # 1.1 MB, compressible, several zstd blocks
+    noise = rng.integers(0, 256, 300000).astype(np.uint8)                      # raw blocks
+    raws = [rows, noise, rng.integers(0, 3, 4000).astype(np.uint8)]
+    frames = [oracle.zstd_ref_compress(r, 3) for r in raws]
+    got = vm.encoding.decompress_zstd_batch(frames)
+    for g, r in zip(got, raws):
+        assert np.array_equal(g, r)
+    ck = [oracle.zstd_ref_compress_checksum(r, 3) for r in raws]
+    assert all((f[4] >> 2) & 1 for f in ck)                                     # Content_Checksum_Flag
+    got = vm.encoding.decompress_zstd_batch(ck)
+    for g, r in zip(got, raws):
+        assert np.array_equal(g, r)
+    bad = ck[1].copy()
+    bad[len(bad) // 2] ^= 0x40                                                  # inside a Raw block: decodes, but to other content
+    with pytest.raises(vm.VmbError):
+        vm.encoding.decompress_zstd_batch([bad])
+    bad2 = ck[0].copy()
+    bad2[-1] ^= 1                                                               # the checksum itself
+    with pytest.raises(vm.VmbError):
+        vm.encoding.decompress_zstd_batch([bad2])
 
 
 def _make_part(rng, nseries, max_index_block):

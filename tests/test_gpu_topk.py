@@ -106,23 +106,50 @@ def test_topk_two_shards_protocol():
     dev, cands = [], []
     for rows in shards:
         t = torch.from_numpy(np.ascontiguousarray(vals[rows])).cuda()
-        c = torch.empty(G * P * K, dtype=torch.float64, device="cuda")
+        c = torch.empty(G * P * K * 2, dtype=torch.float64, device="cuda")  # {value, global series id} per entry
         g = np.ascontiguousarray(groups[rows])
         _lib.check(_lib.lib().vmb_topk_candidates(ctx.h, C.c_void_p(t.data_ptr()), len(rows), P, g.ctypes.data_as(_lib.u32p), G, K, 0,
-                                                  C.c_void_p(c.data_ptr())))
+                                                  len(dev) * S, C.c_void_p(c.data_ptr())))
         dev.append((t, g))
         cands.append(c)
     gathered = torch.cat(cands)  # what an all-gather delivers on every rank
-    merged = torch.empty(G * P * K, dtype=torch.float64, device="cuda")
+    merged = torch.empty(G * P * K * 2, dtype=torch.float64, device="cuda")
     _lib.check(_lib.lib().vmb_topk_merge(ctx.h, C.c_void_p(gathered.data_ptr()), 2, G * P, K, 0, C.c_void_p(merged.data_ptr())))
     ks = np.full(P, float(K))
     got = np.empty_like(vals)
     keep = np.zeros(S, dtype=bool)
-    for rows, (t, g) in zip(shards, dev):
+    for r, (rows, (t, g)) in enumerate(zip(shards, dev)):
         flags = np.zeros(len(rows), dtype=np.uint8)
         _lib.check(_lib.lib().vmb_topk_apply(ctx.h, C.c_void_p(t.data_ptr()), len(rows), P, g.ctypes.data_as(_lib.u32p), G,
                                              gsz.ctypes.data_as(_lib.u32p), C.c_void_p(merged.data_ptr()), K,
-                                             ks.ctypes.data_as(_lib.f64p), 0, flags.ctypes.data_as(_lib.u8p)))
+                                             ks.ctypes.data_as(_lib.f64p), 0, r * S, flags.ctypes.data_as(_lib.u8p)))
         got[rows] = t.cpu().numpy()
         keep[rows] = flags.astype(bool)
     assert _same(got, exp) and keep.tolist() == ekeep.tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reverse", [False, True])
+def test_topk_ties_keep_exactly_k(reverse):
+    """topk(5, up)-like input: many equal values.  The reference keeps exactly k series per (group, point) (aggr.go:646 +
+    fillNaNsAtIdx :786), an arbitrary subset of the tied ones (unstable sort.Slice); here the k lowest series ids of the tie."""
+    import victoriametrics_b200 as vm
+    rng = np.random.default_rng(SEED0 + 5150)
+    S, P, G, K = 120, 40, 3, 5
+    vals = rng.integers(0, 3, (S, P)).astype(np.float64)  # heavy ties
+    vals[:, 0] = 1.0                                       # one point where every series ties
+    vals[rng.random((S, P)) < 0.05] = NAN
+    groups = (np.arange(S) % G).astype(np.uint32)
+    got, keep = _run(vm, vals, K, groups, G, reverse)
+    for g in range(G):
+        rows = np.nonzero(groups == g)[0]
+        for p in range(P):
+            col = vals[rows, p]
+            alive = ~np.isnan(got[rows, p])
+            nvalid = int((~np.isnan(col)).sum())
+            assert alive.sum() == min(K, nvalid), (g, p)
+            # the survivors are the k best under (value, ascending series id)
+            order = sorted((i for i in range(len(rows)) if not np.isnan(col[i])), key=lambda i: ((col[i] if reverse else -col[i]), rows[i]))
+            assert sorted(np.nonzero(alive)[0].tolist()) == sorted(order[:K]), (g, p)
+            assert np.array_equal(got[rows, p][alive], col[alive])
+    assert keep.tolist() == (~np.all(np.isnan(got), axis=1)).tolist()

@@ -223,3 +223,25 @@ def test_block_header_roundtrip(oracle):
     for f, _ in oracle.BlockHeader._fields_:
         a, b = getattr(bh, f), getattr(bh2, f)
         assert (bytes(a) == bytes(b)) if f == "tsid" else (a == b), f
+
+
+def test_pow10_is_the_published_go_table_product(oracle):
+    """Go's math.Pow10 (src/math/pow10.go, unchanged since Go 1.11):
+         0 <= n <= 308:   pow10postab32[n/32] * pow10tab[n%32]      (tables of the decimal literals 1e0..1e31 and 1e0,1e32,..,1e288)
+         -323 <= n <= 0:  pow10negtab32[-n/32] / pow10tab[-n%32]    (1e-0, 1e-32, .., 1e-320)
+         else +Inf / 0.
+    Every entry rebuilt here from correctly rounded literals (Python's float() is IEEE round-to-nearest like the Go compiler's
+    constant conversion) -- for n >= 32 the product can differ from the literal 1eN by one ulp, which is what decimal.go:100 sees."""
+    L = oracle.lib()
+    differs_from_literal = 0
+    for n in range(-330, 316):
+        got = L.vmo_pow10(n)
+        if 0 <= n <= 308:
+            exp = float("1e%d" % (32 * (n // 32))) * float("1e%d" % (n % 32))
+            differs_from_literal += exp != float("1e%d" % n)
+        elif -323 <= n <= 0:
+            exp = float("1e-%d" % (32 * ((-n) // 32))) / float("1e%d" % ((-n) % 32))
+        else:
+            exp = float("inf") if n > 0 else 0.0
+        assert got == exp and np.float64(got).view(np.uint64) == np.float64(exp).view(np.uint64), n
+    assert differs_from_literal > 0  # the table product is not the same thing as the literal: the restatement must use the product

@@ -120,9 +120,9 @@ def lib():
         "vmb_eval_rollup_aggr_device": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.POINTER(RollupCfg), C.c_int, u32p, C.c_uint32,
                                                   vp, vp, u64p]),
         "vmb_ctx_set_dedup_interval": (C.c_int, [vp, C.c_int64]),
-        "vmb_topk_candidates": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, u32p, C.c_uint32, C.c_uint32, C.c_int, vp]),
+        "vmb_topk_candidates": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, vp]),
         "vmb_topk_merge": (C.c_int, [vp, vp, C.c_uint32, C.c_size_t, C.c_uint32, C.c_int, vp]),
-        "vmb_topk_apply": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, u32p, C.c_uint32, u32p, vp, C.c_uint32, f64p, C.c_int, u8p]),
+        "vmb_topk_apply": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, u32p, C.c_uint32, u32p, vp, C.c_uint32, f64p, C.c_int, C.c_uint64, u8p]),
         "vmb_host_alloc": (vp, [sz]),
         "vmb_host_free": (None, [vp]),
         "vmb_ctx_last_stage_ms": (C.c_float, [vp, C.c_int]),

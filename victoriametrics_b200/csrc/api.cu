@@ -125,6 +125,9 @@ struct vmb_series {
     int32_t* d_blk_status = nullptr;
     bool stale_dropped = false, resets_removed = false;
     uint32_t pre_applied = 0;  // VMB_RC_PRE_* already applied to the values (at most one of them, once)
+    bool rolled = false;       // a rollup ran on this batch: its values were processed in place with the flags below
+    uint32_t applied_mut = 0;  // VMB_RC_DROP_STALE_NANS | VMB_RC_REMOVE_COUNTER_RESETS of that first call
+    int64_t applied_max_stale = 0;  // removeCounterResets' staleness interval of that call (rollup.go:380-387)
     bool values_are_int = false;
 };
 
@@ -384,6 +387,7 @@ struct BlocksPlan {
     std::vector<uint64_t> ser_merge_off;
     uint64_t rows = 0, compressed = 0, scratch_total = 0, merge_rows = 0, seq_total = 0;
     bool needs_lit = false;
+    unsigned long long content_bound = 0;  // vmb_zstd_decompress_batch: cap on Frame_Content_Size instead of 10 bytes per row
 };
 // row layout of the decoded blocks, the series map and the merge area: needs the descriptors only
 static void plan_layout(BlocksPlan& pl, const vmb_block_desc* descs, size_t nblocks) {
@@ -452,7 +456,7 @@ static int plan_blocks(BlocksPlan& pl, const vmb_block_desc* descs, size_t nbloc
             uint32_t cs = 0;
             bool needs_lit = false;
             uint32_t nseq = 0;
-            ci.kind = zstd_classify_host(src, len, d.rows <= 16384 ? d.rows : 0, &cs, &needs_lit, &nseq);
+            ci.kind = zstd_classify_host(src, len, d.rows <= 16384 ? d.rows : 0, &cs, &needs_lit, &nseq, pl.content_bound);
             if (ci.kind == VMB_ZK_HUF && nseq) {
                 if (pl.seq_total + nseq > 0xffffffffull) {
                     vmb_set_error("more than 2^32 zstd sequences in one batch: split it");
@@ -497,11 +501,12 @@ static int upload_vec(T** dptr, const std::vector<T>& v, cudaStream_t st) {
     return 0;
 }
 
-extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload,
-                                 size_t payload_len, vmb_blocks** out) {
+static int blocks_upload_impl(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload, size_t payload_len,
+                              vmb_blocks** out, unsigned long long content_bound) {
     if (!ctx || !out || (nblocks && !descs) || (payload_len && !payload) || nblocks > 0x7fffffffu / 2) return VMB_ERR_INVALID_ARG;
     CU(cudaSetDevice(ctx->device));
     BlocksPlan pl;
+    pl.content_bound = content_bound;
     int rc = plan_blocks(pl, descs, nblocks, payload, payload_len);
     if (rc) return rc;
     vmb_blocks* b = new vmb_blocks();
@@ -518,6 +523,15 @@ extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size
     b->n_gen = (uint32_t)pl.gen.size();
     b->n_bad = (uint32_t)pl.bad.size();
     cudaStream_t st = ctx->stream;
+#define CUB(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            vmb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            vmb_blocks_free(b);                                                                    \
+            return VMB_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
 #define TRY(x)                 \
     do {                       \
         int rc_ = (x);         \
@@ -527,13 +541,13 @@ extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size
         }                      \
     } while (0)
     TRY(dev_alloc(&b->d_descs, nblocks));
-    if (nblocks) CU(cudaMemcpyAsync(b->d_descs, descs, nblocks * sizeof(vmb_block_desc), cudaMemcpyHostToDevice, st));
+    if (nblocks) CUB(cudaMemcpyAsync(b->d_descs, descs, nblocks * sizeof(vmb_block_desc), cudaMemcpyHostToDevice, st));
     // 64 bytes of slack on both sides: the bitstream windows of zstd.cu read up to 11 bytes before a stream's first byte
     TRY(dev_alloc(&b->d_payload_alloc, payload_len + 128));
     b->d_payload = b->d_payload_alloc + 64;
-    CU(cudaMemsetAsync(b->d_payload_alloc, 0, 64, st));
-    if (payload_len) CU(cudaMemcpyAsync(b->d_payload, payload, payload_len, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(b->d_payload + payload_len, 0, 64, st));
+    CUB(cudaMemsetAsync(b->d_payload_alloc, 0, 64, st));
+    if (payload_len) CUB(cudaMemcpyAsync(b->d_payload, payload, payload_len, cudaMemcpyHostToDevice, st));
+    CUB(cudaMemsetAsync(b->d_payload + payload_len, 0, 64, st));
     TRY(upload_vec(&b->d_cols, pl.cols, st));
     TRY(upload_vec(&b->d_row_off, pl.row_off, st));
     TRY(upload_vec(&b->d_huf_list, pl.huf, st));
@@ -550,9 +564,14 @@ extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size
     b->h_ser_nblocks = pl.ser_nblocks;
     b->h_fused = pl.fused;
     b->h_unfused = pl.unfused;
-    CU(cudaStreamSynchronize(st));  // the host vectors go out of scope
+    CUB(cudaStreamSynchronize(st));  // the host vectors go out of scope
     *out = b;
     return VMB_OK;
+#undef CUB
+}
+extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload,
+                                 size_t payload_len, vmb_blocks** out) {
+    return blocks_upload_impl(ctx, descs, nblocks, payload, payload_len, out, 0);
 }
 
 // ------------------------------------------------------------------------------------------------ series batches
@@ -738,6 +757,18 @@ static int collect_stage_times(vmb_ctx* ctx, int first_ev, int nstages, int firs
     return 0;
 }
 
+// CU() for code that owns a freshly allocated vmb_series `s` (and possibly a scratch device pointer): release before returning
+#define CUS(call, extra)                                                                           \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            vmb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            vmb_series_free(s);                                                                    \
+            cudaFree(extra);                                                                       \
+            return VMB_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
 extern "C" int vmb_decode_blocks(vmb_ctx* ctx, const vmb_blocks* b, int64_t tr_min, int64_t tr_max, uint32_t flags,
                                  int32_t* block_status, vmb_series** out) {
     if (!ctx || !b || !out) return VMB_ERR_INVALID_ARG;
@@ -751,17 +782,17 @@ extern "C" int vmb_decode_blocks(vmb_ctx* ctx, const vmb_blocks* b, int64_t tr_m
         return rc;
     }
     unsigned int* d_failed = (unsigned int*)ctx->counters.p;
-    CU(cudaMemsetAsync(d_failed, 0, 64, ctx->stream));
+    CUS(cudaMemsetAsync(d_failed, 0, 64, ctx->stream), nullptr);
     rc = run_decode(ctx, b, s, tr_min, tr_max, flags, d_failed);
     if (rc) {
         vmb_series_free(s);
         return rc;
     }
     unsigned int* h_failed = (unsigned int*)ctx->h_pinned;
-    CU(cudaMemcpyAsync(h_failed, d_failed, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUS(cudaMemcpyAsync(h_failed, d_failed, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream), nullptr);
     if (block_status && b->nblocks)
-        CU(cudaMemcpyAsync(block_status, s->d_blk_status, b->nblocks * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+        CUS(cudaMemcpyAsync(block_status, s->d_blk_status, b->nblocks * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream), nullptr);
+    CUS(cudaStreamSynchronize(ctx->stream), nullptr);
     collect_stage_times(ctx, 0, 2, 0);
     *out = s;
     if (*h_failed) {
@@ -808,15 +839,15 @@ extern "C" int vmb_series_from_host(vmb_ctx* ctx, const int64_t* timestamps, con
     }
     cudaStream_t st = ctx->stream;
     if (rows) {
-        CU(cudaMemcpyAsync(s->d_ts, timestamps, rows * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(s->d_vals, values, rows * 8, cudaMemcpyHostToDevice, st));
+        CUS(cudaMemcpyAsync(s->d_ts, timestamps, rows * 8, cudaMemcpyHostToDevice, st), d_off);
+        CUS(cudaMemcpyAsync(s->d_vals, values, rows * 8, cudaMemcpyHostToDevice, st), d_off);
     }
-    CU(cudaMemcpyAsync(d_off, offsets, (nseries + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUS(cudaMemcpyAsync(d_off, offsets, (nseries + 1) * 8, cudaMemcpyHostToDevice, st), d_off);
     if (nseries) {
         k_meta_from_offsets<<<(unsigned)((nseries + 127) / 128), 128, 0, st>>>(s->d_meta, d_off, (uint32_t)nseries);
         count_launch(ctx);
     }
-    CU(cudaStreamSynchronize(st));
+    CUS(cudaStreamSynchronize(st), d_off);
     cudaFree(d_off);
     *out = s;
     return VMB_OK;
@@ -931,7 +962,10 @@ extern "C" int vmb_calibrate_scale(int64_t* a, size_t na, int16_t ae, int64_t* b
 // encoding.DecompressZSTD (compress.go:27) for a batch of frames, on the GPU.  Every frame travels as the values column of a
 // pseudo block (MarshalTypeZSTDNearestDelta over the frame's bytes) through the same kernels as the block payloads; only the
 // zstd stage runs.  Layout of dst: frame i at dst_offs[i] (16-byte aligned, in frame order), dst_lens[i] bytes.
-static const uint32_t kZstdBatchRows = 16384;  // content bound = 10 bytes x rows = 163840 >= 2*maxBlockSize (part.go index blocks)
+static const uint32_t kZstdBatchRows = 16384;  // (pseudo blocks: the row count plays no role below)
+// metaindex.bin is decompressed by the reference without a size limit (metaindex_row.go:134): the bound is the frame's own
+// Frame_Content_Size under a sanity cap
+static const unsigned long long kZstdBatchMaxContent = 1ull << 27;
 extern "C" int vmb_zstd_decompress_bound(const uint8_t* frames, const uint64_t* offs, size_t n, uint64_t* out_bytes) {
     if (!out_bytes || (n && (!frames || !offs))) return VMB_ERR_INVALID_ARG;
     uint64_t tot = 0;
@@ -939,7 +973,7 @@ extern "C" int vmb_zstd_decompress_bound(const uint8_t* frames, const uint64_t* 
         if (offs[i + 1] < offs[i] || offs[i + 1] - offs[i] > 0xffffffffull) return VMB_ERR_INVALID_ARG;
         uint32_t cs = 0, nseq = 0;
         bool lit = false;
-        const uint8_t kind = zstd_classify_host(frames + offs[i], (uint32_t)(offs[i + 1] - offs[i]), kZstdBatchRows, &cs, &lit, &nseq);
+        const uint8_t kind = zstd_classify_host(frames + offs[i], (uint32_t)(offs[i + 1] - offs[i]), kZstdBatchRows, &cs, &lit, &nseq, kZstdBatchMaxContent);
         if (kind != VMB_ZK_BAD) tot += ((uint64_t)cs + 15) & ~(uint64_t)15;
     }
     *out_bytes = tot;
@@ -963,7 +997,7 @@ extern "C" int vmb_zstd_decompress_batch(vmb_ctx* ctx, const uint8_t* frames, co
         d.series_idx = (uint32_t)i;
     }
     vmb_blocks* b = nullptr;
-    int rc = vmb_blocks_upload(ctx, descs.data(), n, frames, (size_t)offs[n], &b);
+    int rc = blocks_upload_impl(ctx, descs.data(), n, frames, (size_t)offs[n], &b, kZstdBatchMaxContent);
     if (rc) return rc;
     std::vector<ColInfo> cols(2 * n);
     std::vector<int32_t> st(2 * n, 0);
@@ -1064,8 +1098,21 @@ static int run_rollup(vmb_ctx* ctx, vmb_series* s, const vmb_rollup_cfg* cfg, in
     R.scanned = d_scanned;
     R.nseries = (uint32_t)s->nseries;
     R.npoints = (uint32_t)points;
-    // data-mutating parts of the preamble run once per batch
+    // data-mutating parts of the preamble run once per batch; a later call must ask for the same mutations (the rows it would
+    // read have been processed for the first one: dropStaleNaNs, removeCounterResets with its staleness interval)
     uint32_t flags = cfg->flags;
+    {
+        const uint32_t mut = flags & (VMB_RC_DROP_STALE_NANS | VMB_RC_REMOVE_COUNTER_RESETS);
+        const int64_t max_stale = (flags & VMB_RC_REMOVE_COUNTER_RESETS) && cfg->lookback_delta != 0 ? cfg->lookback_delta + cfg->window : 0;
+        if (s->rolled && (mut != s->applied_mut || max_stale != s->applied_max_stale)) {
+            vmb_set_error("this batch was already rolled up with other in-place preprocessing (dropStaleNaNs / removeCounterResets / "
+                          "staleness interval): decode it again");
+            return VMB_ERR_INVALID_ARG;
+        }
+        s->rolled = true;
+        s->applied_mut = mut;
+        s->applied_max_stale = max_stale;
+    }
     if (s->stale_dropped) flags &= ~VMB_RC_DROP_STALE_NANS;
     if (s->resets_removed) flags &= ~VMB_RC_REMOVE_COUNTER_RESETS;
     {
@@ -1227,6 +1274,7 @@ static int eval_device_async(vmb_ctx* ctx, const vmb_blocks* b, vmb_series* s, i
                              unsigned long long* d_scanned) {
     s->stale_dropped = s->resets_removed = false;
     s->pre_applied = 0;
+    s->rolled = false;
     int rc = run_decode(ctx, b, s, tr_min, tr_max, 0, d_failed);
     if (rc) return rc;
     return run_rollup(ctx, s, cfg, points, d_out, d_scanned);

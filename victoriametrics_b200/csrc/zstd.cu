@@ -558,6 +558,64 @@ __host__ __device__ inline bool parse_frame_header(FrameHdr* h, const uint8_t* s
     return true;
 }
 
+// XXH64 (seed 0) of the decompressed content: RFC 8878 3.1.1 Content_Checksum = its low 32 bits.  Frames that carry one are
+// rare on this path (gozstd and klauspost/compress write none) and always take the serial decoder, which verifies it.
+__device__ __forceinline__ unsigned long long xxh_rotl(unsigned long long x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ unsigned long long xxh_read64(const uint8_t* p) {
+    unsigned long long v = 0;
+    for (int i = 0; i < 8; i++) v |= (unsigned long long)p[i] << (8 * i);
+    return v;
+}
+__device__ unsigned long long xxh64(const uint8_t* p, unsigned long long len) {
+    const unsigned long long P1 = 11400714785074694791ULL, P2 = 14029467366897019727ULL, P3 = 1609587929392839161ULL,
+                             P4 = 9650029242287828579ULL, P5 = 2870177450012600261ULL;
+    const uint8_t* const end = p + len;
+    unsigned long long h;
+    auto round = [&](unsigned long long acc, unsigned long long in) { return xxh_rotl(acc + in * P2, 31) * P1; };
+    auto merge = [&](unsigned long long acc, unsigned long long v) { return (acc ^ round(0, v)) * P1 + P4; };
+    if (len >= 32) {
+        unsigned long long v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0ULL - P1;
+        const uint8_t* const lim = end - 32;
+        do {
+            v1 = round(v1, xxh_read64(p));
+            v2 = round(v2, xxh_read64(p + 8));
+            v3 = round(v3, xxh_read64(p + 16));
+            v4 = round(v4, xxh_read64(p + 24));
+            p += 32;
+        } while (p <= lim);
+        h = xxh_rotl(v1, 1) + xxh_rotl(v2, 7) + xxh_rotl(v3, 12) + xxh_rotl(v4, 18);
+        h = merge(h, v1);
+        h = merge(h, v2);
+        h = merge(h, v3);
+        h = merge(h, v4);
+    } else {
+        h = P5;
+    }
+    h += len;
+    while (p + 8 <= end) {
+        h ^= round(0, xxh_read64(p));
+        h = xxh_rotl(h, 27) * P1 + P4;
+        p += 8;
+    }
+    if (p + 4 <= end) {
+        unsigned long long w = (unsigned long long)p[0] | ((unsigned long long)p[1] << 8) | ((unsigned long long)p[2] << 16) | ((unsigned long long)p[3] << 24);
+        h ^= w * P1;
+        h = xxh_rotl(h, 23) * P2 + P3;
+        p += 4;
+    }
+    while (p < end) {
+        h ^= (unsigned long long)(*p) * P5;
+        h = xxh_rotl(h, 11) * P1;
+        p++;
+    }
+    h ^= h >> 33;
+    h *= P2;
+    h ^= h >> 29;
+    h *= P3;
+    h ^= h >> 32;
+    return h;
+}
+
 __device__ bool decode_frame_serial(SerialWs* ws, uint8_t* out, uint32_t out_cap, uint8_t* litbuf, const uint8_t* src,
                                     uint32_t len) {
     FrameHdr h;
@@ -595,9 +653,14 @@ __device__ bool decode_frame_serial(SerialWs* ws, uint8_t* out, uint32_t out_cap
         }
         if (last) break;
     }
-    if (h.checksum) pos += 4;
-    if (pos != len) return false;
-    return (unsigned long long)o == (unsigned long long)out_cap;
+    if ((unsigned long long)o != (unsigned long long)out_cap) return false;
+    if (h.checksum) {
+        if (pos + 4 > len) return false;
+        const uint32_t want = src[pos] | ((uint32_t)src[pos + 1] << 8) | ((uint32_t)src[pos + 2] << 16) | ((uint32_t)src[pos + 3] << 24);
+        if ((uint32_t)xxh64(out, (unsigned long long)o) != want) return false;  // corrupted content
+        pos += 4;
+    }
+    return pos == len;
 }
 
 }  // namespace
@@ -1407,15 +1470,16 @@ void launch_zstd_serial(const ZstdParams& P, int mode, cudaStream_t st) {
 
 // ---- host-side classification at upload time: reads only the frame / block / literals headers
 // returns kind; fills content_size; *needs_lit = the literal arena is required for this column
+// content_bound = 0: a block payload, at most 10 bytes per row; else the caller's cap on Frame_Content_Size
 uint8_t zstd_classify_host(const uint8_t* src, uint32_t len, uint32_t rows, uint32_t* content_size, bool* needs_lit,
-                           uint32_t* nseq) {
+                           uint32_t* nseq, unsigned long long content_bound = 0) {
     *needs_lit = false;
     *content_size = 0;
     *nseq = 0;
     FrameHdr h;
     if (!parse_frame_header(&h, src, len)) return VMB_ZK_BAD;
     // a valid payload holds rows-1 varints of <= 10 bytes
-    unsigned long long bound = (unsigned long long)rows * 10ull;
+    unsigned long long bound = content_bound ? content_bound : (unsigned long long)rows * 10ull;
     if (!h.has_fcs || h.fcs > bound) return VMB_ZK_BAD;
     *content_size = (uint32_t)h.fcs;
     uint32_t pos = h.hdr_size;
@@ -1426,7 +1490,7 @@ uint8_t zstd_classify_host(const uint8_t* src, uint32_t len, uint32_t rows, uint
     bool last = bh & 1;
     int btype = (bh >> 1) & 3;
     *needs_lit = true;
-    if (!last || btype != 2) return VMB_ZK_GENERIC;
+    if (!last || btype != 2 || h.checksum) return VMB_ZK_GENERIC;  // (a content checksum is verified by the serial decoder)
     if (pos + bsize + (h.checksum ? 4u : 0u) != len || bsize < 3) return VMB_ZK_GENERIC;
     const uint8_t* blk = src + pos;
     int type = blk[0] & 3, sf = (blk[0] >> 2) & 3;

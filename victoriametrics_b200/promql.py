@@ -397,11 +397,13 @@ def eval_rollup_func_multi(func_name, blocks, start, end, step, window=0, lookba
 
 # ---- topk / bottomk over the [series x points] matrix (aggr.go:646 newAggrFuncTopK) -------------------------------------
 def topk(ks, vals_dev_ptr, nseries, points, device_alloc, group_ids=None, ngroups=1, reverse=False, ctx=None,
-         all_gather=None, group_sizes=None):
+         all_gather=None, group_sizes=None, series_id_base=0):
     """topk(k, q) (reverse=True: bottomk) on a DEVICE matrix [nseries x points] of float64, masked in place: per group and
     point only the k best values survive (fillNaNsAtIdx aggr.go:786).  ks: scalar or one k per point.
     device_alloc(nbytes) -> object with .ptr.  Several processes (series sharded by rank): all_gather(buf, nbytes) ->
-    (gathered_buf, nparts) over the candidate lists, and group_sizes = series per group over ALL processes.
+    (gathered_buf, nparts) over the candidate lists (all_gather="nccl": the library's own ncclAllGather over the ctx's communicator),
+    group_sizes = series per group over ALL processes, series_id_base = global id of this process's row 0 (equal values rank by
+    ascending global series id: exactly k survive per group and point).
     -> np.bool_[nseries]: rows that still hold a value (removeEmptySeries drops the others)"""
     ctx = ctx or _lib.default_context()
     g = np.zeros(nseries, dtype=np.uint32) if group_ids is None else np.ascontiguousarray(group_ids, dtype=np.uint32)
@@ -415,16 +417,21 @@ def topk(ks, vals_dev_ptr, nseries, points, device_alloc, group_ids=None, ngroup
     if kmax > 64:
         raise ValueError("topk on the GPU supports k <= 64 (got %d)" % kmax)
     cells = int(ngroups) * int(points)
-    cand = device_alloc(cells * kmax * 8)
+    cand = device_alloc(cells * kmax * 16)  # {value, global series id} per entry
     rev = 1 if reverse else 0
     check(lib().vmb_topk_candidates(ctx.h, C.c_void_p(int(vals_dev_ptr)), nseries, points, g.ctypes.data_as(_lib.u32p), int(ngroups),
-                                    kmax, rev, C.c_void_p(cand.ptr)))
-    if all_gather is not None:
+                                    kmax, rev, int(series_id_base), C.c_void_p(cand.ptr)))
+    if all_gather == "nccl":
+        nparts = ctx.comm_size
+        parts = device_alloc(nparts * cells * kmax * 16)
+        check(lib().vmb_topk_allgather(ctx.h, C.c_void_p(cand.ptr), cells * kmax * 2, C.c_void_p(parts.ptr)))
+        check(lib().vmb_topk_merge(ctx.h, C.c_void_p(parts.ptr), int(nparts), cells, kmax, rev, C.c_void_p(cand.ptr)))
+    elif all_gather is not None:
         ctx.synchronize()
-        parts, nparts = all_gather(cand, cells * kmax * 8)
+        parts, nparts = all_gather(cand, cells * kmax * 16)
         check(lib().vmb_topk_merge(ctx.h, C.c_void_p(parts.ptr), int(nparts), cells, kmax, rev, C.c_void_p(cand.ptr)))
     flags = np.zeros(max(nseries, 1), dtype=np.uint8)
     check(lib().vmb_topk_apply(ctx.h, C.c_void_p(int(vals_dev_ptr)), nseries, points, g.ctypes.data_as(_lib.u32p), int(ngroups),
                                gs.ctypes.data_as(_lib.u32p), C.c_void_p(cand.ptr), kmax, kk.ctypes.data_as(_lib.f64p), rev,
-                               flags.ctypes.data_as(_lib.u8p)))
+                               int(series_id_base), flags.ctypes.data_as(_lib.u8p)))
     return flags[:nseries].astype(bool)
