@@ -1313,6 +1313,30 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
 #define SEQX_WARPS 4
 #define SEQX_G 8  /* lanes per frame: matches are short (a dozen bytes), 32 lanes per copy would idle */
 __device__ __forceinline__ void groupx_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int sub) {
+    if (n >= 128u) {
+        // long run (the literals behind the last sequence of a barely compressible column: most of the frame): 16 bytes per lane
+        // and step -- destination aligned to 16, the source read as five aligned words and funnel-shifted into place
+        uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+        for (uint32_t k = sub; k < head; k += SEQX_G) dst[k] = src[k];
+        const uint32_t chunks = (n - head) >> 4;
+        const uint8_t* s0 = src + head;
+        const uint32_t sh = (uint32_t)((uintptr_t)s0 & 3u) * 8u;
+        const uint32_t* sw = (const uint32_t*)((uintptr_t)s0 & ~(uintptr_t)3);
+        uint4* d4 = (uint4*)(dst + head);
+        for (uint32_t c = sub; c < chunks; c += SEQX_G) {
+            const uint32_t* w = sw + 4 * c;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
+            uint4 v;
+            v.x = __funnelshift_r(w0, w1, sh);
+            v.y = __funnelshift_r(w1, w2, sh);
+            v.z = __funnelshift_r(w2, w3, sh);
+            v.w = __funnelshift_r(w3, w4, sh);
+            d4[c] = v;
+        }
+        const uint32_t done = head + 16u * chunks;
+        for (uint32_t k = done + sub; k < n; k += SEQX_G) dst[k] = src[k];  // <= 15 tail bytes
+        return;
+    }
     uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
     if (head > n) head = n;
     if ((uint32_t)sub < head) dst[sub] = src[sub];
