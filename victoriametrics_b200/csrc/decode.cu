@@ -52,6 +52,17 @@ struct Dec {  // decimal.AppendDecimalToFloat decimal.go:100 for one block (scal
             rcp = __drcp_rn(e10);
         }
     }
+    // the arithmetic of conv() alone: for mantissas that are not one of the three special values (the caller checks)
+    __device__ __forceinline__ double conv_plain(int64_t v) const {
+        double f = __ll2double_rn(v);
+        if (mode == -2) {
+            double q = __dmul_rn(f, rcp);
+            double rem = __fma_rn(-q, e10, f);
+            f = __fma_rn(rem, rcp, q);
+        } else if (mode < 0) f = __ddiv_rn(f, e10);
+        else if (mode > 0) f = __dmul_rn(f, e10);
+        return f;
+    }
     __device__ __forceinline__ double conv(int64_t v) const {
         double f = __ll2double_rn(v);
         if (mode == -2) {

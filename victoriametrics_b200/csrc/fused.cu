@@ -31,6 +31,7 @@
 //   4. every lane replays its values with the scanned prefix, converts mantissa -> float64 (decimal.go:100) and overwrites
 //      the raw value in place.
 #pragma once
+#include <type_traits>
 
 #define FU_THREADS 256
 #define FU_WARPS 8
@@ -153,6 +154,23 @@ __device__ __forceinline__ double fu_ld(const double* s, uint32_t row) {
 }
 __device__ __forceinline__ double& fu_ref(double* s, uint32_t row) {
     return *reinterpret_cast<double*>(reinterpret_cast<char*>(s) + fu_swz_b(row));
+}
+// the same through a 32-bit shared-space address of val[] (no generic -> shared window arithmetic per access)
+__device__ __forceinline__ double fu_lds(uint32_t val_s, uint32_t row) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(val_s + fu_swz_b(row)));
+    return v;
+}
+__device__ __forceinline__ void fu_sts(uint32_t val_s, uint32_t row, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(val_s + fu_swz_b(row)), "d"(v) : "memory");
+}
+__device__ __forceinline__ long long fu_lds_i64(uint32_t val_s, uint32_t row) {
+    long long v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(val_s + fu_swz_b(row)));
+    return v;
+}
+__device__ __forceinline__ void fu_sts_i64(uint32_t val_s, uint32_t row, long long v) {
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(val_s + fu_swz_b(row)), "l"(v) : "memory");
 }
 struct FuVals {  // read view for the rollup functions: element i is row r + i
     const double* s;
@@ -415,6 +433,8 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
     extern __shared__ __align__(16) unsigned char fu_raw[];
     FusedSmem& S = *reinterpret_cast<FusedSmem*>(fu_raw);
     const FuValsRW RV{S.val};  // RV[absolute row]
+    uint32_t val_s = smem_u32(S.val);
+    asm volatile("" : "+r"(val_s));  // opaque: kept in a register instead of being rebuilt from the CTA's shared window per access
     const vmb_rollup_cfg& rc = P.cfg;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     unsigned long long scanned_cta = 0;  // this thread's share of samplesScanned over the series the CTA finished
@@ -518,11 +538,22 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                 const int64_t g0 = (int64_t)fs + off;
                 const uint4 own = *reinterpret_cast<const uint4*>(st + off);
                 const uint4 prv = *reinterpret_cast<const uint4*>(st + off - 16);
-                const uint32_t vm = fu_valid16(g0, vlo, vhi);
-                const uint32_t tm = fu_term_mask16(own) & vm;
-                // boundaries of the previous 16 bytes: terminators, and everything in front of the stream start
-                const uint32_t pvm = fu_valid16(g0 - 16, vlo, vhi);
-                const uint32_t pbm = ((fu_term_mask16(prv) & pvm) | (g0 - 16 < vlo ? ~pvm : 0u)) & 0xffffu;
+                const uint32_t t_own = fu_term_mask16(own);
+                uint32_t vm, tm, pbm;
+                const int64_t gw = (int64_t)fs + w * FU_TILE;  // first byte of the warp's tile
+                if (gw - 16 >= vlo && gw + FU_TILE <= vhi) {
+                    // the tile and the 16 bytes in front of it lie inside the stream (all but the first and last tile of a column)
+                    vm = 0xffffu;
+                    tm = t_own;
+                    pbm = __shfl_up_sync(VMB_FULL, t_own, 1);
+                    if (lane == 0) pbm = fu_term_mask16(prv);
+                } else {
+                    vm = fu_valid16(g0, vlo, vhi);
+                    tm = t_own & vm;
+                    // boundaries of the previous 16 bytes: terminators, and everything in front of the stream start
+                    const uint32_t pvm = fu_valid16(g0 - 16, vlo, vhi);
+                    pbm = ((fu_term_mask16(prv) & pvm) | (g0 - 16 < vlo ? ~pvm : 0u)) & 0xffffu;
+                }
                 const uint32_t cl = (uint32_t)__popc(tm);
                 uint32_t incl = cl;
 #pragma unroll
@@ -565,23 +596,18 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                     uint64_t s1 = 0, s2 = 0;
                     const uint32_t row0 = base + cnt + rb + incl - cl;  // absolute row of the lane's first value
                     bool bad = false;
+                    // carried-in bytes: behind the last boundary of the previous 16 bytes
+                    const uint32_t carry = pbm ? (uint32_t)__clz((int)pbm) - 16u : 16u;  // 15 - msb(pbm)
+                    // does any varint that ends in this warp's tile have more than 4 bytes?  Continuation bytes of [previous 16 |
+                    // own 16] as one mask: a run of four of them that reaches into the last 4 + 16 bytes (conservative)
+                    const uint32_t c32 = ((~pbm) & 0xffffu) | ((~t_own & vm) << 16);
+                    const uint32_t run4 = c32 & (c32 >> 1) & (c32 >> 2) & (c32 >> 3);
+                    const bool any_long = __any_sync(VMB_FULL, w < K && cl && (((run4 >> 12) != 0u) || carry > 3u)) != 0;
                     if (w < K && cl) {
-                        // carried-in bytes: behind the last boundary of the previous 16 bytes
-                        const uint32_t carry = pbm ? (uint32_t)__clz((int)pbm) - 16u : 16u;  // 15 - msb(pbm)
                         uint32_t m = tm;
                         // 7-bit groups of the own 16 bytes as a 112-bit number q3:q2:q1:q0
                         const uint32_t c0 = compact7(own.x), c1 = compact7(own.y), c2 = compact7(own.z), c3 = compact7(own.w);
                         uint32_t q0 = c0 | (c1 << 28), q1 = (c1 >> 4) | (c2 << 24), q2 = (c2 >> 8) | (c3 << 20), q3 = c3 >> 12;
-                        uint32_t cval = 0, cbits = 0;  // value and width of the carried-in bytes
-                        bool first_slow = false;
-                        if (carry) {
-                            if (carry <= 3) {
-                                cval = compact7(prv.w) >> (7u * (4u - carry));
-                                cbits = 7u * carry;
-                            } else {
-                                first_slow = true;
-                            }
-                        }
                         auto drop_groups = [&](uint32_t sh) {  // q >>= sh (sh = 7 * bytes <= 112)
                             while (sh >= 32u) {
                                 q0 = q1; q1 = q2; q2 = q3; q3 = 0;
@@ -598,48 +624,67 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                             m >>= pos;
                             drop_groups(7u * pos);
                         }
-                        while (m) {
-                            const uint32_t L = (uint32_t)__ffs((int)m);  // own bytes of this varint
-                            long long v;
-                            if (!first_slow && L * 7u + cbits <= 28u) {
-                                const uint32_t u = ((q0 & ((1u << (7u * L)) - 1u)) << cbits) | cval;
-                                v = (long long)(int)((u >> 1) ^ (0u - (u & 1u)));
-                            } else {
-                                // long varint (> 4 bytes): byte loop over the staged bytes, int.go:196-284
-                                const int sb = (int)(off + pos) - (int)(k == 0 ? carry : 0u);  // first byte, relative to st
-                                const uint32_t vl = L + (k == 0 ? carry : 0u);
-                                uint64_t u = 0;
-                                if (vl > 10) {
-                                    bad = true;
-                                } else {
-                                    for (uint32_t bb = 0; bb < vl; bb++) {
-                                        const uint32_t byte = st[sb + (int)bb];
-                                        if (bb == 9) {
-                                            if (byte > 1u) bad = true;
-                                            u |= (uint64_t)1 << 63;
-                                        } else {
-                                            u |= (uint64_t)(byte & 0x7fu) << (7 * bb);
-                                        }
-                                    }
-                                }
-                                v = (long long)(u >> 1) ^ -(long long)(u & 1);
+                        if (!any_long) {
+                            // every varint of the tile has <= 4 bytes (28 bits): one shift-and-mask per value, no branches inside
+                            uint32_t cval = 0, cbits = 0;  // value and width of the carried-in bytes (first varint only)
+                            if (carry) {
+                                cval = compact7(prv.w) >> (7u * (4u - carry));
+                                cbits = 7u * carry;
                             }
-                            first_slow = false;
-                            cval = 0;
-                            cbits = 0;
-                            RV[row0 + k] = __longlong_as_double(v);  // raw zig-zag decoded delta, replaced by the value in step 4
-                            s1 += (uint64_t)v;
-                            s2 += s1;
-                            k++;
-                            pos += L;
-                            m >>= L;
-                            if (L <= 4u) {  // (the usual case: one funnel shift per word)
+                            uint32_t row = row0;
+                            while (m) {
+                                const uint32_t L = (uint32_t)__ffs((int)m);  // own bytes of this varint
                                 const uint32_t sh = 7u * L;
+                                const uint32_t u = ((q0 & ~(0xffffffffu << sh)) << cbits) | cval;
+                                const int v32 = (int)((u >> 1) ^ (0u - (u & 1u)));
+                                const long long v = (long long)v32;
+                                fu_sts_i64(val_s, row, v);  // raw zig-zag decoded delta, replaced by the value in step 4
+                                s1 += (uint64_t)v;
+                                s2 += s1;
+                                row++;
+                                m >>= L;
                                 q0 = __funnelshift_r(q0, q1, sh);
                                 q1 = __funnelshift_r(q1, q2, sh);
                                 q2 = __funnelshift_r(q2, q3, sh);
                                 q3 >>= sh;
-                            } else {
+                                cval = 0;
+                                cbits = 0;
+                            }
+                        } else {
+                            while (m) {
+                                const uint32_t L = (uint32_t)__ffs((int)m);  // own bytes of this varint
+                                const uint32_t cb = k == 0 ? carry : 0u;
+                                long long v;
+                                if (7u * (L + cb) <= 28u) {
+                                    const uint32_t cval = cb ? compact7(prv.w) >> (7u * (4u - cb)) : 0u;
+                                    const uint32_t u = ((q0 & ~(0xffffffffu << (7u * L))) << (7u * cb)) | cval;
+                                    v = (long long)(int)((u >> 1) ^ (0u - (u & 1u)));
+                                } else {
+                                    // long varint (> 4 bytes): byte loop over the staged bytes, int.go:196-284
+                                    const int sb = (int)(off + pos) - (int)cb;  // first byte, relative to st
+                                    const uint32_t vl = L + cb;
+                                    uint64_t u = 0;
+                                    if (vl > 10) {
+                                        bad = true;
+                                    } else {
+                                        for (uint32_t bb = 0; bb < vl; bb++) {
+                                            const uint32_t byte = st[sb + (int)bb];
+                                            if (bb == 9) {
+                                                if (byte > 1u) bad = true;
+                                                u |= (uint64_t)1 << 63;
+                                            } else {
+                                                u |= (uint64_t)(byte & 0x7fu) << (7 * bb);
+                                            }
+                                        }
+                                    }
+                                    v = (long long)(u >> 1) ^ -(long long)(u & 1);
+                                }
+                                fu_sts_i64(val_s, row0 + k, v);
+                                s1 += (uint64_t)v;
+                                s2 += s1;
+                                k++;
+                                pos += L;
+                                m >>= L;
                                 drop_groups(7u * L);
                             }
                         }
@@ -706,32 +751,40 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                         uint64_t d1 = D1 + fs1;
                         uint64_t v = delta2 ? (V + fs2 + (uint64_t)fcnt * D1) : (V + fs1);
                         bool saw_stale = false;
-                        for (uint32_t k = 0; k < cl; k++) {
-                            const uint64_t pv = v;
-                            const uint64_t x = (uint64_t)__double_as_longlong(RV[row0 + k]);
-                            if (delta2) {
-                                d1 += x;
-                                v += d1;
-                            } else {
-                                v += x;
-                            }
-                            const double f = dec.conv((int64_t)v);
-                            if ((uint64_t)v - 0x7FFFFFFFFFFFFFFEull < 3ull) saw_stale |= ((int64_t)v == VMB_V_STALE_NAN);
-                            if (do_rcr && (int64_t)v < (int64_t)pv) {
-                                // candidate counter reset (the conversion is monotone): the exact test is on the floats, rollup.go:928
-                                const double pf = dec.conv((int64_t)pv);
-                                const double dd = f - pf;
-                                if (dd < 0) {
-                                    const double amt = ((-dd * 8) < pf) ? (pf - f) : pf;
-                                    const uint32_t e = atomicAdd(&S.nev, 1u);
-                                    if (e < FU_MAX_EVENTS) {
-                                        S.ev_row[e] = row0 + k;
-                                        S.ev_amt[e] = amt;
+                        auto emit_run = [&](auto is_delta2) {
+                            constexpr bool D2 = decltype(is_delta2)::value;
+                            for (uint32_t k = 0; k < cl; k++) {
+                                const uint64_t pv = v;
+                                const uint64_t x = (uint64_t)fu_lds_i64(val_s, row0 + k);
+                                if (D2) {
+                                    d1 += x;
+                                    v += d1;
+                                } else {
+                                    v += x;
+                                }
+                                double f = dec.conv_plain((int64_t)v);
+                                if ((uint64_t)v - 0x7FFFFFFFFFFFFFFEull < 3ull) {  // vStaleNaN / vInfPos / vInfNeg (decimal.go:403-417)
+                                    f = dec.conv((int64_t)v);
+                                    saw_stale |= ((int64_t)v == VMB_V_STALE_NAN);
+                                }
+                                if (do_rcr && (int64_t)v < (int64_t)pv) {
+                                    // candidate counter reset (the conversion is monotone): the exact test is on the floats, rollup.go:928
+                                    const double pf = dec.conv((int64_t)pv);
+                                    const double dd = f - pf;
+                                    if (dd < 0) {
+                                        const double amt = ((-dd * 8) < pf) ? (pf - f) : pf;
+                                        const uint32_t e = atomicAdd(&S.nev, 1u);
+                                        if (e < FU_MAX_EVENTS) {
+                                            S.ev_row[e] = row0 + k;
+                                            S.ev_amt[e] = amt;
+                                        }
                                     }
                                 }
+                                fu_sts(val_s, row0 + k, f);
                             }
-                            RV[row0 + k] = f;
-                        }
+                        };
+                        if (delta2) emit_run(std::true_type{});
+                        else emit_run(std::false_type{});
                         if (saw_stale && stale_matters) S.flags = 1u;
                     }
                     // ---- carries
@@ -787,10 +840,7 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                 } else if (nev == 0 && corr != 0.0 && isfinite(corr) && fu_ld(S.val, base + cnt_old) + corr >= fu_ld(S.val, base + cnt_old - 1)) {
                     // no value drop inside the fill (nor at its front) and its first corrected row is not below the last output: raw
                     // rows are non-decreasing, x -> RN(x + corr) keeps the order, so the clamp of rollup.go:954 cannot fire: one pass
-                    for (uint32_t k = cnt_old + tid; k < cnt; k += FU_THREADS) {
-                        double& rv = fu_ref(S.val, base + k);
-                        rv = rv + corr;
-                    }
+                    for (uint32_t k = cnt_old + tid; k < cnt; k += FU_THREADS) fu_sts(val_s, base + k, fu_lds(val_s, base + k) + corr);
                     __syncthreads();
                 } else if (nev || corr != 0.0) {
                     if (tid == 0) {
@@ -873,21 +923,24 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                 uint32_t sc32 = 0;
                 const FuVals WV{S.val, base};  // WV[k] = resident row base + k
                 const bool to_aggr = P.aggr_values != nullptr;
-                const size_t out_base = (to_aggr ? (size_t)blockIdx.x : (size_t)s) * P.npoints;
-                auto put = [&](uint32_t q, double v) { P.out[out_base + q] = v; };
+                double* out_row = P.out + (to_aggr ? (size_t)blockIdx.x : (size_t)s) * P.npoints;
+                asm volatile("" : "+l"(out_row));  // (kept in registers: the loops below are tight)
+                auto put = [&](uint32_t q, double v) { out_row[q] = v; };
+                uint32_t sc_interior = spc ? spc : (uint32_t)rate_rows;  // samplesScanned of an interior rate() point
+                asm volatile("" : "+r"(sc_interior));
 #pragma unroll 2
                 for (uint32_t q = p + tid; q < p_end; q += FU_THREADS) {
                     if (F == VMB_RF_RATE && lin && rate_dt > 0 && prev_always) {
                         // interior point: the window [i, j) holds rate_rows rows and row i - 1 exists: (v[j-1] - v[i-1]) / D
                         const int32_t is_ = iq0 + (int32_t)q * lin_k;
                         if (is_ >= 1 && is_ + rate_rows <= (int32_t)n) {
-                            const double vp = fu_ld(S.val, (uint32_t)is_ - 1u), vl = fu_ld(S.val, (uint32_t)(is_ + rate_rows) - 1u);
+                            const double vp = fu_lds(val_s, (uint32_t)is_ - 1u), vl = fu_lds(val_s, (uint32_t)(is_ + rate_rows) - 1u);
                             const double x = vl - vp;
                             const uint32_t ex = ((uint32_t)__double2hiint(x) >> 20) & 0x7ffu;
                             if (!isnan(vp) && (x == 0.0 || ex - 123u < 1800u)) {
                                 const double q0 = __dmul_rn(x, rate_R);
                                 const double rem = __fma_rn(-q0, rate_D, x);
-                                sc32 += spc ? spc : (uint32_t)rate_rows;
+                                sc32 += sc_interior;
                                 put(q, x == 0.0 ? x : __fma_rn(rem, rate_R, q0));
                                 continue;
                             }
