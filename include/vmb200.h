@@ -138,6 +138,12 @@ int vmb_zstd_compress(uint8_t* dst, size_t cap, size_t* out_len, const uint8_t* 
  * back to back into dst, offs[ncols+1] receives their offsets, mts/firsts the MarshalType and first value of each. */
 int vmb_marshal_columns(uint8_t* dst, size_t cap, uint64_t* offs, uint8_t* mts, int64_t* firsts, const int64_t* vals,
                         size_t ncols, size_t rows, uint8_t precision_bits, int nthreads);
+/* The same with the int64 work on the GPU (csrc/encode.cu): isConst / isDeltaConst / isGauge (encoding.go:289-369) as one pass of warp
+ * reductions per column, nearest-delta / delta2 (lossless, and the lossy precisionBits < 64 state machine of nearest_delta.go:83),
+ * zig-zag varint packing by warp scans; the zstd stage of streams >= 128 bytes and the 0.9 rule (encoding.go:152-167) follow on
+ * `nthreads` host threads.  Byte-identical to vmb_marshal_columns.  vals: HOST [ncols x rows]. */
+int vmb_marshal_columns_gpu(vmb_ctx* ctx, uint8_t* dst, size_t cap, uint64_t* offs, uint8_t* mts, int64_t* firsts,
+                            const int64_t* vals, size_t ncols, size_t rows, uint8_t precision_bits, int nthreads);
 /* decimal.AppendFloatToDecimal decimal.go:173 (host-side, write path) */
 int vmb_float_to_decimal(int64_t* dst, int16_t* out_scale, const double* src, size_t n);
 /* decimal.CalibrateScale decimal.go:13 (host-side; block merge path lib/storage/merge.go): a and b are rescaled in place to
@@ -165,6 +171,12 @@ int vmb_decode_blocks(vmb_ctx* ctx, const vmb_blocks* blocks, int64_t tr_min, in
  * rollupConfig.Do): series s owns rows [offsets[s], offsets[s+1]) */
 int vmb_series_from_host(vmb_ctx* ctx, const int64_t* timestamps, const double* values, const uint64_t* offsets,
                          size_t nseries, vmb_series** out);
+/* the feed of evalRollupFuncWithSubquery (eval.go:910): the inner expression's result, a DEVICE matrix [nseries x points] on the grid
+ * start, start + step, ..., becomes a batch of series -- removeNanValues (eval.go:1027) drops the NaN points of every row together
+ * with their timestamps -- for vmb_rollup with the outer function's config (its preFunc flags apply as usual; dropStaleNaNs does not,
+ * there is nothing stale left).  The matrix is not modified and not retained. */
+int vmb_series_from_matrix(vmb_ctx* ctx, const double* d_matrix, size_t nseries, size_t points, int64_t start, int64_t step,
+                           vmb_series** out);
 void vmb_series_free(vmb_series* s);
 size_t vmb_series_count(const vmb_series* s);
 uint64_t vmb_series_rows(const vmb_series* s); /* allocated rows (before trimming / stale-NaN drop) */
@@ -293,6 +305,28 @@ int vmb_eval_rollup_aggr_host_partial(vmb_ctx* ctx, const vmb_block_desc* descs,
 int vmb_eval_rollup_aggr_device(vmb_ctx* ctx, const vmb_blocks* blocks, int64_t tr_min, int64_t tr_max,
                                 const vmb_rollup_cfg* cfg, int aggr_id, const uint32_t* group_ids, uint32_t ngroups,
                                 double* d_values, double* d_counts, uint64_t* samples_scanned);
+
+/* ---- post-rollup operations on DEVICE matrices [series x points] (keep a query's intermediate results in HBM across the expression
+ * tree) ------------------------------------------------------------------------------------------------------------------ */
+enum vmb_binop { /* binary_op.go:15-43; the element functions of vendor/.../metricsql/binaryop/funcs.go */
+    VMB_BO_PLUS = 0, VMB_BO_MINUS, VMB_BO_MUL, VMB_BO_DIV, VMB_BO_MOD, VMB_BO_POW, VMB_BO_ATAN2, VMB_BO_EQ, VMB_BO_NEQ, VMB_BO_GT,
+    VMB_BO_LT, VMB_BO_GTE, VMB_BO_LTE, VMB_BO_DEFAULT, VMB_BO_IF, VMB_BO_IFNOT
+};
+/* newBinaryOpFunc binary_op.go:155-203: d_dst[i][j] = op(d_left[left_rows[i]][j], d_right[right_rows[i]][j]) for the npairs series
+ * pairs the host matched by tag set (adjustBinaryOpTags :205).  left_rows / right_rows: HOST row indices or NULL = row i; a scalar
+ * operand is a one-row matrix with all indices 0.  Comparisons: without is_bool they filter (left or NaN), with it they give 1 / 0
+ * (NaN for a NaN left) -- newBinaryOpCmpFunc :132.  d_dst may alias d_left when left_rows is NULL. */
+int vmb_binary_op(vmb_ctx* ctx, int op, int is_bool, const double* d_left, const uint32_t* left_rows, const double* d_right,
+                  const uint32_t* right_rows, size_t npairs, size_t points, double* d_dst);
+/* mergeSeries rollup_result_cache.go:618: d_dst[nrows x (pa + pb)], row i = d_a[a_rows[i]] ++ d_b[b_rows[i]]; a negative index
+ * stands for a series missing on that side (NaNs, :677-690).  a_rows / b_rows: HOST, matched by metric name by the caller. */
+int vmb_matrix_merge_rows(vmb_ctx* ctx, const double* d_a, const int64_t* a_rows, size_t pa, const double* d_b, const int64_t* b_rows,
+                          size_t pb, size_t nrows, double* d_dst);
+/* quantile(phi, q) by (...) / median(q) by (...)  aggr.go:1217-1240 newAggrQuantileFunc: d_out[ngroups x P], phis = one phi per
+ * point (HOST).  Per (group, point) the NaNs are dropped and aggr.go:870 quantile applies; rank selection, quadratic in the group
+ * size: groups of more than 2048 series return VMB_ERR_CAP. */
+int vmb_aggr_quantile(vmb_ctx* ctx, const double* d_vals, size_t nseries, size_t points, const uint32_t* group_ids, uint32_t ngroups,
+                      const double* phis, double* d_out);
 
 /* ---- multi-GPU: one process per GPU, the ONE exchange step of the path inside the library ------------------
  * aggr(rollup(m[d])) by (...): every rank folds its shard of the series into {values, counts}[G x P] (the per-worker

@@ -92,6 +92,7 @@ def lib():
         "vmb_float_to_decimal": (C.c_int, [i64p, C.POINTER(C.c_int16), f64p, sz]),
         "vmb_zstd_compress": (C.c_int, [u8p, sz, C.POINTER(sz), u8p, sz]),
         "vmb_marshal_columns": (C.c_int, [u8p, sz, u64p, u8p, i64p, i64p, sz, sz, C.c_uint8, C.c_int]),
+        "vmb_marshal_columns_gpu": (C.c_int, [vp, u8p, sz, u64p, u8p, i64p, i64p, sz, sz, C.c_uint8, C.c_int]),
         "vmb_blocks_upload": (C.c_int, [vp, C.POINTER(BlockDesc), sz, u8p, sz, C.POINTER(vp)]),
         "vmb_blocks_free": (None, [vp]),
         "vmb_blocks_count": (sz, [vp]),
@@ -99,6 +100,7 @@ def lib():
         "vmb_blocks_compressed_bytes": (C.c_uint64, [vp]),
         "vmb_decode_blocks": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_uint32, i32p, C.POINTER(vp)]),
         "vmb_series_from_host": (C.c_int, [vp, i64p, f64p, u64p, sz, C.POINTER(vp)]),
+        "vmb_series_from_matrix": (C.c_int, [vp, vp, sz, sz, C.c_int64, C.c_int64, C.POINTER(vp)]),
         "vmb_series_free": (None, [vp]),
         "vmb_series_count": (sz, [vp]),
         "vmb_series_rows": (C.c_uint64, [vp]),
@@ -123,6 +125,9 @@ def lib():
         "vmb_topk_candidates": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, vp]),
         "vmb_topk_merge": (C.c_int, [vp, vp, C.c_uint32, C.c_size_t, C.c_uint32, C.c_int, vp]),
         "vmb_topk_apply": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, u32p, C.c_uint32, u32p, vp, C.c_uint32, f64p, C.c_int, C.c_uint64, u8p]),
+        "vmb_binary_op": (C.c_int, [vp, C.c_int, C.c_int, vp, u32p, vp, u32p, sz, sz, vp]),
+        "vmb_matrix_merge_rows": (C.c_int, [vp, vp, i64p, sz, vp, i64p, sz, sz, vp]),
+        "vmb_aggr_quantile": (C.c_int, [vp, vp, sz, sz, u32p, C.c_uint32, f64p, vp]),
         "vmb_host_alloc": (vp, [sz]),
         "vmb_host_free": (None, [vp]),
         "vmb_ctx_last_stage_ms": (C.c_float, [vp, C.c_int]),

@@ -17,6 +17,7 @@
 #include "fused.cu"
 #include "zstd.cu"
 #include "marshal.inc"
+#include "encode.cu"
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512];
@@ -74,6 +75,7 @@ struct vmb_ctx {
     DevBuf zseq;  // decoded zstd sequences (8 B each) between k_zstd_seq_decode and k_zstd_seq_exec
     DevBuf zscratch, zlit, zstatus, zjobs, zws, args1, args2, rolled, counters, tmp_out, grp, mheap, mnext;
     DevBuf bail, sub_arrays;  // fused path: series handed to the un-fused pipeline, and that sub-batch's arrays
+    DevBuf enc_vals, enc_deltas, enc_out, enc_meta;  // vmb_marshal_columns_gpu
     DevBuf aggr_state, grp_ids;  // vmb_eval_rollup_aggr_dist: {values, counts}[G x P]; device copy of the per-series group ids
     void* comm = nullptr;     // ncclComm_t (comm.inc); nullptr = single GPU
     bool comm_owned = false;
@@ -172,7 +174,7 @@ extern "C" void vmb_ctx_destroy(vmb_ctx* c) {
     if (c->col_cache) vmb_series_free(c->col_cache);
     c->col_cache = nullptr;
     DevBuf* bufs[] = {&c->zscratch, &c->zlit, &c->zstatus, &c->zjobs, &c->zws, &c->args1, &c->args2, &c->rolled,
-                      &c->counters, &c->tmp_out, &c->grp, &c->mheap, &c->mnext, &c->zseq, &c->bail, &c->sub_arrays, &c->aggr_state, &c->grp_ids};
+                      &c->counters, &c->tmp_out, &c->grp, &c->mheap, &c->mnext, &c->zseq, &c->bail, &c->sub_arrays, &c->aggr_state, &c->grp_ids, &c->enc_vals, &c->enc_deltas, &c->enc_out, &c->enc_meta};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 6; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -849,6 +851,70 @@ extern "C" int vmb_series_from_host(vmb_ctx* ctx, const int64_t* timestamps, con
     }
     CUS(cudaStreamSynchronize(st), d_off);
     cudaFree(d_off);
+    *out = s;
+    return VMB_OK;
+}
+
+// removeNanValues (eval.go:1027) for every row of a DEVICE matrix at once: the feed of evalRollupFuncWithSubquery (eval.go:910), whose
+// inner expression was evaluated on the shared grid start, start + step, ...: row s becomes a series of its non-NaN points with
+// their grid timestamps (one warp per row, ballot compaction; capacity `points` rows per series)
+__global__ void __launch_bounds__(128) k_series_from_matrix(const double* __restrict__ m, uint32_t nseries, uint32_t points, int64_t start,
+                                                            int64_t step, int64_t* ts, double* vals, SeriesMeta* meta) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t wpg = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < nseries; s += wpg) {
+        const double* row = m + (size_t)s * points;
+        const size_t o0 = (size_t)s * points;
+        uint32_t o = 0;
+        for (uint32_t b = 0; b < points; b += 32) {
+            const uint32_t i = b + lane;
+            const double x = i < points ? row[i] : 0.0;
+            const bool keep = i < points && !isnan(x);
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const uint32_t r = o + __popc(bal & ((1u << lane) - 1u));
+                vals[o0 + r] = x;
+                ts[o0 + r] = start + (int64_t)i * step;
+            }
+            o += __popc(bal);
+        }
+        if (lane == 0) {
+            SeriesMeta mm;
+            mm.start = o0;
+            mm.n = o;
+            mm._pad = 2u;  // no staleness markers can be left (they are NaNs); value drops unknown => removeCounterResets scans
+            mm.max_prev_interval = 0;
+            mm.window = 0;
+            meta[s] = mm;
+        }
+    }
+}
+
+extern "C" int vmb_series_from_matrix(vmb_ctx* ctx, const double* d_matrix, size_t nseries, size_t points, int64_t start, int64_t step,
+                                      vmb_series** out) {
+    if (!ctx || !out || (nseries && points && !d_matrix) || step <= 0 || nseries > 0x7fffffffu || points > 0x7fffffffu)
+        return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    vmb_series* s = new vmb_series();
+    s->ctx = ctx;
+    s->nseries = nseries;
+    s->rows = (uint64_t)nseries * points;
+    int rc = 0;
+    if (!rc) rc = dev_alloc(&s->d_ts, s->rows + 8);
+    if (!rc) rc = dev_alloc(&s->d_vals, s->rows + 8);
+    if (!rc) rc = dev_alloc(&s->d_meta, nseries);
+    if (rc) {
+        vmb_series_free(s);
+        return rc;
+    }
+    if (nseries) {
+        uint32_t grid = (uint32_t)((nseries + 3) / 4);
+        if (grid > 148u * 16u) grid = 148u * 16u;
+        k_series_from_matrix<<<grid, 128, 0, ctx->stream>>>(d_matrix, (uint32_t)nseries, (uint32_t)points, start, step, s->d_ts, s->d_vals,
+                                                           s->d_meta);
+        count_launch(ctx);
+    }
+    CUS(cudaGetLastError(), nullptr);
     *out = s;
     return VMB_OK;
 }
@@ -1590,6 +1656,7 @@ extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t
 #include "aggr_eval.inc"
 #include "topk.inc"
 #include "comm.inc"
+#include "matrix_ops.inc"
 
 // ------------------------------------------------------------------------------------------------ batched host encoder
 #include <atomic>
@@ -1621,6 +1688,102 @@ extern "C" int vmb_marshal_columns(uint8_t* dst, size_t cap, uint64_t* offs, uin
         for (auto& t : th) t.join();
     }
     if (err.load()) return err.load();
+    uint64_t o = 0;
+    for (size_t c = 0; c < ncols; c++) {
+        offs[c] = o;
+        if (o + outs[c].size() > cap) return VMB_ERR_CAP;
+        if (!outs[c].empty()) memcpy(dst + o, outs[c].data(), outs[c].size());
+        o += outs[c].size();
+    }
+    offs[ncols] = o;
+    return VMB_OK;
+}
+
+// Block.MarshalData (block.go:192) for many equal-length columns with the int64 work on the GPU (csrc/encode.cu): type detection,
+// nearest-delta / delta2 (lossless and lossy precisionBits), zig-zag varint packing; the zstd stage of streams >= 128 bytes and the
+// 0.9 rule (encoding.go:152-167) follow on `nthreads` host threads with the library's zstd writer.  Same output layout and the same
+// bytes as vmb_marshal_columns.
+extern "C" int vmb_marshal_columns_gpu(vmb_ctx* ctx, uint8_t* dst, size_t cap, uint64_t* offs, uint8_t* mts, int64_t* firsts,
+                                       const int64_t* vals, size_t ncols, size_t rows, uint8_t precision_bits, int nthreads) {
+    if (!ctx || !dst || !offs || !mts || !firsts || !vals || rows == 0 || rows > 16384 || ncols > 0x7fffffffu || precision_bits < 1 ||
+        precision_bits > 64)
+        return VMB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (ncols == 0) {
+        offs[0] = 0;
+        return VMB_OK;
+    }
+    int rc;
+    const size_t nvals = ncols * rows;
+    if ((rc = ctx->enc_vals.reserve(nvals * 8))) return rc;
+    // per column: u32 size | u8 mt (padded to 4) | i64 first | u64 offset
+    const size_t o_sizes = 0, o_mts = al16(o_sizes + ncols * 4), o_firsts = al16(o_mts + ncols), o_offs = al16(o_firsts + ncols * 8);
+    if ((rc = ctx->enc_meta.reserve(al16(o_offs + ncols * 8) + 64))) return rc;
+    const bool may_be_lossy = precision_bits < 64;
+    if (may_be_lossy && (rc = ctx->enc_deltas.reserve(nvals * 8))) return rc;
+    CU(cudaMemcpyAsync(ctx->enc_vals.p, vals, nvals * 8, cudaMemcpyHostToDevice, st));
+    uint8_t* dm = (uint8_t*)ctx->enc_meta.p;
+    MarshalParams M;
+    memset(&M, 0, sizeof(M));
+    M.vals = (const int64_t*)ctx->enc_vals.p;
+    M.deltas = may_be_lossy ? (int64_t*)ctx->enc_deltas.p : nullptr;
+    M.sizes = (uint32_t*)(dm + o_sizes);
+    M.mts = dm + o_mts;
+    M.firsts = (int64_t*)(dm + o_firsts);
+    M.offs = (const uint64_t*)(dm + o_offs);
+    M.ncols = (uint32_t)ncols;
+    M.rows = (uint32_t)rows;
+    M.pb = precision_bits;
+    launch_marshal_plan(M, st);
+    count_launch(ctx);
+    std::vector<uint32_t> sizes(ncols);
+    std::vector<uint8_t> pmts(ncols);
+    CU(cudaMemcpyAsync(sizes.data(), M.sizes, ncols * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(pmts.data(), M.mts, ncols, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(firsts, M.firsts, ncols * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::vector<uint64_t> soffs(ncols + 1, 0);
+    for (size_t c = 0; c < ncols; c++) soffs[c + 1] = soffs[c] + sizes[c];
+    const uint64_t total = soffs[ncols];
+    if ((rc = ctx->enc_out.reserve(total + 64))) return rc;
+    CU(cudaMemcpyAsync(dm + o_offs, soffs.data(), ncols * 8, cudaMemcpyHostToDevice, st));
+    M.out = (uint8_t*)ctx->enc_out.p;
+    launch_marshal_pack(M, st);
+    count_launch(ctx);
+    std::vector<uint8_t> streams(total + 1);
+    if (total) CU(cudaMemcpyAsync(streams.data(), M.out, total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    // ---- zstd stage + the 0.9 rule on host threads
+    std::vector<std::vector<uint8_t>> outs(ncols);
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const size_t c = next.fetch_add(1);
+            if (c >= ncols) break;
+            const uint8_t* bb = streams.data() + soffs[c];
+            const size_t blen = sizes[c];
+            uint8_t mt = pmts[c];
+            if (mt == 1 || mt == 4) {
+                const size_t min_compressible = 128;  // encoding.go:15
+                if (blen >= min_compressible) vmb_host::zstd_compress_huf(outs[c], bb, blen);
+                if (blen < min_compressible || (double)outs[c].size() > 0.9 * (double)blen) {  // encoding.go:156
+                    mt = mt == 1 ? 5 : 6;
+                    outs[c].assign(bb, bb + blen);
+                }
+            } else {
+                outs[c].assign(bb, bb + blen);
+            }
+            mts[c] = mt;
+        }
+    };
+    if (nthreads <= 1) worker();
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++) th.emplace_back(worker);
+        for (auto& t : th) t.join();
+    }
     uint64_t o = 0;
     for (size_t c = 0; c < ncols; c++) {
         offs[c] = o;

@@ -80,9 +80,11 @@ def decompress_zstd_batch(frames, ctx=None):
     return [dst[int(o):int(o) + int(l)] for o, l in zip(doffs, dlens)]
 
 
-def marshal_columns(vals2d, precision_bits=64, nthreads=None):
+def marshal_columns(vals2d, precision_bits=64, nthreads=None, ctx=None):
     """batched MarshalValues for equal-length columns: vals2d [ncols x rows] int64
-    -> (payload np.uint8, offs np.uint64[ncols+1], mts np.uint8[ncols], firsts np.int64[ncols])"""
+    -> (payload np.uint8, offs np.uint64[ncols+1], mts np.uint8[ncols], firsts np.int64[ncols]).
+    ctx given: type detection, delta coding and varint packing run on the GPU (vmb_marshal_columns_gpu, csrc/encode.cu), the zstd
+    stage on host threads; the bytes are the same either way."""
     import os
     a = np.ascontiguousarray(vals2d, dtype=np.int64)
     ncols, rows = a.shape
@@ -91,7 +93,12 @@ def marshal_columns(vals2d, precision_bits=64, nthreads=None):
     offs = np.zeros(ncols + 1, dtype=np.uint64)
     mts = np.zeros(ncols, dtype=np.uint8)
     firsts = np.zeros(ncols, dtype=np.int64)
-    check(lib().vmb_marshal_columns(dst.ctypes.data_as(_lib.u8p), dst.size, offs.ctypes.data_as(_lib.u64p),
-                                    mts.ctypes.data_as(_lib.u8p), firsts.ctypes.data_as(_lib.i64p),
-                                    a.ctypes.data_as(_lib.i64p), ncols, rows, precision_bits, nthreads))
+    if ctx is not None:
+        check(lib().vmb_marshal_columns_gpu(ctx.h, dst.ctypes.data_as(_lib.u8p), dst.size, offs.ctypes.data_as(_lib.u64p),
+                                            mts.ctypes.data_as(_lib.u8p), firsts.ctypes.data_as(_lib.i64p),
+                                            a.ctypes.data_as(_lib.i64p), ncols, rows, precision_bits, nthreads))
+    else:
+        check(lib().vmb_marshal_columns(dst.ctypes.data_as(_lib.u8p), dst.size, offs.ctypes.data_as(_lib.u64p),
+                                        mts.ctypes.data_as(_lib.u8p), firsts.ctypes.data_as(_lib.i64p),
+                                        a.ctypes.data_as(_lib.i64p), ncols, rows, precision_bits, nthreads))
     return dst[:int(offs[-1])].copy(), offs, mts, firsts

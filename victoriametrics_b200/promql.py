@@ -163,6 +163,22 @@ def eval_rollup_func(func_name, blocks, start, end, step, window=0, lookback_del
         series.close()
 
 
+def eval_rollup_func_with_subquery(func_name, inner_dev_ptr, nseries, sq_start, sq_end, sq_step, start, end, step, window,
+                                   lookback_delta=0, args=None, args2=None, out_dev_ptr=None, ctx=None):
+    """evalRollupFuncWithSubquery eval.go:910 with the inner result resident on the device: `inner_dev_ptr` = [nseries x Psq] float64
+    on the subquery grid sq_start..sq_end step sq_step (already aligned by the caller, eval.go:932); every row loses its NaN points
+    (removeNanValues), goes through the outer function's preFunc and rollupConfig.Do on the outer grid.
+    -> ([nseries x points] np.float64 or None, samplesScanned)"""
+    rc = get_rollup_configs(func_name, start, end, step, window, lookback_delta, args, args2)
+    rc.dropStaleNaNs = False  # the subquery path has no dropStaleNaNs (eval.go:958-964)
+    psq = 1 + (sq_end - sq_start) // sq_step
+    series = storage.Series.from_matrix(inner_dev_ptr, nseries, psq, sq_start, sq_step, ctx)
+    try:
+        return rc.do_series(series, out_dev_ptr)
+    finally:
+        series.close()
+
+
 def eval_rollup_func_host(func_name, descs, payload, start, end, step, window=0, lookback_delta=0, args=None, args2=None,
                           tr_min=storage.INT64_MIN, tr_max=storage.INT64_MAX, out=None, nseries=None, ctx=None, rc=None):
     """the whole path with HOST buffers in one call (vmb_eval_rollup_host): H2D, decode, rollup, D2H."""
@@ -435,3 +451,38 @@ def topk(ks, vals_dev_ptr, nseries, points, device_alloc, group_ids=None, ngroup
                                gs.ctypes.data_as(_lib.u32p), C.c_void_p(cand.ptr), kmax, kk.ctypes.data_as(_lib.f64p), rev,
                                int(series_id_base), flags.ctypes.data_as(_lib.u8p)))
     return flags[:nseries].astype(bool)
+
+
+# ---- post-rollup operations on device matrices (binary_op.go, aggr.go:1217 quantile, rollup_result_cache.go:618 mergeSeries) ----------
+BINARY_OPS = {"+": 0, "-": 1, "*": 2, "/": 3, "%": 4, "^": 5, "atan2": 6, "==": 7, "!=": 8, ">": 9, "<": 10, ">=": 11, "<=": 12,
+              "default": 13, "if": 14, "ifnot": 15}
+
+
+def binary_op(op, left_dev_ptr, right_dev_ptr, npairs, points, dst_dev_ptr, left_rows=None, right_rows=None, is_bool=False, ctx=None):
+    """newBinaryOpFunc binary_op.go:155: dst[i] = left[left_rows[i]] op right[right_rows[i]] element by element on DEVICE matrices;
+    the row lists come from the host's tag matching (adjustBinaryOpTags), a scalar operand is a one-row matrix with rows all 0"""
+    ctx = ctx or _lib.default_context()
+    lr = None if left_rows is None else np.ascontiguousarray(left_rows, dtype=np.uint32)
+    rr = None if right_rows is None else np.ascontiguousarray(right_rows, dtype=np.uint32)
+    check(lib().vmb_binary_op(ctx.h, BINARY_OPS[op.lower()], int(bool(is_bool)), C.c_void_p(int(left_dev_ptr)),
+                              lr.ctypes.data_as(_lib.u32p) if lr is not None else None, C.c_void_p(int(right_dev_ptr)),
+                              rr.ctypes.data_as(_lib.u32p) if rr is not None else None, int(npairs), int(points), C.c_void_p(int(dst_dev_ptr))))
+
+
+def merge_series(a_dev_ptr, a_rows, pa, b_dev_ptr, b_rows, pb, dst_dev_ptr, ctx=None):
+    """mergeSeries rollup_result_cache.go:618 on DEVICE matrices: dst row i = a[a_rows[i]] ++ b[b_rows[i]], -1 = series missing (NaNs)"""
+    ctx = ctx or _lib.default_context()
+    ar = np.ascontiguousarray(a_rows, dtype=np.int64)
+    br = np.ascontiguousarray(b_rows, dtype=np.int64)
+    assert ar.size == br.size
+    check(lib().vmb_matrix_merge_rows(ctx.h, C.c_void_p(int(a_dev_ptr)), ar.ctypes.data_as(_lib.i64p), int(pa), C.c_void_p(int(b_dev_ptr)),
+                                      br.ctypes.data_as(_lib.i64p), int(pb), ar.size, C.c_void_p(int(dst_dev_ptr))))
+
+
+def aggr_quantile(phis, vals_dev_ptr, nseries, points, out_dev_ptr, group_ids=None, ngroups=1, ctx=None):
+    """quantile(phi, q) by (...) / median (phi = 0.5)  aggr.go:1217 on a DEVICE matrix -> out_dev_ptr [ngroups x points]"""
+    ctx = ctx or _lib.default_context()
+    g = np.zeros(nseries, dtype=np.uint32) if group_ids is None else np.ascontiguousarray(group_ids, dtype=np.uint32)
+    ph = np.ascontiguousarray(np.broadcast_to(np.asarray(phis, dtype=np.float64), (points,)))
+    check(lib().vmb_aggr_quantile(ctx.h, C.c_void_p(int(vals_dev_ptr)), int(nseries), int(points), g.ctypes.data_as(_lib.u32p), int(ngroups),
+                                  ph.ctypes.data_as(_lib.f64p), C.c_void_p(int(out_dev_ptr))))

@@ -248,6 +248,15 @@ class Series:
                                          offs.ctypes.data_as(_lib.u64p), len(values_list), C.byref(h)))
         return cls(h, ctx)
 
+    @classmethod
+    def from_matrix(cls, dev_ptr, nseries, points, start, step, ctx=None):
+        """series batch from a DEVICE matrix [nseries x points] on the grid start + i * step, NaN points removed per row
+        (removeNanValues eval.go:1027): the feed of a subquery's outer rollup"""
+        ctx = ctx or _lib.default_context()
+        h = C.c_void_p()
+        check(lib().vmb_series_from_matrix(ctx.h, C.c_void_p(int(dev_ptr)), int(nseries), int(points), int(start), int(step), C.byref(h)))
+        return cls(h, ctx)
+
     @property
     def count(self):
         return int(lib().vmb_series_count(self.h))
