@@ -146,6 +146,9 @@ int vmb_marshal_columns_gpu(vmb_ctx* ctx, uint8_t* dst, size_t cap, uint64_t* of
                             const int64_t* vals, size_t ncols, size_t rows, uint8_t precision_bits, int nthreads);
 /* decimal.AppendFloatToDecimal decimal.go:173 (host-side, write path) */
 int vmb_float_to_decimal(int64_t* dst, int16_t* out_scale, const double* src, size_t n);
+/* ... for ncols equal-length columns on the GPU (one warp per column: FromFloat per value, min-exponent / overflow reductions,
+ * rescale); dst HOST [ncols x rows], scales HOST [ncols], src HOST [ncols x rows].  Same results as the call above per column. */
+int vmb_float_to_decimal_columns(vmb_ctx* ctx, int64_t* dst, int16_t* scales, const double* src, size_t ncols, size_t rows);
 /* decimal.CalibrateScale decimal.go:13 (host-side; block merge path lib/storage/merge.go): a and b are rescaled in place to
  * the common exponent returned in *out_e. */
 int vmb_calibrate_scale(int64_t* a, size_t na, int16_t ae, int64_t* b, size_t nb, int16_t be, int16_t* out_e);

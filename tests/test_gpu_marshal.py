@@ -87,3 +87,40 @@ def test_gpu_marshal_blocks_decode_and_roll_up(oracle):
         oracle.lib().vmo_remove_counter_resets(fv.ctypes.data_as(oracle.f64p), ts.ctypes.data_as(oracle.i64p), rows, 0)
         exp, _ = oracle.rollup_do(RF["increase"], fv, ts, start, end, step, window, samples_scanned_per_call=2)
         assert np.allclose(got[s], exp, rtol=1e-12, atol=0, equal_nan=True)
+
+
+def test_gpu_float_to_decimal_columns(oracle, kats):
+    """decimal.AppendFloatToDecimal on the GPU == the host encoder == the oracle, per column: mantissas and common exponent"""
+    import victoriametrics_b200 as vm
+    from conftest import STALE_NAN
+    rng = np.random.default_rng(SEED0 + 600)
+    cols = []
+    rows = 257
+    for k in range(40):
+        kind = k % 8
+        if kind == 0:
+            c = np.round(rng.normal(50, 20, rows), 2)
+        elif kind == 1:
+            c = rng.integers(0, 10 ** 9, rows).astype(np.float64)
+        elif kind == 2:
+            c = rng.normal(0, 1, rows) * 10.0 ** rng.integers(-12, 12, rows)
+        elif kind == 3:
+            c = np.zeros(rows)
+        elif kind == 4:
+            c = np.ones(rows)
+        elif kind == 5:
+            c = np.round(rng.normal(0, 1e6, rows), 3)
+            c[rng.integers(0, rows, 5)] = [np.inf, -np.inf, STALE_NAN, 0.0, 1e300]
+        elif kind == 6:
+            c = rng.integers(-5, 5, rows) * 0.001
+        else:
+            c = np.cumsum(rng.integers(0, 1500, rows)) / 100.0
+        cols.append(c)
+    src = np.stack(cols)
+    ctx = vm.default_context()
+    got, scales = vm.decimal.append_float_to_decimal_columns(src, ctx)
+    for k in range(src.shape[0]):
+        hv, he = vm.decimal.append_float_to_decimal(src[k])
+        ov, oe = oracle.float_to_decimal(src[k])
+        assert he == oe and np.array_equal(hv, ov)
+        assert int(scales[k]) == oe and np.array_equal(got[k], ov), k

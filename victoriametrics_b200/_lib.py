@@ -90,6 +90,7 @@ def lib():
         "vmb_decimal_to_float": (C.c_int, [vp, f64p, i64p, sz, C.c_int16]),
         "vmb_marshal_int64": (C.c_int, [u8p, sz, C.POINTER(sz), C.POINTER(C.c_int), i64p, i64p, sz, C.c_uint8]),
         "vmb_float_to_decimal": (C.c_int, [i64p, C.POINTER(C.c_int16), f64p, sz]),
+        "vmb_float_to_decimal_columns": (C.c_int, [vp, i64p, C.POINTER(C.c_int16), f64p, sz, sz]),
         "vmb_zstd_compress": (C.c_int, [u8p, sz, C.POINTER(sz), u8p, sz]),
         "vmb_marshal_columns": (C.c_int, [u8p, sz, u64p, u8p, i64p, i64p, sz, sz, C.c_uint8, C.c_int]),
         "vmb_marshal_columns_gpu": (C.c_int, [vp, u8p, sz, u64p, u8p, i64p, i64p, sz, sz, C.c_uint8, C.c_int]),

@@ -1794,3 +1794,31 @@ extern "C" int vmb_marshal_columns_gpu(vmb_ctx* ctx, uint8_t* dst, size_t cap, u
     offs[ncols] = o;
     return VMB_OK;
 }
+
+// decimal.AppendFloatToDecimal (decimal.go:173) for ncols equal-length float64 columns on the GPU: dst [ncols x rows] mantissas,
+// scales[ncols] the common exponent of each column (what Block.Init / the ingest path compute per block before MarshalData)
+extern "C" int vmb_float_to_decimal_columns(vmb_ctx* ctx, int64_t* dst, int16_t* scales, const double* src, size_t ncols, size_t rows) {
+    if (!ctx || !dst || !scales || !src || rows == 0 || ncols > 0x7fffffffu || rows > 0x7fffffffu) return VMB_ERR_INVALID_ARG;
+    if (ncols == 0) return VMB_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n = ncols * rows;
+    int rc;
+    if ((rc = ctx->enc_vals.reserve(n * 8))) return rc;
+    if ((rc = ctx->enc_deltas.reserve(n * 8))) return rc;
+    if ((rc = ctx->enc_meta.reserve(al16(n * 2) + al16(ncols * 2) + 64))) return rc;
+    double* d_src = (double*)ctx->enc_vals.p;
+    int64_t* d_dst = (int64_t*)ctx->enc_deltas.p;
+    int16_t* d_ea = (int16_t*)ctx->enc_meta.p;
+    int16_t* d_sc = (int16_t*)((uint8_t*)ctx->enc_meta.p + al16(n * 2));
+    CU(cudaMemcpyAsync(d_src, src, n * 8, cudaMemcpyHostToDevice, st));
+    uint32_t grid = (uint32_t)((ncols + 3) / 4);
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    k_float_to_decimal<<<grid, 128, 0, st>>>(d_src, d_dst, d_ea, d_sc, (uint32_t)ncols, (uint32_t)rows);
+    count_launch(ctx);
+    CU(cudaMemcpyAsync(dst, d_dst, n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(scales, d_sc, ncols * 2, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return VMB_OK;
+}

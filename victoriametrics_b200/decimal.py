@@ -25,6 +25,19 @@ def append_float_to_decimal(src):
     return dst, e.value
 
 
+def append_float_to_decimal_columns(src2d, ctx=None):
+    """decimal.AppendFloatToDecimal for equal-length columns on the GPU (vmb_float_to_decimal_columns): src2d [ncols x rows] float64
+    -> (np.int64[ncols, rows], np.int16[ncols] scales)"""
+    ctx = ctx or _lib.default_context()
+    f = np.ascontiguousarray(src2d, dtype=np.float64)
+    ncols, rows = f.shape
+    dst = np.empty((ncols, rows), dtype=np.int64)
+    scales = np.zeros(ncols, dtype=np.int16)
+    check(lib().vmb_float_to_decimal_columns(ctx.h, dst.ctypes.data_as(_lib.i64p), scales.ctypes.data_as(C.POINTER(C.c_int16)),
+                                             f.ctypes.data_as(_lib.f64p), ncols, rows))
+    return dst, scales
+
+
 def calibrate_scale(a, ae, b, be):
     """decimal.CalibrateScale decimal.go:13 (host, merge path) -> (a', b', e): both arrays rescaled to the common exponent e"""
     a = np.array(a, dtype=np.int64)
