@@ -158,6 +158,14 @@ int vmb_calibrate_scale(int64_t* a, size_t na, int16_t ae, int64_t* b, size_t nb
 /* copies descriptors + payload host->device (the one H2D of the path). payload_len bytes are copied. */
 int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size_t nblocks, const uint8_t* payload,
                       size_t payload_len, vmb_blocks** out);
+/* The same from a part on disk: `headers` = nblocks marshaled blockHeaders (81 bytes each) -- what vmselect keeps per block in its
+ * tmpBlocksFile (tmp_blocks_file.go:110 WriteBlockRefData, parsed back by BlockRef.Init lib/storage/search.go:38) --, in series
+ * order (consecutive headers with the same TSID form one series; netstorage.go groups BlockRefs that way); timestamps_bin /
+ * values_bin = the part's two data files (mmap'ed or read), addressed by TimestampsBlockOffset / ValuesBlockOffset like
+ * BlockRef.MustReadBlock search.go:73.  Only the referenced byte ranges are copied.  Errors: a header that fails
+ * blockHeader.validate, offsets outside the files (VMB_ERR_SHORT_SRC). */
+int vmb_blocks_upload_part(vmb_ctx* ctx, const uint8_t* headers, size_t nblocks, const uint8_t* timestamps_bin, size_t ts_len,
+                           const uint8_t* values_bin, size_t val_len, vmb_blocks** out);
 void vmb_blocks_free(vmb_blocks* b);
 size_t vmb_blocks_count(const vmb_blocks* b);
 uint64_t vmb_blocks_rows(const vmb_blocks* b);           /* sum of RowsCount */

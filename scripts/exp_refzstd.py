@@ -11,7 +11,8 @@ NB = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 ctx = vm.default_context()
 T0 = 1_700_000_000_000
 TKIND = sys.argv[2] if len(sys.argv) > 2 else "regular"
-for kind in ("counter", "counter_smooth", "gauge", "gauge_small"):
+KINDS = sys.argv[3].split(",") if len(sys.argv) > 3 else ("counter", "counter_smooth", "gauge", "gauge_small")
+for kind in KINDS:
     rng = np.random.default_rng(1)
     uniq = [blockgen.OBlock(blockgen.gen_timestamps(rng, TKIND, 8192, T0), blockgen.gen_values(rng, kind, 8192), -2, 64, 0)
             for _ in range(64)]
@@ -35,5 +36,5 @@ for kind in ("counter", "counter_smooth", "gauge", "gauge_small"):
     promql.eval_rollup_func("rate", B, start, end, step, 300000, out_dev_ptr=out.data_ptr())
     st = ctx.stage_ms()
     ctx.enable_stage_timing(False)
-    print("%-15s val_mt %s  %.2f B/sample  stages ms zstd %.3f decode %.3f preamble %.3f rollup %.3f  (%d blocks)" %
-          (kind, mts, ratio, st[0], st[1], st[2], st[3], NB), flush=True)
+    print("%-15s val_mt %s  %.2f B/sample  stages ms zstd %.3f decode %.3f preamble %.3f rollup %.3f fused %.3f  (%d blocks)" %
+          (kind, mts, ratio, st[0], st[1], st[2], st[3], st[5], NB), flush=True)

@@ -191,6 +191,42 @@ def test_part_collect_blocks_decode_and_rollup(oracle, max_index_block):
     assert sorted(set(int(x) for x in d2["series_idx"])) == [0, 1]
 
 
+def test_block_refs_feed_matches_collect_blocks(oracle):
+    """vmb_blocks_upload_part: the tmpBlocksFile form of a query (marshaled headers + the part's two data files)"""
+    import victoriametrics_b200 as vm
+    if not oracle.lib().vmo_zstd_ref_available():
+        pytest.skip("oracle/_ref (the reference's libzstd) was not built")
+    rng = np.random.default_rng(SEED0 + 777)
+    series, files = _make_part(rng, 120, partgen.MAX_BLOCK_SIZE)
+    # a query keeps some of the series: their headers, in series order, like netstorage.go groups BlockRefs by metric name
+    keep = sorted(rng.choice(len(series), 70, replace=False).tolist())
+    keep_tsids = {series[i][0] for i in keep}
+    hdrs = b"".join(partgen.pack_header(tsid, h) for tsid, h in files["headers"] if tsid in keep_tsids)
+    B = vm.storage.Blocks.from_block_refs(hdrs, files["timestamps_bin"], files["values_bin"])
+    assert B.count == sum(len(series[i][1]) for i in keep)
+    ser, status = vm.storage.decode_blocks(B)
+    assert not status.any()
+    got = ser.to_lists()
+    ser.close()
+    assert len(got) == len(keep)
+    for g, i in zip(got, keep):
+        tss, vs = [], []
+        for b in series[i][1]:
+            rc, ts, fv, _ = b.oracle_unmarshal()
+            assert rc == 0
+            tss.append(ts)
+            vs.append(fv)
+        assert np.array_equal(g[0], np.concatenate(tss)), i
+        assert _same(g[1], np.concatenate(vs)), i
+    # offsets outside the files / a damaged header are refused
+    bad = bytearray(hdrs[:81])
+    bad[56:64] = (len(files["values_bin"]) + 5).to_bytes(8, "big")  # ValuesBlockOffset
+    with pytest.raises(vm.VmbError):
+        vm.storage.Blocks.from_block_refs(bytes(bad), files["timestamps_bin"], files["values_bin"])
+    with pytest.raises(ValueError):
+        vm.storage.Blocks.from_block_refs(hdrs[:100], files["timestamps_bin"], files["values_bin"])
+
+
 def test_zstd_decompress_empty_content_frame(oracle):
     import victoriametrics_b200 as vm
     if not oracle.lib().vmo_zstd_ref_available():

@@ -95,6 +95,7 @@ def lib():
         "vmb_marshal_columns": (C.c_int, [u8p, sz, u64p, u8p, i64p, i64p, sz, sz, C.c_uint8, C.c_int]),
         "vmb_marshal_columns_gpu": (C.c_int, [vp, u8p, sz, u64p, u8p, i64p, i64p, sz, sz, C.c_uint8, C.c_int]),
         "vmb_blocks_upload": (C.c_int, [vp, C.POINTER(BlockDesc), sz, u8p, sz, C.POINTER(vp)]),
+        "vmb_blocks_upload_part": (C.c_int, [vp, u8p, sz, u8p, sz, u8p, sz, C.POINTER(vp)]),
         "vmb_blocks_free": (None, [vp]),
         "vmb_blocks_count": (sz, [vp]),
         "vmb_blocks_rows": (C.c_uint64, [vp]),

@@ -576,6 +576,46 @@ extern "C" int vmb_blocks_upload(vmb_ctx* ctx, const vmb_block_desc* descs, size
     return blocks_upload_impl(ctx, descs, nblocks, payload, payload_len, out, 0);
 }
 
+// The feed of a query from a part on disk: what netstorage keeps per block in its tmpBlocksFile is the marshaled blockHeader
+// (tmp_blocks_file.go:110 WriteBlockRefData; BlockRef.Init lib/storage/search.go:38 parses it back) and the block itself is
+// read from the part's timestamps.bin / values.bin at the header's offsets (BlockRef.MustReadBlock search.go:73).  Here: all
+// BlockRefs of a query at once -- the referenced byte ranges are gathered into one arena and go to the device in one copy.
+extern "C" int vmb_blocks_upload_part(vmb_ctx* ctx, const uint8_t* headers, size_t nblocks, const uint8_t* timestamps_bin, size_t ts_len,
+                                      const uint8_t* values_bin, size_t val_len, vmb_blocks** out) {
+    if (!ctx || !out || (nblocks && !headers) || (ts_len && !timestamps_bin) || (val_len && !values_bin)) return VMB_ERR_INVALID_ARG;
+    std::vector<vmb_block_desc> descs(nblocks);
+    size_t total = 0;
+    uint8_t prev_tsid[24], tsid[24];
+    uint32_t series = 0;
+    for (size_t i = 0; i < nblocks; i++) {
+        vmb_block_desc& d = descs[i];
+        int rc = vmb_block_desc_from_header(&d, headers + i * 81, tsid);
+        if (rc) return rc;
+        if (d.ts_off > ts_len || d.ts_size > ts_len - d.ts_off || d.val_off > val_len || d.val_size > val_len - d.val_off) {
+            vmb_set_error("block %zu references bytes outside the part files (timestamps [%llu, +%u) of %zu, values [%llu, +%u) of %zu)", i,
+                          (unsigned long long)d.ts_off, d.ts_size, ts_len, (unsigned long long)d.val_off, d.val_size, val_len);
+            return VMB_ERR_SHORT_SRC;
+        }
+        // the blocks of one series are consecutive (netstorage.go:1414 groups the BlockRefs by metric name = by TSID)
+        if (i && memcmp(tsid, prev_tsid, 24) != 0) series++;
+        memcpy(prev_tsid, tsid, 24);
+        d.series_idx = series;
+        total += al16((size_t)d.ts_size) + al16((size_t)d.val_size);
+    }
+    std::vector<uint8_t> arena(total + 16);
+    size_t pos = 0;
+    for (size_t i = 0; i < nblocks; i++) {
+        vmb_block_desc& d = descs[i];
+        if (d.ts_size) memcpy(arena.data() + pos, timestamps_bin + d.ts_off, d.ts_size);
+        d.ts_off = pos;
+        pos += al16((size_t)d.ts_size);
+        if (d.val_size) memcpy(arena.data() + pos, values_bin + d.val_off, d.val_size);
+        d.val_off = pos;
+        pos += al16((size_t)d.val_size);
+    }
+    return blocks_upload_impl(ctx, descs.data(), nblocks, arena.data(), pos, out, 0);
+}
+
 // ------------------------------------------------------------------------------------------------ series batches
 extern "C" void vmb_series_free(vmb_series* s) {
     if (!s) return;

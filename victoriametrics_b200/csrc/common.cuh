@@ -48,7 +48,8 @@ struct HufJob {
     uint8_t table_log;       // Max_Number_of_Bits
     uint8_t nstreams;        // 1 or 4; 0 = job invalid
     uint8_t dst_is_lit;      // 1: dst_off is into the literal arena (sequences will run afterwards)
-    uint8_t _pad[5];
+    uint8_t seq_big;         // set by k_zstd_seq_decode<false>: a sequence table has > 256 states, decoded by the second launch
+    uint8_t _pad[4];
 };
 static_assert(sizeof(HufJob) == 312, "HufJob layout");
 

@@ -136,8 +136,10 @@ struct ValEmit {
 };
 
 __device__ __forceinline__ uint32_t term_mask4(uint32_t w) {
-    uint32_t t = ~w & 0x80808080u;
-    return ((t >> 7) & 1u) | ((t >> 14) & 2u) | ((t >> 21) & 4u) | ((t >> 28) & 8u);
+    // the four sign bits moved to bits 0, 8, 16, 24, then gathered by one multiplication: t * (2^21 + 2^14 + 2^7 + 1) puts them at
+    // bits 21..24 (every other partial product lands on a bit of its own below 21 or above 24: no carries)
+    const uint32_t t = (~w & 0x80808080u) >> 7;
+    return ((t * 0x204081u) >> 21) & 0xfu;
 }
 
 // UnmarshalVarInt64 int.go:173 (binary.Uvarint + zig-zag) on <= 11 bytes, executed redundantly by every lane

@@ -691,18 +691,24 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                     }
                     // a run of continuation bytes over a whole 16-byte group inside the stream: a varint of > 16 bytes
                     if (w < K && vm == 0xffffu && tm == 0 && pbm == 0) bad = true;
-                    // ---- scan (count, s1, s2) over the warp; combine(A then B): s2 = s2A + s2B + cntB * s1A
-                    uint32_t icnt = w < K ? cl : 0u;
-                    uint64_t is1 = s1, is2 = s2;
+                    // ---- scan (s1, s2) over the warp.  combine(A then B): s2 = s2A + s2B + cntB * s1A, so with E1(l) = the plain
+                    // exclusive prefix of s1, the inclusive prefix of s2 is the plain prefix sum of t_l = s2_l + cnt_l * E1(l): two sum
+                    // scans (wrapping int64 arithmetic: bit-identical to the sequential Go loop), the counts are known from step 1
+                    const uint32_t mycnt = w < K ? cl : 0u;
+                    uint64_t is1 = s1;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
-                        uint32_t acnt = __shfl_up_sync(VMB_FULL, icnt, o);
-                        uint64_t as1 = shfl_up_u64(is1, o);
-                        uint64_t as2 = shfl_up_u64(is2, o);
-                        if (lane >= (uint32_t)o) {
-                            if (delta2) is2 = as2 + is2 + (uint64_t)icnt * as1;
-                            is1 += as1;
-                            icnt += acnt;
+                        const uint64_t a = shfl_up_u64(is1, o);
+                        if (lane >= (uint32_t)o) is1 += a;
+                    }
+                    const uint64_t es1_ = is1 - s1;  // lanes in front of this one
+                    const uint64_t t2 = s2 + (uint64_t)mycnt * es1_;
+                    uint64_t is2 = t2;
+                    if (delta2) {
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint64_t a = shfl_up_u64(is2, o);
+                            if (lane >= (uint32_t)o) is2 += a;
                         }
                     }
                     if (lane == 31) {
@@ -718,16 +724,25 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                     uint64_t ps1, ps2, ts1, ts2;
                     {
                         const bool act = lane < K;
-                        uint32_t c_ = act ? S.w_cnt[lane] : 0u;
-                        uint64_t a1 = act ? S.w_s1[lane] : 0ull, a2 = act ? S.w_s2[lane] : 0ull;
+                        const uint32_t c0_ = act ? S.w_cnt[lane] : 0u;
+                        const uint64_t a1_0 = act ? S.w_s1[lane] : 0ull, a2_0 = act ? S.w_s2[lane] : 0ull;
+                        uint32_t c_ = c0_;
+                        uint64_t a1 = a1_0;
 #pragma unroll
                         for (int o = 1; o < FU_WARPS; o <<= 1) {
                             const uint32_t bc = __shfl_up_sync(VMB_FULL, c_, o);
-                            const uint64_t b1 = shfl_up_u64(a1, o), b2 = shfl_up_u64(a2, o);
+                            const uint64_t b1 = shfl_up_u64(a1, o);
                             if (lane >= (uint32_t)o) {
-                                if (delta2) a2 = b2 + a2 + (uint64_t)c_ * b1;
                                 a1 += b1;
                                 c_ += bc;
+                            }
+                        }
+                        uint64_t a2 = a2_0 + (uint64_t)c0_ * (a1 - a1_0);  // the same two-scan form over the warps
+                        if (delta2) {
+#pragma unroll
+                            for (int o = 1; o < FU_WARPS; o <<= 1) {
+                                const uint64_t b2 = shfl_up_u64(a2, o);
+                                if (lane >= (uint32_t)o) a2 += b2;
                             }
                         }
                         const int src_p = w ? (int)w - 1 : 0, src_t = (int)K - 1;
@@ -740,9 +755,8 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                         ts2 = shfl_u64(a2, src_t);
                     }
                     // ---- emit: replay the lane's values with the scanned prefix, mantissa -> float64 in place
-                    uint32_t ecnt = __shfl_up_sync(VMB_FULL, icnt, 1);  // (all lanes take part in the shuffles)
-                    uint64_t es1 = shfl_up_u64(is1, 1), es2 = shfl_up_u64(is2, 1);
-                    if (lane == 0) { ecnt = 0; es1 = 0; es2 = 0; }
+                    const uint32_t ecnt = incl - cl;         // lanes in front, this warp (step 1)
+                    const uint64_t es1 = es1_, es2 = is2 - t2;
                     if (!bail && w < K && cl) {
                         // prefix in front of the lane = (warps in front) then (lanes in front)
                         const uint32_t fcnt = pc + ecnt;

@@ -776,6 +776,7 @@ __global__ void k_zstd_prepare(ZstdParams P) {
         if (!has_seq && (job->seq_size != 1 || regen != ci.content_size)) break;
         if (has_seq && !P.lit) break;
         job->dst_is_lit = has_seq ? 1 : 0;
+        job->seq_big = 0;
         job->dst_off = ci.scratch_off;
         job->nstreams = (uint8_t)streams;
         rc = 0;
@@ -1055,10 +1056,14 @@ __global__ void __launch_bounds__(HUF_WARPS * 32) k_huf_decode(ZstdParams P) {
 #define SEQ_REC_LL(r) ((uint32_t)((r) >> 44))
 #define SEQ_REC_ML(r) ((uint32_t)((r) >> 24) & 0xfffffu)
 #define SEQ_REC_OF(r) ((uint32_t)(r) & 0xffffffu)
-// decoding tables of one frame, 3 bytes per state (16-bit nbits|base + 8-bit symbol) so that more frames fit an SM
-struct SeqTables {
-    unsigned short ll_nb[512], ml_nb[512], of_nb[256];  // (nbits << 12) | base, base < 512
-    uint8_t ll_sym[512], ml_sym[512], of_sym[256];
+// decoding tables of one frame, 3 bytes per state (16-bit nbits|base + 8-bit symbol) so that more frames fit an SM.  Two
+// capacities: libzstd picks accuracy log 8 for the ~1300 sequences of an 8192-row column (measured; the format allows 9 / 8 / 9),
+// so the kernel runs first with 256-state tables (2304 B per frame: twelve warps of eight frames per SM) and frames whose
+// tables are larger are flagged (HufJob::seq_big) for a second launch with full-size tables.
+template <int LLC, int MLC, int OFC>
+struct SeqTablesT {
+    unsigned short ll_nb[LLC], ml_nb[MLC], of_nb[OFC];  // (nbits << 12) | base, base < 512
+    uint8_t ll_sym[LLC], ml_sym[MLC], of_sym[OFC];
 };
 
 // fse_build for the packed layout (same spreading, RFC 8878 4.1.1)
@@ -1094,10 +1099,15 @@ __device__ bool fse_build_packed(uint8_t* sym, unsigned short* nbbase, const sho
 }
 
 // Symbol_Compression_Mode of one sequence table (RFC 8878 3.1.1.3.2.1) -> packed table; returns bytes consumed.
-// Repeat mode is invalid here: a prepared frame holds a single block.
+// Repeat mode is invalid here: a prepared frame holds a single block.  *big: the table has more than 2^cap_log states
+// (nothing is built; the frame belongs to the launch with full-size tables).
+struct SeqWs {  // scratch of the table builder (global memory, one per frame group of the grid)
+    short norm[256];
+    unsigned short next[256];
+};
 __device__ uint32_t read_seq_table_packed(uint8_t* sym, unsigned short* nbbase, int* tlog, int mode, const short* defnorm, int defn,
-                                          int deflog, int max_sym, int max_log, const uint8_t* src, uint32_t len, SerialWs* ws,
-                                          bool* ok) {
+                                          int deflog, int max_sym, int max_log, int cap_log, const uint8_t* src, uint32_t len,
+                                          SeqWs* ws, bool* ok, bool* big) {
     *ok = true;
     if (mode == 0) {
         for (int i = 0; i < defn; i++) ws->norm[i] = defnorm[i];
@@ -1118,7 +1128,15 @@ __device__ uint32_t read_seq_table_packed(uint8_t* sym, unsigned short* nbbase, 
     if (mode == 2) {
         int nsym, log;
         const uint32_t used = fse_read_ncount(ws->norm, &nsym, &log, max_sym, max_log, src, len);
-        if (!used || !fse_build_packed(sym, nbbase, ws->norm, nsym, log, ws->next)) {
+        if (!used) {
+            *ok = false;
+            return 0;
+        }
+        if (log > cap_log) {
+            *big = true;
+            return used;
+        }
+        if (!fse_build_packed(sym, nbbase, ws->norm, nsym, log, ws->next)) {
             *ok = false;
             return 0;
         }
@@ -1129,8 +1147,74 @@ __device__ uint32_t read_seq_table_packed(uint8_t* sym, unsigned short* nbbase, 
     return 0;
 }
 
+// Backward bitstream of the sequences section for the decode loop: MSB-aligned 64-bit window in two registers (every field is
+// cut with funnel shifts, no 64-bit variable shifts), fed by ALIGNED 32-bit words loaded one refill ahead (the load's latency
+// is covered by the sequences decoded in between).  Words in front of the stream start hold other bytes of the frame: they can
+// only be consumed by a stream that over-reads, which `left` < 0 reports.
+struct SeqBits {
+    const uint32_t* wp;     // aligned word that the NEXT prefetch reads
+    const uint32_t* wmin;   // never read below this word
+    uint32_t w_hi, w_lo;    // aligned words around the next 4 stream bytes (w_lo may still be in flight)
+    uint32_t sh;            // (address of the stream bytes & 3) * 8
+    uint32_t hi, lo;        // the window, next bit at the top of hi
+    int cnt;                // bits in the window
+    int left;               // payload bits not yet consumed; < 0 => over-read
+
+    __device__ __forceinline__ void refill() {  // requires cnt <= 32
+        const uint32_t w = __funnelshift_r(w_lo, w_hi, sh);
+        hi |= __funnelshift_rc(w, 0u, (uint32_t)cnt);
+        lo = __funnelshift_lc(0u, w, 32u - (uint32_t)cnt);
+        cnt += 32;
+        w_hi = w_lo;
+        w_lo = *wp;
+        if (wp > wmin) wp--;
+    }
+    __device__ bool init(const uint8_t* src, uint32_t len) {
+        if (len == 0) return false;
+        const uint32_t last = src[len - 1];
+        if (last == 0) return false;
+        const uintptr_t a = (uintptr_t)(src + len) - 4;  // the first four bytes to pull (the stream's last four)
+        sh = (uint32_t)(a & 3u) * 8u;
+        const uint32_t* w0 = (const uint32_t*)(a & ~(uintptr_t)3);
+        wmin = (const uint32_t*)(((uintptr_t)src - 4) & ~(uintptr_t)3);
+        w_hi = sh ? w0[1] : 0u;
+        w_lo = w0[0];
+        wp = w0 - 1;
+        if (wp < wmin) wp = wmin;
+        hi = lo = 0;
+        cnt = 0;
+        left = (int)((len - 1) * 8u) + hb32(last);
+        refill();
+        if (len < 4) {  // bytes in front of the section ended up in the low end of the first word: zero them like padding
+            const uint32_t keep = 8u * len;
+            hi &= ~(0xffffffffu >> keep);
+        }
+        const uint32_t skip = 8u - (uint32_t)hb32(last);  // zero padding + the final-bit marker
+        hi = __funnelshift_lc(lo, hi, skip);
+        lo = __funnelshift_lc(0u, lo, skip);
+        cnt -= (int)skip;
+        return true;
+    }
+    __device__ __forceinline__ uint32_t take(uint32_t nb) {  // 0 <= nb <= 32, nb <= cnt
+        const uint32_t x = __funnelshift_rc(hi, 0u, 32u - nb);
+        hi = __funnelshift_lc(lo, hi, nb);
+        lo = __funnelshift_lc(0u, lo, nb);
+        return x;
+    }
+    __device__ __forceinline__ uint32_t read_slow(uint32_t nb) {  // any window state
+        if (cnt < (int)nb) refill();
+        const uint32_t x = take(nb);
+        cnt -= (int)nb;
+        left -= (int)nb;
+        return x;
+    }
+};
+
+template <bool BIG>
 __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P) {
-    __shared__ SeqTables s_tab[SEQ_WARPS * SEQ_FPW];
+    typedef SeqTablesT<BIG ? 512 : 256, BIG ? 512 : 256, 256> Tables;
+    constexpr int LL_CAP = BIG ? 9 : 8, ML_CAP = BIG ? 9 : 8, OF_CAP = 8;
+    __shared__ Tables s_tab[SEQ_WARPS * SEQ_FPW];
     // code -> (base value, extra bits): copies in shared memory, because the groups of a warp index them with different codes
     // (constant memory would serve one address per pass)
     __shared__ uint32_t s_ll_base[36], s_ml_base[53];
@@ -1145,14 +1229,15 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
     const int grp = lane / SEQ_G, sub = lane % SEQ_G;
     const uint32_t gslot = (blockIdx.x * SEQ_WARPS + warp) * SEQ_FPW + grp;  // this group's workspace slot
     const uint32_t nslots = gridDim.x * SEQ_WARPS * SEQ_FPW;
-    SeqTables* T = &s_tab[warp * SEQ_FPW + grp];
-    SerialWs* ws = (SerialWs*)P.ws + gslot;  // scratch of the table builder (launch guarantees gslot < ws_count)
+    Tables* T = &s_tab[warp * SEQ_FPW + grp];
+    SeqWs* ws = (SeqWs*)P.ws + gslot;  // scratch of the table builder (the launch guarantees the slot exists)
     for (uint32_t i0 = (blockIdx.x * SEQ_WARPS + warp) * SEQ_FPW; i0 < P.count; i0 += nslots) {
         const uint32_t i = i0 + grp;
         // ---- per group: locate the frame, read the section header, expand the table descriptions (group leader)
         bool act = i < P.count;
-        const HufJob* job = act ? &P.jobs[i] : nullptr;
+        HufJob* job = act ? &P.jobs[i] : nullptr;
         if (act && (job->nstreams == 0 || !job->dst_is_lit)) act = false;
+        if (act && (job->seq_big != 0) != BIG) act = false;  // the other launch's frame
         uint32_t col = 0;
         if (act) {
             col = job->col;
@@ -1160,10 +1245,10 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
         }
         bool ok = true;
         const uint8_t* src = nullptr;
-        uint32_t len = 0, lit_len = 0, nseq = 0, pos = 0;
-        long long out_cap = 0;
+        uint32_t len = 0, lit_len = 0, nseq = 0, pos = 0, out_cap = 0;
         unsigned long long* rec = nullptr;
         int ll_log = 0, of_log = 0, ml_log = 0;
+        bool big = false;
         if (act) {
             const ColInfo ci = P.cols[col];
             const uint8_t* fsrc;
@@ -1171,7 +1256,7 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
             col_src(P, col, &fsrc, &flen);
             src = fsrc + job->seq_off;
             len = job->seq_size;
-            out_cap = ci.content_size;
+            out_cap = ci.content_size;  // (<= 163840: everything below fits 32 bits)
             lit_len = job->regen_size;
             rec = P.seq_rec + ci.seq_rec_off;
             if (len < 1) ok = false;
@@ -1193,137 +1278,132 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
                 if (modes & 3) ok = false;
                 if (ok && sub == 0) {
                     bool tok;
-                    pos += read_seq_table_packed(T->ll_sym, T->ll_nb, &ll_log, (modes >> 6) & 3, c_ll_default, 36, 6, 35, 9, src + pos,
-                                                 len - pos, ws, &tok);
+                    pos += read_seq_table_packed(T->ll_sym, T->ll_nb, &ll_log, (modes >> 6) & 3, c_ll_default, 36, 6, 35, 9, LL_CAP,
+                                                 src + pos, len - pos, ws, &tok, &big);
                     if (tok)
-                        pos += read_seq_table_packed(T->of_sym, T->of_nb, &of_log, (modes >> 4) & 3, c_of_default, 29, 5, 31, 8,
-                                                     src + pos, len - pos, ws, &tok);
+                        pos += read_seq_table_packed(T->of_sym, T->of_nb, &of_log, (modes >> 4) & 3, c_of_default, 29, 5, 31, 8, OF_CAP,
+                                                     src + pos, len - pos, ws, &tok, &big);
                     if (tok)
-                        pos += read_seq_table_packed(T->ml_sym, T->ml_nb, &ml_log, (modes >> 2) & 3, c_ml_default, 53, 6, 52, 9,
-                                                     src + pos, len - pos, ws, &tok);
+                        pos += read_seq_table_packed(T->ml_sym, T->ml_nb, &ml_log, (modes >> 2) & 3, c_ml_default, 53, 6, 52, 9, ML_CAP,
+                                                     src + pos, len - pos, ws, &tok, &big);
                     if (!tok || pos >= len) ok = false;  // (leader only; the group learns it from the broadcast below)
+                    if (tok && big) job->seq_big = 1;    // (BIG launch: cannot happen, its tables hold every legal log)
                 }
             }
         }
         {   // broadcast the leader's view inside each group (uniform code: all 32 lanes execute the shuffles)
             const int leader = grp * SEQ_G;
             ok = __shfl_sync(VMB_FULL, (int)ok, leader) != 0;
+            big = __shfl_sync(VMB_FULL, (int)big, leader) != 0;
             pos = __shfl_sync(VMB_FULL, pos, leader);
             ll_log = __shfl_sync(VMB_FULL, ll_log, leader);
             of_log = __shfl_sync(VMB_FULL, of_log, leader);
             ml_log = __shfl_sync(VMB_FULL, ml_log, leader);
         }
+        if (big) act = false;  // decoded by the launch with full-size tables
         __syncwarp();
-        BitR bb;
-        bb.base = nullptr; bb.pos = 0; bb.buf = 0; bb.cnt = 0; bb.left = 0;
+        SeqBits bb;
+        bb.wp = bb.wmin = (const uint32_t*)P.payload;
+        bb.w_hi = bb.w_lo = bb.sh = bb.hi = bb.lo = 0;
+        bb.cnt = 64;  // (idle groups never refill)
+        bb.left = 0;
         uint32_t sll = 0, sof = 0, sml = 0;
         if (act && ok) {
             if (!bb.init(src + pos, len - pos)) ok = false;
             else {
-                sll = bb.read(ll_log);
-                sof = bb.read(of_log);
-                sml = bb.read(ml_log);
+                sll = bb.read_slow((uint32_t)ll_log);
+                sof = bb.read_slow((uint32_t)of_log);
+                sml = bb.read_slow((uint32_t)ml_log);
             }
         }
         uint32_t rep0 = 1, rep1 = 4, rep2 = 8;  // one block per prepared frame: the repeat offsets start fresh
-        uint32_t o = 0, lit_pos = 0;          // (everything fits 32 bits: content_size <= 163840)
+        uint32_t o = 0, lit_pos = 0;
+        uint32_t bad = 0;
         // The loop is the same for every group of the warp (trip count = the longest frame, work predicated, no early
         // exit): groups that left a loop at different times would never run in lockstep again, and the redundant
-        // instruction stream would be issued once per group instead of once per warp.
+        // instruction stream would be issued once per group instead of once per warp.  Inside, everything but the rare
+        // "fields do not fit the window" case is branch-free for the same reason.
         uint32_t nmax = (act && ok) ? nseq : 0u;
 #pragma unroll
         for (int off = 16; off; off >>= 1) nmax = max(nmax, __shfl_xor_sync(VMB_FULL, nmax, off));
+        const bool live = act && ok;
+        if (!live) nseq = 0;
         for (uint32_t q = 0; q < nmax; q++) {
-            const bool run = act && ok && q < nseq;
+            const bool run = q < nseq;
             if (run) {
                 const uint32_t ell = T->ll_nb[sll], eof = T->of_nb[sof], eml = T->ml_nb[sml];  // (nbits << 12) | base
-                const uint32_t yll = T->ll_sym[sll], yof = T->of_sym[sof], yml = T->ml_sym[sml];
-                const uint32_t ofc = min(yof, 31u), mlc = min(yml, 52u), llc = min(yll, 35u);
-                if (yof > 31 || yml > 52 || yll > 35) ok = false;
-                // all the bits of this sequence in one go when the window holds them (it nearly always does): the six fields
-                // are cut out of the 64-bit window at precomputed offsets instead of six dependent read-and-shift steps
+                const uint32_t yll = T->ll_sym[sll], yof = T->of_sym[sof], yml = T->ml_sym[sml];  // (<= 35 / 31 / 52 by construction)
                 const bool more = q + 1 < nseq;
-                const uint32_t b_of = ofc, b_ml = s_ml_bits[mlc], b_ll = s_ll_bits[llc];
+                const uint32_t b_of = yof, b_ml = s_ml_bits[yml], b_ll = s_ll_bits[yll];
                 const uint32_t n_ll = more ? (ell >> 12) : 0u, n_ml = more ? (eml >> 12) : 0u, n_of = more ? (eof >> 12) : 0u;
-                const uint32_t o1 = b_of, o2 = o1 + b_ml, o3 = o2 + b_ll, o4 = o3 + n_ll, o5 = o4 + n_ml, need = o5 + n_of;
+                const uint32_t need = b_of + b_ml + b_ll + n_ll + n_ml + n_of;
                 if (bb.cnt <= 32) bb.refill();
                 uint32_t x_of, x_ml, x_ll, x_sl, x_sm, x_so;
                 if ((int)need <= bb.cnt) {
-                    const uint64_t w = bb.buf;
-#define SEQ_CUT(off, nb) ((nb) ? (uint32_t)((w << (off)) >> (64u - (nb))) : 0u)
-                    x_of = SEQ_CUT(0u, b_of);
-                    x_ml = SEQ_CUT(o1, b_ml);
-                    x_ll = SEQ_CUT(o2, b_ll);
-                    x_sl = SEQ_CUT(o3, n_ll);
-                    x_sm = SEQ_CUT(o4, n_ml);
-                    x_so = SEQ_CUT(o5, n_of);
-#undef SEQ_CUT
-                    bb.buf = need < 64u ? (w << need) : 0ull;
+                    // all the bits of this sequence are in the window (nearly always): six funnel-shift cuts
+                    x_of = bb.take(b_of);
+                    x_ml = bb.take(b_ml);
+                    x_ll = bb.take(b_ll);
+                    x_sl = bb.take(n_ll);
+                    x_sm = bb.take(n_ml);
+                    x_so = bb.take(n_of);
                     bb.cnt -= (int)need;
-                    bb.left -= need;
+                    bb.left -= (int)need;
                 } else {
-                    x_of = bb.read((int)b_of);
-                    x_ml = bb.read((int)b_ml);
-                    x_ll = bb.read((int)b_ll);
-                    x_sl = bb.read((int)n_ll);
-                    x_sm = bb.read((int)n_ml);
-                    x_so = bb.read((int)n_of);
+                    x_of = bb.read_slow(b_of);
+                    x_ml = bb.read_slow(b_ml);
+                    x_ll = bb.read_slow(b_ll);
+                    x_sl = bb.read_slow(n_ll);
+                    x_sm = bb.read_slow(n_ml);
+                    x_so = bb.read_slow(n_of);
                 }
-                const uint32_t ofv = (1u << ofc) + x_of;  // offset codes > 24 cannot be valid here and fail the range check
-                const uint32_t mlen = s_ml_base[mlc] + x_ml, llen = s_ll_base[llc] + x_ll;
-                if (more) {
-                    sll = (ell & 0xfffu) + x_sl;
-                    sml = (eml & 0xfffu) + x_sm;
-                    sof = (eof & 0xfffu) + x_so;
-                }
-                if (bb.left < 0) ok = false;
-                if (ofc > 24) ok = false;
-                uint32_t offset;
-                if (ofv > 3) {
-                    offset = ofv - 3;
-                    rep2 = rep1; rep1 = rep0; rep0 = offset;
-                } else {
-                    const uint32_t idx = ofv - 1 + (llen == 0 ? 1 : 0);
-                    if (idx == 0) offset = rep0;
-                    else {
-                        offset = idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1);
-                        if (offset == 0) ok = false;
-                        if (idx > 1) rep2 = rep1;
-                        rep1 = rep0;
-                        rep0 = offset;
-                    }
-                }
-                if (lit_pos + llen > lit_len || (unsigned long long)o + llen + mlen > (unsigned long long)out_cap || offset > o + llen ||
-                    offset == 0)
-                    ok = false;
+                sll = (ell & 0xfffu) + x_sl;  // (after the last sequence: base + 0, never used)
+                sml = (eml & 0xfffu) + x_sm;
+                sof = (eof & 0xfffu) + x_so;
+                const uint32_t ofv = (1u << (yof & 31u)) + x_of;
+                const uint32_t mlen = s_ml_base[yml] + x_ml, llen = s_ll_base[yll] + x_ll;
+                // offset codes > 24 cannot be valid here (the window is at most the 160 KiB column)
+                bad |= (uint32_t)(yof > 24u) | (uint32_t)(bb.left < 0);
+                // repeat offsets (RFC 8878 3.1.1.5), as selects: idx 0 = rep0 unchanged, 1 = swap in rep1, 2 = rotate in rep2,
+                // 3 = rep0 - 1 or a new offset (both push the history down)
+                const bool is_new = ofv > 3u;
+                const uint32_t idx = is_new ? 3u : ofv - 1u + (llen == 0u ? 1u : 0u);
+                const uint32_t from_hist = idx == 0u ? rep0 : (idx == 1u ? rep1 : (idx == 2u ? rep2 : rep0 - 1u));
+                const uint32_t offset = is_new ? ofv - 3u : from_hist;
+                rep2 = idx >= 2u ? rep1 : rep2;
+                rep1 = idx >= 1u ? rep0 : rep1;
+                rep0 = offset;
+                bad |= (uint32_t)(lit_pos + llen > lit_len) | (uint32_t)(o + llen + mlen > out_cap) | (uint32_t)(offset > o + llen) |
+                       (uint32_t)(offset == 0u);
                 o += llen + mlen;
                 lit_pos += llen;
-                if (sub == 0 && ok) rec[q] = SEQ_REC(llen, mlen, offset);
+                if (sub == 0 && !bad) rec[q] = SEQ_REC(llen, mlen, offset);
             }
         }
-        if (act && ok) {
+        if (bad) ok = false;
+        if (live && ok) {
             if (bb.left != 0) ok = false;
-            if (ok && (long long)o + (long long)(lit_len - lit_pos) != out_cap) ok = false;
+            if (ok && o + (lit_len - lit_pos) != out_cap) ok = false;
         }
-        if (act && sub == 0 && !ok) P.status[col] = VMB_ERR_ZSTD;
+        if (live && sub == 0 && !ok) P.status[col] = VMB_ERR_ZSTD;
+        if (act && !live && sub == 0 && !ok) P.status[col] = VMB_ERR_ZSTD;
         __syncwarp();
     }
 }
 
 #define SEQX_WARPS 4
-#define SEQX_G 8  /* lanes per frame: matches are short (a dozen bytes), 32 lanes per copy would idle */
-__device__ __forceinline__ void groupx_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int sub) {
-    if (n >= 128u) {
-        // long run (the literals behind the last sequence of a barely compressible column: most of the frame): 16 bytes per lane
-        // and step -- destination aligned to 16, the source read as five aligned words and funnel-shifted into place
+// n bytes src -> dst by the whole warp (no overlap between the two ranges within n): long runs go 16 bytes per lane and step
+// -- destination aligned to 16, the source read as five aligned words and funnel-shifted into place
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+    if (n >= 64u) {
         uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
-        for (uint32_t k = sub; k < head; k += SEQX_G) dst[k] = src[k];
+        if ((uint32_t)lane < head) dst[lane] = src[lane];
         const uint32_t chunks = (n - head) >> 4;
         const uint8_t* s0 = src + head;
         const uint32_t sh = (uint32_t)((uintptr_t)s0 & 3u) * 8u;
         const uint32_t* sw = (const uint32_t*)((uintptr_t)s0 & ~(uintptr_t)3);
         uint4* d4 = (uint4*)(dst + head);
-        for (uint32_t c = sub; c < chunks; c += SEQX_G) {
+        for (uint32_t c = lane; c < chunks; c += 32) {
             const uint32_t* w = sw + 4 * c;
             const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
             uint4 v;
@@ -1334,24 +1414,21 @@ __device__ __forceinline__ void groupx_copy(uint8_t* dst, const uint8_t* src, ui
             d4[c] = v;
         }
         const uint32_t done = head + 16u * chunks;
-        for (uint32_t k = done + sub; k < n; k += SEQX_G) dst[k] = src[k];  // <= 15 tail bytes
+        if (done + lane < n) dst[done + lane] = src[done + lane];  // <= 15 tail bytes
         return;
     }
-    uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
-    if (head > n) head = n;
-    if ((uint32_t)sub < head) dst[sub] = src[sub];
-    const uint32_t words = (n - head) >> 2;
-    for (uint32_t w = sub; w < words; w += SEQX_G) *(uint32_t*)(dst + head + 4 * w) = load_u32_unaligned(src + head + 4 * w);
-    const uint32_t done = head + 4 * words;
-    if (done + sub < n) dst[done + sub] = src[done + sub];  // <= 3 tail bytes
+    for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
 }
 
+// One warp per frame, 32 sequences per step, one sequence per lane: positions by two warp scans; every lane copies its own
+// literal run (independent of everything else) and, when its match reads only bytes in front of the step's first output byte
+// -- final since the previous step --, its own match too; the remaining matches (sources inside the step's own output) follow
+// in order, each copied by the whole warp.  Matches of smooth series are short (4-13 bytes) and reach a few hundred bytes
+// back: three quarters of them are of the first kind.
 __global__ void __launch_bounds__(SEQX_WARPS * 32) k_zstd_seq_exec(ZstdParams P) {
-    const int lane = lane_id(), sub = lane % SEQX_G;
-    const uint32_t gmask = ((1u << SEQX_G) - 1u) << (lane - sub);  // the lanes of this frame's group: all syncs are group-wide
-    const uint32_t gg = (blockIdx.x * SEQX_WARPS + (threadIdx.x >> 5)) * (32 / SEQX_G) + lane / SEQX_G;
-    const uint32_t ng = gridDim.x * SEQX_WARPS * (32 / SEQX_G);
-    for (uint32_t i = gg; i < P.count; i += ng) {
+    const int lane = lane_id();
+    const uint32_t wi = blockIdx.x * SEQX_WARPS + (threadIdx.x >> 5), nw = gridDim.x * SEQX_WARPS;
+    for (uint32_t i = wi; i < P.count; i += nw) {
         const HufJob* job = &P.jobs[i];
         if (job->nstreams == 0 || !job->dst_is_lit) continue;
         const uint32_t col = job->col;
@@ -1361,61 +1438,53 @@ __global__ void __launch_bounds__(SEQX_WARPS * 32) k_zstd_seq_exec(ZstdParams P)
         const uint32_t nseq = ci.nseq;
         uint8_t* out = P.scratch + ci.scratch_off;
         const uint8_t* lits = P.lit + ci.scratch_off;
-        // ---- pass 1: literal runs (independent of everything else).  Positions: exclusive scans of (ll + ml) and ll.
         uint32_t o_base = 0, l_base = 0;
-        for (uint32_t c = 0; c < nseq; c += SEQX_G) {
-            const uint32_t q = c + sub;
-            const unsigned long long r = q < nseq ? rec[q] : 0ull;
-            const uint32_t ll = SEQ_REC_LL(r), tot = ll + SEQ_REC_ML(r);
-            uint32_t so = tot, sl = ll;
-#pragma unroll
-            for (int off = 1; off < SEQX_G; off <<= 1) {
-                const uint32_t a = __shfl_up_sync(gmask, so, off, SEQX_G), b = __shfl_up_sync(gmask, sl, off, SEQX_G);
-                if (sub >= off) { so += a; sl += b; }
-            }
-            const uint32_t o = o_base + so - tot, lp = l_base + sl - ll;  // where this sequence's literals go / come from
-            if (__reduce_max_sync(gmask, ll) <= 8) {
-                for (uint32_t k = 0; k < ll; k++) out[o + k] = lits[lp + k];
-            } else {
-                for (int j = 0; j < SEQX_G; j++) {
-                    const uint32_t n = __shfl_sync(gmask, ll, j, SEQX_G);
-                    const uint32_t oj = __shfl_sync(gmask, o, j, SEQX_G), lj = __shfl_sync(gmask, lp, j, SEQX_G);
-                    if (n) groupx_copy(out + oj, lits + lj, n, sub);
-                }
-            }
-            o_base += __shfl_sync(gmask, so, SEQX_G - 1, SEQX_G);
-            l_base += __shfl_sync(gmask, sl, SEQX_G - 1, SEQX_G);
-        }
-        groupx_copy(out + o_base, lits + l_base, job->regen_size - l_base, sub);  // literals after the last sequence
-        __syncwarp(gmask);
-        // ---- pass 2: the matches, in order
-        o_base = 0;
-        for (uint32_t c = 0; c < nseq; c += SEQX_G) {
-            const uint32_t q = c + sub;
+        for (uint32_t c = 0; c < nseq; c += 32) {
+            const uint32_t q = c + lane;
             const unsigned long long r = q < nseq ? rec[q] : 0ull;
             const uint32_t ll = SEQ_REC_LL(r), ml = SEQ_REC_ML(r), of = SEQ_REC_OF(r);
-            uint32_t so = ll + ml;
+            const uint32_t tot = ll + ml;
+            uint32_t so = tot, sl = ll;
 #pragma unroll
-            for (int off = 1; off < SEQX_G; off <<= 1) {
-                const uint32_t a = __shfl_up_sync(gmask, so, off, SEQX_G);
-                if (sub >= off) so += a;
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t a = __shfl_up_sync(VMB_FULL, so, off), b = __shfl_up_sync(VMB_FULL, sl, off);
+                if (lane >= off) { so += a; sl += b; }
             }
-            const uint32_t dst = o_base + so - ml;  // first byte of this sequence's match
-            const uint32_t cnt = min((uint32_t)SEQX_G, nseq - c);
-            for (uint32_t j = 0; j < cnt; j++) {
-                const uint32_t d = __shfl_sync(gmask, dst, j, SEQX_G), m = __shfl_sync(gmask, ml, j, SEQX_G);
-                const uint32_t f = __shfl_sync(gmask, of, j, SEQX_G);
-                if (m <= SEQX_G) {  // the common case: one byte per lane, one step
-                    if ((uint32_t)sub < m) out[d + sub] = out[d - f + (f >= m ? (uint32_t)sub : (uint32_t)sub % f)];
-                } else if (f >= m) groupx_copy(out + d, out + d - f, m, sub);
-                else {
-                    const uint8_t* pat = out + d - f;
-                    for (uint32_t k = sub; k < m; k += SEQX_G) out[d + k] = pat[k % f];
+            const uint32_t o = o_base + so - tot, lp = l_base + sl - ll;  // where this sequence's literals go / come from
+            const uint32_t d = o + ll;                                    // first byte of its match
+            // ---- literal runs
+            const uint32_t long_ll = __ballot_sync(VMB_FULL, ll > 16u);
+            if (ll <= 16u)
+                for (uint32_t k = 0; k < ll; k++) out[o + k] = lits[lp + k];
+            for (uint32_t mm = long_ll; mm; mm &= mm - 1u) {
+                const int j = __ffs((int)mm) - 1;
+                warp_copy(out + __shfl_sync(VMB_FULL, o, j), lits + __shfl_sync(VMB_FULL, lp, j), __shfl_sync(VMB_FULL, ll, j), lane);
+            }
+            // ---- matches whose source is final already: one per lane
+            const bool early = ml && d - of + ml <= o_base;  // (offset <= d was checked by the decoder)
+            __syncwarp();
+            if (early)
+                for (uint32_t k = 0; k < ml; k++) out[d + k] = out[d - of + k];
+            __syncwarp();
+            // ---- the others, in order
+            for (uint32_t mm = __ballot_sync(VMB_FULL, ml && !early); mm; mm &= mm - 1u) {
+                const int j = __ffs((int)mm) - 1;
+                const uint32_t dj = __shfl_sync(VMB_FULL, d, j), m = __shfl_sync(VMB_FULL, ml, j), f = __shfl_sync(VMB_FULL, of, j);
+                if (m <= 32u) {  // the common case: one byte per lane, one step
+                    if ((uint32_t)lane < m) out[dj + lane] = out[dj - f + (f >= m ? (uint32_t)lane : (uint32_t)lane % f)];
+                } else if (f >= m) {
+                    warp_copy(out + dj, out + dj - f, m, lane);
+                } else {
+                    const uint8_t* pat = out + dj - f;  // the match overlaps itself: a pattern of f bytes, all written before
+                    for (uint32_t k = lane; k < m; k += 32) out[dj + k] = pat[k % f];
                 }
-                __syncwarp(gmask);
+                __syncwarp();
             }
-            o_base += __shfl_sync(gmask, so, SEQX_G - 1, SEQX_G);
+            o_base += __shfl_sync(VMB_FULL, so, 31);
+            l_base += __shfl_sync(VMB_FULL, sl, 31);
         }
+        warp_copy(out + o_base, lits + l_base, job->regen_size - l_base, lane);  // literals after the last sequence
+        __syncwarp();
     }
 }
 
@@ -1475,14 +1544,16 @@ void launch_huf_decode(const ZstdParams& P, cudaStream_t st) {
 void launch_zstd_sequences(const ZstdParams& P, cudaStream_t st) {
     if (!P.count || !P.ws_count || !P.seq_rec) return;
     const uint32_t per_cta = SEQ_WARPS * SEQ_FPW;
-    uint32_t groups = P.count < P.ws_count ? P.count : P.ws_count;  // one workspace slot per frame group
-    uint32_t grid = (groups + per_cta - 1) / per_cta;
-    if ((uint64_t)grid * per_cta > P.ws_count) grid = P.ws_count / per_cta;
+    // one SeqWs slot per frame group of the grid, carved out of the serial kernel's workspace
+    const uint64_t slots = (uint64_t)P.ws_count * sizeof(SerialWs) / sizeof(SeqWs);
+    uint64_t groups = P.count < slots ? P.count : slots;
+    uint32_t grid = (uint32_t)((groups + per_cta - 1) / per_cta);
+    if ((uint64_t)grid * per_cta > slots) grid = (uint32_t)(slots / per_cta);
     if (grid == 0) grid = 1;
-    k_zstd_seq_decode<<<grid, SEQ_WARPS * 32, 0, st>>>(P);
-    const uint32_t xper = SEQX_WARPS * (32 / SEQX_G);
-    uint32_t xgrid = (P.count + xper - 1) / xper;
-    if (xgrid > 148u * 16u) xgrid = 148u * 16u;
+    k_zstd_seq_decode<false><<<grid, SEQ_WARPS * 32, 0, st>>>(P);
+    k_zstd_seq_decode<true><<<grid, SEQ_WARPS * 32, 0, st>>>(P);  // frames flagged by the first launch (normally none)
+    uint32_t xgrid = (P.count + SEQX_WARPS - 1) / SEQX_WARPS;
+    if (xgrid > 148u * 64u) xgrid = 148u * 64u;
     k_zstd_seq_exec<<<xgrid, SEQX_WARPS * 32, 0, st>>>(P);
 }
 

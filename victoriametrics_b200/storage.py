@@ -205,6 +205,25 @@ class Blocks:
         self.h = h
         self.count = n
 
+    @classmethod
+    def from_block_refs(cls, headers, timestamps_bin, values_bin, ctx=None):
+        """the BlockRefs of a query (tmp_blocks_file.go:110: one marshaled 81-byte blockHeader per block, series order) + the part's
+        timestamps.bin / values.bin -> device-resident blocks (vmb_blocks_upload_part == BlockRef.MustReadBlock search.go:73 for all)"""
+        self = cls.__new__(cls)
+        self.ctx = ctx or _lib.default_context()
+        hb = np.frombuffer(bytes(headers), dtype=np.uint8) if not isinstance(headers, np.ndarray) else np.ascontiguousarray(headers, dtype=np.uint8)
+        if hb.size % 81:
+            raise ValueError("headers: %d bytes is not a whole number of 81-byte blockHeaders" % hb.size)
+        tb = np.frombuffer(timestamps_bin, dtype=np.uint8) if not isinstance(timestamps_bin, np.ndarray) else timestamps_bin
+        vb = np.frombuffer(values_bin, dtype=np.uint8) if not isinstance(values_bin, np.ndarray) else values_bin
+        h = C.c_void_p()
+        self.h = None
+        check(lib().vmb_blocks_upload_part(self.ctx.h, hb.ctypes.data_as(_lib.u8p), hb.size // 81, tb.ctypes.data_as(_lib.u8p), tb.size,
+                                           vb.ctypes.data_as(_lib.u8p), vb.size, C.byref(h)))
+        self.h = h
+        self.count = hb.size // 81
+        return self
+
     @property
     def rows(self):
         return int(lib().vmb_blocks_rows(self.h))
