@@ -1152,9 +1152,10 @@ __device__ uint32_t read_seq_table_packed(uint8_t* sym, unsigned short* nbbase, 
 // is covered by the sequences decoded in between).  Words in front of the stream start hold other bytes of the frame: they can
 // only be consumed by a stream that over-reads, which `left` < 0 reports.
 struct SeqBits {
-    const uint32_t* wp;     // aligned word that the NEXT prefetch reads
-    const uint32_t* wmin;   // never read below this word
-    uint32_t w_hi, w_lo;    // aligned words around the next 4 stream bytes (w_lo may still be in flight)
+    const uint32_t* wbase;  // aligned word that holds the byte 4 in front of the stream start: never read below it
+    uint32_t widx;          // word index (from wbase) that the NEXT prefetch reads
+    uint32_t w_hi, w_lo;    // aligned words around the next 4 stream bytes
+    uint32_t w_next;        // the word below them, loaded one refill ahead (may still be in flight: touched by the next refill only)
     uint32_t sh;            // (address of the stream bytes & 3) * 8
     uint32_t hi, lo;        // the window, next bit at the top of hi
     int cnt;                // bits in the window
@@ -1166,8 +1167,13 @@ struct SeqBits {
         lo = __funnelshift_lc(0u, w, 32u - (uint32_t)cnt);
         cnt += 32;
         w_hi = w_lo;
-        w_lo = *wp;
-        if (wp > wmin) wp--;
+        w_lo = w_next;
+        w_next = wbase[widx];
+        // The eight frames of a warp refill at different steps, so nearly every step of the warp carries this load for somebody;
+        // the stream is walked backwards (no hardware prefetch), and a sector that misses L1 would stall all eight: ask for the
+        // sector 96 bytes further down now (no destination register, nothing waits)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(wbase + (widx > 24u ? widx - 24u : 0u)));
+        widx -= (widx != 0u);
     }
     __device__ bool init(const uint8_t* src, uint32_t len) {
         if (len == 0) return false;
@@ -1176,11 +1182,13 @@ struct SeqBits {
         const uintptr_t a = (uintptr_t)(src + len) - 4;  // the first four bytes to pull (the stream's last four)
         sh = (uint32_t)(a & 3u) * 8u;
         const uint32_t* w0 = (const uint32_t*)(a & ~(uintptr_t)3);
-        wmin = (const uint32_t*)(((uintptr_t)src - 4) & ~(uintptr_t)3);
+        wbase = (const uint32_t*)(((uintptr_t)src - 4) & ~(uintptr_t)3);
         w_hi = sh ? w0[1] : 0u;
         w_lo = w0[0];
-        wp = w0 - 1;
-        if (wp < wmin) wp = wmin;
+        const uint32_t i0 = (uint32_t)(w0 - wbase);  // >= 0: w0 holds byte src + len - 4 >= src - 3
+        widx = i0 ? i0 - 1u : 0u;
+        w_next = wbase[widx];
+        widx -= (widx != 0u);
         hi = lo = 0;
         cnt = 0;
         left = (int)((len - 1) * 8u) + hb32(last);
@@ -1229,8 +1237,8 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
     const int grp = lane / SEQ_G, sub = lane % SEQ_G;
     const uint32_t gslot = (blockIdx.x * SEQ_WARPS + warp) * SEQ_FPW + grp;  // this group's workspace slot
     const uint32_t nslots = gridDim.x * SEQ_WARPS * SEQ_FPW;
-    Tables* T = &s_tab[warp * SEQ_FPW + grp];
     SeqWs* ws = (SeqWs*)P.ws + gslot;  // scratch of the table builder (the launch guarantees the slot exists)
+    Tables* T = &s_tab[warp * SEQ_FPW + grp];
     for (uint32_t i0 = (blockIdx.x * SEQ_WARPS + warp) * SEQ_FPW; i0 < P.count; i0 += nslots) {
         const uint32_t i = i0 + grp;
         // ---- per group: locate the frame, read the section header, expand the table descriptions (group leader)
@@ -1303,8 +1311,9 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
         if (big) act = false;  // decoded by the launch with full-size tables
         __syncwarp();
         SeqBits bb;
-        bb.wp = bb.wmin = (const uint32_t*)P.payload;
-        bb.w_hi = bb.w_lo = bb.sh = bb.hi = bb.lo = 0;
+        bb.wbase = (const uint32_t*)P.payload;
+        bb.widx = 0;
+        bb.w_hi = bb.w_lo = bb.w_next = bb.sh = bb.hi = bb.lo = 0;
         bb.cnt = 64;  // (idle groups never refill)
         bb.left = 0;
         uint32_t sll = 0, sof = 0, sml = 0;
@@ -1318,7 +1327,7 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
         }
         uint32_t rep0 = 1, rep1 = 4, rep2 = 8;  // one block per prepared frame: the repeat offsets start fresh
         uint32_t o = 0, lit_pos = 0;
-        uint32_t bad = 0;
+        uint32_t bad = 0, last_state_bits = 0;
         // The loop is the same for every group of the warp (trip count = the longest frame, work predicated, no early
         // exit): groups that left a loop at different times would never run in lockstep again, and the redundant
         // instruction stream would be issued once per group instead of once per warp.  Inside, everything but the rare
@@ -1333,10 +1342,11 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
             if (run) {
                 const uint32_t ell = T->ll_nb[sll], eof = T->of_nb[sof], eml = T->ml_nb[sml];  // (nbits << 12) | base
                 const uint32_t yll = T->ll_sym[sll], yof = T->of_sym[sof], yml = T->ml_sym[sml];  // (<= 35 / 31 / 52 by construction)
-                const bool more = q + 1 < nseq;
                 const uint32_t b_of = yof, b_ml = s_ml_bits[yml], b_ll = s_ll_bits[yll];
-                const uint32_t n_ll = more ? (ell >> 12) : 0u, n_ml = more ? (eml >> 12) : 0u, n_of = more ? (eof >> 12) : 0u;
+                // (the last sequence reads no state bits; the loop reads them anyway and the totals are put right after it)
+                const uint32_t n_ll = ell >> 12, n_ml = eml >> 12, n_of = eof >> 12;
                 const uint32_t need = b_of + b_ml + b_ll + n_ll + n_ml + n_of;
+                last_state_bits = n_ll + n_ml + n_of;
                 if (bb.cnt <= 32) bb.refill();
                 uint32_t x_of, x_ml, x_ll, x_sl, x_sm, x_so;
                 if ((int)need <= bb.cnt) {
@@ -1357,13 +1367,13 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
                     x_sm = bb.read_slow(n_ml);
                     x_so = bb.read_slow(n_of);
                 }
-                sll = (ell & 0xfffu) + x_sl;  // (after the last sequence: base + 0, never used)
+                sll = (ell & 0xfffu) + x_sl;
                 sml = (eml & 0xfffu) + x_sm;
                 sof = (eof & 0xfffu) + x_so;
                 const uint32_t ofv = (1u << (yof & 31u)) + x_of;
                 const uint32_t mlen = s_ml_base[yml] + x_ml, llen = s_ll_base[yll] + x_ll;
-                // offset codes > 24 cannot be valid here (the window is at most the 160 KiB column)
-                bad |= (uint32_t)(yof > 24u) | (uint32_t)(bb.left < 0);
+                // offset codes > 24 cannot be valid here (the window is at most the column)
+                bad |= (uint32_t)(yof > 24u);
                 // repeat offsets (RFC 8878 3.1.1.5), as selects: idx 0 = rep0 unchanged, 1 = swap in rep1, 2 = rotate in rep2,
                 // 3 = rep0 - 1 or a new offset (both push the history down)
                 const bool is_new = ofv > 3u;
@@ -1373,13 +1383,16 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
                 rep2 = idx >= 2u ? rep1 : rep2;
                 rep1 = idx >= 1u ? rep0 : rep1;
                 rep0 = offset;
-                bad |= (uint32_t)(lit_pos + llen > lit_len) | (uint32_t)(o + llen + mlen > out_cap) | (uint32_t)(offset > o + llen) |
-                       (uint32_t)(offset == 0u);
-                o += llen + mlen;
+                o += llen;
+                bad |= (uint32_t)(offset > o) | (uint32_t)(offset == 0u);
+                o += mlen;
+                bad |= (uint32_t)(o > out_cap);  // (sticky, so o stays within 2^32; lit_pos <= o: its bound is checked after the loop)
                 lit_pos += llen;
-                if (sub == 0 && !bad) rec[q] = SEQ_REC(llen, mlen, offset);
+                if (sub == 0) rec[q] = SEQ_REC(llen, mlen, offset);
             }
         }
+        bb.left += (int)last_state_bits;  // the state update behind the last sequence does not exist in the stream
+        if (lit_pos > lit_len) bad = 1;
         if (bad) ok = false;
         if (live && ok) {
             if (bb.left != 0) ok = false;
