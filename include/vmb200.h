@@ -329,6 +329,16 @@ enum vmb_binop { /* binary_op.go:15-43; the element functions of vendor/.../metr
  * (NaN for a NaN left) -- newBinaryOpCmpFunc :132.  d_dst may alias d_left when left_rows is NULL. */
 int vmb_binary_op(vmb_ctx* ctx, int op, int is_bool, const double* d_left, const uint32_t* left_rows, const double* d_right,
                   const uint32_t* right_rows, size_t npairs, size_t points, double* d_dst);
+/* The set operators on top of it.  Their right-hand side is first reduced per tag-set group (createTimeseriesMapByTagSet binary_op.go:657
+ * puts several series under one key): d_out[g][j] = the first non-NaN value among the rows with group_ids[row] == g at point j, in row
+ * order, NaN when there is none -- all that addRightNaNsToLeft (:444), addLeftNaNsIfNoRightNaNs (:625) and fillLeftNaNsWithRightValues
+ * (:516) read from tssRight.  Then, with right_rows[i] = the group of left row i:
+ *   `and` (binaryOpAnd :430) / `if` = vmb_binary_op(VMB_BO_IF),  `unless` (:610) / `ifnot` = VMB_BO_IFNOT,  `default` = VMB_BO_DEFAULT;
+ * left rows whose key has no right group are dropped (`and`) or kept as they are (`unless`, `default`) by the host's tag matching, which
+ * also owns removeEmptySeries (exec.go:193).  `or` (:483) is a union of row sets plus the same fill: left rows, then the right rows of
+ * keys the left side lacks. */
+int vmb_group_first_value(vmb_ctx* ctx, const double* d_vals, size_t nseries, size_t points, const uint32_t* group_ids, uint32_t ngroups,
+                          double* d_out);
 /* mergeSeries rollup_result_cache.go:618: d_dst[nrows x (pa + pb)], row i = d_a[a_rows[i]] ++ d_b[b_rows[i]]; a negative index
  * stands for a series missing on that side (NaNs, :677-690).  a_rows / b_rows: HOST, matched by metric name by the caller. */
 int vmb_matrix_merge_rows(vmb_ctx* ctx, const double* d_a, const int64_t* a_rows, size_t pa, const double* d_b, const int64_t* b_rows,

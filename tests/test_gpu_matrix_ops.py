@@ -127,3 +127,42 @@ def test_merge_series_concat():
         ea = a[a_rows[i]] if a_rows[i] >= 0 else np.full(pa, NAN)
         eb = b[b_rows[i]] if b_rows[i] >= 0 else np.full(pb, NAN)
         assert np.array_equal(np.concatenate([ea, eb]), got[i], equal_nan=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op", ["and", "unless", "default"])
+def test_set_operators_with_right_groups(op):
+    """binaryOpAnd / binaryOpUnless / binaryOpDefault (binary_op.go:430,610,463): several right series under one tag-set key"""
+    import torch
+    import victoriametrics_b200 as vm
+    rng = np.random.default_rng(4242 + len(op))
+    P, G = 97, 23
+    nl, nr = 60, 75
+    left = rng.normal(size=(nl, P))
+    right = rng.normal(size=(nr, P))
+    left[rng.random(left.shape) < 0.3] = np.nan
+    right[rng.random(right.shape) < 0.6] = np.nan
+    lg = rng.integers(0, G, nl).astype(np.uint32)
+    rg = np.concatenate([np.arange(G), rng.integers(0, G, nr - G)]).astype(np.uint32)  # every key present on the right
+    rng.shuffle(rg)
+    # the reference loops, restated on numpy
+    want = left.copy()
+    for i in range(nl):
+        rows = [r for r in range(nr) if rg[r] == lg[i]]
+        for j in range(P):
+            has = [right[r, j] for r in rows if not np.isnan(right[r, j])]
+            if op == "and" and not has:
+                want[i, j] = np.nan
+            if op == "unless" and has:
+                want[i, j] = np.nan
+            if op == "default" and np.isnan(want[i, j]) and has:
+                want[i, j] = has[0]
+    dl = torch.from_numpy(left).cuda()
+    dr = torch.from_numpy(right).cuda()
+    tmp = torch.empty((G, P), dtype=torch.float64, device="cuda")
+    dst = torch.empty((nl, P), dtype=torch.float64, device="cuda")
+    vm.promql.set_op(op, dl.data_ptr(), lg, nl, dr.data_ptr(), rg, nr, G, P, dst.data_ptr(), tmp.data_ptr())
+    torch.cuda.synchronize()
+    got = dst.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])

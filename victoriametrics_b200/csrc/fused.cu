@@ -36,7 +36,8 @@
 #define FU_THREADS 256
 #define FU_WARPS 8
 #define FU_CAP 4096                       /* rows of one series resident in shared memory */
-#define FU_TILE 512
+#define FU_G 1                            /* 16-byte groups per lane and fill (2 was measured: the 4096-row ring then takes 6 of 8 tiles per fill and the step gets 5 % slower) */
+#define FU_TILE (512 * FU_G)
 #define FU_FILL (FU_WARPS * FU_TILE)      /* bytes staged per fill */
 #define FU_STAGE (16 + FU_FILL + 16)      /* 16 bytes of the previous tile in front, 16 bytes of padding behind */
 #define FU_MAX_EVENTS 32                  /* counter resets inside one fill handled by the parallel path */
@@ -534,27 +535,38 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                     copy_pending = false;
                 }
                 const uint8_t* st = &S.stage[buf][16];  // aligned stream byte `fs` sits at st[0]
-                const uint32_t off = w * FU_TILE + lane * 16u;
+                const uint32_t off = w * FU_TILE + lane * (16u * FU_G);
                 const int64_t g0 = (int64_t)fs + off;
-                const uint4 own = *reinterpret_cast<const uint4*>(st + off);
-                const uint4 prv = *reinterpret_cast<const uint4*>(st + off - 16);
-                const uint32_t t_own = fu_term_mask16(own);
-                uint32_t vm, tm, pbm;
+                uint32_t t_own[FU_G], vm[FU_G], tm[FU_G], pbm[FU_G];
+#pragma unroll
+                for (int g = 0; g < FU_G; g++) t_own[g] = fu_term_mask16(*reinterpret_cast<const uint4*>(st + off + 16 * g));
+                const uint32_t prv_w = *reinterpret_cast<const uint32_t*>(st + off - 4);  // the four bytes in front of the lane's bytes
                 const int64_t gw = (int64_t)fs + w * FU_TILE;  // first byte of the warp's tile
                 if (gw - 16 >= vlo && gw + FU_TILE <= vhi) {
                     // the tile and the 16 bytes in front of it lie inside the stream (all but the first and last tile of a column)
-                    vm = 0xffffu;
-                    tm = t_own;
-                    pbm = __shfl_up_sync(VMB_FULL, t_own, 1);
-                    if (lane == 0) pbm = fu_term_mask16(prv);
+                    uint32_t t_prev = __shfl_up_sync(VMB_FULL, t_own[FU_G - 1], 1);
+                    if (lane == 0) t_prev = fu_term_mask16(*reinterpret_cast<const uint4*>(st + off - 16));
+#pragma unroll
+                    for (int g = 0; g < FU_G; g++) {
+                        vm[g] = 0xffffu;
+                        tm[g] = t_own[g];
+                        pbm[g] = g ? t_own[g - 1] : t_prev;
+                    }
                 } else {
-                    vm = fu_valid16(g0, vlo, vhi);
-                    tm = t_own & vm;
-                    // boundaries of the previous 16 bytes: terminators, and everything in front of the stream start
-                    const uint32_t pvm = fu_valid16(g0 - 16, vlo, vhi);
-                    pbm = ((fu_term_mask16(prv) & pvm) | (g0 - 16 < vlo ? ~pvm : 0u)) & 0xffffu;
+                    const uint32_t t_prv = fu_term_mask16(*reinterpret_cast<const uint4*>(st + off - 16));
+#pragma unroll
+                    for (int g = 0; g < FU_G; g++) {
+                        const int64_t gg = g0 + 16 * g;
+                        vm[g] = fu_valid16(gg, vlo, vhi);
+                        tm[g] = t_own[g] & vm[g];
+                        // boundaries of the previous 16 bytes: terminators, and everything in front of the stream start
+                        const uint32_t pvm = fu_valid16(gg - 16, vlo, vhi);
+                        pbm[g] = (((g ? t_own[g - 1] : t_prv) & pvm) | (gg - 16 < vlo ? ~pvm : 0u)) & 0xffffu;
+                    }
                 }
-                const uint32_t cl = (uint32_t)__popc(tm);
+                uint32_t cl = 0;
+#pragma unroll
+                for (int g = 0; g < FU_G; g++) cl += (uint32_t)__popc(tm[g]);
                 uint32_t incl = cl;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -596,101 +608,118 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                     uint64_t s1 = 0, s2 = 0;
                     const uint32_t row0 = base + cnt + rb + incl - cl;  // absolute row of the lane's first value
                     bool bad = false;
-                    // carried-in bytes: behind the last boundary of the previous 16 bytes
-                    const uint32_t carry = pbm ? (uint32_t)__clz((int)pbm) - 16u : 16u;  // 15 - msb(pbm)
-                    // does any varint that ends in this warp's tile have more than 4 bytes?  Continuation bytes of [previous 16 |
-                    // own 16] as one mask: a run of four of them that reaches into the last 4 + 16 bytes (conservative)
-                    const uint32_t c32 = ((~pbm) & 0xffffu) | ((~t_own & vm) << 16);
-                    const uint32_t run4 = c32 & (c32 >> 1) & (c32 >> 2) & (c32 >> 3);
-                    const bool any_long = __any_sync(VMB_FULL, w < K && cl && (((run4 >> 12) != 0u) || carry > 3u)) != 0;
+                    // per group: carried-in bytes = behind the last boundary of the previous 16 bytes (15 - msb(pbm)); does any varint
+                    // that ends in this warp's tile have more than 4 bytes?  Continuation bytes of [previous 16 | own 16] as one mask:
+                    // a run of four of them that reaches into the last 4 + 16 bytes (conservative)
+                    uint32_t carry[FU_G];
+                    bool lng = false;
+#pragma unroll
+                    for (int g = 0; g < FU_G; g++) {
+                        carry[g] = pbm[g] ? (uint32_t)__clz((int)pbm[g]) - 16u : 16u;
+                        const uint32_t c32 = ((~pbm[g]) & 0xffffu) | ((~t_own[g] & vm[g]) << 16);
+                        const uint32_t run4 = c32 & (c32 >> 1) & (c32 >> 2) & (c32 >> 3);
+                        lng |= tm[g] && (((run4 >> 12) != 0u) || carry[g] > 3u);
+                        // a run of continuation bytes over a whole 16-byte group inside the stream: a varint of > 16 bytes
+                        if (w < K && vm[g] == 0xffffu && tm[g] == 0 && pbm[g] == 0) bad = true;
+                    }
+                    const bool any_long = __any_sync(VMB_FULL, w < K && lng) != 0;
                     if (w < K && cl) {
-                        uint32_t m = tm;
-                        // 7-bit groups of the own 16 bytes as a 112-bit number q3:q2:q1:q0
-                        const uint32_t c0 = compact7(own.x), c1 = compact7(own.y), c2 = compact7(own.z), c3 = compact7(own.w);
-                        uint32_t q0 = c0 | (c1 << 28), q1 = (c1 >> 4) | (c2 << 24), q2 = (c2 >> 8) | (c3 << 20), q3 = c3 >> 12;
-                        auto drop_groups = [&](uint32_t sh) {  // q >>= sh (sh = 7 * bytes <= 112)
-                            while (sh >= 32u) {
-                                q0 = q1; q1 = q2; q2 = q3; q3 = 0;
-                                sh -= 32u;
-                            }
-                            q0 = __funnelshift_r(q0, q1, sh);
-                            q1 = __funnelshift_r(q1, q2, sh);
-                            q2 = __funnelshift_r(q2, q3, sh);
-                            q3 >>= sh;
-                        };
-                        uint32_t k = 0, pos = 0;  // value index inside the lane, byte position of the current varint's first own byte
-                        if (!(vm & 1u)) {  // the stream starts inside this group: skip the bytes in front of it
-                            pos = (uint32_t)__ffs((int)vm) - 1u;
-                            m >>= pos;
-                            drop_groups(7u * pos);
-                        }
-                        if (!any_long) {
-                            // every varint of the tile has <= 4 bytes (28 bits): one shift-and-mask per value, no branches inside
-                            uint32_t cval = 0, cbits = 0;  // value and width of the carried-in bytes (first varint only)
-                            if (carry) {
-                                cval = compact7(prv.w) >> (7u * (4u - carry));
-                                cbits = 7u * carry;
-                            }
-                            uint32_t row = row0;
-                            while (m) {
-                                const uint32_t L = (uint32_t)__ffs((int)m);  // own bytes of this varint
-                                const uint32_t sh = 7u * L;
-                                const uint32_t u = ((q0 & ~(0xffffffffu << sh)) << cbits) | cval;
-                                const int v32 = (int)((u >> 1) ^ (0u - (u & 1u)));
-                                const long long v = (long long)v32;
-                                fu_sts_i64(val_s, row, v);  // raw zig-zag decoded delta, replaced by the value in step 4
-                                s1 += (uint64_t)v;
-                                s2 += s1;
-                                row++;
-                                m >>= L;
+                        uint32_t row = row0;
+                        // the varints whose terminator lies in one 16-byte group; prev_w = the four bytes in front of the group
+                        auto parse16 = [&](const uint4 own, const uint32_t prev_w, uint32_t m, const uint32_t vmg, const uint32_t cr,
+                                           const uint32_t boff) {
+                            // 7-bit groups of the own 16 bytes as a 112-bit number q3:q2:q1:q0
+                            const uint32_t c0 = compact7(own.x), c1 = compact7(own.y), c2 = compact7(own.z), c3 = compact7(own.w);
+                            uint32_t q0 = c0 | (c1 << 28), q1 = (c1 >> 4) | (c2 << 24), q2 = (c2 >> 8) | (c3 << 20), q3 = c3 >> 12;
+                            auto drop_groups = [&](uint32_t sh) {  // q >>= sh (sh = 7 * bytes <= 112)
+                                while (sh >= 32u) {
+                                    q0 = q1; q1 = q2; q2 = q3; q3 = 0;
+                                    sh -= 32u;
+                                }
                                 q0 = __funnelshift_r(q0, q1, sh);
                                 q1 = __funnelshift_r(q1, q2, sh);
                                 q2 = __funnelshift_r(q2, q3, sh);
                                 q3 >>= sh;
-                                cval = 0;
-                                cbits = 0;
+                            };
+                            uint32_t pos = 0;  // byte position of the current varint's first own byte
+                            if (!(vmg & 1u)) {  // the stream starts inside this group: skip the bytes in front of it
+                                pos = (uint32_t)__ffs((int)vmg) - 1u;
+                                m >>= pos;
+                                drop_groups(7u * pos);
                             }
-                        } else {
-                            while (m) {
-                                const uint32_t L = (uint32_t)__ffs((int)m);  // own bytes of this varint
-                                const uint32_t cb = k == 0 ? carry : 0u;
-                                long long v;
-                                if (7u * (L + cb) <= 28u) {
-                                    const uint32_t cval = cb ? compact7(prv.w) >> (7u * (4u - cb)) : 0u;
-                                    const uint32_t u = ((q0 & ~(0xffffffffu << (7u * L))) << (7u * cb)) | cval;
-                                    v = (long long)(int)((u >> 1) ^ (0u - (u & 1u)));
-                                } else {
-                                    // long varint (> 4 bytes): byte loop over the staged bytes, int.go:196-284
-                                    const int sb = (int)(off + pos) - (int)cb;  // first byte, relative to st
-                                    const uint32_t vl = L + cb;
-                                    uint64_t u = 0;
-                                    if (vl > 10) {
-                                        bad = true;
+                            if (!any_long) {
+                                // every varint of the tile has <= 4 bytes (28 bits): one shift-and-mask per value, no branches inside
+                                uint32_t cval = 0, cbits = 0;  // value and width of the carried-in bytes (first varint only)
+                                if (cr) {
+                                    cval = compact7(prev_w) >> (7u * (4u - cr));
+                                    cbits = 7u * cr;
+                                }
+                                while (m) {
+                                    const uint32_t L = (uint32_t)__ffs((int)m);  // own bytes of this varint
+                                    const uint32_t sh = 7u * L;
+                                    const uint32_t u = ((q0 & ~(0xffffffffu << sh)) << cbits) | cval;
+                                    const int v32 = (int)((u >> 1) ^ (0u - (u & 1u)));
+                                    const long long v = (long long)v32;
+                                    fu_sts_i64(val_s, row, v);  // raw zig-zag decoded delta, replaced by the value in step 4
+                                    s1 += (uint64_t)v;
+                                    s2 += s1;
+                                    row++;
+                                    m >>= L;
+                                    q0 = __funnelshift_r(q0, q1, sh);
+                                    q1 = __funnelshift_r(q1, q2, sh);
+                                    q2 = __funnelshift_r(q2, q3, sh);
+                                    q3 >>= sh;
+                                    cval = 0;
+                                    cbits = 0;
+                                }
+                            } else {
+                                uint32_t cb = cr;  // carried-in bytes of the first varint
+                                while (m) {
+                                    const uint32_t L = (uint32_t)__ffs((int)m);  // own bytes of this varint
+                                    long long v;
+                                    if (7u * (L + cb) <= 28u) {
+                                        const uint32_t cval = cb ? compact7(prev_w) >> (7u * (4u - cb)) : 0u;
+                                        const uint32_t u = ((q0 & ~(0xffffffffu << (7u * L))) << (7u * cb)) | cval;
+                                        v = (long long)(int)((u >> 1) ^ (0u - (u & 1u)));
                                     } else {
-                                        for (uint32_t bb = 0; bb < vl; bb++) {
-                                            const uint32_t byte = st[sb + (int)bb];
-                                            if (bb == 9) {
-                                                if (byte > 1u) bad = true;
-                                                u |= (uint64_t)1 << 63;
-                                            } else {
-                                                u |= (uint64_t)(byte & 0x7fu) << (7 * bb);
+                                        // long varint (> 4 bytes): byte loop over the staged bytes, int.go:196-284
+                                        const int sb = (int)(boff + pos) - (int)cb;  // first byte, relative to st
+                                        const uint32_t vl = L + cb;
+                                        uint64_t u = 0;
+                                        if (vl > 10) {
+                                            bad = true;
+                                        } else {
+                                            for (uint32_t bb = 0; bb < vl; bb++) {
+                                                const uint32_t byte = st[sb + (int)bb];
+                                                if (bb == 9) {
+                                                    if (byte > 1u) bad = true;
+                                                    u |= (uint64_t)1 << 63;
+                                                } else {
+                                                    u |= (uint64_t)(byte & 0x7fu) << (7 * bb);
+                                                }
                                             }
                                         }
+                                        v = (long long)(u >> 1) ^ -(long long)(u & 1);
                                     }
-                                    v = (long long)(u >> 1) ^ -(long long)(u & 1);
+                                    fu_sts_i64(val_s, row, v);
+                                    s1 += (uint64_t)v;
+                                    s2 += s1;
+                                    row++;
+                                    cb = 0;
+                                    pos += L;
+                                    m >>= L;
+                                    drop_groups(7u * L);
                                 }
-                                fu_sts_i64(val_s, row0 + k, v);
-                                s1 += (uint64_t)v;
-                                s2 += s1;
-                                k++;
-                                pos += L;
-                                m >>= L;
-                                drop_groups(7u * L);
                             }
+                        };
+#pragma unroll
+                        for (int g = 0; g < FU_G; g++) {
+                            if (tm[g])
+                                parse16(*reinterpret_cast<const uint4*>(st + off + 16 * g),
+                                        g ? *reinterpret_cast<const uint32_t*>(st + off + 16 * g - 4) : prv_w, tm[g], vm[g], carry[g],
+                                        off + 16u * g);
                         }
                     }
-                    // a run of continuation bytes over a whole 16-byte group inside the stream: a varint of > 16 bytes
-                    if (w < K && vm == 0xffffu && tm == 0 && pbm == 0) bad = true;
                     // ---- scan (s1, s2) over the warp.  combine(A then B): s2 = s2A + s2B + cntB * s1A, so with E1(l) = the plain
                     // exclusive prefix of s1, the inclusive prefix of s2 is the plain prefix sum of t_l = s2_l + cnt_l * E1(l): two sum
                     // scans (wrapping int64 arithmetic: bit-identical to the sequential Go loop), the counts are known from step 1

@@ -45,8 +45,28 @@ struct AbsDev {
 // quantile aggr.go:870 = drop NaNs, sort, quantileSorted aggr.go:922
 template <class VP, class T>
 __device__ double quantile_tf(double phi, VP v, uint32_t n, T tf) {
+    // one pass: the number of non-NaN values and the four largest of them, sorted in registers (phi = 0.9 ... 1 over the usual
+    // 20-sample window needs nothing else)
     uint32_t m = 0;
-    for (uint32_t a = 0; a < n; a++) m += !isnan(tf(v[a]));
+    double t0 = -D_INF, t1 = -D_INF, t2 = -D_INF, t3 = -D_INF;  // t0 >= t1 >= t2 >= t3
+    for (uint32_t a = 0; a < n; a++) {
+        double x = tf(v[a]);
+        const bool nn_ = !isnan(x);
+        m += nn_;
+        x = nn_ ? x : -D_INF;  // (inserting -Inf changes nothing)
+        // insertion as a max / min ladder: no data-dependent branch (half the elements of a 20-sample window enter the top four,
+        // never the same ones in the 32 lanes)
+        const double a0 = fmax(t0, x);
+        x = fmin(t0, x);
+        const double a1 = fmax(t1, x);
+        x = fmin(t1, x);
+        const double a2 = fmax(t2, x);
+        x = fmin(t2, x);
+        t3 = fmax(t3, x);
+        t0 = a0;
+        t1 = a1;
+        t2 = a2;
+    }
     if (m == 0 || isnan(phi)) return D_NAN;
     if (phi < 0) return -D_INF;
     if (phi > 1) return D_INF;
@@ -58,33 +78,25 @@ __device__ double quantile_tf(double phi, VP v, uint32_t n, T tf) {
     const uint32_t kl = (uint32_t)(int)lower, ku = (uint32_t)(int)upper;
     double vlo, vhi;
     if (m - 1 - kl <= 3) {
-        // both order statistics are among the four largest values (phi = 0.9 ... 1 for the usual 20-sample window):
-        // one pass with the four largest kept sorted in registers
-        double t0 = -D_INF, t1 = -D_INF, t2 = -D_INF, t3 = -D_INF;  // t0 >= t1 >= t2 >= t3
-        for (uint32_t a = 0; a < n; a++) {
-            double x = tf(v[a]);
-            if (isnan(x)) continue;
-            if (x > t3) {
-                t3 = x;
-                if (t3 > t2) { double s = t2; t2 = t3; t3 = s; }
-                if (t2 > t1) { double s = t1; t1 = t2; t2 = s; }
-                if (t1 > t0) { double s = t0; t0 = t1; t1 = s; }
-            }
-        }
+        // both order statistics are among the four largest values
         const uint32_t dl = m - 1 - kl, du = m - 1 - ku;  // distance from the maximum
         vlo = dl == 0 ? t0 : (dl == 1 ? t1 : (dl == 2 ? t2 : t3));
         vhi = du == 0 ? t0 : (du == 1 ? t1 : (du == 2 ? t2 : t3));
     } else if (ku <= 3) {
-        double t0 = D_INF, t1 = D_INF, t2 = D_INF, t3 = D_INF;  // t0 <= t1 <= t2 <= t3: the four smallest
+        t0 = t1 = t2 = t3 = D_INF;  // now t0 <= t1 <= t2 <= t3: the four smallest
         for (uint32_t a = 0; a < n; a++) {
             double x = tf(v[a]);
-            if (isnan(x)) continue;
-            if (x < t3) {
-                t3 = x;
-                if (t3 < t2) { double s = t2; t2 = t3; t3 = s; }
-                if (t2 < t1) { double s = t1; t1 = t2; t2 = s; }
-                if (t1 < t0) { double s = t0; t0 = t1; t1 = s; }
-            }
+            x = isnan(x) ? D_INF : x;
+            const double a0 = fmin(t0, x);
+            x = fmax(t0, x);
+            const double a1 = fmin(t1, x);
+            x = fmax(t1, x);
+            const double a2 = fmin(t2, x);
+            x = fmax(t2, x);
+            t3 = fmin(t3, x);
+            t0 = a0;
+            t1 = a1;
+            t2 = a2;
         }
         vlo = kl == 0 ? t0 : (kl == 1 ? t1 : (kl == 2 ? t2 : t3));
         vhi = ku == 0 ? t0 : (ku == 1 ? t1 : (ku == 2 ? t2 : t3));

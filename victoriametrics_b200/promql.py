@@ -479,6 +479,24 @@ def merge_series(a_dev_ptr, a_rows, pa, b_dev_ptr, b_rows, pb, dst_dev_ptr, ctx=
                                       br.ctypes.data_as(_lib.i64p), int(pb), ar.size, C.c_void_p(int(dst_dev_ptr))))
 
 
+def group_first_value(vals_dev_ptr, nseries, points, group_ids, ngroups, out_dev_ptr, ctx=None):
+    """the right-hand side of a set operator reduced per tag-set group (vmb_group_first_value): out[g][j] = first non-NaN value of
+    the group's rows at point j, in row order"""
+    ctx = ctx or _lib.default_context()
+    g = np.ascontiguousarray(group_ids, dtype=np.uint32)
+    check(lib().vmb_group_first_value(ctx.h, C.c_void_p(int(vals_dev_ptr)), int(nseries), int(points), g.ctypes.data_as(_lib.u32p), int(ngroups),
+                                      C.c_void_p(int(out_dev_ptr))))
+
+
+def set_op(op, left_dev_ptr, left_groups, nleft, right_dev_ptr, right_groups, nright, ngroups, points, dst_dev_ptr, tmp_dev_ptr, ctx=None):
+    """`and` (binaryOpAnd binary_op.go:430), `unless` (:610), `if` (:416), `ifnot` (:595), `default` (:463) between two DEVICE matrices
+    whose rows the host has keyed by tag set (left_groups / right_groups: dense key ids < ngroups, every left key present on the
+    right): the right side is reduced per key into tmp_dev_ptr [ngroups x points], then one element pass over the left rows"""
+    el = {"and": "if", "if": "if", "unless": "ifnot", "ifnot": "ifnot", "default": "default"}[op.lower()]
+    group_first_value(right_dev_ptr, nright, points, right_groups, ngroups, tmp_dev_ptr, ctx=ctx)
+    binary_op(el, left_dev_ptr, tmp_dev_ptr, nleft, points, dst_dev_ptr, right_rows=np.asarray(left_groups, dtype=np.uint32), ctx=ctx)
+
+
 def aggr_quantile(phis, vals_dev_ptr, nseries, points, out_dev_ptr, group_ids=None, ngroups=1, ctx=None):
     """quantile(phi, q) by (...) / median (phi = 0.5)  aggr.go:1217 on a DEVICE matrix -> out_dev_ptr [ngroups x points]"""
     ctx = ctx or _lib.default_context()
