@@ -137,6 +137,44 @@ func (c *Ctx) EvalRollupAggr(descs []BlockDesc, payload []byte, trMin, trMax int
 	return uint64(scanned), nil
 }
 
+// Blocks are the compressed blocks of a query resident in HBM (vmb_blocks).
+type Blocks struct{ p *C.vmb_blocks }
+
+func (b *Blocks) Close() {
+	if b.p != nil {
+		C.vmb_blocks_free(b.p)
+		b.p = nil
+	}
+}
+
+// UploadBlockRefs == BlockRef.Init + BlockRef.MustReadBlock (lib/storage/search.go:38,73) for every block of a query that
+// lives in one part: headers is what tmpBlocksFile.WriteBlockRefData (tmp_blocks_file.go:110) kept per block -- the
+// marshaled 81-byte blockHeaders, in series order --, timestampsBin / valuesBin are the part's mmap'ed data files.
+func (c *Ctx) UploadBlockRefs(headers, timestampsBin, valuesBin []byte) (*Blocks, error) {
+	var b *C.vmb_blocks
+	rc := C.vmb_blocks_upload_part(c.p, bytePtr(headers), C.size_t(len(headers)/81), bytePtr(timestampsBin), C.size_t(len(timestampsBin)),
+		bytePtr(valuesBin), C.size_t(len(valuesBin)), &b)
+	runtime.KeepAlive(headers)
+	runtime.KeepAlive(timestampsBin)
+	runtime.KeepAlive(valuesBin)
+	if rc != 0 {
+		return nil, lastError(rc, "vmb_blocks_upload_part")
+	}
+	return &Blocks{p: b}, nil
+}
+
+// EvalRollupResident == the per-series closure of evalRollupNoIncrementalAggregate (eval.go:1855-1866) for every series of
+// b, with the result left in device memory (dOut: a device pointer to [nseries*points] float64) for the operators that
+// follow in the expression tree (vmb_binary_op, vmb_aggr_quantile, vmb_topk_*, vmb_series_from_matrix for a subquery).
+func (c *Ctx) EvalRollupResident(b *Blocks, trMin, trMax int64, cfg *RollupCfg, dOut unsafe.Pointer) (uint64, error) {
+	var scanned C.uint64_t
+	rc := C.vmb_eval_rollup_device(c.p, b.p, C.int64_t(trMin), C.int64_t(trMax), cfg, (*C.double)(dOut), &scanned)
+	if rc != 0 {
+		return 0, lastError(rc, "vmb_eval_rollup_device")
+	}
+	return uint64(scanned), nil
+}
+
 // ---- multi-GPU: one vmselect process per GPU; the partial states of aggr(rollup) by (...) are merged by the library's NCCL
 // all-reduce (include/vmb200.h "multi-GPU").  The 128-byte unique id travels over vmselect's own RPC.
 
