@@ -120,13 +120,33 @@ def numa_layout():
 
 
 _POOLS = {}
+try:
+    _AFFINITY0 = os.sched_getaffinity(0)
+except Exception:
+    _AFFINITY0 = None
 
 
 def get_pool(nthreads):
     """persistent worker pool of the oracle (created once, outside every timed region)"""
     O, L = oracle()
     if nthreads not in _POOLS:
-        _POOLS[nthreads] = C.c_void_p(L.vmo_pool_create(nthreads))
+        # worker threads inherit the creating thread's CPU mask: create them under the process' original mask, not under the
+        # GPU-local one the main thread wears while it allocates pinned buffers (a 64-thread pool born there would sit on 32 cores)
+        cur = None
+        try:
+            cur = os.sched_getaffinity(0)
+            if _AFFINITY0 and cur != _AFFINITY0:
+                os.sched_setaffinity(0, _AFFINITY0)
+        except Exception:
+            cur = None
+        try:
+            _POOLS[nthreads] = C.c_void_p(L.vmo_pool_create(nthreads))
+        finally:
+            if cur is not None and _AFFINITY0 and cur != _AFFINITY0:
+                try:
+                    os.sched_setaffinity(0, cur)
+                except Exception:
+                    pass
     return _POOLS[nthreads]
 
 
