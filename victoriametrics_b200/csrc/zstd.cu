@@ -15,6 +15,7 @@
 //   k_zstd_serial  : one thread per frame: (a) executes the sequences section of prepared frames, (b) decodes any
 //                    frame of another shape (raw/RLE blocks, multi-block, raw/RLE/treeless literals) completely.
 #include "common.cuh"
+#include <mutex>
 
 // ------------------------------------------------------------------------------------------------ shared pieces
 namespace {
@@ -1101,17 +1102,37 @@ __device__ bool fse_build_packed(uint8_t* sym, unsigned short* nbbase, const sho
 // Symbol_Compression_Mode of one sequence table (RFC 8878 3.1.1.3.2.1) -> packed table; returns bytes consumed.
 // Repeat mode is invalid here: a prepared frame holds a single block.  *big: the table has more than 2^cap_log states
 // (nothing is built; the frame belongs to the launch with full-size tables).
+// The three predefined distributions (RFC 8878 3.1.1.3.2.2) as packed decoding tables, built once per device
+// (k_zstd_seq_defaults): frames that use Predefined_Mode copy 160 states instead of running the builder.
+#define SEQ_DEF_LL 0
+#define SEQ_DEF_OF 64
+#define SEQ_DEF_ML 96
+__device__ unsigned short g_seq_def_nb[160];
+__device__ uint8_t g_seq_def_sym[160];
+__global__ void k_zstd_seq_defaults() {
+    if (blockIdx.x || threadIdx.x) return;
+    short norm[64];
+    unsigned short next[64];
+    for (int i = 0; i < 36; i++) norm[i] = c_ll_default[i];
+    fse_build_packed(g_seq_def_sym + SEQ_DEF_LL, g_seq_def_nb + SEQ_DEF_LL, norm, 36, 6, next);
+    for (int i = 0; i < 29; i++) norm[i] = c_of_default[i];
+    fse_build_packed(g_seq_def_sym + SEQ_DEF_OF, g_seq_def_nb + SEQ_DEF_OF, norm, 29, 5, next);
+    for (int i = 0; i < 53; i++) norm[i] = c_ml_default[i];
+    fse_build_packed(g_seq_def_sym + SEQ_DEF_ML, g_seq_def_nb + SEQ_DEF_ML, norm, 53, 6, next);
+}
+
 struct SeqWs {  // scratch of the table builder (global memory, one per frame group of the grid)
     short norm[256];
     unsigned short next[256];
 };
-__device__ uint32_t read_seq_table_packed(uint8_t* sym, unsigned short* nbbase, int* tlog, int mode, const short* defnorm, int defn,
-                                          int deflog, int max_sym, int max_log, int cap_log, const uint8_t* src, uint32_t len,
-                                          SeqWs* ws, bool* ok, bool* big) {
+__device__ uint32_t read_seq_table_packed(uint8_t* sym, unsigned short* nbbase, int* tlog, int mode, int def_off, int deflog, int max_sym,
+                                          int max_log, int cap_log, const uint8_t* src, uint32_t len, SeqWs* ws, bool* ok, bool* big) {
     *ok = true;
     if (mode == 0) {
-        for (int i = 0; i < defn; i++) ws->norm[i] = defnorm[i];
-        if (!fse_build_packed(sym, nbbase, ws->norm, defn, deflog, ws->next)) *ok = false;
+        for (int i = 0; i < (1 << deflog); i++) {
+            sym[i] = g_seq_def_sym[def_off + i];
+            nbbase[i] = g_seq_def_nb[def_off + i];
+        }
         *tlog = deflog;
         return 0;
     }
@@ -1286,13 +1307,13 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) k_zstd_seq_decode(ZstdParams P
                 if (modes & 3) ok = false;
                 if (ok && sub == 0) {
                     bool tok;
-                    pos += read_seq_table_packed(T->ll_sym, T->ll_nb, &ll_log, (modes >> 6) & 3, c_ll_default, 36, 6, 35, 9, LL_CAP,
+                    pos += read_seq_table_packed(T->ll_sym, T->ll_nb, &ll_log, (modes >> 6) & 3, SEQ_DEF_LL, 6, 35, 9, LL_CAP,
                                                  src + pos, len - pos, ws, &tok, &big);
                     if (tok)
-                        pos += read_seq_table_packed(T->of_sym, T->of_nb, &of_log, (modes >> 4) & 3, c_of_default, 29, 5, 31, 8, OF_CAP,
+                        pos += read_seq_table_packed(T->of_sym, T->of_nb, &of_log, (modes >> 4) & 3, SEQ_DEF_OF, 5, 31, 8, OF_CAP,
                                                      src + pos, len - pos, ws, &tok, &big);
                     if (tok)
-                        pos += read_seq_table_packed(T->ml_sym, T->ml_nb, &ml_log, (modes >> 2) & 3, c_ml_default, 53, 6, 52, 9, ML_CAP,
+                        pos += read_seq_table_packed(T->ml_sym, T->ml_nb, &ml_log, (modes >> 2) & 3, SEQ_DEF_ML, 6, 52, 9, ML_CAP,
                                                      src + pos, len - pos, ws, &tok, &big);
                     if (!tok || pos >= len) ok = false;  // (leader only; the group learns it from the broadcast below)
                     if (tok && big) job->seq_big = 1;    // (BIG launch: cannot happen, its tables hold every legal log)
@@ -1563,6 +1584,17 @@ void launch_zstd_sequences(const ZstdParams& P, cudaStream_t st) {
     uint32_t grid = (uint32_t)((groups + per_cta - 1) / per_cta);
     if ((uint64_t)grid * per_cta > slots) grid = (uint32_t)(slots / per_cta);
     if (grid == 0) grid = 1;
+    {   // the predefined tables, once per device (a second context of the same device must not run ahead of the build)
+        static std::mutex mu;
+        static bool built[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        if (!built[dev & 63]) {
+            k_zstd_seq_defaults<<<1, 32, 0, st>>>();
+            if (cudaStreamSynchronize(st) == cudaSuccess) built[dev & 63] = true;
+        }
+    }
     k_zstd_seq_decode<false><<<grid, SEQ_WARPS * 32, 0, st>>>(P);
     k_zstd_seq_decode<true><<<grid, SEQ_WARPS * 32, 0, st>>>(P);  // frames flagged by the first launch (normally none)
     uint32_t xgrid = (P.count + SEQX_WARPS - 1) / SEQX_WARPS;
