@@ -339,6 +339,26 @@ int vmb_binary_op(vmb_ctx* ctx, int op, int is_bool, const double* d_left, const
  * keys the left side lacks. */
 int vmb_group_first_value(vmb_ctx* ctx, const double* d_vals, size_t nseries, size_t points, const uint32_t* group_ids, uint32_t ngroups,
                           double* d_out);
+
+/* Transform functions that only look at values (app/vmselect/promql/transform.go), in place on a DEVICE matrix [nrows x points]; labels,
+ * sorting and the choice of series stay with the host.  Element functions (newTransformFuncOneArg :180 and friends) are applied to
+ * every value, NaN included, like doTransformValues :195; row functions walk each series in point order like the reference (float
+ * addition order is part of the result).  arg1 / arg2: HOST arrays of `points` values = getScalar of the scalar arguments:
+ *   clamp(q, min, max): arg1 = min, arg2 = max;  clamp_min / clamp_max: arg1;  round(q, nearest): arg1 = nearest, arg2 =
+ *   math.Pow10(-e) with (_, e) = decimal.FromFloat(nearest) (transform.go:2341; vmb_float_to_decimal gives e).  Others: NULL.
+ * exp / ln / log2 / log10 / trigonometric / hyperbolic functions are the CUDA math library's (<= 2 ulp from Go's); everything else is
+ * bit-exact. */
+enum vmb_transform_func {
+    VMB_TF_ABS = 0, VMB_TF_CEIL, VMB_TF_FLOOR, VMB_TF_SQRT, VMB_TF_EXP, VMB_TF_LN, VMB_TF_LOG2, VMB_TF_LOG10, VMB_TF_SIN, VMB_TF_COS,
+    VMB_TF_TAN, VMB_TF_ASIN, VMB_TF_ACOS, VMB_TF_ATAN, VMB_TF_SINH, VMB_TF_COSH, VMB_TF_TANH, VMB_TF_ASINH, VMB_TF_ACOSH, VMB_TF_ATANH,
+    VMB_TF_DEG, VMB_TF_RAD, VMB_TF_SGN, VMB_TF_CLAMP, VMB_TF_CLAMP_MIN, VMB_TF_CLAMP_MAX, VMB_TF_ROUND,
+    /* row functions: running_* (:1308), range_* = running + setLastValues (:1335, :1650), range_first / range_last (:1620, :1640),
+     * keep_last_value / keep_next_value (:1214, :1237), remove_resets = removeCounterResetsMaybeNaNs (:2906) */
+    VMB_TF_RUNNING_SUM = 32, VMB_TF_RUNNING_MIN, VMB_TF_RUNNING_MAX, VMB_TF_RUNNING_AVG, VMB_TF_RANGE_SUM, VMB_TF_RANGE_MIN,
+    VMB_TF_RANGE_MAX, VMB_TF_RANGE_AVG, VMB_TF_RANGE_FIRST, VMB_TF_RANGE_LAST, VMB_TF_KEEP_LAST_VALUE, VMB_TF_KEEP_NEXT_VALUE,
+    VMB_TF_REMOVE_RESETS
+};
+int vmb_transform(vmb_ctx* ctx, int func, double* d_matrix, size_t nrows, size_t points, const double* arg1, const double* arg2);
 /* mergeSeries rollup_result_cache.go:618: d_dst[nrows x (pa + pb)], row i = d_a[a_rows[i]] ++ d_b[b_rows[i]]; a negative index
  * stands for a series missing on that side (NaNs, :677-690).  a_rows / b_rows: HOST, matched by metric name by the caller. */
 int vmb_matrix_merge_rows(vmb_ctx* ctx, const double* d_a, const int64_t* a_rows, size_t pa, const double* d_b, const int64_t* b_rows,

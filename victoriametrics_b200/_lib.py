@@ -131,6 +131,7 @@ def lib():
         "vmb_matrix_merge_rows": (C.c_int, [vp, vp, i64p, sz, vp, i64p, sz, sz, vp]),
         "vmb_aggr_quantile": (C.c_int, [vp, vp, sz, sz, u32p, C.c_uint32, f64p, vp]),
         "vmb_group_first_value": (C.c_int, [vp, vp, sz, sz, u32p, C.c_uint32, vp]),
+        "vmb_transform": (C.c_int, [vp, C.c_int, vp, sz, sz, f64p, f64p]),
         "vmb_host_alloc": (vp, [sz]),
         "vmb_host_free": (None, [vp]),
         "vmb_ctx_last_stage_ms": (C.c_float, [vp, C.c_int]),

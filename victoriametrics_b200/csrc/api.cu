@@ -1697,6 +1697,7 @@ extern "C" int vmb_eval_rollup_device(vmb_ctx* ctx, const vmb_blocks* b, int64_t
 #include "topk.inc"
 #include "comm.inc"
 #include "matrix_ops.inc"
+#include "transform.inc"
 
 // ------------------------------------------------------------------------------------------------ batched host encoder
 #include <atomic>

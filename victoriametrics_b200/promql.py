@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib, storage
+from . import _lib, decimal, storage
 from ._lib import RollupCfg, check, lib
 
 # enum vmb_rollup_func order (include/vmb200.h); keys are the MetricsQL names of rollup.go:24-108
@@ -495,6 +495,41 @@ def set_op(op, left_dev_ptr, left_groups, nleft, right_dev_ptr, right_groups, nr
     el = {"and": "if", "if": "if", "unless": "ifnot", "ifnot": "ifnot", "default": "default"}[op.lower()]
     group_first_value(right_dev_ptr, nright, points, right_groups, ngroups, tmp_dev_ptr, ctx=ctx)
     binary_op(el, left_dev_ptr, tmp_dev_ptr, nleft, points, dst_dev_ptr, right_rows=np.asarray(left_groups, dtype=np.uint32), ctx=ctx)
+
+
+TRANSFORM_FUNCS = {n: i for i, n in enumerate(
+    ["abs", "ceil", "floor", "sqrt", "exp", "ln", "log2", "log10", "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh",
+     "acosh", "atanh", "deg", "rad", "sgn", "clamp", "clamp_min", "clamp_max", "round"])}
+TRANSFORM_FUNCS.update({n: 32 + i for i, n in enumerate(
+    ["running_sum", "running_min", "running_max", "running_avg", "range_sum", "range_min", "range_max", "range_avg", "range_first",
+     "range_last", "keep_last_value", "keep_next_value", "remove_resets"])})
+
+
+def transform(name, dev_ptr, nrows, points, *scalar_args, ctx=None):
+    """transform.go value functions in place on a DEVICE matrix [nrows x points] (vmb_transform).  scalar_args: the function's scalar
+    arguments (numbers or per-point arrays, getScalar): clamp(min, max), clamp_min(min), clamp_max(max), round(nearest = 1)"""
+    ctx = ctx or _lib.default_context()
+    name = name.lower()
+    bc = lambda x: np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (points,)))
+    a1 = a2 = None
+    if name == "clamp":
+        a1, a2 = bc(scalar_args[0]), bc(scalar_args[1])
+    elif name in ("clamp_min", "clamp_max"):
+        a1 = bc(scalar_args[0])
+    elif name == "round":
+        a1 = bc(scalar_args[0] if scalar_args else 1.0)
+        # p10 = math.Pow10(-e), (_, e) = decimal.FromFloat(nearest)  transform.go:2341
+        uniq, inv = np.unique(a1, return_inverse=True)
+        p10u = np.empty(uniq.size)
+        for k, n in enumerate(uniq):
+            if np.isnan(n) or np.isinf(n) or n == 0:
+                p10u[k] = 1.0
+                continue
+            _, e = decimal.append_float_to_decimal(np.array([n], dtype=np.float64))
+            p10u[k] = float("1e%d" % (-int(e)))
+        a2 = np.ascontiguousarray(p10u[inv])
+    fp = lambda a: a.ctypes.data_as(_lib.f64p) if a is not None else None
+    check(lib().vmb_transform(ctx.h, TRANSFORM_FUNCS[name], C.c_void_p(int(dev_ptr)), int(nrows), int(points), fp(a1), fp(a2)))
 
 
 def aggr_quantile(phis, vals_dev_ptr, nseries, points, out_dev_ptr, group_ids=None, ngroups=1, ctx=None):
