@@ -92,7 +92,8 @@ struct FusedSmem {
     double ev_amt[FU_MAX_EVENTS], ev_cum[FU_MAX_EVENTS];
     uint32_t ev_row[FU_MAX_EVENTS];
     uint32_t nev;
-    uint32_t flags;  // bit 0: bail, bit 1: slow removeCounterResets pass needed
+    uint32_t flags;  // bit 0: bail (set while parsing, read behind the barrier that ends the parse)
+    uint32_t flags_emit;  // the same for the emit pass: a word of its own, so that a warp already emitting cannot race a warp still reading `flags`
     unsigned long long s_part[FU_WARPS];
     FuSeries ser;
 };
@@ -454,6 +455,7 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
         if (tid == 0) {
             fu_series_setup(P, s, &S.ser);
             S.flags = 0;
+            S.flags_emit = 0;
             S.nev = 0;
         }
         __syncthreads();
@@ -828,7 +830,7 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                         };
                         if (delta2) emit_run(std::true_type{});
                         else emit_run(std::false_type{});
-                        if (saw_stale && stale_matters) S.flags = 1u;
+                        if (saw_stale && stale_matters) S.flags_emit = 1u;
                     }
                     // ---- carries
                     if (delta2) {
@@ -848,7 +850,7 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                         if (N != nvar) bail = true;
                     }
                     __syncthreads();
-                    if (S.flags & 1u) bail = true;
+                    if ((S.flags | S.flags_emit) & 1u) bail = true;
                     if (stream_done && !bail) {
                         const uint32_t last_al = (uint32_t)(vhi - 1);  // aligned position of the last stream byte
                         if (A[last_al] >= 0x80) bail = true;
