@@ -50,5 +50,5 @@ torch.cuda.synchronize(); dt = (time.perf_counter() - t) / 5
 print("4 blocks x 2048 rows per series: %.3f ms/step (%.1f G samples/s); stages zstd %.3f decode %.3f preamble %.3f rollup %.3f" %
       (dt * 1e3, NS * NB * ROWS / dt / 1e9, st[0], st[1], st[2], st[3]))
 # same result as the single-block layout?
-d1, p1 = bench.gen_blocks(64, NB * ROWS, 99)
+d1, p1, _ = bench.gen_blocks(64, NB * ROWS, 99)
 print("nan rows:", int(torch.isnan(out).all(dim=1).sum().item()), "of", NS)

@@ -9,7 +9,7 @@ from victoriametrics_b200 import promql, storage
 NB = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 start, end, step = bench.query_range(8192, 300000, 15000)
 points = 1 + (end - start) // step
-descs, payload = bench.gen_blocks(NB, 8192, 1234)
+descs, payload, _ = bench.gen_blocks(NB, 8192, 1234)
 for K in (1, 2, 4):
     per = NB // K
     parts = []
