@@ -412,7 +412,7 @@ __device__ void fu_series_setup(const FusedParams& P, uint32_t s, FuSeries* out)
     }
     o.rate_dt = -1;
     o.rate_D = o.rate_R = 1.0;
-    if (!bail && rc.func_id == VMB_RF_RATE) {
+    if (!bail && (rc.func_id == VMB_RF_RATE || rc.func_id == VMB_RF_DELTA)) {  // (delta / increase use rate_rows, rate_dt > 0 only)
         const int32_t dt_row = (int32_t)dts;
         const int32_t rows_w = o.lin ? o.jq0 - o.iq0 : o.win32 / dt_row;
         if (rows_w >= 1 && (int64_t)rows_w * dt_row < ((int64_t)1 << 30)) {
@@ -975,19 +975,27 @@ __global__ void __launch_bounds__(FU_THREADS, 4) k_fused_rollup(FusedParams P) {
                 asm volatile("" : "+r"(sc_interior));
 #pragma unroll 2
                 for (uint32_t q = p + tid; q < p_end; q += FU_THREADS) {
-                    if (F == VMB_RF_RATE && lin && rate_dt > 0 && prev_always) {
+                    if ((F == VMB_RF_RATE || F == VMB_RF_DELTA) && lin && rate_dt > 0 && prev_always) {
                         // interior point: the window [i, j) holds rate_rows rows and row i - 1 exists: (v[j-1] - v[i-1]) / D
                         const int32_t is_ = iq0 + (int32_t)q * lin_k;
                         if (is_ >= 1 && is_ + rate_rows <= (int32_t)n) {
                             const double vp = fu_lds(val_s, (uint32_t)is_ - 1u), vl = fu_lds(val_s, (uint32_t)(is_ + rate_rows) - 1u);
                             const double x = vl - vp;
-                            const uint32_t ex = ((uint32_t)__double2hiint(x) >> 20) & 0x7ffu;
-                            if (!isnan(vp) && (x == 0.0 || ex - 123u < 1800u)) {
-                                const double q0 = __dmul_rn(x, rate_R);
-                                const double rem = __fma_rn(-q0, rate_D, x);
-                                sc32 += sc_interior;
-                                put(q, x == 0.0 ? x : __fma_rn(rem, rate_R, q0));
-                                continue;
+                            if (F == VMB_RF_DELTA) {  // rollupDelta rollup.go:1859 with a previous value: values[n - 1] - prevValue
+                                if (!isnan(vp)) {
+                                    sc32 += sc_interior;
+                                    put(q, x);
+                                    continue;
+                                }
+                            } else {
+                                const uint32_t ex = ((uint32_t)__double2hiint(x) >> 20) & 0x7ffu;
+                                if (!isnan(vp) && (x == 0.0 || ex - 123u < 1800u)) {
+                                    const double q0 = __dmul_rn(x, rate_R);
+                                    const double rem = __fma_rn(-q0, rate_D, x);
+                                    sc32 += sc_interior;
+                                    put(q, x == 0.0 ? x : __fma_rn(rem, rate_R, q0));
+                                    continue;
+                                }
                             }
                         }
                     }
