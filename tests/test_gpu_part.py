@@ -235,3 +235,57 @@ def test_zstd_decompress_empty_content_frame(oracle):
     one = oracle.zstd_ref_compress(np.array([9], dtype=np.uint8), 3)
     got = vm.encoding.decompress_zstd_batch([one, f, one])
     assert [g.tolist() for g in got] == [[9], [], [9]]
+
+
+def _ll_table_log(frame):
+    """accuracy log of the literal-lengths FSE table of a single-block frame with compressed literals (RFC 8878 3.1.1.3.2.1), or None"""
+    b = bytes(frame)
+    fhd = b[4]
+    fcs, ss, did = fhd >> 6, (fhd >> 5) & 1, fhd & 3
+    pos = 5 + (0 if ss else 1) + [0, 1, 2, 4][did] + ([1, 2, 4, 8][fcs] if (fcs or ss) else 0)
+    bh = b[pos] | (b[pos + 1] << 8) | (b[pos + 2] << 16)
+    if not (bh & 1) or ((bh >> 1) & 3) != 2:
+        return None  # not one compressed block
+    blk = b[pos + 3: pos + 3 + (bh >> 3)]
+    if (blk[0] & 3) != 2:
+        return None
+    sf = (blk[0] >> 2) & 3
+    if sf in (0, 1):
+        hs, comp = 3, ((blk[0] | (blk[1] << 8) | (blk[2] << 16)) >> 14) & 0x3ff
+    elif sf == 2:
+        hs, comp = 4, (int.from_bytes(blk[:4], "little") >> 18) & 0x3fff
+    else:
+        hs, comp = 5, (int.from_bytes(blk[:5], "little") >> 22) & 0x3ffff
+    p = hs + comp
+    b0 = blk[p]
+    p += 1 if b0 < 128 else (2 if b0 < 255 else 3)
+    if b0 == 0:
+        return None
+    modes = blk[p]
+    return (blk[p + 1] & 15) + 5 if (modes >> 6) & 3 == 2 else None
+
+
+def test_zstd_sequence_tables_above_256_states(oracle):
+    """frames whose FSE tables have accuracy log 9 take the second k_zstd_seq_decode launch (full-size tables)"""
+    import victoriametrics_b200 as vm
+    if not oracle.lib().vmo_zstd_ref_available():
+        pytest.skip("oracle/_ref (the reference's libzstd) was not built")
+    rng = np.random.default_rng(SEED0 + 4321)
+    srcs, frames, logs = [], [], []
+    for trial in range(24):
+        n = int(rng.choice([30000, 60000, 100000]))
+        if trial % 2:
+            a = np.repeat(rng.integers(0, 255, n // 7 + 1).astype(np.uint8), 7)[:n].copy()
+            a[rng.random(n) < 0.05] = 1
+        else:
+            words = [bytes(rng.integers(97, 123, int(rng.integers(3, 12))).astype(np.uint8)) for _ in range(200)]
+            a = np.frombuffer(b" ".join(words[int(i)] for i in rng.integers(0, 200, n // 6)), dtype=np.uint8)[:n].copy()
+        f = oracle.zstd_ref_compress(a, int(rng.choice([1, 3])))
+        srcs.append(a)
+        frames.append(f)
+        logs.append(_ll_table_log(f))
+    assert any(l == 9 for l in logs), logs            # the shape this test is about
+    small = [oracle.zstd_ref_compress(np.cumsum(rng.integers(0, 3, 8192)).astype(np.uint8), 1) for _ in range(8)]  # log <= 8 beside them
+    got = vm.encoding.decompress_zstd_batch(frames + small)
+    for g, a in zip(got[:len(srcs)], srcs):
+        assert np.array_equal(g, a)
