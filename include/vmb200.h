@@ -356,7 +356,7 @@ enum vmb_transform_func {
      * keep_last_value / keep_next_value (:1214, :1237), remove_resets = removeCounterResetsMaybeNaNs (:2906) */
     VMB_TF_RUNNING_SUM = 32, VMB_TF_RUNNING_MIN, VMB_TF_RUNNING_MAX, VMB_TF_RUNNING_AVG, VMB_TF_RANGE_SUM, VMB_TF_RANGE_MIN,
     VMB_TF_RANGE_MAX, VMB_TF_RANGE_AVG, VMB_TF_RANGE_FIRST, VMB_TF_RANGE_LAST, VMB_TF_KEEP_LAST_VALUE, VMB_TF_KEEP_NEXT_VALUE,
-    VMB_TF_REMOVE_RESETS
+    VMB_TF_REMOVE_RESETS, VMB_TF_INTERPOLATE /* :1261 */
 };
 int vmb_transform(vmb_ctx* ctx, int func, double* d_matrix, size_t nrows, size_t points, const double* arg1, const double* arg2);
 /* mergeSeries rollup_result_cache.go:618: d_dst[nrows x (pa + pb)], row i = d_a[a_rows[i]] ++ d_b[b_rows[i]]; a negative index

@@ -110,11 +110,35 @@ def _row_ref(name, values):
             prev = v[i]
             v[i] = v[i] + corr
         return v
+    if name == "interpolate":  # :1261
+        lo, hi = 0, len(v)
+        while lo < hi and math.isnan(v[lo]):
+            lo += 1
+        while hi > lo and math.isnan(v[hi - 1]):
+            hi -= 1
+        w = v[lo:hi]
+        i = 0
+        while i < len(w):
+            if not math.isnan(w[i]):
+                i += 1
+                continue
+            prev = w[i - 1]
+            j = i + 1
+            while j < len(w) and math.isnan(w[j]):
+                j += 1
+            nxt = w[j]
+            delta = (nxt - prev) / float(j - i + 1)
+            while i < j:
+                prev += delta
+                w[i] = prev
+                i += 1
+        return v
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("name", ["running_sum", "running_min", "running_max", "running_avg", "range_sum", "range_min", "range_max",
-                                  "range_avg", "range_first", "range_last", "keep_last_value", "keep_next_value", "remove_resets"])
+                                  "range_avg", "range_first", "range_last", "keep_last_value", "keep_next_value", "remove_resets",
+                                  "interpolate"])
 @pytest.mark.parametrize("shape", [(70, 97), (33, 32), (5, 1), (1, 400)])
 def test_row_functions_bit_exact(name, shape):
     rng = np.random.default_rng(SEED0 + 900 + len(name) * 7 + shape[1])

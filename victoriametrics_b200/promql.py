@@ -502,7 +502,7 @@ TRANSFORM_FUNCS = {n: i for i, n in enumerate(
      "acosh", "atanh", "deg", "rad", "sgn", "clamp", "clamp_min", "clamp_max", "round"])}
 TRANSFORM_FUNCS.update({n: 32 + i for i, n in enumerate(
     ["running_sum", "running_min", "running_max", "running_avg", "range_sum", "range_min", "range_max", "range_avg", "range_first",
-     "range_last", "keep_last_value", "keep_next_value", "remove_resets"])})
+     "range_last", "keep_last_value", "keep_next_value", "remove_resets", "interpolate"])})
 
 
 def transform(name, dev_ptr, nrows, points, *scalar_args, ctx=None):
