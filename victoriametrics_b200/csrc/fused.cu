@@ -26,8 +26,9 @@
 //   2. a lane decodes the varints whose terminator lies in its 16 bytes (7-bit groups compacted once per lane, then one
 //      shift-and-mask per value; the bytes of a varint that starts in the previous 16 bytes are carried in), zig-zag decodes
 //      them, stores them raw at their rows and keeps (count, sum, sum of prefix sums);
-//   3. one warp scan + one 8-entry scan over the warps of those triples -- associative under wrapping int64 arithmetic, so
-//      the prefix sums are bit-identical to the sequential Go loop;
+//   3. the triples are combined over the lanes and over the 8 warps -- (s2A + s2B + cntB * s1A) is associative under wrapping
+//      int64 arithmetic, so the prefix sums are bit-identical to the sequential Go loop; with the counts known from step 1 the
+//      combination is two plain sum scans: s1, then t = s2 + cnt * (exclusive prefix of s1);
 //   4. every lane replays its values with the scanned prefix, converts mantissa -> float64 (decimal.go:100) and overwrites
 //      the raw value in place.
 #pragma once
