@@ -855,6 +855,55 @@ def run_configs2(a, ctx, nseries, out_dev, time_steps, start, end, step, points)
             r["parity_check"] = parity_check(arm, lambda idx: out_dev[torch.from_numpy(idx).cuda()].cpu().numpy(), 200)
             assert r["parity_check"]["ok"], (func, r["parity_check"])
             rec[func] = r
+        if kind == "counter":
+            # configs[3] per GPU: sum(rate(m[5m])) by (label) over the same nseries series, 1024 groups.  Every chunk is folded inside
+            # the fused kernel into a partial {values, counts}[G x P] and merged into the running state (updateTimeseries +
+            # the merge of aggr_incremental.go:141); then the library's all-reduce (a no-op on one GPU), finalize, result to the host
+            import ctypes as C
+            from victoriametrics_b200 import _lib
+            G = 1024
+            rcfg = promql.get_rollup_configs("rate", start, end, step, a.window_ms)
+            cfg = rcfg._cfg()
+            cells = G * points
+            tot = torch.empty(2 * cells, dtype=torch.float64, device="cuda")
+            part = torch.empty(2 * cells, dtype=torch.float64, device="cuda")
+            gids = [((np.arange(bl.count, dtype=np.int64) + 131 * k) % G).astype(np.uint32) for k, bl in enumerate(chunks)]
+            res = np.empty((G, points), dtype=np.float64)
+            L = _lib.lib()
+            SUM = promql.AGGR_FUNCS["sum"]
+
+            def fn_aggr():
+                sc = C.c_uint64(0)
+                for k, bl in enumerate(chunks):
+                    dst = tot if k == 0 else part
+                    _lib.check(L.vmb_eval_rollup_aggr_device(ctx.h, bl.h, storage.INT64_MIN, storage.INT64_MAX, C.byref(cfg), SUM,
+                                                             gids[k].ctypes.data_as(_lib.u32p), G, C.c_void_p(dst.data_ptr()),
+                                                             C.c_void_p(dst.data_ptr() + cells * 8), C.byref(sc)))
+                    if k:
+                        _lib.check(L.vmb_aggr_merge(ctx.h, SUM, C.c_void_p(tot.data_ptr()), C.c_void_p(tot.data_ptr() + cells * 8),
+                                                    C.c_void_p(part.data_ptr()), C.c_void_p(part.data_ptr() + cells * 8), cells))
+                _lib.check(L.vmb_aggr_allreduce(ctx.h, SUM, C.c_void_p(tot.data_ptr()), C.c_void_p(tot.data_ptr() + cells * 8), cells))
+                _lib.check(L.vmb_aggr_finalize(ctx.h, SUM, C.c_void_p(tot.data_ptr()), C.c_void_p(tot.data_ptr() + cells * 8), cells,
+                                               res.ctypes.data_as(_lib.f64p)))
+                return res
+            ms_, launches_, _, _ = time_steps(fn_aggr, 1, 2)
+            # check against the (parity-checked) per-series result: chunk 0's rows summed by group, then the same path on chunk 0 alone
+            promql.eval_rollup_func("rate", chunks[0], start, end, step, a.window_ms, out_dev_ptr=out_dev.data_ptr())
+            rows0 = out_dev[: chunks[0].count]
+            want = torch.zeros((G, points), dtype=torch.float64, device="cuda")
+            want.index_add_(0, torch.from_numpy(gids[0].astype(np.int64)).cuda(), torch.nan_to_num(rows0, nan=0.0))
+            got0, _ = promql.eval_rollup_aggr_dist("sum", "rate", chunks[0], gids[0], G, start, end, step, a.window_ms)
+            w = want.cpu().numpy()
+            ok = bool(np.allclose(np.nan_to_num(got0, nan=0.0), w, rtol=1e-9, atol=1e-9))
+            assert ok, "sum(rate) by over chunk 0 differs from the per-series result summed by group"
+            rec["sum_rate_by_1024_groups"] = {
+                "value": nseries * a.rows / (ms_ / 1e3), "unit": "samples/s", "ms_per_step": ms_, "gpu_launches_per_step": launches_ / 2,
+                "groups": G, "result": "[1024 x %d] f64 finalized and copied to the host inside the timed region" % points,
+                "api": "per chunk vmb_eval_rollup_aggr_device (fold inside the fused kernel) + vmb_aggr_merge; then vmb_aggr_allreduce "
+                       "(NCCL inside the library; a no-op on one GPU) + vmb_aggr_finalize",
+                "note": "BASELINE.json configs[3] is this on 8 GPUs x 1 M series each; the N = 8 `aggr` record of this bench shows the "
+                        "all-reduce of [1024 x %d] adds 0.7 ms" % points,
+                "check": {"chunk0_vs_per_series_rows_summed_by_group_rtol_1e-9": ok}}
         for bl in chunks:
             bl.close()
         del chunks, first
