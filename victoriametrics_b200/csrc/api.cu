@@ -1432,6 +1432,15 @@ static void launch_fused(const FusedParams& P, cudaStream_t st) {
         FUSED_CASE(VMB_RF_COUNT)
         FUSED_CASE(VMB_RF_QUANTILE)
         FUSED_CASE(VMB_RF_DEFAULT_ROLLUP)
+        // the next most common dashboard functions: a lean instantiation instead of the all-functions one (which spills)
+        FUSED_CASE(VMB_RF_IDERIV)
+        FUSED_CASE(VMB_RF_IDELTA)
+        FUSED_CASE(VMB_RF_LAST)
+        FUSED_CASE(VMB_RF_FIRST)
+        FUSED_CASE(VMB_RF_STDDEV)
+        FUSED_CASE(VMB_RF_STDVAR)
+        FUSED_CASE(VMB_RF_CHANGES)
+        FUSED_CASE(VMB_RF_DERIV)
 #undef FUSED_CASE
         default: FUSED_LAUNCH((k_fused_rollup<-1>), smem0); break;
     }
