@@ -505,6 +505,15 @@ TRANSFORM_FUNCS.update({n: 32 + i for i, n in enumerate(
      "range_last", "keep_last_value", "keep_next_value", "remove_resets", "interpolate"])})
 
 
+def _go_pow10(n):
+    """Go's math.Pow10 (src/math/pow10.go): a PRODUCT / QUOTIENT of two table literals, not the literal 1eN itself for |n| >= 32"""
+    if 0 <= n <= 308:
+        return float("1e%d" % (n // 32 * 32)) * float("1e%d" % (n % 32))
+    if -323 <= n <= 0:
+        return float("1e-%d" % ((-n) // 32 * 32)) / float("1e%d" % ((-n) % 32))
+    return 0.0 if n < 0 else float("inf")
+
+
 def transform(name, dev_ptr, nrows, points, *scalar_args, ctx=None):
     """transform.go value functions in place on a DEVICE matrix [nrows x points] (vmb_transform).  scalar_args: the function's scalar
     arguments (numbers or per-point arrays, getScalar): clamp(min, max), clamp_min(min), clamp_max(max), round(nearest = 1)"""
@@ -526,7 +535,7 @@ def transform(name, dev_ptr, nrows, points, *scalar_args, ctx=None):
                 p10u[k] = 1.0
                 continue
             _, e = decimal.append_float_to_decimal(np.array([n], dtype=np.float64))
-            p10u[k] = float("1e%d" % (-int(e)))
+            p10u[k] = _go_pow10(-int(e))
         a2 = np.ascontiguousarray(p10u[inv])
     fp = lambda a: a.ctypes.data_as(_lib.f64p) if a is not None else None
     check(lib().vmb_transform(ctx.h, TRANSFORM_FUNCS[name], C.c_void_p(int(dev_ptr)), int(nrows), int(points), fp(a1), fp(a2)))
